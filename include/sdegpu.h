@@ -1,0 +1,171 @@
+/* sdegpu.h — C ABI of libsdegpu.so, the B200 (sm_100a) ensemble SDE integrator
+ * behind the SDEtools sample-path API.
+ *
+ * The reference (Uffe-H-Thygesen/SDEtools) is interpreted R with no FFI
+ * (NAMESPACE:1-34 has no useDynLib), so this boundary is new surface.  Each
+ * entry point names the reference interface it replaces; the R-side `.Call`
+ * shim that binds them is r/src/sdegpu_shim.c.
+ *
+ * Conventions: extern "C", plain pointers and sizes, no C++/torch/R types, no
+ * exceptions across the boundary.  Every function returns 0 on success or a
+ * negative sdegpu_status; sdegpu_last_error() gives the thread-local message.
+ * All matrices use the reference's layout: column-major, time fastest —
+ *   X[(p*nx + j)*nt + i]   path p, state component j, time index i
+ *   B[(p*nB + k)*nt + i]   path p, Brownian channel k, time index i
+ * i.e. for one path X is exactly R's `nt x nx` matrix (R/sdetools.R:439-441,464)
+ * and an ensemble is the `nt x nx x npaths` array sapply/replicate would build.
+ * Pointers are host pointers unless SDEGPU_DEVICE_PTRS is set in `flags`.
+ */
+#ifndef SDEGPU_H
+#define SDEGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDEGPU_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SDEGPU_API __attribute__((visibility("default")))
+#else
+#define SDEGPU_API
+#endif
+
+typedef struct sdegpu_ctx sdegpu_ctx;
+
+typedef enum {
+    SDEGPU_OK = 0,
+    SDEGPU_ERR_ARG = -1,      /* invalid argument / unsupported combination */
+    SDEGPU_ERR_CUDA = -2,     /* CUDA runtime failure (message has the cudaError string) */
+    SDEGPU_ERR_NOMEM = -3,    /* device or host allocation failed */
+    SDEGPU_ERR_NODEVICE = -4  /* no sm_100 device / wrong architecture */
+} sdegpu_status;
+
+/* Model catalogue: drift/diffusion closures cannot be arbitrary R functions on
+ * the device (reference: `f`,`g` arguments of euler/heun, R/sdetools.R:375,240),
+ * so they are selected by id with a parameter vector.  Operation order is fixed
+ * as the R closure would evaluate it.  All have nB = 1
+ * (vector-valued g, R/sdetools.R:422-424) except LINEAR. */
+typedef enum {
+    SDEGPU_MODEL_OU = 0,         /* f = lambda*(xi-x)          g = sigma               params {lambda, xi, sigma} */
+    SDEGPU_MODEL_CIR = 1,        /* f = lambda*(xi-x)          g = gamma*sqrt(abs(x))  params {lambda, xi, gamma} */
+    SDEGPU_MODEL_VDP = 2,        /* f = (v, v*(mu-x*x)-x)      g = (0, sigma)          params {mu, sigma}; nx = 2 */
+    SDEGPU_MODEL_LOGISTIC = 3,   /* f = x*(1-x) - c*(x*x)      g = sigma*x             params {sigma, c} */
+    SDEGPU_MODEL_GBM = 4,        /* f = mu*x                   g = sigma*x             params {mu, sigma} */
+    SDEGPU_MODEL_DOUBLEWELL = 5, /* f = x - x*x*x              g = sigma               params {sigma} */
+    SDEGPU_MODEL_LINEAR = 6      /* f = A %*% x                g = G (nx x nB)         params {A col-major, G col-major} */
+} sdegpu_model;
+
+typedef enum { SDEGPU_EULER = 0, SDEGPU_HEUN = 1 } sdegpu_scheme;            /* euler :375-470 / heun :240-338 */
+typedef enum { SDEGPU_PROJ_IDENTITY = 0, SDEGPU_PROJ_ABS = 1, SDEGPU_PROJ_RELU = 2 } sdegpu_projection; /* `p` argument */
+
+/* STRICT: one correctly rounded IEEE op per R operator, reference order, no FMA
+ *         -> bit-identical to the reference arithmetic for nB = 1.
+ * FAST:   FMA contraction and algebraically equivalent regrouping allowed. */
+typedef enum { SDEGPU_ARITH_STRICT = 0, SDEGPU_ARITH_FAST = 1 } sdegpu_arith;
+
+enum {
+    SDEGPU_DEVICE_PTRS = 1u,  /* B, per-path x0 and every output buffer are device pointers */
+    SDEGPU_ACCUMULATE = 2u    /* add into power_sums / hist_counts instead of overwriting */
+};
+
+/* One euler()/heun() ensemble: npaths independent calls of the reference function. */
+typedef struct {
+    uint32_t struct_size;     /* = sizeof(sdegpu_problem), for forward compatibility */
+    int32_t model;            /* sdegpu_model */
+    int32_t scheme;           /* sdegpu_scheme */
+    int32_t arith;            /* sdegpu_arith */
+    int32_t projection;       /* sdegpu_projection */
+    int32_t nx, nB;           /* length(x0); Brownian channels (R/sdetools.R:377,420-428) */
+    int32_t nparams;
+    const double *params;     /* host, nparams doubles */
+    int32_t nt;               /* length(times) >= 2 */
+    int32_t x0_stride;        /* 0: one x0 shared by all paths (host ptr); nx: x0[p*nx+j] per path */
+    const double *times;      /* host, nt doubles; dt_i = times[i+1]-times[i] is never assumed constant (:446) */
+    const double *x0;
+    const double *B;          /* Brownian paths (`B` argument, :431-437) or NULL: increments are then drawn in-kernel
+                                 from Philox4x32-10, dB = sqrt(dt_i)*Z, keyed by (seed; path_offset+p, step, channel) */
+    uint64_t npaths;
+    uint64_t path_offset;     /* global id of path 0: shards of one ensemble use disjoint id ranges */
+    uint64_t seed;
+    uint32_t flags;
+    uint32_t reserved;
+} sdegpu_problem;
+
+/* Caller-allocated outputs; any pointer may be NULL. */
+typedef struct {
+    uint32_t struct_size;     /* = sizeof(sdegpu_output) */
+    int32_t hist_component;   /* state component the histogram is taken on */
+    double *X;                /* nt*nx*npaths: the `X` of list(times=,X=) for every path (:464) */
+    double *XT;               /* nx*npaths: terminal state X[nt,] of every path, XT[p*nx+j] */
+    double *power_sums;       /* 5*nx: per component {n, S1, S2, S3, S4}, S_k = sum_p (X_T - center[j])^k over finite X_T */
+    const double *center;     /* host, nx doubles (NULL = 0): shift for the power sums */
+    uint64_t *hist_counts;    /* hist_nbins+3: {under, bins..., over, nan}; equal-width breaks on [lo,hi] with R's
+                                 hist(right=TRUE, include.lowest=TRUE) convention: bin k = (lo+k*w, lo+(k+1)*w], lo in bin 0 */
+    double hist_lo, hist_hi;
+    int32_t hist_nbins;
+    int32_t reserved;
+    float *elapsed_ms;        /* host: CUDA-event time of the kernels of this call (no copies) */
+} sdegpu_output;
+
+typedef struct {
+    char name[64];
+    int32_t sm_count, cc_major, cc_minor, clock_khz;
+    uint64_t global_mem_bytes;
+} sdegpu_devinfo;
+
+SDEGPU_API int sdegpu_abi_version(void);
+SDEGPU_API const char *sdegpu_last_error(void);
+
+/* One context per process per GPU.  `device` is the CUDA ordinal. */
+SDEGPU_API int sdegpu_create(int device, sdegpu_ctx **ctx);
+SDEGPU_API int sdegpu_destroy(sdegpu_ctx *ctx);
+SDEGPU_API int sdegpu_device_info(sdegpu_ctx *ctx, sdegpu_devinfo *info);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream. */
+SDEGPU_API int sdegpu_set_stream(sdegpu_ctx *ctx, void *cuda_stream);
+SDEGPU_API int sdegpu_synchronize(sdegpu_ctx *ctx);
+
+/* Replaces sapply/replicate around euler() (R/sdetools.R:375-470) or heun() (:240-338).
+ * Blocking unless SDEGPU_DEVICE_PTRS is set, in which case work is only enqueued on the stream. */
+SDEGPU_API int sdegpu_run(sdegpu_ctx *ctx, const sdegpu_problem *prob, sdegpu_output *out);
+
+/* Stochastic integrals on stored paths, batched over ncols columns of length n
+ * (column c at a + c*n).  Partial sums follow R's cumsum exactly: an x87 80-bit
+ * accumulator rounded to double per element (emulated in integer arithmetic on
+ * the device), so results are bit-identical to the reference on x86-64.
+ *   sdegpu_stochint   stochint(f,g,rule)        R/sdetools.R:105-113; l, r, c may each be NULL
+ *   sdegpu_itointegral itointegral(G,B)         R/sdetools.R:155-158
+ *   sdegpu_qv         QuadraticVariation(X)     R/sdetools.R:134-137
+ *   sdegpu_crossvar   CrossVariation(X,Y)       R/sdetools.R:184-187 */
+SDEGPU_API int sdegpu_stochint(sdegpu_ctx *ctx, const double *f, const double *g, uint64_t n, uint64_t ncols,
+                    double *l, double *r, double *c, uint32_t flags);
+SDEGPU_API int sdegpu_itointegral(sdegpu_ctx *ctx, const double *G, const double *B, uint64_t n, uint64_t ncols,
+                       double *out, uint32_t flags);
+SDEGPU_API int sdegpu_qv(sdegpu_ctx *ctx, const double *X, uint64_t n, uint64_t ncols, double *out, uint32_t flags);
+SDEGPU_API int sdegpu_crossvar(sdegpu_ctx *ctx, const double *X, const double *Y, uint64_t n, uint64_t ncols,
+                    double *out, uint32_t flags);
+
+/* rvBM(times, n) for an ensemble (R/sdetools.R:16-22,40-46): column c is
+ * B0 + cumsum(N(u*dt, sigma^2 dt)) with dt = c(times[1], diff(times)), 80-bit
+ * cumsum, normals from the fused Philox generator keyed by (seed; path_offset+c). */
+SDEGPU_API int sdegpu_rvbm(sdegpu_ctx *ctx, const double *times, int32_t nt, uint64_t ncols, double sigma, double B0,
+                double u, uint64_t seed, uint64_t path_offset, double *B, uint32_t flags);
+
+/* Generator introspection (tests / known-answer vectors). */
+SDEGPU_API int sdegpu_philox4x32_10(sdegpu_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* z[i*npaths + p] = standard normal handed to step i, channel `channel`, of path path_offset+p (host ptr). */
+SDEGPU_API int sdegpu_normals(sdegpu_ctx *ctx, uint64_t seed, uint64_t path_offset, uint64_t npaths, uint32_t channel,
+                   int32_t nsteps, double *z);
+
+/* Roofline denominators measured on this device: a dependent-free DFMA stream
+ * (TFLOP/s, 2 flops per FMA) and a device-to-device copy (GB/s, read+write). */
+SDEGPU_API int sdegpu_measure_fp64_peak(sdegpu_ctx *ctx, double *tflops);
+SDEGPU_API int sdegpu_measure_hbm_peak(sdegpu_ctx *ctx, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDEGPU_H */

@@ -62,7 +62,7 @@ static void diffusion(int model, const double *P, int nx, int nB, const double *
 static inline double project(int proj, double v)
 {
     if (proj == P_ABS) return fabs(v);
-    if (proj == P_RELU) return v > 0.0 ? v : 0.0;     /* pmax(x,0) */
+    if (proj == P_RELU) return v < 0.0 ? 0.0 : v;     /* pmax(x,0); NaN stays NaN */
     return v;
 }
 
@@ -90,8 +90,8 @@ static void normal_pair(uint64_t seed, uint64_t path, uint32_t block, uint32_t c
 {
     uint32_t c[4] = { (uint32_t)path, (uint32_t)(path >> 32), block, channel };
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    uint64_t b1 = (((uint64_t)c[1] << 32) | c[0]) >> 11, b2 = (((uint64_t)c[3] << 32) | c[2]) >> 11;
-    double u1 = ((double)b1 + 0.5) * 0x1p-53, u2 = ((double)b2 + 0.5) * 0x1p-53;
+    uint64_t m1 = (((uint64_t)c[1] << 32) | c[0]) >> 12, m2 = (((uint64_t)c[3] << 32) | c[2]) >> 12;
+    double u1 = 2.0 - (1.0 + (double)m1 * 0x1p-52), u2 = (double)m2 * 0x1p-52;
     double rad = sqrt(-2.0 * log(u1)), a = 6.283185307179586476925 * u2;
     z[0] = rad * cos(a);
     z[1] = rad * sin(a);

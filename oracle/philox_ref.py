@@ -10,11 +10,12 @@ stream can be checked draw by draw:
   key      = (seed & 0xffffffff, seed >> 32)
   counter  = (path & 0xffffffff, path >> 32, block, channel)
   r0..r3   = philox4x32_10(counter, key)
-  u1       = (((r1<<32 | r0) >> 11) + 0.5) * 2^-53      in (0,1)
-  u2       = (((r3<<32 | r2) >> 11) + 0.5) * 2^-53
+  m1, m2   = top 52 bits of r1:r0 and of r3:r2
+  u1       = 2 - (1 + m1 * 2^-52)                       in (0,1]
+  v        =      1 + m2 * 2^-52                        in [1,2)   (angle fraction + 1)
   rad      = sqrt(-2 log u1)
-  z[2*block]   = rad * cospi(2 u2)        (Box-Muller pair, one block = two steps)
-  z[2*block+1] = rad * sinpi(2 u2)
+  z[2*block]   = rad * cospi(2 v)         (Box-Muller pair, one block = two steps)
+  z[2*block+1] = rad * sinpi(2 v)
   dB[i,k]  = sqrt(dt[i]) * z[i]   for channel k
 """
 from __future__ import annotations
@@ -48,10 +49,10 @@ def uniforms(path, block, channel, seed):
     path = np.asarray(path, dtype=np.uint64)
     r0, r1, r2, r3 = philox4x32_10(path & MASK, path >> np.uint64(32), block, channel,
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    b1 = ((r1 << np.uint64(32)) | r0) >> np.uint64(11)
-    b2 = ((r3 << np.uint64(32)) | r2) >> np.uint64(11)
-    u1 = (b1.astype(np.float64) + 0.5) * 2.0 ** -53
-    u2 = (b2.astype(np.float64) + 0.5) * 2.0 ** -53
+    m1 = ((r1 << np.uint64(32)) | r0) >> np.uint64(12)
+    m2 = ((r3 << np.uint64(32)) | r2) >> np.uint64(12)
+    u1 = 2.0 - (1.0 + m1.astype(np.float64) * 2.0 ** -52)
+    u2 = m2.astype(np.float64) * 2.0 ** -52          # v - 1: cospi/sinpi have period 2
     return u1, u2
 
 
@@ -62,11 +63,9 @@ def normals(paths, nsteps, channel, seed):
     blk = np.arange(nblk, dtype=np.uint64)[:, None]
     u1, u2 = uniforms(paths[None, :], blk, channel, seed)
     rad = np.sqrt(-2.0 * np.log(u1))
-    ang = 2.0 * np.pi * u2
     # cospi/sinpi evaluated with exact quadrant reduction like the device does
     z0 = rad * _cospi(2.0 * u2)
     z1 = rad * _sinpi(2.0 * u2)
-    del ang
     z = np.empty((2 * nblk, paths.shape[0]))
     z[0::2] = z0
     z[1::2] = z1

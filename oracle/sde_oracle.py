@@ -286,7 +286,7 @@ def catalogue(model: str, params):
 
 
 def projection(name: str):
-    return {"identity": (lambda x: x), "abs": np.abs, "relu": (lambda x: np.maximum(x, 0.0))}[name]
+    return {"identity": (lambda x: x), "abs": np.abs, "relu": (lambda x: np.where(x < 0.0, 0.0, x))}[name]
 
 
 def ensemble(scheme, model, params, times, x0, B=None, dB=None, proj="identity", full=True):

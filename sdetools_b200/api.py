@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's sample-path API (same names, argument
+order and return layout as R/sdetools.R), running on libsdegpu.so.
+
+    euler(f, g, times, x0, B=None, p=..., h=None, r=None, S0=1, Stau=None)   R/sdetools.R:375
+    heun (f, g, times, x0, B=None, p=..., h=None, r=None, S0=1, Stau=None)   R/sdetools.R:240
+    stochint(f, g, rule="l")  :105    itointegral(G, B)  :155
+    QuadraticVariation(X)     :134    CrossVariation(X, Y) :184
+    rBM(times, sigma, B0, u)  :16     rvBM(times, n, sigma, B0, u) :40     rBrownianBridge :62
+
+New arguments are keyword-only and appended after the reference's, so every
+positional call of the reference keeps its meaning.  Arrays use the reference's
+column-major layout: numpy results are Fortran-ordered, `X[i, j]` (one path) or
+`X[i, j, p]` (ensemble) is time i, component j, path p.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import catalogue as _cat
+from .engine import default_engine
+
+
+def _catalogue_model(f, g):
+    fm, gm = getattr(f, "sdegpu_model", None), getattr(g, "sdegpu_model", None)
+    if fm is None or gm is None:
+        raise TypeError("f and g must come from sdetools_b200.catalogue: arbitrary closures cannot run on the "
+                        "device and this package has no interpreted fallback")
+    if fm != gm or not np.array_equal(f.sdegpu_params, g.sdegpu_params) or f.role != "drift" or g.role != "diffusion":
+        raise TypeError("f and g must be the (drift, diffusion) pair returned by one catalogue constructor")
+    return fm, f.sdegpu_params, f.nx, f.nB
+
+
+def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith,
+              device, path_offset):
+    if h is not None or r is not None:
+        raise NotImplementedError("stopping (h) and killing (r) are not in the device catalogue yet")
+    model, params, nx, nB = _catalogue_model(f, g)
+    proj = _cat.projection_id(p)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    nt = times.size
+    x0 = np.asarray(x0, dtype=np.float64)
+    names = None
+    if x0.ndim == 2:                       # (nx, npaths): one initial condition per path
+        if x0.shape[0] != nx:
+            raise ValueError(f"x0 must have {nx} rows")
+        x0c = np.ascontiguousarray(x0.T)   # x0[p*nx+j]
+        npaths_x0 = x0.shape[1]
+    else:
+        if x0.size != nx:
+            raise ValueError(f"length(x0) must be {nx} for this model")
+        x0c, npaths_x0 = np.ascontiguousarray(x0.ravel()), None
+    ensemble = True
+    if B is not None:
+        Bh = np.asarray(B, dtype=np.float64)
+        if Bh.ndim == 1:                   # :435  matrix(B, nrow=nt, ncol=nB): a vector is recycled into nB columns
+            Bh = np.repeat(Bh[:, None], nB, axis=1)
+        if Bh.ndim == 2:
+            if Bh.shape != (nt, nB):
+                raise ValueError(f"B must be length(times) x nB = {nt} x {nB}")
+            Bh, ensemble = Bh[:, :, None], npaths is not None and npaths != 1
+        if Bh.shape[:2] != (nt, nB):
+            raise ValueError(f"B must be {nt} x {nB} x npaths")
+        if npaths is not None and npaths != Bh.shape[2]:
+            raise ValueError("npaths disagrees with the third dimension of B")
+        npaths = Bh.shape[2]
+        Bdev = np.asfortranarray(Bh)       # memory: B[(p*nB+k)*nt+i]
+    else:
+        Bdev = None
+        if npaths is None:
+            npaths, ensemble = (npaths_x0 or 1), npaths_x0 is not None
+    if npaths_x0 is not None and npaths_x0 != npaths:
+        raise ValueError("x0 has one column per path; its column count must equal npaths")
+    if seed is None:
+        seed = int(np.random.default_rng().integers(0, 2 ** 63))
+    eng = default_engine(device)
+    want_path = output == "path"
+    if output not in ("path", "terminal", "none"):
+        raise ValueError("output must be 'path', 'terminal' or 'none'")
+    X = np.empty((nt, nx, npaths), order="F") if want_path else None
+    XT = np.empty((nx, npaths), order="F") if output in ("path", "terminal") else None
+    ps = np.zeros((5, nx), order="F") if moments else None
+    hc = np.zeros(hist[2] + 3, dtype=np.uint64) if hist is not None else None
+    eng.run(model, scheme, params, times, x0c, nx=nx, nB=nB, npaths=npaths, B=Bdev, projection=proj, arith=arith,
+            seed=seed, path_offset=path_offset, X=X, XT=XT, power_sums=ps, center=center, hist_counts=hc, hist=hist)
+    res = {"times": times}
+    if want_path:
+        res["X"] = X if ensemble else X[:, :, 0]
+    if XT is not None:
+        res["XT"] = XT if ensemble else XT[:, 0]
+    if ps is not None:
+        res["power_sums"] = ps
+        res["moments"] = moments_from_power_sums(ps, np.zeros(nx) if center is None else np.ravel(center))
+    if hc is not None:
+        lo, hi, nb = hist[:3]
+        res["hist"] = {"breaks": lo + (hi - lo) * np.arange(nb + 1) / nb, "counts": hc[1:nb + 1].astype(np.int64),
+                       "under": int(hc[0]), "over": int(hc[nb + 1]), "nan": int(hc[nb + 2])}
+    res["seed"] = seed
+    return res
+
+
+def moments_from_power_sums(ps, center):
+    """{n, mean, var, skewness, kurtosis} per component from shifted power sums (5, nx)."""
+    ps = np.asarray(ps, dtype=np.float64).reshape(5, -1)
+    n = ps[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m1, m2, m3, m4 = ps[1] / n, ps[2] / n, ps[3] / n, ps[4] / n
+        var = m2 - m1 * m1
+        mu3 = m3 - 3 * m1 * m2 + 2 * m1 ** 3
+        mu4 = m4 - 4 * m1 * m3 + 6 * m1 * m1 * m2 - 3 * m1 ** 4
+        return {"n": n, "mean": np.asarray(center) + m1, "var": var * n / (n - 1),
+                "skewness": mu3 / var ** 1.5, "kurtosis": mu4 / (var * var)}
+
+
+def euler(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *, npaths=None, seed=None,
+          output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0):
+    """Euler-Maruyama for the Ito SDE dX = f dt + g dB (R/sdetools.R:375-470).
+
+    With the reference's arguments only, returns dict(times=, X=) with X the `nt x nx` matrix of one
+    path, exactly like the reference's list(times=,X=).  `npaths` / a 3-d `B` (nt x nB x npaths) /
+    a 2-d `x0` (nx x npaths) turn the call into the ensemble the reference builds with sapply
+    (vignettes/Killing.Rmd:183-189): X is then `nt x nx x npaths`.  If B is None the Brownian
+    increments are drawn on the device (Philox, `seed`).  `output='terminal'` skips the trajectory;
+    `moments=True` / `hist=(lo, hi, nbins[, component])` reduce the terminal states on the device."""
+    return _simulate("euler", f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist,
+                     arith, device, path_offset)
+
+
+def heun(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *, npaths=None, seed=None,
+         output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0):
+    """Heun's method for the Stratonovich SDE dX = f dt + g o dB (R/sdetools.R:240-338); see `euler`."""
+    return _simulate("heun", f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist,
+                     arith, device, path_offset)
+
+
+# ---- integrals ------------------------------------------------------------------
+def _cols(*arrs):
+    """Reference vectors (n,) or ensembles (n, ncols) -> Fortran buffers (column c at c*n)."""
+    out = []
+    shape = None
+    for a in arrs:
+        a = np.asarray(a, dtype=np.float64)
+        a2 = a.reshape(a.shape[0], -1)
+        if shape is None:
+            shape = a.shape
+        elif a.shape != shape:
+            raise ValueError("arguments must have the same shape")
+        out.append(np.asfortranarray(a2))
+    return out, shape
+
+
+def stochint(f, g, rule="l", *, device=None):
+    """R/sdetools.R:105-113.  One rule -> array like f; several -> dict of columns in `rule` order."""
+    (fb, gb), shape = _cols(f, g)
+    n, nc = fb.shape
+    rules = [rule] if isinstance(rule, str) else list(rule)
+    if any(k not in ("l", "r", "c") for k in rules):
+        raise ValueError("rule must be drawn from 'l', 'r', 'c'")
+    bufs = {k: np.empty((n, nc), order="F") for k in set(rules)}
+    default_engine(device).stochint(fb, gb, n, nc, bufs.get("l"), bufs.get("r"), bufs.get("c"))
+    if isinstance(rule, str):
+        return bufs[rule].reshape(shape, order="F")
+    return {k: bufs[k].reshape(shape, order="F") for k in rules}
+
+
+def itointegral(G, B, *, device=None):
+    """R/sdetools.R:155-158."""
+    (gb, bb), shape = _cols(G, B)
+    out = np.empty(gb.shape, order="F")
+    default_engine(device).itointegral(gb, bb, gb.shape[0], gb.shape[1], out)
+    return out.reshape(shape, order="F")
+
+
+def QuadraticVariation(X, *, device=None):
+    """R/sdetools.R:134-137."""
+    (xb,), shape = _cols(X)
+    out = np.empty(xb.shape, order="F")
+    default_engine(device).qv(xb, xb.shape[0], xb.shape[1], out)
+    return out.reshape(shape, order="F")
+
+
+def CrossVariation(X, Y, *, device=None):
+    """R/sdetools.R:184-187."""
+    (xb, yb), shape = _cols(X, Y)
+    out = np.empty(xb.shape, order="F")
+    default_engine(device).crossvar(xb, yb, xb.shape[0], xb.shape[1], out)
+    return out.reshape(shape, order="F")
+
+
+# ---- Brownian motion -----------------------------------------------------------------
+def rvBM(times, n=1, sigma=1.0, B0=0.0, u=0.0, *, seed=None, device=None, path_offset=0):
+    """R/sdetools.R:40-46: `nt x n`, one column per sample path.  (Vector-valued sigma/B0/u as in the
+    reference are applied column-wise on the host side by calling once per distinct value.)"""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    if seed is None:
+        seed = int(np.random.default_rng().integers(0, 2 ** 63))
+    sig, b0, uu = (np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)) for v in (sigma, B0, u))
+    out = np.empty((times.size, n), order="F")
+    eng = default_engine(device)
+    if np.all(sig == sig[0]) and np.all(b0 == b0[0]) and np.all(uu == uu[0]):
+        eng.rvbm(times, n, out, sig[0], b0[0], uu[0], seed, path_offset)
+    else:
+        col = np.empty((times.size, 1), order="F")
+        for i in range(n):
+            eng.rvbm(times, 1, col, sig[i], b0[i], uu[i], seed, path_offset + i)
+            out[:, i] = col[:, 0]
+    return out
+
+
+def rBM(times, sigma=1.0, B0=0.0, u=0.0, *, seed=None, device=None):
+    """R/sdetools.R:16-22."""
+    return rvBM(times, 1, sigma, B0, u, seed=seed, device=device)[:, 0]
+
+
+def rBrownianBridge(times, B0T=(0.0, 0.0), sigma=1.0, *, seed=None, device=None):
+    """R/sdetools.R:62-73: linear detrending of one rBM path."""
+    times = np.asarray(times, dtype=np.float64)
+    B = rBM(times, sigma=sigma, seed=seed, device=device)
+    n = times.size
+    slope = (B0T[1] - B0T[0] - B[n - 1] + B[0]) / (times[n - 1] - times[0])
+    return B + B0T[0] - B[0] + slope * (times - times[0])

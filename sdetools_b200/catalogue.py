@@ -1,0 +1,101 @@
+"""Compiled model catalogue.
+
+The reference takes arbitrary R closures `f`, `g` (R/sdetools.R:375, :240); a
+device kernel cannot call back into an interpreter, so drift and diffusion come
+from this catalogue.  Each constructor returns a pair of ordinary callables
+`(f, g)` — usable exactly like the closures in the reference's examples — that
+carry the attributes `sdegpu_model` / `sdegpu_params`, which is what `euler` and
+`heun` dispatch on.  Operation order of every formula is the one the matching
+R closure evaluates and is what the kernels reproduce in
+STRICT arithmetic.
+
+Calling the closures evaluates the formula with numpy; that is a convenience
+for plotting drift/diffusion, never the simulation path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class CatalogueFunction:
+    """A drift or diffusion closure tagged with its catalogue identity."""
+
+    def __init__(self, role, model, params, fn, nx, nB):
+        self.role, self.sdegpu_model, self.fn = role, model, fn
+        self.sdegpu_params = np.ascontiguousarray(params, dtype=np.float64)
+        self.nx, self.nB = nx, nB
+
+    def __call__(self, *args):          # f(x) or f(t,x), like the reference accepts (:381-394)
+        return self.fn(np.asarray(args[-1], dtype=np.float64))
+
+    def __repr__(self):
+        return f"<catalogue {self.role} {self.sdegpu_model} params={self.sdegpu_params.tolist()}>"
+
+
+def _pair(model, params, f, g, nx=1, nB=1):
+    return (CatalogueFunction("drift", model, params, f, nx, nB),
+            CatalogueFunction("diffusion", model, params, g, nx, nB))
+
+
+def ou(lambda_=1.0, xi=0.0, sigma=1.0):
+    """dX = lambda*(xi-X) dt + sigma dB  (R/sdetools.R:718; Killing.Rmd:157-161)."""
+    return _pair("ou", [lambda_, xi, sigma], lambda x: lambda_ * (xi - x), lambda x: sigma + 0.0 * x)
+
+
+def cir(lambda_=1.0, xi=1.0, gamma=1.0):
+    """dX = lambda*(xi-X) dt + gamma*sqrt(abs(X)) dB; use p=abs (HMM-filtering-of-scalar-SDEs.Rmd:33-51)."""
+    return _pair("cir", [lambda_, xi, gamma], lambda x: lambda_ * (xi - x), lambda x: gamma * np.sqrt(np.abs(x)))
+
+
+def vdp(mu=1.0, sigma=0.5):
+    """van der Pol: f = c(v, v*(mu-x^2)-x), g = c(0,sigma)  (vanderPol.Rmd:27-53); nx = 2, one channel."""
+    return _pair("vdp", [mu, sigma],
+                 lambda x: np.stack([x[1], x[1] * (mu - x[0] * x[0]) - x[0]]),
+                 lambda x: np.stack([0.0 * x[0], sigma + 0.0 * x[0]]), nx=2)
+
+
+def logistic(sigma=0.5, harvest=0.0):
+    """Logistic fisheries: f = x*(1-x) - harvest*x^2, g = sigma*x  (FisheriesManagement.Rmd:30-51)."""
+    return _pair("logistic", [sigma, harvest], lambda x: x * (1.0 - x) - harvest * (x * x), lambda x: sigma * x)
+
+
+def gbm(mu=0.0, sigma=1.0):
+    """Geometric Brownian motion f = mu*x, g = sigma*x  (R/sdetools.R:222-228)."""
+    return _pair("gbm", [mu, sigma], lambda x: mu * x, lambda x: sigma * x)
+
+
+def doublewell(sigma=0.5):
+    """f = x - x^3 (evaluated x - x*x*x), g = sigma  (SDEtools.Rmd:50-55)."""
+    return _pair("doublewell", [sigma], lambda x: x - x * x * x, lambda x: sigma + 0.0 * x)
+
+
+def linear(A, G):
+    """dX = A X dt + G dB with matrix-valued g: nB = ncol(G) channels (R/sdetools.R:360-368)."""
+    A = np.atleast_2d(np.asarray(A, dtype=np.float64))
+    d = A.shape[0]
+    G = np.asarray(G, dtype=np.float64).reshape(d, -1)
+    params = np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
+    return _pair("linear", params, lambda x: A @ x, lambda x: G, nx=d, nB=G.shape[1])
+
+
+def relu(x):
+    """Projection pmax(x, 0)."""
+    return np.where(np.asarray(x) < 0, 0.0, x)
+
+
+def identity(x):
+    return x
+
+
+def projection_id(p) -> str:
+    """Map the reference's `p` argument onto a catalogue projection."""
+    if p is None or p is identity:
+        return "identity"
+    if isinstance(p, str) and p in ("identity", "abs", "relu"):
+        return p
+    if p is abs or p is np.abs or p is np.absolute or p is np.fabs:
+        return "abs"
+    if p is relu:
+        return "relu"
+    raise TypeError("projection p must be None, abs, catalogue.relu or one of 'identity'/'abs'/'relu': "
+                    "arbitrary closures cannot run on the device")

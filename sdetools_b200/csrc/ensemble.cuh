@@ -1,0 +1,255 @@
+// Ensemble kernels: P independent euler()/heun() calls, one thread per path,
+// state in registers across all steps (replaces the sapply/replicate idiom around
+// R/sdetools.R:375-470 / :240-338, e.g. vignettes/Killing.Rmd:183-189).
+//
+//   k_terminal : increments from the fused Philox generator, nothing but terminal
+//                state / power sums / histogram leaves the SM   (FP64-pipe bound)
+//   k_tiled    : supplied B read through shared-memory tiles and/or the full
+//                trajectory X written through shared-memory tiles (HBM bound)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "models.cuh"
+#include "philox.cuh"
+
+namespace sdegpu {
+
+constexpr int MAX_NX = 2;           // catalogue models handled here have nx <= 2
+constexpr int TERMINAL_THREADS = 256;
+constexpr int TILE_PATHS = 128;     // paths (= threads) per block in k_tiled
+constexpr int TILE_STEPS = 32;      // time steps staged per tile
+constexpr int TILE_LD = TILE_STEPS + 1;   // odd leading dimension: conflict-free column walks
+
+struct RunArgs {
+    KParams P;
+    const double2 *dtsq;            // [nt-1] {dt_i, sqrt(dt_i)},  dt_i = times[i+1]-times[i]  (:446)
+    const double *x0;               // per-path x0 (device) or nullptr
+    double x0s[MAX_NX];             // shared x0
+    const double *B;                // device, B[p*nt+i]  (nB = 1)
+    double *X;                      // device, X[(p*nx+j)*nt+i]
+    double *XT;                     // device, XT[p*nx+j]
+    double *partials;               // [gridDim.x][5*nx] block partial power sums, or nullptr
+    unsigned long long *hist;       // [nbins+3] or nullptr
+    double center[MAX_NX];
+    double hist_lo, hist_hi, hist_invw;
+    uint64_t npaths, path_offset, seed;
+    int nt, hist_nbins, hist_comp;
+};
+
+// ---- terminal statistics ---------------------------------------------------
+// Histogram bin of R's hist(right=TRUE, include.lowest=TRUE) on equal-width breaks;
+// index arithmetic uses individually rounded ops so the CPU oracle reproduces it.
+__device__ __forceinline__ int hist_bin(double x, const RunArgs &a)
+{
+    if (x != x) return a.hist_nbins + 2;
+    if (x < a.hist_lo) return 0;
+    if (x > a.hist_hi) return a.hist_nbins + 1;
+    int k = (int)ceil(__dmul_rn(__dsub_rn(x, a.hist_lo), a.hist_invw)) - 1;
+    k = k < 0 ? 0 : (k >= a.hist_nbins ? a.hist_nbins - 1 : k);
+    return k + 1;
+}
+
+template <int NX>
+__device__ __forceinline__ void accumulate_terminal(const RunArgs &a, const double (&x)[NX], double (&acc)[NX][5],
+                                                    unsigned int *sh_hist)
+{
+    if (a.partials) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            const double d = x[j] - a.center[j];
+            if (isfinite(d)) {
+                const double d2 = d * d;
+                acc[j][0] += 1.0; acc[j][1] += d; acc[j][2] += d2; acc[j][3] += d2 * d; acc[j][4] += d2 * d2;
+            }
+        }
+    }
+    if (a.hist) atomicAdd(&sh_hist[hist_bin(x[a.hist_comp < NX ? a.hist_comp : 0], a)], 1u);
+}
+
+// Deterministic block reduction: shuffle tree per warp, then warps in index order.
+template <int NX, int THREADS>
+__device__ __forceinline__ void flush_block_stats(const RunArgs &a, double (&acc)[NX][5], unsigned int *sh_hist)
+{
+    constexpr int NW = THREADS / 32;
+    __shared__ double sh_red[NW][NX * 5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.partials) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                double v = acc[j][m];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) sh_red[warp][j * 5 + m] = v;
+            }
+    }
+    __syncthreads();
+    if (a.partials && threadIdx.x < NX * 5) {
+        double v = 0.0;
+        for (int w = 0; w < NW; ++w) v += sh_red[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * (NX * 5) + threadIdx.x] = v;
+    }
+    if (a.hist)
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += THREADS)
+            if (sh_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)sh_hist[i]);
+}
+
+template <int NX>
+__device__ __forceinline__ void load_x0(const RunArgs &a, uint64_t p, double (&x)[NX])
+{
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = a.x0 ? a.x0[p * NX + j] : a.x0s[j];
+}
+
+// ---- register-resident, fused-generator kernel ------------------------------
+template <class M, int SCHEME, int PROJ>
+__global__ void __launch_bounds__(TERMINAL_THREADS) k_terminal(const RunArgs a)
+{
+    constexpr int NX = M::NX;
+    extern __shared__ unsigned int sh_hist[];
+    if (a.hist) {
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TERMINAL_THREADS) sh_hist[i] = 0u;
+        __syncthreads();
+    }
+    double acc[NX][5];
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
+
+    const int nsteps = a.nt - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * TERMINAL_THREADS;
+    for (uint64_t p = (uint64_t)blockIdx.x * TERMINAL_THREADS + threadIdx.x; p < a.npaths; p += stride) {
+        double x[NX];
+        load_x0<NX>(a, p, x);
+        const uint64_t gp = a.path_offset + p;
+        int i = 0;
+        for (; i + 1 < nsteps; i += 2) {
+            double z0, z1;
+            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, z0, z1);
+            const double2 d0 = __ldg(&a.dtsq[i]), d1 = __ldg(&a.dtsq[i + 1]);
+            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
+            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d1.x, d1.y * z1);
+        }
+        if (i < nsteps) {
+            double z0, z1;
+            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, z0, z1);
+            const double2 d0 = __ldg(&a.dtsq[i]);
+            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
+        }
+        if (a.XT) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+        }
+        accumulate_terminal<NX>(a, x, acc, sh_hist);
+    }
+    flush_block_stats<NX, TERMINAL_THREADS>(a, acc, sh_hist);
+}
+
+// ---- tiled kernel: supplied B in, and/or full trajectory out ----------------
+// Shared memory (dynamic): [hist: nbins+3 u32, padded to 16 B]
+//                          [sB: TILE_PATHS x TILE_LD doubles]            if SRC_B
+//                          [sX: NX x TILE_PATHS x TILE_LD doubles]       if a.X
+template <class M, int SCHEME, int PROJ, class A, bool SRC_B>
+__global__ void __launch_bounds__(TILE_PATHS) k_tiled(const RunArgs a, const int hist_words)
+{
+    constexpr int NX = M::NX;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(smem_raw);
+    double *sB = reinterpret_cast<double *>(smem_raw + (size_t)hist_words * 4);
+    double *sX = sB + (SRC_B ? TILE_PATHS * TILE_LD : 0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.hist) {
+        for (int i = tid; i < a.hist_nbins + 3; i += TILE_PATHS) sh_hist[i] = 0u;
+    }
+    __syncthreads();
+    double acc[NX][5];
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
+
+    const int nsteps = a.nt - 1;
+    const uint64_t ntiles = (a.npaths + TILE_PATHS - 1) / TILE_PATHS;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t p0 = tile * TILE_PATHS, p = p0 + tid;
+        const bool valid = p < a.npaths;
+        const int rows = (int)((a.npaths - p0 < (uint64_t)TILE_PATHS) ? (a.npaths - p0) : TILE_PATHS);
+        double x[NX];
+        if (valid) load_x0<NX>(a, p, x);
+        else {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) x[j] = 0.0;
+        }
+        if (a.X && valid) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt] = x[j];      // X[1,] <- x0  (:441)
+        }
+        const uint64_t gp = a.path_offset + p;
+        double z0 = 0.0, z1 = 0.0;
+        for (int i0 = 0; i0 < nsteps; i0 += TILE_STEPS) {
+            const int nc = (nsteps - i0 < TILE_STEPS) ? (nsteps - i0) : TILE_STEPS;
+            if (SRC_B) {
+                // rows of the B tile are contiguous in time: one warp streams one row at a time
+                for (int r = warp; r < rows; r += TILE_PATHS / 32) {
+                    const double *src = a.B + (p0 + r) * (uint64_t)a.nt + i0;
+                    for (int c = lane; c <= nc; c += 32) sB[r * TILE_LD + c] = __ldg(src + c);
+                }
+                __syncthreads();
+            }
+            if (valid) {
+#pragma unroll 2
+                for (int c = 0; c < nc; ++c) {
+                    const int i = i0 + c;
+                    const double2 d = __ldg(&a.dtsq[i]);
+                    double dB;
+                    if (SRC_B) {
+                        dB = A::sub(sB[tid * TILE_LD + c + 1], sB[tid * TILE_LD + c]);   // dB = diff(B)  (:437)
+                    } else {
+                        if ((c & 1) == 0) normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, z0, z1);
+                        dB = d.y * ((c & 1) ? z1 : z0);
+                    }
+                    sde_step<M, SCHEME, PROJ, A>(a.P, x, d.x, dB);
+                    if (a.X) {
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) sX[(j * TILE_PATHS + tid) * TILE_LD + c] = x[j];
+                    }
+                }
+            }
+            if (a.X) {
+                __syncthreads();
+                for (int r = warp; r < rows * NX; r += TILE_PATHS / 32) {
+                    const int row = r / NX, j = r - row * NX;
+                    double *dst = a.X + ((p0 + row) * NX + j) * (uint64_t)a.nt + i0 + 1;
+                    const double *srow = sX + (j * TILE_PATHS + row) * TILE_LD;
+                    for (int c = lane; c < nc; c += 32) dst[c] = srow[c];
+                }
+            }
+            __syncthreads();
+        }
+        if (valid) {
+            if (a.XT) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+            }
+            accumulate_terminal<NX>(a, x, acc, sh_hist);
+        }
+    }
+    flush_block_stats<NX, TILE_PATHS>(a, acc, sh_hist);
+}
+
+// ---- host-side launch signature shared by the per-model translation units ---
+struct LaunchCfg {
+    int scheme, proj, arith;
+    bool src_b, want_x;
+    int grid;            // 0: choose from occupancy
+    int sm_count;
+    cudaStream_t stream;
+};
+// returns cudaError_t as int; *grid_used gets the grid size actually launched
+typedef int (*model_launcher)(const RunArgs &, const LaunchCfg &, int *grid_used);
+int launch_model(int model, const RunArgs &, const LaunchCfg &, int *grid_used);
+
+}  // namespace sdegpu

@@ -1,0 +1,80 @@
+// One translation unit per catalogue model (compiled with -DSDEGPU_TU_MODEL=<id>):
+// instantiates k_terminal / k_tiled for every scheme x projection x arithmetic
+// combination of that model and exposes one launcher.
+#include "ensemble.cuh"
+
+#ifndef SDEGPU_TU_MODEL
+#error "compile with -DSDEGPU_TU_MODEL=<sdegpu_model id>"
+#endif
+
+namespace sdegpu {
+
+using M = Model<SDEGPU_TU_MODEL>;
+
+template <class K>
+static int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, uint64_t work_blocks)
+{
+    int per_sm = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t g = (uint64_t)per_sm * sm_count;
+    if (g > work_blocks) g = work_blocks;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <int SCHEME, int PROJ>
+static int launch_terminal(const RunArgs &a, const LaunchCfg &c, int *grid_used)
+{
+    auto kernel = k_terminal<M, SCHEME, PROJ>;
+    const size_t smem = a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0;
+    const uint64_t work = (a.npaths + TERMINAL_THREADS - 1) / TERMINAL_THREADS;
+    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TERMINAL_THREADS, smem, c.sm_count, work);
+    kernel<<<grid, TERMINAL_THREADS, smem, c.stream>>>(a);
+    *grid_used = grid;
+    return (int)cudaGetLastError();
+}
+
+template <int SCHEME, int PROJ, class A, bool SRC_B>
+static int launch_tiled(const RunArgs &a, const LaunchCfg &c, int *grid_used)
+{
+    auto kernel = k_tiled<M, SCHEME, PROJ, A, SRC_B>;
+    const int hist_words = a.hist ? ((a.hist_nbins + 3 + 3) / 4) * 4 : 0;
+    const size_t smem = (size_t)hist_words * 4 +
+                        sizeof(double) * TILE_PATHS * TILE_LD * ((SRC_B ? 1 : 0) + (a.X ? M::NX : 0));
+    const uint64_t work = (a.npaths + TILE_PATHS - 1) / TILE_PATHS;
+    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TILE_PATHS, smem, c.sm_count, work);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, TILE_PATHS, smem, c.stream>>>(a, hist_words);
+    *grid_used = grid;
+    return (int)cudaGetLastError();
+}
+
+template <int SCHEME, int PROJ>
+static int dispatch_mode(const RunArgs &a, const LaunchCfg &c, int *g)
+{
+    if (c.src_b)
+        return c.arith == SDEGPU_ARITH_STRICT ? launch_tiled<SCHEME, PROJ, Strict, true>(a, c, g)
+                                              : launch_tiled<SCHEME, PROJ, Fast, true>(a, c, g);
+    if (c.want_x) return launch_tiled<SCHEME, PROJ, Fast, false>(a, c, g);
+    return launch_terminal<SCHEME, PROJ>(a, c, g);
+}
+
+template <int SCHEME>
+static int dispatch_proj(const RunArgs &a, const LaunchCfg &c, int *g)
+{
+    switch (c.proj) {
+    case SDEGPU_PROJ_IDENTITY: return dispatch_mode<SCHEME, SDEGPU_PROJ_IDENTITY>(a, c, g);
+    case SDEGPU_PROJ_ABS: return dispatch_mode<SCHEME, SDEGPU_PROJ_ABS>(a, c, g);
+    default: return dispatch_mode<SCHEME, SDEGPU_PROJ_RELU>(a, c, g);
+    }
+}
+
+#define SDEGPU_CAT2(a, b) a##b
+#define SDEGPU_CAT(a, b) SDEGPU_CAT2(a, b)
+int SDEGPU_CAT(launch_model_, SDEGPU_TU_MODEL)(const RunArgs &a, const LaunchCfg &c, int *g)
+{
+    return c.scheme == SDEGPU_EULER ? dispatch_proj<SDEGPU_EULER>(a, c, g) : dispatch_proj<SDEGPU_HEUN>(a, c, g);
+}
+
+}  // namespace sdegpu

@@ -1,0 +1,151 @@
+// Linear SDE kernels.
+//   k_linear_generic : any d, any nB, STRICT or FAST, supplied B or fused generator.
+//       One thread per (path, state row); x lives in shared memory, A streams through L1/L2.
+//       `A %*% x` is accumulated in column order k = 0..d-1 with separate multiply and add
+//       (reference dgemv order) when strict.
+#include "linear.cuh"
+
+#include "../../include/sdegpu.h"
+#include "philox.cuh"
+
+namespace sdegpu {
+
+constexpr int LIN_THREADS = 256;
+
+template <bool STRICT>
+__device__ __forceinline__ double madd(double acc, double a, double b)
+{
+    return STRICT ? __dadd_rn(acc, __dmul_rn(a, b)) : fma(a, b, acc);
+}
+
+// dynamic smem: xs[PT*d] ys[PT*d] ns[PT*d] dBs[PT*nB] zs[PT*nB]
+template <bool STRICT>
+__global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs a, const int PT)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int d = a.d, nB = a.nB, nsteps = a.nt - 1;
+    double *xs = sm, *ys = xs + (size_t)PT * d, *ns = ys + (size_t)PT * d;
+    double *dBs = ns + (size_t)PT * d, *zs = dBs + (size_t)PT * nB;
+    const int tid = threadIdx.x;
+    const bool heun = a.scheme == SDEGPU_HEUN;
+    const uint64_t ngroups = (a.npaths + PT - 1) / PT;
+    for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const uint64_t p0 = grp * PT;
+        const int np = (int)((a.npaths - p0 < (uint64_t)PT) ? (a.npaths - p0) : PT);
+        for (int e = tid; e < np * d; e += LIN_THREADS) {
+            const int q = e / d, j = e - q * d;
+            const double v = a.x0 ? a.x0[(p0 + q) * d + j] : a.x0_shared[j];
+            xs[e] = v;
+            if (a.X) a.X[((p0 + q) * d + j) * (uint64_t)a.nt] = v;          // X[1,] <- x0 (:441)
+        }
+        __syncthreads();
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 ds = __ldg(&a.dtsq[i]);
+            // increments of this step for every (path, channel)
+            for (int e = tid; e < np * nB; e += LIN_THREADS) {
+                const int q = e / nB, k = e - q * nB;
+                if (a.B) {
+                    const double *b = a.B + ((p0 + q) * nB + k) * (uint64_t)a.nt + i;
+                    dBs[e] = __dsub_rn(b[1], b[0]);                           // dB <- apply(B,2,diff) (:437)
+                } else if ((i & 1) == 0) {
+                    double z0, z1;
+                    normal_pair(a.seed, a.path_offset + p0 + q, (uint32_t)(i >> 1), (uint32_t)k, z0, z1);
+                    zs[e] = z1;
+                    dBs[e] = ds.y * z0;
+                } else dBs[e] = ds.y * zs[e];
+            }
+            __syncthreads();
+            // Y = (x + (A x) dt) + G dB        (euler :453 / heun predictor :318)
+            for (int e = tid; e < np * d; e += LIN_THREADS) {
+                const int q = e / d, j = e - q * d;
+                const double *x = xs + q * d, *db = dBs + q * nB;
+                double f = STRICT ? __dmul_rn(a.A[j], x[0]) : a.A[j] * x[0];
+                for (int k = 1; k < d; ++k) f = madd<STRICT>(f, a.A[(size_t)k * d + j], x[k]);
+                double gdb = STRICT ? __dmul_rn(a.G[j], db[0]) : a.G[j] * db[0];
+                for (int k = 1; k < nB; ++k) gdb = madd<STRICT>(gdb, a.G[(size_t)k * d + j], db[k]);
+                ys[e] = STRICT ? __dadd_rn(__dadd_rn(x[j], __dmul_rn(f, ds.x)), gdb) : (x[j] + f * ds.x) + gdb;
+            }
+            __syncthreads();
+            const double *fresh = ys;
+            if (heun) {
+                // corrector (:323): x' = (x + (0.5*(fX+fY))*dt) + 0.5*((gX+gY) %*% dB); g is constant, gX+gY = G+G
+                for (int e = tid; e < np * d; e += LIN_THREADS) {
+                    const int q = e / d, j = e - q * d;
+                    const double *x = xs + q * d, *y = ys + q * d, *db = dBs + q * nB;
+                    double fx = STRICT ? __dmul_rn(a.A[j], x[0]) : a.A[j] * x[0];
+                    double fy = STRICT ? __dmul_rn(a.A[j], y[0]) : a.A[j] * y[0];
+                    for (int k = 1; k < d; ++k) {
+                        const double ajk = a.A[(size_t)k * d + j];
+                        fx = madd<STRICT>(fx, ajk, x[k]);
+                        fy = madd<STRICT>(fy, ajk, y[k]);
+                    }
+                    const double g0 = a.G[j];
+                    double gdb = STRICT ? __dmul_rn(__dadd_rn(g0, g0), db[0]) : (g0 + g0) * db[0];
+                    for (int k = 1; k < nB; ++k) {
+                        const double gk = a.G[(size_t)k * d + j];
+                        gdb = madd<STRICT>(gdb, STRICT ? __dadd_rn(gk, gk) : gk + gk, db[k]);
+                    }
+                    ns[e] = STRICT
+                        ? __dadd_rn(__dadd_rn(x[j], __dmul_rn(__dmul_rn(0.5, __dadd_rn(fx, fy)), ds.x)), __dmul_rn(0.5, gdb))
+                        : (x[j] + (0.5 * (fx + fy)) * ds.x) + 0.5 * gdb;
+                }
+                __syncthreads();
+                fresh = ns;
+            }
+            for (int e = tid; e < np * d; e += LIN_THREADS) {
+                const double v = fresh[e];
+                xs[e] = v;
+                if (a.X) {
+                    const int q = e / d, j = e - q * d;
+                    a.X[((p0 + q) * d + j) * (uint64_t)a.nt + i + 1] = v;
+                }
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < np * d; e += LIN_THREADS) {
+            const int q = e / d, j = e - q * d;
+            const double v = xs[e];
+            if (a.XT) a.XT[(p0 + q) * d + j] = v;
+            if (a.moments) {
+                const double dd = v - a.center[j];
+                if (isfinite(dd)) {
+                    const double d2 = dd * dd;
+                    atomicAdd(&a.moments[j * 5 + 0], 1.0);
+                    atomicAdd(&a.moments[j * 5 + 1], dd);
+                    atomicAdd(&a.moments[j * 5 + 2], d2);
+                    atomicAdd(&a.moments[j * 5 + 3], d2 * dd);
+                    atomicAdd(&a.moments[j * 5 + 4], d2 * d2);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream)
+{
+    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * a.d, stream);
+    int PT = LIN_THREADS / a.d;                        // paths per block: one thread per (path, row) when d <= 256
+    if (PT < 1) PT = 1;
+    if (PT > 64) PT = 64;
+    auto need = [&](int pt) { return sizeof(double) * ((size_t)3 * pt * a.d + (size_t)2 * pt * a.nB); };
+    size_t smem = need(PT);
+    while (smem > 200 * 1024 && PT > 1) { PT /= 2; smem = need(PT); }
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+    const uint64_t ngroups = (a.npaths + PT - 1) / PT;
+    auto ks = k_linear_generic<true>;
+    auto kf = k_linear_generic<false>;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, a.strict ? ks : kf, LIN_THREADS, smem);
+    uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
+    if (grid > ngroups) grid = ngroups;
+    if (a.strict) ks<<<(int)grid, LIN_THREADS, smem, stream>>>(a, PT);
+    else kf<<<(int)grid, LIN_THREADS, smem, stream>>>(a, PT);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sdegpu

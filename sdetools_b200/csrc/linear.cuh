@@ -1,0 +1,25 @@
+// Linear SDE dX = A X dt + G dB with matrix-valued g (nB channels, R/sdetools.R:425-428):
+// the drift is `A %*% x` (R/sdetools.R:360-368; vignettes/NoisyOscillator.Rmd:38-54).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdegpu {
+
+struct LinearArgs {
+    const double *A;          // device, d x d column-major
+    const double *G;          // device, d x nB column-major
+    const double2 *dtsq;      // [nt-1] {dt, sqrt(dt)}
+    const double *x0;         // per-path x0[p*d+j] or nullptr
+    const double *x0_shared;  // device, d doubles (used when x0 == nullptr)
+    const double *B;          // device, B[(p*nB+k)*nt+i] or nullptr (fused generator)
+    double *X, *XT;           // X[(p*d+j)*nt+i], XT[p*d+j]
+    double *moments;          // [5*d] {n,S1..S4} per component about center, or nullptr
+    const double *center;     // device, d doubles
+    uint64_t npaths, path_offset, seed;
+    int nt, d, nB, scheme, strict, accumulate;
+};
+
+int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream);
+
+}  // namespace sdegpu

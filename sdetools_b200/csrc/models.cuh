@@ -1,0 +1,113 @@
+// Model catalogue and the euler / heun step in reference operation order.
+//   euler step  R/sdetools.R:450-453   X' = p( (X + fX*dt) + gX*dB )
+//   heun step   R/sdetools.R:316-323   Y  = p( (X + fX*dt) + gX*dB )
+//                                      X' = p( (X + (0.5*(fX+fY))*dt) + 0.5*((gX+gY)*dB) )
+// All catalogue models below have a vector-valued g (one Brownian channel, :422-424).
+#pragma once
+#include "../../include/sdegpu.h"
+
+namespace sdegpu {
+
+struct KParams { double p[4]; };
+
+// STRICT: every R operator is one correctly rounded op, never contracted.
+struct Strict {
+    static constexpr bool strict = true;
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double sqrt_(double a) { return __dsqrt_rn(a); }
+};
+// FAST: plain expressions, nvcc contracts a*b+c into DFMA.
+struct Fast {
+    static constexpr bool strict = false;
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
+};
+
+template <int MODEL> struct Model;
+
+template <> struct Model<SDEGPU_MODEL_OU> {            // R/sdetools.R:718; Killing.Rmd:157-161
+    static constexpr int NX = 1, NPARAMS = 3;
+    template <class A> static __device__ __forceinline__ void f(const KParams &P, const double *x, double *o)
+    { o[0] = A::mul(P.p[0], A::sub(P.p[1], x[0])); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *, double *o) { o[0] = P.p[2]; }
+};
+template <> struct Model<SDEGPU_MODEL_CIR> {           // HMM-filtering-of-scalar-SDEs.Rmd:33-51
+    static constexpr int NX = 1, NPARAMS = 3;
+    template <class A> static __device__ __forceinline__ void f(const KParams &P, const double *x, double *o)
+    { o[0] = A::mul(P.p[0], A::sub(P.p[1], x[0])); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *x, double *o)
+    { o[0] = A::mul(P.p[2], A::sqrt_(fabs(x[0]))); }
+};
+template <> struct Model<SDEGPU_MODEL_VDP> {           // vanderPol.Rmd:27-53
+    static constexpr int NX = 2, NPARAMS = 2;
+    template <class A> static __device__ __forceinline__ void f(const KParams &P, const double *x, double *o)
+    { o[0] = x[1]; o[1] = A::sub(A::mul(x[1], A::sub(P.p[0], A::mul(x[0], x[0]))), x[0]); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *, double *o)
+    { o[0] = 0.0; o[1] = P.p[1]; }
+};
+template <> struct Model<SDEGPU_MODEL_LOGISTIC> {      // FisheriesManagement.Rmd:30-51; ItosFormula.Rmd:38-45
+    static constexpr int NX = 1, NPARAMS = 2;
+    template <class A> static __device__ __forceinline__ void f(const KParams &P, const double *x, double *o)
+    { o[0] = A::sub(A::mul(x[0], A::sub(1.0, x[0])), A::mul(P.p[1], A::mul(x[0], x[0]))); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *x, double *o)
+    { o[0] = A::mul(P.p[0], x[0]); }
+};
+template <> struct Model<SDEGPU_MODEL_GBM> {           // R/sdetools.R:222-228
+    static constexpr int NX = 1, NPARAMS = 2;
+    template <class A> static __device__ __forceinline__ void f(const KParams &P, const double *x, double *o)
+    { o[0] = A::mul(P.p[0], x[0]); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *x, double *o)
+    { o[0] = A::mul(P.p[1], x[0]); }
+};
+template <> struct Model<SDEGPU_MODEL_DOUBLEWELL> {    // SDEtools.Rmd:50-55 (x^3 written x*x*x)
+    static constexpr int NX = 1, NPARAMS = 1;
+    template <class A> static __device__ __forceinline__ void f(const KParams &, const double *x, double *o)
+    { o[0] = A::sub(x[0], A::mul(A::mul(x[0], x[0]), x[0])); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *, double *o) { o[0] = P.p[0]; }
+};
+
+template <int PROJ> __device__ __forceinline__ double project(double v)
+{
+    if (PROJ == SDEGPU_PROJ_ABS) return fabs(v);
+    if (PROJ == SDEGPU_PROJ_RELU) return v < 0.0 ? 0.0 : v;
+    return v;
+}
+
+// One time step of one path, state in registers.
+template <class M, int SCHEME, int PROJ, class A>
+__device__ __forceinline__ void sde_step(const KParams &P, double (&x)[M::NX], double dt, double dB)
+{
+    constexpr int NX = M::NX;
+    double fX[NX], gX[NX];
+    M::template f<A>(P, x, fX);
+    M::template g<A>(P, x, gX);
+    if (SCHEME == SDEGPU_EULER) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            x[j] = project<PROJ>(A::add(A::add(x[j], A::mul(fX[j], dt)), A::mul(gX[j], dB)));
+    } else {
+        double Y[NX], fY[NX], gY[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            Y[j] = project<PROJ>(A::add(A::add(x[j], A::mul(fX[j], dt)), A::mul(gX[j], dB)));
+        M::template f<A>(P, Y, fY);
+        M::template g<A>(P, Y, gY);
+        if (A::strict) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                x[j] = project<PROJ>(A::add(A::add(x[j], A::mul(A::mul(0.5, A::add(fX[j], fY[j])), dt)),
+                                            A::mul(0.5, A::mul(A::add(gX[j], gY[j]), dB))));
+        } else {
+            const double hdt = 0.5 * dt, hdB = 0.5 * dB;     // scaling by 0.5 is exact: same value, fewer ops
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                x[j] = project<PROJ>((x[j] + (fX[j] + fY[j]) * hdt) + (gX[j] + gY[j]) * hdB);
+        }
+    }
+}
+
+}  // namespace sdegpu

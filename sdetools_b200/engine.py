@@ -1,0 +1,176 @@
+"""Engine: one libsdegpu context on one GPU, with host (numpy) and device (torch
+CUDA tensor) entry points.  PyTorch is plumbing only here: device memory, the
+current stream and torch.distributed; all compute is in libsdegpu.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ARITH, MODEL, PROJ, SCHEME, Output, Problem, check
+
+
+def _is_torch(x) -> bool:
+    return x is not None and type(x).__module__.startswith("torch")
+
+
+def _ptr(a):
+    """Raw address of a numpy array or torch tensor (None -> NULL)."""
+    if a is None:
+        return None
+    if _is_torch(a):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.sdegpu_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        info = _lib.DevInfo()
+        check(self.lib.sdegpu_device_info(self._h, C.byref(info)))
+        self.info = {"name": info.name.decode(), "sm_count": info.sm_count, "cc": (info.cc_major, info.cc_minor),
+                     "clock_khz": info.clock_khz, "global_mem_bytes": info.global_mem_bytes}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sdegpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- streams ------------------------------------------------------------
+    def use_torch_stream(self):
+        """Launch on torch's current stream so torch.cuda.Event timing sees the kernels."""
+        import torch
+        check(self.lib.sdegpu_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def use_own_stream(self):
+        check(self.lib.sdegpu_set_stream(self._h, None))
+
+    def synchronize(self):
+        check(self.lib.sdegpu_synchronize(self._h))
+
+    # -- ensembles ------------------------------------------------------------
+    def run(self, model, scheme, params, times, x0, *, nx, nB=1, npaths, B=None, projection="identity",
+            arith=None, seed=0, path_offset=0, X=None, XT=None, power_sums=None, center=None,
+            hist_counts=None, hist=None, accumulate=False, want_time=False):
+        """Thin, allocation-free call of sdegpu_run.  B / per-path x0 / outputs are either all numpy
+        (host pointers) or all torch CUDA tensors (device pointers, work is only enqueued).
+        Layouts are the reference's: B[(p*nB+k)*nt+i], X[(p*nx+j)*nt+i], XT[p*nx+j]."""
+        bufs = [b for b in (B, X, XT, power_sums, hist_counts) if b is not None]
+        on_dev = any(_is_torch(b) for b in bufs)
+        if on_dev and not all(_is_torch(b) and b.is_cuda for b in bufs):
+            raise TypeError("mixing host and device buffers in one call is not supported")
+        for b in bufs:
+            if _is_torch(b):
+                if not b.is_contiguous():
+                    raise ValueError("device buffers must be contiguous")
+            elif not b.flags["C_CONTIGUOUS"] and not b.flags["F_CONTIGUOUS"]:
+                raise ValueError("host buffers must be contiguous")
+        params = np.ascontiguousarray(np.ravel(params), dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        per_path_x0 = _is_torch(x0) or (np.size(x0) != nx)
+        if per_path_x0:
+            if _is_torch(x0) != on_dev and bufs:
+                raise TypeError("per-path x0 must live where the other buffers live")
+            x0_keep = x0 if _is_torch(x0) else np.ascontiguousarray(x0, dtype=np.float64)
+            on_dev = on_dev or _is_torch(x0)
+        else:
+            x0_keep = np.ascontiguousarray(np.ravel(x0), dtype=np.float64)
+        if arith is None:
+            arith = "strict" if B is not None else "fast"
+        pr = Problem()
+        pr.struct_size = C.sizeof(Problem)
+        pr.model, pr.scheme = MODEL[model], SCHEME[scheme]
+        pr.arith, pr.projection = ARITH[arith], PROJ[projection]
+        pr.nx, pr.nB, pr.nparams = int(nx), int(nB), int(params.size)
+        pr.params, pr.times, pr.nt = _ptr(params), _ptr(times), int(times.size)
+        pr.x0, pr.x0_stride = _ptr(x0_keep), (int(nx) if per_path_x0 else 0)
+        pr.B = _ptr(B)
+        pr.npaths, pr.path_offset, pr.seed = int(npaths), int(path_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
+        pr.flags = (_lib.DEVICE_PTRS if on_dev else 0) | (_lib.ACCUMULATE if accumulate else 0)
+        out = Output()
+        out.struct_size = C.sizeof(Output)
+        out.X, out.XT, out.power_sums, out.hist_counts = _ptr(X), _ptr(XT), _ptr(power_sums), _ptr(hist_counts)
+        center_keep = None
+        if center is not None:
+            center_keep = np.ascontiguousarray(np.ravel(center), dtype=np.float64)
+            out.center = _ptr(center_keep)
+        if hist is not None:
+            lo, hi, nbins = hist[:3]
+            out.hist_lo, out.hist_hi, out.hist_nbins = float(lo), float(hi), int(nbins)
+            out.hist_component = int(hist[3]) if len(hist) > 3 else 0
+        ms = C.c_float(0.0)
+        if want_time:
+            out.elapsed_ms = C.addressof(ms)
+        check(self.lib.sdegpu_run(self._h, C.byref(pr), C.byref(out)))
+        return ms.value if want_time else None
+
+    # -- integrals --------------------------------------------------------------
+    def _flags(self, *bufs):
+        dev = [_is_torch(b) for b in bufs if b is not None]
+        if any(dev) and not all(dev):
+            raise TypeError("mixing host and device buffers in one call is not supported")
+        return _lib.DEVICE_PTRS if any(dev) else 0
+
+    def stochint(self, f, g, n, ncols, l=None, r=None, c=None):
+        check(self.lib.sdegpu_stochint(self._h, _ptr(f), _ptr(g), n, ncols, _ptr(l), _ptr(r), _ptr(c), self._flags(f, g, l, r, c)))
+
+    def itointegral(self, G, B, n, ncols, out):
+        check(self.lib.sdegpu_itointegral(self._h, _ptr(G), _ptr(B), n, ncols, _ptr(out), self._flags(G, B, out)))
+
+    def qv(self, X, n, ncols, out):
+        check(self.lib.sdegpu_qv(self._h, _ptr(X), n, ncols, _ptr(out), self._flags(X, out)))
+
+    def crossvar(self, X, Y, n, ncols, out):
+        check(self.lib.sdegpu_crossvar(self._h, _ptr(X), _ptr(Y), n, ncols, _ptr(out), self._flags(X, Y, out)))
+
+    def rvbm(self, times, ncols, out, sigma=1.0, B0=0.0, u=0.0, seed=0, path_offset=0):
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        check(self.lib.sdegpu_rvbm(self._h, _ptr(times), int(times.size), int(ncols), float(sigma), float(B0), float(u),
+                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(path_offset), _ptr(out), self._flags(out)))
+
+    # -- introspection ------------------------------------------------------------
+    def philox4x32_10(self, ctr, key):
+        a = (C.c_uint32 * 4)(*ctr)
+        k = (C.c_uint32 * 2)(*key)
+        o = (C.c_uint32 * 4)()
+        check(self.lib.sdegpu_philox4x32_10(self._h, a, k, o))
+        return tuple(o)
+
+    def normals(self, seed, path_offset, npaths, nsteps, channel=0):
+        z = np.empty((nsteps, npaths))
+        check(self.lib.sdegpu_normals(self._h, int(seed), int(path_offset), int(npaths), int(channel), int(nsteps), _ptr(z)))
+        return z
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        check(self.lib.sdegpu_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_hbm_peak(self) -> float:
+        v = C.c_double(0.0)
+        check(self.lib.sdegpu_measure_hbm_peak(self._h, C.byref(v)))
+        return v.value
+
+
+_engines = {}
+
+
+def default_engine(device=None) -> Engine:
+    """Process-wide engine per device (device=None: LOCAL_RANK or 0)."""
+    import os
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

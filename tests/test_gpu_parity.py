@@ -1,0 +1,330 @@
+"""GPU parity: the CUDA path (through the C ABI / host mirror) against the CPU oracle.
+Bar: bit-exact for supplied-B STRICT runs, histogram counts and the integrals;
+1e-12 relative for FAST arithmetic; Monte-Carlo tolerances (stated per test) for
+fused-generator ensembles against the exact laws."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, laws, philox_ref
+from oracle import sde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SCH = {"euler": 0, "heun": 1}
+
+
+@pytest.fixture(scope="module")
+def sde(gpu):
+    import sdetools_b200
+    return sdetools_b200
+
+
+@pytest.fixture(scope="module")
+def eng(sde):
+    return sde.default_engine(0)
+
+
+def brownian(nt, nB, npaths, seed, dt=0.01):
+    """B as rBM builds it (80-bit cumsum of sqrt(dt)*Z), reference layout (nt, nB, npaths)."""
+    rng = np.random.default_rng(seed)
+    t = O.r_seq(0, (nt - 1) * dt, dt)
+    z = rng.standard_normal((nt, nB * npaths))
+    z[0] = 0.0
+    B = O.r_cumsum_cols(np.sqrt(np.concatenate(([0.0], O.r_diff(t))))[:, None] * z)
+    return t, B.reshape(nt, nB, npaths)
+
+
+def oracle_X(scheme, model, params, nx, nB, proj, t, x0, B):
+    """C oracle on reference-layout B (nt,nB,np) -> X (nt,nx,np)."""
+    X, _ = c_oracle.ensemble(SCH[scheme], O.MODEL_IDS[model], params, nx, nB, O.PROJ_IDS[proj], t, np.asarray(x0, float),
+                             B=np.ascontiguousarray(B.transpose(2, 1, 0)), nthreads=8)
+    return X.transpose(2, 1, 0)
+
+
+# ---- config C1: scalar OU euler(), 1000 paths x 1000 steps, supplied B, bit-level -------------
+@pytest.mark.parametrize("lam,xi,sig,x0", [(1.0, 0.0, 1.0, 0.0), (1.3, 0.7, 0.9, 2.0)])
+def test_c1_ou_euler_supplied_B_bit_identical(sde, lam, xi, sig, x0):
+    rng = np.random.default_rng(20261019)
+    t = O.r_seq(0, 10, 0.01)
+    nt, P = t.size, 1000
+    z = rng.standard_normal((P, nt)).T                       # drawn path-major
+    z[0] = 0.0
+    B = O.r_cumsum_cols(np.sqrt(np.concatenate(([0.0], O.r_diff(t))))[:, None] * z).reshape(nt, 1, P)
+    f, g = sde.catalogue.ou(lam, xi, sig)
+    got = sde.euler(f, g, t, x0, B)
+    assert got["X"].shape == (nt, 1, P) and got["times"] is not None
+    want = oracle_X("euler", "ou", [lam, xi, sig], 1, 1, "identity", t, [x0], B)
+    assert np.array_equal(got["X"], want)
+    # the numpy restatement of R's loop, one path per call, agrees too
+    fo, go, _, _ = O.catalogue("ou", [lam, xi, sig])
+    for p in (0, 499, 999):
+        assert np.array_equal(O.euler(fo, go, t, x0, B=B[:, :, p])["X"], got["X"][:, :, p])
+    # single-path call returns the reference's nt x nx matrix
+    one = sde.euler(f, g, t, x0, B[:, 0, 7])
+    assert one["X"].shape == (nt, 1) and np.array_equal(one["X"], want[:, :, 7])
+
+
+CASES = [("ou", [1.3, 0.7, 0.9], [2.0], "identity"), ("cir", [1.0, 1.0, 1.0], [1.0], "abs"),
+         ("cir", [0.5, 0.2, 1.5], [0.05], "relu"), ("vdp", [1.0, 0.5], [0.1, -0.2], "identity"),
+         ("logistic", [0.5, 1.0], [0.3], "identity"), ("gbm", [0.4, 1.0], [1.0], "abs"),
+         ("doublewell", [0.5], [0.2], "identity")]
+
+
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+@pytest.mark.parametrize("model,params,x0,proj", CASES)
+def test_all_models_strict_bit_identical_and_fast_close(eng, scheme, model, params, x0, proj):
+    nx = len(x0)
+    t, B = brownian(204, 1, 333, 5)                         # ragged: 333 paths = 2.6 tiles, 203 steps = 6.3 tiles
+    want = oracle_X(scheme, model, params, nx, 1, proj, t, x0, B)
+    Bf = np.asfortranarray(B)
+    X = np.empty((t.size, nx, 333), order="F")
+    XT = np.empty((nx, 333), order="F")
+    eng.run(model, scheme, params, t, x0, nx=nx, npaths=333, B=Bf, projection=proj, arith="strict", X=X, XT=XT)
+    assert np.array_equal(X, want)
+    assert np.array_equal(XT, want[-1])
+    eng.run(model, scheme, params, t, x0, nx=nx, npaths=333, B=Bf, projection=proj, arith="fast", X=X)
+    assert np.allclose(X, want, rtol=1e-12, atol=1e-13)     # north star: 1e-12 relative with the same B
+
+
+def test_per_path_x0_and_terminal_only(eng):
+    t, B = brownian(65, 1, 130, 8)
+    x0 = np.random.default_rng(1).uniform(0.5, 2.0, (1, 130))
+    Xo, XTo = c_oracle.ensemble(1, 1, [1.0, 1.0, 0.7], 1, 1, 1, t, np.ascontiguousarray(x0.T),
+                                B=np.ascontiguousarray(B.transpose(2, 1, 0)))
+    XT = np.empty((1, 130), order="F")
+    eng.run("cir", "heun", [1.0, 1.0, 0.7], t, np.ascontiguousarray(x0.T), nx=1, npaths=130, B=np.asfortranarray(B),
+            projection="abs", XT=XT)
+    assert np.array_equal(XT, XTo.T)
+
+
+# ---- the fused generator ----------------------------------------------------------------------
+KATS = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+
+
+@pytest.mark.parametrize("ctr,key,out", KATS)
+def test_philox_known_answers_on_device(eng, ctr, key, out):
+    assert eng.philox4x32_10(ctr, key) == out
+
+
+def test_device_normals_match_reference_stream(eng):
+    seed, off = 0x5DE70015, (1 << 33) + 5                    # path ids beyond 32 bits
+    z = eng.normals(seed, off, 257, 101)
+    want = philox_ref.normals(off + np.arange(257), 101, 0, seed)
+    assert np.max(np.abs(z - want)) < 1e-13
+    assert np.array_equal(eng.normals(seed, off + 100, 3, 7), z[:7, 100:103])     # keyed by global id
+    assert not np.array_equal(eng.normals(seed, off, 4, 6, channel=1), z[:6, :4])
+
+
+@pytest.mark.parametrize("scheme,model,params,x0,proj", [("heun", "cir", [1.0, 1.0, 1.0], [1.0], "abs"),
+                                                         ("euler", "vdp", [1.0, 0.5], [0.0, 0.0], "identity"),
+                                                         ("euler", "ou", [1.3, 0.7, 0.9], [2.0], "identity")])
+def test_fused_generator_paths_follow_oracle(eng, scheme, model, params, x0, proj):
+    """Same increments (device normals) through the oracle's loop reproduce the device paths."""
+    nx, P, nt, seed, off = len(x0), 200, 78, 99, 1000
+    t = O.r_seq(0, (nt - 1) * 0.01, 0.01)
+    X = np.empty((nt, nx, P), order="F")
+    XT = np.empty((nx, P), order="F")
+    eng.run(model, scheme, params, t, x0, nx=nx, npaths=P, projection=proj, seed=seed, path_offset=off, X=X)
+    eng.run(model, scheme, params, t, x0, nx=nx, npaths=P, projection=proj, seed=seed, path_offset=off, XT=XT)
+    z = eng.normals(seed, off, P, nt - 1)
+    dB = (np.sqrt(O.r_diff(t))[:, None] * z)[:, None, :]
+    want = O.ensemble(scheme, model, params, t, x0, dB=dB, proj=proj)
+    assert np.allclose(X, want, rtol=1e-12, atol=1e-13)      # FAST arithmetic vs reference order
+    assert np.allclose(XT, X[-1], rtol=1e-13, atol=0)        # register-resident kernel == trajectory kernel
+    # and the CPU oracle's own fused generator (libm log/sin/cos) gives the same paths to rounding
+    _, XTc = c_oracle.ensemble(SCH[scheme], O.MODEL_IDS[model], params, nx, 1, O.PROJ_IDS[proj], t, np.array(x0),
+                               seed=seed, path_offset=off, npaths=P, full=False)
+    assert np.allclose(XT, XTc.T, rtol=1e-9, atol=1e-11)
+
+
+def test_sharding_by_path_offset_is_invariant(eng):
+    t = O.r_seq(0, 0.5, 0.01)
+    args = dict(nx=1, projection="abs", seed=7, hist=(0.0, 4.0, 64), center=[1.0])
+    full_XT, full_h, full_ps = np.empty((1, 1000), order="F"), np.zeros(67, np.uint64), np.zeros((5, 1), order="F")
+    eng.run("cir", "heun", [1, 1, 1], t, [1.0], npaths=1000, XT=full_XT, hist_counts=full_h, power_sums=full_ps, **args)
+    h, ps = np.zeros(67, np.uint64), np.zeros((5, 1), order="F")
+    parts = []
+    for lo, hi in ((0, 300), (300, 1000)):
+        xt = np.empty((1, hi - lo), order="F")
+        eng.run("cir", "heun", [1, 1, 1], t, [1.0], npaths=hi - lo, path_offset=lo, XT=xt, hist_counts=h, power_sums=ps,
+                accumulate=True, **args)
+        parts.append(xt)
+    assert np.array_equal(np.concatenate(parts, axis=1), full_XT)
+    assert np.array_equal(h, full_h) and h.sum() == 1000
+    assert np.allclose(ps, full_ps, rtol=1e-13)
+
+
+def test_terminal_statistics_match_oracle_definitions(eng):
+    t = O.r_seq(0, 1, 0.02)
+    P = 5000
+    XT, h, ps = np.empty((2, P), order="F"), np.zeros(35, np.uint64), np.zeros((5, 2), order="F")
+    eng.run("vdp", "euler", [1.0, 0.5], t, [0.5, 0.0], nx=2, npaths=P, seed=3, XT=XT, hist_counts=h, hist=(-0.6, 0.6, 32, 1),
+            power_sums=ps, center=[0.3, -0.1])
+    assert np.array_equal(h.astype(np.int64), O.hist_counts(XT[1], -0.6, 0.6, 32))          # integer work: bit-exact
+    for j, c in enumerate((0.3, -0.1)):
+        assert np.allclose(ps[:, j], O.power_sums(XT[j], c), rtol=1e-12)
+
+
+# ---- statistical acceptance ---------------------------------------------------
+def test_ou_ensemble_matches_exact_discrete_law(sde):
+    lam, xi, sig, x0, n, h = 1.3, 0.7, 0.9, 2.0, 100, 0.01
+    N = 1 << 21
+    t = np.arange(n + 1) * h
+    for scheme in ("euler", "heun"):
+        m, s = laws.ou_discrete_law(scheme, x0, lam, xi, sig, h, n)
+        fn = sde.euler if scheme == "euler" else sde.heun
+        res = fn(*sde.catalogue.ou(lam, xi, sig), t, x0, npaths=N, seed=0x5DE70005, output="none", moments=True, center=[m],
+                 hist=(m - 6 * s, m + 6 * s, 128))
+        mom = res["moments"]
+        assert abs(mom["mean"][0] - m) < 5 * s / np.sqrt(N)                       # MC error only
+        assert abs(mom["var"][0] - s * s) < 5 * s * s * np.sqrt(2 / N)
+        assert abs(mom["kurtosis"][0] - 3) < 5 * np.sqrt(24 / N)
+        from scipy import stats
+        edges = res["hist"]["breaks"]
+        prob = np.diff(stats.norm.cdf(edges, m, s))
+        keep = prob * N > 50
+        chi2 = (((res["hist"]["counts"] - prob * N) ** 2 / (prob * N))[keep]).sum()
+        assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-4
+        # against dOU the Euler variance is biased by ~ lam*h/2 (App. D): visible at this N, as it should be
+        m0, s0 = laws.ou_parameters(x0, lam, xi, sig, n * h)
+        if scheme == "euler":
+            assert abs(mom["var"][0] / s0 ** 2 - 1 - lam * h / 2) < 3e-3
+
+
+def test_cir_heun_histogram_matches_stratonovich_law(sde):
+    """Config C2 at test size: terminal histogram vs pCIR(Stratonovich=TRUE) (R/sdetools.R:610,669-676);
+    discretisation bias estimated by step halving, as SURVEY.md §8(d) prescribes."""
+    from scipy import stats
+    N, T = 1 << 20, 1.0
+    f, g = sde.catalogue.cir(1.0, 1.0, 1.0)
+    hs = {}
+    for n in (500, 1000):
+        hs[n] = sde.heun(f, g, np.arange(n + 1) * (T / n), 1.0, p=abs, npaths=N, seed=0x5DE70015, output="none",
+                         hist=(0.0, 8.0, 64))["hist"]
+    edges = hs[1000]["breaks"]
+    prob = np.diff(laws.pCIR(edges, 1.0, 1.0, 1.0, 1.0, T, Stratonovich=True))
+    cnt = hs[1000]["counts"].astype(float)
+    bias = hs[1000]["counts"].astype(float) - hs[500]["counts"].astype(float)     # ~ h-halving difference (same seed)
+    keep = prob * N > 100
+    z = (cnt - prob * N)[keep] / np.sqrt((prob * N * (1 - prob))[keep] + bias[keep] ** 2)
+    assert np.all(np.abs(z) < 5), z
+    assert hs[1000]["over"] + hs[1000]["under"] + hs[1000]["nan"] < 1e-4 * N
+
+
+# ---- integrals: bit-exact against R's 80-bit cumsum ------------------------------------------------
+def test_integrals_bit_identical_to_long_double_cumsum(sde):
+    rng = np.random.default_rng(4)
+    n, nc = 1001, 333
+    f = rng.standard_normal((n, nc)) * np.exp(rng.uniform(-20, 20, (1, nc)))
+    g = np.cumsum(rng.standard_normal((n, nc)), axis=0) * 0.1
+    fa, ga = np.ascontiguousarray(f.T), np.ascontiguousarray(g.T)
+    res = sde.stochint(f, g, ["l", "r", "c"])
+    assert np.array_equal(res["l"], c_oracle.integral(0, fa, ga).T)
+    assert np.array_equal(res["r"], c_oracle.integral(1, fa, ga).T)
+    assert np.array_equal(res["c"], c_oracle.integral(2, fa, ga).T)
+    assert np.array_equal(sde.itointegral(f, g), res["l"])
+    assert np.array_equal(sde.QuadraticVariation(g), c_oracle.integral(3, ga).T)
+    assert np.array_equal(sde.CrossVariation(f, g), c_oracle.integral(4, fa, ga).T)
+    # the reference's one-vector calls, against the numpy restatement
+    assert np.array_equal(sde.stochint(f[:, 0], g[:, 0], "c"), O.stochint(f[:, 0], g[:, 0], "c"))
+    assert np.array_equal(sde.itointegral(f[:, 1], g[:, 1]), O.itointegral(f[:, 1], g[:, 1]))
+
+
+def test_integrals_edge_cases(sde):
+    assert sde.itointegral(np.array([3.0]), np.array([1.0])).tolist() == [0.0]          # n = 1 -> c(0)
+    assert sde.itointegral(np.array([3.0, 9.0]), np.array([1.0, 1.5])).tolist() == [0.0, 1.5]
+    x = np.array([1.0, 2.0 ** -60 + 1.0, np.inf, 1.0, np.nan, 2.0])
+    got, want = sde.QuadraticVariation(x), O.QuadraticVariation(x)
+    assert np.array_equal(got, want, equal_nan=True)
+    # a sum a plain-double prefix sum gets wrong: 1 + 2^-60 + 2^-60 - 1
+    inc = np.array([0.0, 1.0, 1.0 + 2.0 ** -60, 1.0 + 2.0 ** -59, 2.0 ** -59])
+    assert sde.itointegral(np.ones(5), inc)[-1] == 2.0 ** -59
+
+
+def test_vignette_identities_on_device(sde):
+    """vignettes/ItoIntegrals.Rmd:82-115,143-153 end to end on the GPU path."""
+    t, B = brownian(101, 1, 64, 7)
+    f, g = sde.catalogue.doublewell(0.5)
+    X = sde.euler(f, g, t, 0.0, B)["X"][:, 0, :]
+    Bm = B[:, 0, :]
+    tt = np.repeat(t[:, None], 64, axis=1)
+    resid = X - sde.itointegral(X - X * X * X, tt) - sde.itointegral(np.full_like(X, 0.5), Bm)
+    assert np.max(np.abs(resid)) < 1e-14
+    G = X + Bm
+    assert np.max(np.abs(sde.stochint(G, X, "c") - sde.itointegral(G, X) - 0.5 * sde.CrossVariation(G, X))) < 1e-14
+
+
+def test_rvbm_matches_reference_construction(sde, eng):
+    t = np.concatenate(([0.5], 0.5 + np.cumsum(np.random.default_rng(2).uniform(0.01, 0.1, 200))))
+    B = sde.rvBM(t, 300, sigma=1.7, B0=0.3, u=-0.2, seed=11, path_offset=40)
+    z = eng.normals(11, 40, 300, t.size)
+    for c in (0, 150, 299):
+        assert np.array_equal(B[:, c], O.rBM(t, 1.7, 0.3, -0.2, z=z[:, c]))
+    # BrownianMotion.Rmd:38-48: cov(B_s, B_t) ~ min(s,t)
+    tt = np.arange(1, 11) * 0.1
+    W = sde.rvBM(tt, 200000, seed=5)
+    assert abs(np.var(W[-1]) - 1.0) < 0.02 and abs(np.mean(W[4] * W[9]) - 0.5) < 0.02
+    bb = sde.rBrownianBridge(tt, (1.0, -1.0), seed=3)
+    assert bb[0] == pytest.approx(1.0) and bb[-1] == pytest.approx(-1.0)
+
+
+# ---- linear SDE -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+def test_linear_strict_bit_identical(sde, scheme):
+    rng = np.random.default_rng(2)
+    d, nB, P = 5, 3, 70
+    A = -np.eye(d) + 0.3 * rng.standard_normal((d, d))
+    G = rng.standard_normal((d, nB))
+    t, B = brownian(52, nB, P, 9)
+    x0 = rng.standard_normal(d)
+    want = O.ensemble(scheme, "linear", (A, G), t, x0, B=B)
+    fn = sde.euler if scheme == "euler" else sde.heun
+    got = fn(*sde.catalogue.linear(A, G), t, x0, B)["X"]
+    assert np.array_equal(got, want)
+    fast = fn(*sde.catalogue.linear(A, G), t, x0, B, arith="fast")["X"]
+    assert np.allclose(fast, want, rtol=1e-12, atol=1e-13)
+
+
+def test_reference_dims_test_on_device(sde):
+    """tests/testthat/test_solvers.R:3-18 with catalogue closures: dim(X) = c(nt, nx), nB = 1 and nB = 2."""
+    times = np.arange(0, 11, dtype=float)
+    sol = sde.euler(*sde.catalogue.linear(-np.eye(3), np.ones((3, 1))), times, np.ones(3), seed=1)
+    assert sol["X"].shape == (11, 3)
+    sol = sde.euler(*sde.catalogue.linear(-np.eye(3), np.random.default_rng(0).random((3, 2))), times, np.ones(3), seed=1)
+    assert sol["X"].shape == (11, 3) and np.isfinite(sol["X"]).all()
+
+
+def test_linear_oscillator_covariance_vs_dLinSDE(sde):
+    """vignettes/NoisyOscillator.Rmd:38-54,94-97: ensemble mean/cov vs dLinSDE and the exact Euler law."""
+    lam, om, s = 0.2, 1.0, 0.5
+    A, G = np.array([[-lam, -om], [om, -lam]]), s * np.eye(2)
+    n, h, N = 400, 0.01, 1 << 18
+    x0 = np.array([1.0, 0.0])
+    res = sde.euler(*sde.catalogue.linear(A, G), np.arange(n + 1) * h, x0, npaths=N, seed=42, output="terminal")
+    XT = res["XT"]
+    m, S = laws.linear_discrete_law(A, G, x0, h, n)
+    assert np.all(np.abs(XT.mean(axis=1) - m) < 5 * np.sqrt(np.diag(S) / N))
+    assert np.all(np.abs(np.cov(XT) - S) < 5 * np.sqrt(2 / N) * np.sqrt(np.outer(np.diag(S), np.diag(S))) + 1e-12)
+    ref = laws.dLinSDE(A, G, n * h, x0=x0)
+    assert np.allclose(XT.mean(axis=1), ref["EX"], atol=0.01) and np.allclose(np.cov(XT), ref["St"], atol=0.01)
+
+
+# ---- error behaviour ----------------------------------------------------------------------------------
+def test_argument_errors(sde, eng):
+    from sdetools_b200._lib import SdeGpuError
+    f, g = sde.catalogue.ou()
+    with pytest.raises(SdeGpuError, match="at least 2 time points"):
+        sde.euler(f, g, [0.0], 0.0)
+    with pytest.raises(SdeGpuError, match="non-decreasing"):
+        sde.euler(f, g, [0.0, 1.0, 0.5], 0.0)
+    with pytest.raises(SdeGpuError, match="STRICT"):
+        sde.euler(f, g, [0.0, 1.0, 2.0], 0.0, arith="strict")
+    with pytest.raises(ValueError):
+        sde.euler(f, g, [0.0, 1.0, 2.0], [0.0, 1.0])
+    with pytest.raises(NotImplementedError):
+        sde.euler(f, g, [0.0, 1.0, 2.0], 0.0, h=lambda t, x: 1)
+    assert sde.euler(f, g, [0.0, 1.0], 0.5, np.array([0.0, 2.0]))["X"].tolist() == [[0.5], [0.5 + -0.5 * 1.0 + 2.0]]   # nt = 2
+    eng.run("ou", "euler", [1, 0, 1], [0.0, 1.0, 2.0], [0.0], nx=1, npaths=0)                  # empty ensemble is a no-op
