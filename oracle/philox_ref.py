@@ -1,22 +1,21 @@
 """numpy reference of the counter-based increment generator the CUDA kernels
 fuse into the step loop.  TEST INFRASTRUCTURE ONLY.
 
-The reference draws increments with R's `rnorm` (R/sdetools.R:19, Mersenne-
-Twister + inversion), a stream that cannot exist on the device; the product
-replaces it with Philox4x32-10 (Salmon et al., SC'11; Random123 KATs in
-SURVEY.md App. F).  This file states that generator exactly so the device
-stream can be checked draw by draw:
+The reference draws increments with R's `rnorm` (R/sdetools.R:19): Mersenne-Twister
+uniforms pushed through qnorm (inversion).  The device keeps the inversion but takes the
+uniform from Philox4x32-10 (Salmon et al., SC'11; Random123 KATs in SURVEY.md App. F), so a
+draw is a pure function of (seed, global path id, step, channel).  This file states that
+generator exactly so the device stream can be checked draw by draw:
 
   key      = (seed & 0xffffffff, seed >> 32)
-  counter  = (path & 0xffffffff, path >> 32, block, channel)
+  counter  = (path & 0xffffffff, path >> 32, block, channel)      one block = two steps
   r0..r3   = philox4x32_10(counter, key)
-  m1, m2   = top 52 bits of r1:r0 and of r3:r2
-  u1       = 2 - (1 + m1 * 2^-52)                       in (0,1]
-  v        =      1 + m2 * 2^-52                        in [1,2)   (angle fraction + 1)
-  rad      = sqrt(-2 log u1)
-  z[2*block]   = rad * cospi(2 v)         (Box-Muller pair, one block = two steps)
-  z[2*block+1] = rad * sinpi(2 v)
+  step 2*block uses (lo,hi) = (r0,r1); step 2*block+1 uses (r2,r3):
+    m    = top 52 bits of hi:lo;  u = m * 2^-52  (u = 2^-52 if m == 0)
+    z    = (-1)^(bit 11 of lo) * -qnorm(u/2)
   dB[i,k]  = sqrt(dt[i]) * z[i]   for channel k
+The device evaluates -qnorm(u/2) from a table of piecewise degree-5 polynomials with
+|error| < 2e-12 (tools/gen_icdf_table.py); here it is scipy's ndtri.
 """
 from __future__ import annotations
 
@@ -45,15 +44,14 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def uniforms(path, block, channel, seed):
-    path = np.asarray(path, dtype=np.uint64)
-    r0, r1, r2, r3 = philox4x32_10(path & MASK, path >> np.uint64(32), block, channel,
-                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    m1 = ((r1 << np.uint64(32)) | r0) >> np.uint64(12)
-    m2 = ((r3 << np.uint64(32)) | r2) >> np.uint64(12)
-    u1 = 2.0 - (1.0 + m1.astype(np.float64) * 2.0 ** -52)
-    u2 = m2.astype(np.float64) * 2.0 ** -52          # v - 1: cospi/sinpi have period 2
-    return u1, u2
+def bits_to_normal(lo, hi):
+    from scipy.special import ndtri
+    lo = np.asarray(lo, dtype=np.uint64)
+    hi = np.asarray(hi, dtype=np.uint64)
+    m = ((hi << np.uint64(32)) | lo) >> np.uint64(12)
+    u = np.where(m == 0, 2.0 ** -52, m.astype(np.float64) * 2.0 ** -52)
+    a = -ndtri(0.5 * u)
+    return np.where((lo & np.uint64(0x800)) != 0, -a, a)
 
 
 def normals(paths, nsteps, channel, seed):
@@ -61,24 +59,9 @@ def normals(paths, nsteps, channel, seed):
     paths = np.asarray(paths, dtype=np.uint64)
     nblk = (nsteps + 1) // 2
     blk = np.arange(nblk, dtype=np.uint64)[:, None]
-    u1, u2 = uniforms(paths[None, :], blk, channel, seed)
-    rad = np.sqrt(-2.0 * np.log(u1))
-    # cospi/sinpi evaluated with exact quadrant reduction like the device does
-    z0 = rad * _cospi(2.0 * u2)
-    z1 = rad * _sinpi(2.0 * u2)
+    r0, r1, r2, r3 = philox4x32_10(paths[None, :] & MASK, paths[None, :] >> np.uint64(32), blk, channel,
+                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     z = np.empty((2 * nblk, paths.shape[0]))
-    z[0::2] = z0
-    z[1::2] = z1
+    z[0::2] = bits_to_normal(r0, r1)
+    z[1::2] = bits_to_normal(r2, r3)
     return z[:nsteps]
-
-
-def _sinpi(x):
-    x = np.mod(x, 2.0)
-    return np.where(x <= 0.25, np.sin(np.pi * x),
-           np.where(x <= 0.75, np.cos(np.pi * (x - 0.5)),
-           np.where(x <= 1.25, -np.sin(np.pi * (x - 1.0)),
-           np.where(x <= 1.75, -np.cos(np.pi * (x - 1.5)), np.sin(np.pi * (x - 2.0))))))
-
-
-def _cospi(x):
-    return _sinpi(x + 0.5)

@@ -8,6 +8,8 @@
 #include <new>
 #include <vector>
 
+// the half-normal quantile table of the fused generator lives in this translation unit
+#define ICDF_TABLE_DEFINE __device__ const double g_icdf_table
 #include "../../include/sdegpu.h"
 #include "ensemble.cuh"
 #include "linear.cuh"
@@ -28,9 +30,11 @@ struct IntegralArgs {
 int launch_integral(int mode, const IntegralArgs &q, int sm_count, cudaStream_t stream);
 struct BMArgs {
     const double2 *dtsq;
+    const double *icdf;
     double *B;
     double sigma, B0, u;
-    uint64_t ncols, path_offset, seed;
+    uint64_t ncols, path_offset;
+    PhiloxKey seed;
     int nt;
 };
 int launch_rvbm(const BMArgs &q, int sm_count, cudaStream_t stream);
@@ -79,6 +83,7 @@ struct sdegpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params;
+    const double *icdf = nullptr;
     int max_grid = 0;
 };
 
@@ -115,6 +120,7 @@ int sdegpu_create(int device, sdegpu_ctx **out)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     c->max_grid = c->prop.multiProcessorCount * 32;
     if (e == cudaSuccess) e = c->partials.reserve(sizeof(double) * (size_t)c->max_grid * 5 * MAX_NX);
+    if (e == cudaSuccess) e = cudaGetSymbolAddress((void **)&c->icdf, g_icdf_table);
     if (e != cudaSuccess) {
         delete c;
         return fail(SDEGPU_ERR_CUDA, "sdegpu_create: %s", cudaGetErrorString(e));
@@ -290,6 +296,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         memset(&a, 0, sizeof a);
         for (int i = 0; i < pr->nparams; ++i) a.P.p[i] = pr->params[i];
         a.dtsq = dtsq;
+        a.icdf = c->icdf;
         a.x0 = dx0;
         if (!pr->x0_stride) for (int j = 0; j < nx; ++j) a.x0s[j] = pr->x0[j];
         a.B = dB; a.X = dX; a.XT = dXT;
@@ -298,7 +305,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         for (int j = 0; j < nx; ++j) a.center[j] = out->center ? out->center[j] : 0.0;
         a.hist_lo = out->hist_lo; a.hist_hi = out->hist_hi;
         a.hist_invw = dh ? (double)out->hist_nbins / (out->hist_hi - out->hist_lo) : 0.0;
-        a.npaths = pr->npaths; a.path_offset = pr->path_offset; a.seed = pr->seed;
+        a.npaths = pr->npaths; a.path_offset = pr->path_offset; a.seed = make_philox_key(pr->seed);
         a.nt = nt; a.hist_nbins = out->hist_nbins; a.hist_comp = out->hist_component;
         LaunchCfg cfg;
         cfg.scheme = pr->scheme; cfg.proj = pr->projection; cfg.arith = pr->B ? pr->arith : SDEGPU_ARITH_FAST;
@@ -325,14 +332,14 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         CU(cudaMemcpyAsync(c->params.p, pr->params, sizeof(double) * (size_t)pr->nparams, cudaMemcpyHostToDevice, c->stream));
         la.A = (const double *)c->params.p;
         la.G = la.A + (size_t)nx * nx;
-        la.dtsq = dtsq; la.x0 = pr->x0_stride ? dx0 : nullptr;
+        la.dtsq = dtsq; la.icdf = c->icdf; la.x0 = pr->x0_stride ? dx0 : nullptr;
         if (!pr->x0_stride) {
             CU(c->in1.reserve(sizeof(double) * nx));
             CU(cudaMemcpyAsync(c->in1.p, pr->x0, sizeof(double) * nx, cudaMemcpyHostToDevice, c->stream));
             la.x0_shared = (const double *)c->in1.p;
         }
         la.B = dB; la.X = dX; la.XT = dXT;
-        la.npaths = pr->npaths; la.path_offset = pr->path_offset; la.seed = pr->seed;
+        la.npaths = pr->npaths; la.path_offset = pr->path_offset; la.seed = make_philox_key(pr->seed);
         la.nt = nt; la.d = nx; la.nB = pr->nB; la.scheme = pr->scheme; la.strict = pr->B && pr->arith == SDEGPU_ARITH_STRICT;
         if (out->hist_counts) return fail(SDEGPU_ERR_ARG, "sdegpu_run: histogram output is not available for the linear model");
         la.moments = dps; la.accumulate = accum ? 1 : 0;
@@ -443,7 +450,7 @@ int sdegpu_rvbm(sdegpu_ctx *c, const double *times, int32_t nt, uint64_t ncols, 
     if (rc) return rc;
     const size_t bytes = sizeof(double) * ncols * (size_t)nt;
     BMArgs q;
-    q.dtsq = dtsq; q.sigma = sigma; q.B0 = B0; q.u = u; q.ncols = ncols; q.path_offset = path_offset; q.seed = seed; q.nt = nt;
+    q.dtsq = dtsq; q.icdf = c->icdf; q.sigma = sigma; q.B0 = B0; q.u = u; q.ncols = ncols; q.path_offset = path_offset; q.seed = make_philox_key(seed); q.nt = nt;
     if (dev) q.B = B;
     else { CU(c->out0.reserve(bytes)); q.B = (double *)c->out0.p; }
     int e = launch_rvbm(q, c->prop.multiProcessorCount, c->stream);
@@ -461,17 +468,24 @@ int sdegpu_rvbm(sdegpu_ctx *c, const double *times, int32_t nt, uint64_t ncols, 
 __global__ void k_philox_kat(uint4 ctr, uint2 key, uint32_t *out)
 {
     uint32_t c0 = ctr.x, c1 = ctr.y, c2 = ctr.z, c3 = ctr.w;
-    philox4x32_10(c0, c1, c2, c3, key.x, key.y);
+    PhiloxKey pk;
+    uint32_t k0 = key.x, k1 = key.y;
+    for (int r = 0; r < 10; ++r) { pk.k[2 * r] = k0; pk.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    philox4x32_10(c0, c1, c2, c3, pk);
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void k_normals(uint64_t seed, uint64_t path_offset, uint64_t npaths, uint32_t channel, int nsteps, double *z)
+__global__ void k_normals(const double *icdf, const PhiloxKey seed, uint64_t path_offset, uint64_t npaths, uint32_t channel,
+                          int nsteps, double *z)
 {
+    extern __shared__ __align__(16) double sh_tab[];
+    icdf_stage(sh_tab, icdf, threadIdx.x, blockDim.x);
+    __syncthreads();
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npaths) return;
     for (int i = 0; i < nsteps; i += 2) {
         double z0, z1;
-        normal_pair(seed, path_offset + p, (uint32_t)(i >> 1), channel, z0, z1);
+        normal_pair(seed, path_offset + p, (uint32_t)(i >> 1), channel, sh_tab, z0, z1);
         z[(size_t)i * npaths + p] = z0;
         if (i + 1 < nsteps) z[(size_t)(i + 1) * npaths + p] = z1;
     }
@@ -521,7 +535,8 @@ int sdegpu_normals(sdegpu_ctx *c, uint64_t seed, uint64_t path_offset, uint64_t 
     CU(cudaSetDevice(c->device));
     const size_t bytes = sizeof(double) * npaths * (size_t)nsteps;
     CU(c->out0.reserve(bytes));
-    k_normals<<<(unsigned)((npaths + 127) / 128), 128, 0, c->stream>>>(seed, path_offset, npaths, channel, nsteps, (double *)c->out0.p);
+    k_normals<<<(unsigned)((npaths + 127) / 128), 128, ICDF_TABLE_BYTES, c->stream>>>(c->icdf, make_philox_key(seed), path_offset, npaths, channel,
+                                                                                     nsteps, (double *)c->out0.p);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(z, c->out0.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -16,7 +16,7 @@
 namespace sdegpu {
 
 constexpr int MAX_NX = 2;           // catalogue models handled here have nx <= 2
-constexpr int TERMINAL_THREADS = 256;
+constexpr int TERMINAL_THREADS = 512;
 constexpr int TILE_PATHS = 128;     // paths (= threads) per block in k_tiled
 constexpr int TILE_STEPS = 32;      // time steps staged per tile
 constexpr int TILE_LD = TILE_STEPS + 1;   // odd leading dimension: conflict-free column walks
@@ -24,6 +24,7 @@ constexpr int TILE_LD = TILE_STEPS + 1;   // odd leading dimension: conflict-fre
 struct RunArgs {
     KParams P;
     const double2 *dtsq;            // [nt-1] {dt_i, sqrt(dt_i)},  dt_i = times[i+1]-times[i]  (:446)
+    const double *icdf;             // device, half-normal quantile table (philox.cuh)
     const double *x0;               // per-path x0 (device) or nullptr
     double x0s[MAX_NX];             // shared x0
     const double *B;                // device, B[p*nt+i]  (nB = 1)
@@ -33,7 +34,8 @@ struct RunArgs {
     unsigned long long *hist;       // [nbins+3] or nullptr
     double center[MAX_NX];
     double hist_lo, hist_hi, hist_invw;
-    uint64_t npaths, path_offset, seed;
+    uint64_t npaths, path_offset;
+    PhiloxKey seed;                 // round keys of the run's seed
     int nt, hist_nbins, hist_comp;
 };
 
@@ -108,11 +110,12 @@ template <class M, int SCHEME, int PROJ>
 __global__ void __launch_bounds__(TERMINAL_THREADS) k_terminal(const RunArgs a)
 {
     constexpr int NX = M::NX;
-    extern __shared__ unsigned int sh_hist[];
-    if (a.hist) {
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_TABLE_DOUBLES);
+    icdf_stage(sh_tab, a.icdf, threadIdx.x, TERMINAL_THREADS);
+    if (a.hist)
         for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TERMINAL_THREADS) sh_hist[i] = 0u;
-        __syncthreads();
-    }
+    __syncthreads();
     double acc[NX][5];
 #pragma unroll
     for (int j = 0; j < NX; ++j)
@@ -128,14 +131,14 @@ __global__ void __launch_bounds__(TERMINAL_THREADS) k_terminal(const RunArgs a)
         int i = 0;
         for (; i + 1 < nsteps; i += 2) {
             double z0, z1;
-            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, z0, z1);
+            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
             const double2 d0 = __ldg(&a.dtsq[i]), d1 = __ldg(&a.dtsq[i + 1]);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d1.x, d1.y * z1);
         }
         if (i < nsteps) {
             double z0, z1;
-            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, z0, z1);
+            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
             const double2 d0 = __ldg(&a.dtsq[i]);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
         }
@@ -149,7 +152,8 @@ __global__ void __launch_bounds__(TERMINAL_THREADS) k_terminal(const RunArgs a)
 }
 
 // ---- tiled kernel: supplied B in, and/or full trajectory out ----------------
-// Shared memory (dynamic): [hist: nbins+3 u32, padded to 16 B]
+// Shared memory (dynamic): [quantile table]                               if !SRC_B
+//                          [hist: nbins+3 u32, padded to 16 B]
 //                          [sB: TILE_PATHS x TILE_LD doubles]            if SRC_B
 //                          [sX: NX x TILE_PATHS x TILE_LD doubles]       if a.X
 template <class M, int SCHEME, int PROJ, class A, bool SRC_B>
@@ -157,10 +161,13 @@ __global__ void __launch_bounds__(TILE_PATHS) k_tiled(const RunArgs a, const int
 {
     constexpr int NX = M::NX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(smem_raw);
-    double *sB = reinterpret_cast<double *>(smem_raw + (size_t)hist_words * 4);
+    const double *sh_tab = reinterpret_cast<const double *>(smem_raw);
+    unsigned char *after_tab = smem_raw + (SRC_B ? 0 : ICDF_TABLE_BYTES);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(after_tab);
+    double *sB = reinterpret_cast<double *>(after_tab + (size_t)hist_words * 4);
     double *sX = sB + (SRC_B ? TILE_PATHS * TILE_LD : 0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!SRC_B) icdf_stage(reinterpret_cast<double *>(smem_raw), a.icdf, tid, TILE_PATHS);
     if (a.hist) {
         for (int i = tid; i < a.hist_nbins + 3; i += TILE_PATHS) sh_hist[i] = 0u;
     }
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(TILE_PATHS) k_tiled(const RunArgs a, const int
                     if (SRC_B) {
                         dB = A::sub(sB[tid * TILE_LD + c + 1], sB[tid * TILE_LD + c]);   // dB = diff(B)  (:437)
                     } else {
-                        if ((c & 1) == 0) normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, z0, z1);
+                        if ((c & 1) == 0) normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
                         dB = d.y * ((c & 1) ? z1 : z0);
                     }
                     sde_step<M, SCHEME, PROJ, A>(a.P, x, d.x, dB);

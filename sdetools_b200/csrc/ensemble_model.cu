@@ -27,7 +27,7 @@ template <int SCHEME, int PROJ>
 static int launch_terminal(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
     auto kernel = k_terminal<M, SCHEME, PROJ>;
-    const size_t smem = a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0;
+    const size_t smem = ICDF_TABLE_BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + TERMINAL_THREADS - 1) / TERMINAL_THREADS;
     const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TERMINAL_THREADS, smem, c.sm_count, work);
     kernel<<<grid, TERMINAL_THREADS, smem, c.stream>>>(a);
@@ -40,7 +40,7 @@ static int launch_tiled(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
     auto kernel = k_tiled<M, SCHEME, PROJ, A, SRC_B>;
     const int hist_words = a.hist ? ((a.hist_nbins + 3 + 3) / 4) * 4 : 0;
-    const size_t smem = (size_t)hist_words * 4 +
+    const size_t smem = (SRC_B ? 0 : ICDF_TABLE_BYTES) + (size_t)hist_words * 4 +
                         sizeof(double) * TILE_PATHS * TILE_LD * ((SRC_B ? 1 : 0) + (a.X ? M::NX : 0));
     const uint64_t work = (a.npaths + TILE_PATHS - 1) / TILE_PATHS;
     const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TILE_PATHS, smem, c.sm_count, work);

@@ -110,16 +110,21 @@ int launch_integral(int mode, const IntegralArgs &q, int sm_count, cudaStream_t 
 // Column c: dt <- c(times[1],diff(times)); dB <- u*dt + (sigma*sqrt(dt))*Z; B <- B0+cumsum(dB)
 struct BMArgs {
     const double2 *dtsq;     // [nt] {dt_i, sqrt(dt_i)} with dt_0 = times[0]
+    const double *icdf;      // device, half-normal quantile table (philox.cuh)
     double *B;               // B[c*nt+i]
     double sigma, B0, u;
-    uint64_t ncols, path_offset, seed;
+    uint64_t ncols, path_offset;
+    PhiloxKey seed;
     int nt;
 };
 
 __global__ void __launch_bounds__(IT_COLS) k_rvbm(const BMArgs q)
 {
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table][output tile]
+    double *sm = sh_tab + ICDF_TABLE_DOUBLES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    icdf_stage(sh_tab, q.icdf, tid, IT_COLS);
+    __syncthreads();
     const uint64_t ntiles = (q.ncols + IT_COLS - 1) / IT_COLS;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t c0 = tile * IT_COLS, col = c0 + tid;
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(IT_COLS) k_rvbm(const BMArgs q)
             if (valid) {
                 for (int k = 0; k < nc; ++k) {
                     const int i = i0 + k;
-                    if ((i & 1) == 0) normal_pair(q.seed, q.path_offset + col, (uint32_t)(i >> 1), 0u, z0, z1);
+                    if ((i & 1) == 0) normal_pair(q.seed, q.path_offset + col, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
                     const double2 d = __ldg(&q.dtsq[i]);
                     // rnorm(mean=u*dt, sd=sigma*sqrt(dt)) = mean + sd*Z
                     const double dB = __dadd_rn(__dmul_rn(q.u, d.x), __dmul_rn(__dmul_rn(q.sigma, d.y), (i & 1) ? z1 : z0));
@@ -151,9 +156,10 @@ __global__ void __launch_bounds__(IT_COLS) k_rvbm(const BMArgs q)
 int launch_rvbm(const BMArgs &q, int sm_count, cudaStream_t stream)
 {
     if (q.ncols == 0 || q.nt == 0) return 0;
-    const size_t smem = sizeof(double) * IT_COLS * IT_LD;
+    const size_t smem = ICDF_TABLE_BYTES + sizeof(double) * IT_COLS * IT_LD;
     const uint64_t ntiles = (q.ncols + IT_COLS - 1) / IT_COLS;
     int per_sm = 1;
+    cudaFuncSetAttribute(k_rvbm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rvbm, IT_COLS, smem);
     uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
     if (grid > ntiles) grid = ntiles;

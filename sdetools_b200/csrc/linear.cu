@@ -18,7 +18,7 @@ __device__ __forceinline__ double madd(double acc, double a, double b)
     return STRICT ? __dadd_rn(acc, __dmul_rn(a, b)) : fma(a, b, acc);
 }
 
-// dynamic smem: xs[PT*d] ys[PT*d] ns[PT*d] dBs[PT*nB] zs[PT*nB]
+// dynamic smem: xs[PT*d] ys[PT*d] ns[PT*d] dBs[PT*nB] zs[PT*nB] [quantile table if !B]
 template <bool STRICT>
 __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs a, const int PT)
 {
@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
     const int d = a.d, nB = a.nB, nsteps = a.nt - 1;
     double *xs = sm, *ys = xs + (size_t)PT * d, *ns = ys + (size_t)PT * d;
     double *dBs = ns + (size_t)PT * d, *zs = dBs + (size_t)PT * nB;
+    double *sh_tab = zs + (((size_t)PT * nB + 1) & ~(size_t)1);      // 16-byte aligned
     const int tid = threadIdx.x;
+    if (!a.B) icdf_stage(sh_tab, a.icdf, tid, LIN_THREADS);
+    __syncthreads();
     const bool heun = a.scheme == SDEGPU_HEUN;
     const uint64_t ngroups = (a.npaths + PT - 1) / PT;
     for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
                     dBs[e] = __dsub_rn(b[1], b[0]);                           // dB <- apply(B,2,diff) (:437)
                 } else if ((i & 1) == 0) {
                     double z0, z1;
-                    normal_pair(a.seed, a.path_offset + p0 + q, (uint32_t)(i >> 1), (uint32_t)k, z0, z1);
+                    normal_pair(a.seed, a.path_offset + p0 + q, (uint32_t)(i >> 1), (uint32_t)k, sh_tab, z0, z1);
                     zs[e] = z1;
                     dBs[e] = ds.y * z0;
                 } else dBs[e] = ds.y * zs[e];
@@ -128,7 +131,9 @@ int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream)
     int PT = LIN_THREADS / a.d;                        // paths per block: one thread per (path, row) when d <= 256
     if (PT < 1) PT = 1;
     if (PT > 64) PT = 64;
-    auto need = [&](int pt) { return sizeof(double) * ((size_t)3 * pt * a.d + (size_t)2 * pt * a.nB); };
+    auto need = [&](int pt) {
+        return sizeof(double) * ((size_t)3 * pt * a.d + (size_t)2 * pt * a.nB + 2) + (a.B ? 0 : (size_t)ICDF_TABLE_BYTES);
+    };
     size_t smem = need(PT);
     while (smem > 200 * 1024 && PT > 1) { PT /= 2; smem = need(PT); }
     if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;

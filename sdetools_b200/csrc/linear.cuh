@@ -4,19 +4,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "philox.cuh"
+
 namespace sdegpu {
 
 struct LinearArgs {
     const double *A;          // device, d x d column-major
     const double *G;          // device, d x nB column-major
     const double2 *dtsq;      // [nt-1] {dt, sqrt(dt)}
+    const double *icdf;       // device, half-normal quantile table (philox.cuh)
     const double *x0;         // per-path x0[p*d+j] or nullptr
     const double *x0_shared;  // device, d doubles (used when x0 == nullptr)
     const double *B;          // device, B[(p*nB+k)*nt+i] or nullptr (fused generator)
     double *X, *XT;           // X[(p*d+j)*nt+i], XT[p*d+j]
     double *moments;          // [5*d] {n,S1..S4} per component about center, or nullptr
     const double *center;     // device, d doubles
-    uint64_t npaths, path_offset, seed;
+    uint64_t npaths, path_offset;
+    PhiloxKey seed;
     int nt, d, nB, scheme, strict, accumulate;
 };
 

@@ -1,52 +1,97 @@
 // Counter-based increment generator fused into the step loop.
 // Replaces rnorm() in rBM (R/sdetools.R:19): no increment array ever exists in HBM.
+// Like R's default rnorm it draws by inversion (uniform -> qnorm); the uniform comes from
+// Philox4x32-10 instead of Mersenne-Twister so that a draw is a pure function of
+// (seed, global path id, step, channel).
 //
 //   key     = (seed lo, seed hi)
 //   counter = (path lo, path hi, block, channel)        one block = two consecutive steps
 //   r0..r3  = Philox4x32-10 (Salmon et al. SC'11; KATs in SURVEY.md App. F)
-//   u1 = 2 - [1,2)-double built from the top 52 bits of r1:r0   in (0,1]
-//   v  =     [1,2)-double built from the top 52 bits of r3:r2   (angle fraction + 1)
-//   z0 = sqrt(-2 log u1) * cospi(2 v),  z1 = sqrt(-2 log u1) * sinpi(2 v)
+//   step 2*block   uses (r0, r1), step 2*block+1 uses (r2, r3):
+//     u    = [1,2)-double built from the top 52 bits of hi:lo, minus 1      in [0,1)
+//     sign = bit 11 of lo
+//     z    = sign * a(u),   a(u) = -qnorm(u/2)  (half-normal quantile)
+//   a(u) is a table of degree-5 polynomials on 52 octaves x 16 mantissa sub-intervals
+//   (tools/gen_icdf_table.py, |error| < 2e-12), staged in shared memory: the transform costs
+//   2 DADD + 5 DFMA + 6 LDS and has no transcendental, no branch and no divergence.
 #pragma once
 #include <stdint.h>
+
+#include "icdf_table.inc"
 
 namespace sdegpu {
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+constexpr int ICDF_TABLE_DOUBLES = (ICDF_DEG + 1) * ICDF_NSEG;
+constexpr int ICDF_TABLE_BYTES = ICDF_TABLE_DOUBLES * 8;
 
-__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
-                                              uint32_t k0, uint32_t k1)
+// The ten round keys of a seed, expanded once on the host: as kernel parameters they sit in the
+// constant bank and feed the round's LOP3 directly (no per-step key-schedule instructions).
+struct PhiloxKey {
+    uint32_t k[20];      // k[2r], k[2r+1] = key of round r
+};
+
+inline PhiloxKey make_philox_key(uint64_t seed)
+{
+    PhiloxKey key;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        key.k[2 * r] = k0; key.k[2 * r + 1] = k1;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    return key;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, const PhiloxKey &key)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
         const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        const uint32_t n0 = hi1 ^ c1 ^ key.k[2 * r], n2 = hi0 ^ c3 ^ key.k[2 * r + 1];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += PHILOX_W0; k1 += PHILOX_W1;
     }
 }
 
-// [1,2) double from the top 52 bits of hi:lo
-__device__ __forceinline__ double bits_to_12(uint32_t lo, uint32_t hi)
+// cooperative copy of the quantile table into shared memory (call before __syncthreads)
+__device__ __forceinline__ void icdf_stage(double *sh_tab, const double *__restrict__ g_tab, int tid, int nthreads)
 {
-    return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+    const double2 *src = reinterpret_cast<const double2 *>(g_tab);
+    double2 *dst = reinterpret_cast<double2 *>(sh_tab);
+    for (int i = tid; i < ICDF_TABLE_DOUBLES / 2; i += nthreads) dst[i] = __ldg(src + i);
+}
+
+// one standard normal from 64 random bits
+__device__ __forceinline__ double icdf_normal(uint32_t lo, uint32_t hi, const double *sh_tab)
+{
+    const double y0 = __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+    const double u = y0 - 1.0;                                   // [0,1): exponent = octave, mantissa = position
+    const uint32_t uh = (uint32_t)__double2hiint(u);
+    int t = (int)(uh >> 16) - ICDF_BASE;
+    t = t < 0 ? 0 : t;                                           // u < 2^-52 (incl. 0) -> last segment
+    const uint32_t yh = (uh & 0x000FFFFFu) | 0x3FF00000u;        // y = u * 2^(k+1) in [1,2)
+    const double y = __hiloint2double((int)yh, __double2loint(u));
+    const double c = __hiloint2double((int)((yh & 0xFFFF0000u) | 0x00008000u), 0);   // segment centre
+    const double r = y - c;
+    const double *p = sh_tab + t;
+    double a = p[5 * ICDF_NSEG];
+    a = fma(a, r, p[4 * ICDF_NSEG]);
+    a = fma(a, r, p[3 * ICDF_NSEG]);
+    a = fma(a, r, p[2 * ICDF_NSEG]);
+    a = fma(a, r, p[1 * ICDF_NSEG]);
+    a = fma(a, r, p[0]);
+    return __hiloint2double(__double2hiint(a) ^ (int)((lo << 20) & 0x80000000u), __double2loint(a));
 }
 
 // Two independent standard normals for (path, block, channel).
-__device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t path, uint32_t block, uint32_t channel,
-                                            double &z0, double &z1)
+__device__ __forceinline__ void normal_pair(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
+                                            const double *sh_tab, double &z0, double &z1)
 {
     uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32), c2 = block, c3 = channel;
-    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double u1 = 2.0 - bits_to_12(c0, c1);
-    const double v = bits_to_12(c2, c3);
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * v, &s, &c);
-    z0 = rad * c;
-    z1 = rad * s;
+    philox4x32_10(c0, c1, c2, c3, key);
+    z0 = icdf_normal(c0, c1, sh_tab);
+    z1 = icdf_normal(c2, c3, sh_tab);
 }
 
 }  // namespace sdegpu

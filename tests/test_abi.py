@@ -116,3 +116,33 @@ def test_float80_emulation_matches_x87(tmp_path):
     subprocess.run(["/usr/bin/g++", "-O2", "-o", str(exe), os.path.join(ROOT, "tests", "native", "float80_check.cpp")], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "mismatches=0" in r.stdout, r.stdout + r.stderr
+
+
+def test_icdf_table_matches_qnorm():
+    """The quantile table the fused generator evaluates on the device (csrc/icdf_table.inc), evaluated
+    here exactly as philox.cuh does, against -qnorm(u/2)."""
+    from scipy.special import ndtri
+    txt = open(os.path.join(ROOT, "sdetools_b200", "csrc", "icdf_table.inc")).read()
+    nseg = int(re.search(r"#define ICDF_NSEG (\d+)", txt).group(1))
+    deg = int(re.search(r"#define ICDF_DEG (\d+)", txt).group(1))
+    base = int(re.search(r"#define ICDF_BASE (\d+)", txt).group(1))
+    body = txt[txt.index("= {") + 3:txt.index("};")]
+    tab = np.array([float.fromhex(v.strip()) for v in body.split(",") if v.strip()]).reshape(deg + 1, nseg)
+    rng = np.random.default_rng(0)
+    m = np.concatenate([rng.integers(0, 2 ** 52, 400000), 2 ** rng.integers(0, 52, 2000) + rng.integers(0, 3, 2000),
+                        np.arange(0, 4), 2 ** 52 - 1 - np.arange(0, 4)]).astype(np.uint64)
+    u = m.astype(np.float64) * 2.0 ** -52                       # what y0 - 1.0 gives on the device
+    bits = u.view(np.uint64)
+    uh = (bits >> np.uint64(32)).astype(np.int64)
+    t = np.maximum((uh >> 16) - base, 0)
+    yh = (uh & 0x000FFFFF) | 0x3FF00000
+    y = ((yh.astype(np.uint64) << np.uint64(32)) | (bits & np.uint64(0xFFFFFFFF))).view(np.float64)
+    c = (((yh & 0xFFFF0000) | 0x8000).astype(np.uint64) << np.uint64(32)).view(np.float64)
+    r = y - c
+    a = tab[deg, t]
+    for j in range(deg - 1, -1, -1):
+        a = a * r + tab[j, t]
+    want = -ndtri(0.5 * np.where(m == 0, 2.0 ** -52, u))
+    assert t.max() < nseg and np.max(np.abs(r)) <= 1 / 32
+    assert np.max(np.abs(a - want)) < 3e-12
+    assert np.all(a > -1e-13)           # next to u = 1 the true value (~1e-16) is below the table's error

@@ -113,7 +113,8 @@ def test_device_normals_match_reference_stream(eng):
     seed, off = 0x5DE70015, (1 << 33) + 5                    # path ids beyond 32 bits
     z = eng.normals(seed, off, 257, 101)
     want = philox_ref.normals(off + np.arange(257), 101, 0, seed)
-    assert np.max(np.abs(z - want)) < 1e-13
+    assert np.max(np.abs(z - want)) < 5e-12                  # table quantile vs exact qnorm (ICDF_MAX_ERR 1.7e-12)
+    assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 4 * np.sqrt(2 / z.size)
     assert np.array_equal(eng.normals(seed, off + 100, 3, 7), z[:7, 100:103])     # keyed by global id
     assert not np.array_equal(eng.normals(seed, off, 4, 6, channel=1), z[:6, :4])
 
@@ -240,8 +241,8 @@ def test_integrals_edge_cases(sde):
     got, want = sde.QuadraticVariation(x), O.QuadraticVariation(x)
     assert np.array_equal(got, want, equal_nan=True)
     # a sum a plain-double prefix sum gets wrong: 1 + 2^-60 + 2^-60 - 1
-    inc = np.array([0.0, 1.0, 1.0 + 2.0 ** -60, 1.0 + 2.0 ** -59, 2.0 ** -59])
-    assert sde.itointegral(np.ones(5), inc)[-1] == 2.0 ** -59
+    G = np.array([1.0, 2.0 ** -60, 2.0 ** -60, -1.0, 0.0])
+    assert sde.itointegral(G, np.arange(5.0))[-1] == 2.0 ** -59 and np.cumsum(G)[-2] == 0.0
 
 
 def test_vignette_identities_on_device(sde):

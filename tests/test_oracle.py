@@ -230,3 +230,14 @@ def test_hist_convention():
     c = O.hist_counts([0.0, 0.5, 1.0, 1.0000001, -1e-9, 2.0, np.nan, 0.25], 0.0, 2.0, 4)
     # bins (0,.5],(.5,1],(1,1.5],(1.5,2] with 0 in the first
     assert c.tolist() == [1, 3, 1, 1, 1, 0, 1]
+
+
+def test_as241_qnorm_against_scipy():
+    """The oracle's inversion (Wichura AS241, the algorithm of R's qnorm / default rnorm)."""
+    import ctypes as C
+    from scipy.special import ndtri
+    lib = c_oracle.lib()
+    lib.oracle_qnorm.restype, lib.oracle_qnorm.argtypes = C.c_double, [C.c_double]
+    ps = np.concatenate([np.linspace(1e-6, 1 - 1e-6, 501), 10.0 ** -np.arange(1, 17, 0.37), 2.0 ** -np.arange(2, 54)])
+    got = np.array([lib.oracle_qnorm(float(p)) for p in ps])
+    assert np.max(np.abs(got - ndtri(ps)) / np.maximum(np.abs(ndtri(ps)), 1e-3)) < 1e-13
