@@ -9,7 +9,7 @@
 #include <vector>
 
 // the half-normal quantile table of the fused generator lives in this translation unit
-#define ICDF_TABLE_DEFINE __device__ const double g_icdf_table
+#define ICDF_TABLE_DEFINE __device__ const unsigned long long g_icdf_table
 #include "../../include/sdegpu.h"
 #include "ensemble.cuh"
 #include "linear.cuh"
@@ -535,6 +535,7 @@ int sdegpu_normals(sdegpu_ctx *c, uint64_t seed, uint64_t path_offset, uint64_t 
     CU(cudaSetDevice(c->device));
     const size_t bytes = sizeof(double) * npaths * (size_t)nsteps;
     CU(c->out0.reserve(bytes));
+    cudaFuncSetAttribute(k_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, ICDF_TABLE_BYTES);
     k_normals<<<(unsigned)((npaths + 127) / 128), 128, ICDF_TABLE_BYTES, c->stream>>>(c->icdf, make_philox_key(seed), path_offset, npaths, channel,
                                                                                      nsteps, (double *)c->out0.p);
     CU(cudaGetLastError());

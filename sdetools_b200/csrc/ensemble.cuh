@@ -16,7 +16,13 @@
 namespace sdegpu {
 
 constexpr int MAX_NX = 2;           // catalogue models handled here have nx <= 2
-constexpr int TERMINAL_THREADS = 512;
+#ifndef SDEGPU_TERMINAL_THREADS
+#define SDEGPU_TERMINAL_THREADS 768
+#endif
+#ifndef SDEGPU_TERMINAL_MIN_BLOCKS
+#define SDEGPU_TERMINAL_MIN_BLOCKS 2
+#endif
+constexpr int TERMINAL_THREADS = SDEGPU_TERMINAL_THREADS;
 constexpr int TILE_PATHS = 128;     // paths (= threads) per block in k_tiled
 constexpr int TILE_STEPS = 32;      // time steps staged per tile
 constexpr int TILE_LD = TILE_STEPS + 1;   // odd leading dimension: conflict-free column walks
@@ -107,7 +113,7 @@ __device__ __forceinline__ void load_x0(const RunArgs &a, uint64_t p, double (&x
 
 // ---- register-resident, fused-generator kernel ------------------------------
 template <class M, int SCHEME, int PROJ>
-__global__ void __launch_bounds__(TERMINAL_THREADS) k_terminal(const RunArgs a)
+__global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) k_terminal(const RunArgs a)
 {
     constexpr int NX = M::NX;
     extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]

@@ -124,25 +124,26 @@ def test_icdf_table_matches_qnorm():
     from scipy.special import ndtri
     txt = open(os.path.join(ROOT, "sdetools_b200", "csrc", "icdf_table.inc")).read()
     nseg = int(re.search(r"#define ICDF_NSEG (\d+)", txt).group(1))
-    deg = int(re.search(r"#define ICDF_DEG (\d+)", txt).group(1))
+    shift = int(re.search(r"#define ICDF_SHIFT (\d+)", txt).group(1))
     base = int(re.search(r"#define ICDF_BASE (\d+)", txt).group(1))
-    body = txt[txt.index("= {") + 3:txt.index("};")]
-    tab = np.array([float.fromhex(v.strip()) for v in body.split(",") if v.strip()]).reshape(deg + 1, nseg)
+    body = txt[txt.index("] = {") + 5:txt.index("};")]
+    words =np.array([int(v.strip().rstrip("ul"), 16) for v in body.split(",") if v.strip()], dtype=np.uint64).reshape(3, nseg)
+    c0, c1 = words[0].view(np.float64), words[1].view(np.float64)
+    c2 = (words[2] & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32).astype(np.float64)
+    c3 = (words[2] >> np.uint64(32)).astype(np.uint32).view(np.float32).astype(np.float64)
     rng = np.random.default_rng(0)
     m = np.concatenate([rng.integers(0, 2 ** 52, 400000), 2 ** rng.integers(0, 52, 2000) + rng.integers(0, 3, 2000),
                         np.arange(0, 4), 2 ** 52 - 1 - np.arange(0, 4)]).astype(np.uint64)
     u = m.astype(np.float64) * 2.0 ** -52                       # what y0 - 1.0 gives on the device
     bits = u.view(np.uint64)
     uh = (bits >> np.uint64(32)).astype(np.int64)
-    t = np.maximum((uh >> 16) - base, 0)
+    t = np.maximum((uh >> shift) - base, 0)
     yh = (uh & 0x000FFFFF) | 0x3FF00000
     y = ((yh.astype(np.uint64) << np.uint64(32)) | (bits & np.uint64(0xFFFFFFFF))).view(np.float64)
-    c = (((yh & 0xFFFF0000) | 0x8000).astype(np.uint64) << np.uint64(32)).view(np.float64)
+    c = (((yh & ~((1 << shift) - 1)) | (1 << (shift - 1))).astype(np.uint64) << np.uint64(32)).view(np.float64)
     r = y - c
-    a = tab[deg, t]
-    for j in range(deg - 1, -1, -1):
-        a = a * r + tab[j, t]
+    a = ((c3[t] * r + c2[t]) * r + c1[t]) * r + c0[t]
     want = -ndtri(0.5 * np.where(m == 0, 2.0 ** -52, u))
-    assert t.max() < nseg and np.max(np.abs(r)) <= 1 / 32
-    assert np.max(np.abs(a - want)) < 3e-12
-    assert np.all(a > -1e-13)           # next to u = 1 the true value (~1e-16) is below the table's error
+    assert t.max() < nseg and np.max(np.abs(r)) <= 2.0 ** -(21 - shift)
+    assert np.max(np.abs(a - want)) < 1e-10
+    assert np.all(a > -1e-10)           # next to u = 1 the true value (~1e-16) is below the table's error
