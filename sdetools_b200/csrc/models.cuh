@@ -24,20 +24,19 @@ struct Fast {
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
     static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
-    // sqrt of a finite a >= 0 without the special-case branch of the IEEE routine: MUFU.RSQ64H seed
-    // (2^-22) + two Goldschmidt steps (-> 2^-88 before rounding, <= 1 ulp).  The 1e-300 offset keeps the
-    // seed finite at a = 0 (sqrt(0) comes out as 1e-150).
+    // sqrt of a finite a >= 0 without the special-case branch of the IEEE routine: MUFU.RSQ64H seed y
+    // (relative error e ~ 2^-22) and one third-order step  sqrt(a) = a*y*(1 + e/2 + 3e^2/8 + O(e^3)),
+    // e = 1 - a*y^2, i.e. 5 FP64 instructions and <= 1-2 ulp.  The high word is clamped to the smallest
+    // normal exponent with an integer max so the seed stays finite at a = 0 (sqrt(0) -> 2^-511).
     static __device__ __forceinline__ double sqrt_(double a)
     {
-        a += 1e-300;
+        a = __hiloint2double(max(__double2hiint(a), 0x00100000), __double2loint(a));
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-        double g = a * y, h = 0.5 * y;
-        double r = fma(-h, g, 0.5);
-        g = fma(g, r, g);
-        h = fma(h, r, h);
-        r = fma(-h, g, 0.5);
-        return fma(g, r, g);
+        const double t = a * y;
+        const double e = fma(-t, y, 1.0);
+        const double p = fma(0.375, e, 0.5);
+        return fma(t, p * e, t);
     }
 };
 
