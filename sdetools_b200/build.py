@@ -51,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(u):
         obj, src, defs = u
-        cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+        extra = os.environ.get("SDEGPU_NVCC_EXTRA", "").split()     # tuning experiments, e.g. -DSDEGPU_TERMINAL_THREADS=512
+        cmd = [nvcc, *NVCC_FLAGS, *defs, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)

@@ -134,17 +134,22 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
         double x[NX];
         load_x0<NX>(a, p, x);
         const uint64_t gp = a.path_offset + p;
+        // Software-pipelined: the Philox block of steps (i+2, i+3) is generated while steps (i, i+1)
+        // integrate, so the integer rounds issue in the shadow of the dependent FP64 chain.
         int i = 0;
+        uint32_t r0, r1, r2, r3;
+        philox_block(a.seed, gp, 0u, 0u, r0, r1, r2, r3);
         for (; i + 1 < nsteps; i += 2) {
-            double z0, z1;
-            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
+            uint32_t n0, n1, n2, n3;
+            philox_block(a.seed, gp, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
+            const double z0 = icdf_normal(r0, r1, sh_tab), z1 = icdf_normal(r2, r3, sh_tab);
             const double2 d0 = __ldg(&a.dtsq[i]), d1 = __ldg(&a.dtsq[i + 1]);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d1.x, d1.y * z1);
+            r0 = n0; r1 = n1; r2 = n2; r3 = n3;
         }
         if (i < nsteps) {
-            double z0, z1;
-            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
+            const double z0 = icdf_normal(r0, r1, sh_tab);
             const double2 d0 = __ldg(&a.dtsq[i]);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
         }
@@ -155,6 +160,86 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
         accumulate_terminal<NX>(a, x, acc, sh_hist);
     }
     flush_block_stats<NX, TERMINAL_THREADS>(a, acc, sh_hist);
+}
+
+// ---- full-trajectory kernel, fused generator (HBM-write bound) ----------------
+// X[(p*nx+j)*nt + i] is time-fastest per path (the reference's column-major nt x nx matrix), so the
+// 32 paths of a warp write 32 rows that are nt*8 bytes apart.  Each thread therefore pairs two
+// consecutive time points of its own row in registers and writes them with one 16-byte store on
+// 16-byte-aligned element pairs (2m, 2m+1); rows of odd length shift the pairing per row, the odd
+// element at either end of a row is written alone.  Half-sector stores from a warp's 32 rows meet in
+// L2 (active set = npaths*nx sectors, far below the 126 MB L2) and reach HBM as full sectors.
+constexpr int TRAJ_THREADS = 512;
+
+__device__ __forceinline__ void st_pair(double *p, double a, double b)
+{
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+template <class M, int SCHEME, int PROJ>
+__global__ void __launch_bounds__(TRAJ_THREADS, 2) k_traj(const RunArgs a, const int pair_ok)
+{
+    constexpr int NX = M::NX;
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_TABLE_DOUBLES);
+    icdf_stage(sh_tab, a.icdf, threadIdx.x, TRAJ_THREADS);
+    if (a.hist)
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TRAJ_THREADS) sh_hist[i] = 0u;
+    __syncthreads();
+    double acc[NX][5];
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
+
+    const int nsteps = a.nt - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * TRAJ_THREADS;
+    for (uint64_t p = (uint64_t)blockIdx.x * TRAJ_THREADS + threadIdx.x; p < a.npaths; p += stride) {
+        double x[NX], held[NX];
+        uint64_t e[NX];                                          // global element index of the next write
+        load_x0<NX>(a, p, x);
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {                            // X[1,] <- x0  (:441)
+            e[j] = (p * NX + j) * (uint64_t)a.nt;
+            if (!pair_ok || (e[j] & 1)) a.X[e[j]] = x[j];
+            held[j] = x[j];
+            ++e[j];
+        }
+        const uint64_t gp = a.path_offset + p;
+        uint32_t r0, r1, r2, r3;
+        philox_block(a.seed, gp, 0u, 0u, r0, r1, r2, r3);
+        for (int i = 0; i < nsteps; i += 2) {
+            uint32_t n0, n1, n2, n3;
+            philox_block(a.seed, gp, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
+            const double z0 = icdf_normal(r0, r1, sh_tab), z1 = icdf_normal(r2, r3, sh_tab);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (i + h < nsteps) {
+                    const double2 d = __ldg(&a.dtsq[i + h]);
+                    sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d.x, d.y * (h ? z1 : z0));
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) {
+                        if (!pair_ok) a.X[e[j]] = x[j];
+                        else if (e[j] & 1) st_pair(a.X + e[j] - 1, held[j], x[j]);      // closes the pair (e-1, e)
+                        held[j] = x[j];
+                        ++e[j];
+                    }
+                }
+            }
+            r0 = n0; r1 = n1; r2 = n2; r3 = n3;
+        }
+        if (pair_ok) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                if (e[j] & 1) a.X[e[j] - 1] = held[j];            // last element opened a pair that the next row owns
+        }
+        if (a.XT) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+        }
+        accumulate_terminal<NX>(a, x, acc, sh_hist);
+    }
+    flush_block_stats<NX, TRAJ_THREADS>(a, acc, sh_hist);
 }
 
 // ---- tiled kernel: supplied B in, and/or full trajectory out ----------------

@@ -35,6 +35,19 @@ static int launch_terminal(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     return (int)cudaGetLastError();
 }
 
+template <int SCHEME, int PROJ>
+static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
+{
+    auto kernel = k_traj<M, SCHEME, PROJ>;
+    const size_t smem = ICDF_TABLE_BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    const uint64_t work = (a.npaths + TRAJ_THREADS - 1) / TRAJ_THREADS;
+    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TRAJ_THREADS, smem, c.sm_count, work);
+    const int pair_ok = (reinterpret_cast<uintptr_t>(a.X) & 15) == 0;
+    kernel<<<grid, TRAJ_THREADS, smem, c.stream>>>(a, pair_ok);
+    *grid_used = grid;
+    return (int)cudaGetLastError();
+}
+
 template <int SCHEME, int PROJ, class A, bool SRC_B>
 static int launch_tiled(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
@@ -56,7 +69,7 @@ static int dispatch_mode(const RunArgs &a, const LaunchCfg &c, int *g)
     if (c.src_b)
         return c.arith == SDEGPU_ARITH_STRICT ? launch_tiled<SCHEME, PROJ, Strict, true>(a, c, g)
                                               : launch_tiled<SCHEME, PROJ, Fast, true>(a, c, g);
-    if (c.want_x) return launch_tiled<SCHEME, PROJ, Fast, false>(a, c, g);
+    if (c.want_x) return launch_traj<SCHEME, PROJ>(a, c, g);
     return launch_terminal<SCHEME, PROJ>(a, c, g);
 }
 

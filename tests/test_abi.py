@@ -145,5 +145,5 @@ def test_icdf_table_matches_qnorm():
     a = ((c3[t] * r + c2[t]) * r + c1[t]) * r + c0[t]
     want = -ndtri(0.5 * np.where(m == 0, 2.0 ** -52, u))
     assert t.max() < nseg and np.max(np.abs(r)) <= 2.0 ** -(21 - shift)
-    assert np.max(np.abs(a - want)) < 1e-10
-    assert np.all(a > -1e-10)           # next to u = 1 the true value (~1e-16) is below the table's error
+    assert np.max(np.abs(a - want)) < 1e-9
+    assert np.all(a > -1e-9)          # next to u = 1 the true value (~1e-16) is below the table's error

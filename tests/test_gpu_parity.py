@@ -113,7 +113,7 @@ def test_device_normals_match_reference_stream(eng):
     seed, off = 0x5DE70015, (1 << 33) + 5                    # path ids beyond 32 bits
     z = eng.normals(seed, off, 257, 101)
     want = philox_ref.normals(off + np.arange(257), 101, 0, seed)
-    assert np.max(np.abs(z - want)) < 1e-10                  # table quantile vs exact qnorm (ICDF_MAX_ERR 4.7e-11)
+    assert np.max(np.abs(z - want)) < 1e-9                   # table quantile vs exact qnorm (ICDF_MAX_ERR 7.4e-10)
     assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 4 * np.sqrt(2 / z.size)
     assert np.array_equal(eng.normals(seed, off + 100, 3, 7), z[:7, 100:103])     # keyed by global id
     assert not np.array_equal(eng.normals(seed, off, 4, 6, channel=1), z[:6, :4])

@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's bench contract): the other BASELINE.json configs
+on one GPU, device-resident buffers, CUDA-event timing inside libsdegpu (kernels only).
+
+    python tools/bench_modes.py [--quick] > gpurun_out/modes.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    import torch
+    import sdetools_b200 as sde
+    eng = sde.default_engine(0)
+    dev = torch.device("cuda", 0)
+    hbm = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) \
+        if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+    fp64 = eng.measure_fp64_peak()
+    out = []
+
+    def best_ms(fn, reps=3):
+        fn()
+        return min(fn() for _ in range(reps))
+
+    def emit(name, **kw):
+        kw["name"] = name
+        print(json.dumps(kw), flush=True)
+
+    want = lambda n: not args.only or n in args.only.split(",")
+
+    # C3: van der Pol, full trajectory, fused generator (HBM-write bound; 16 B per path-step)
+    if want("c3"):
+        P = 1 << (15 if args.quick else 17)
+        nt = 10001
+        t = np.arange(nt) * 0.01
+        X = torch.empty(P * 2 * nt, dtype=torch.float64, device=dev)
+        ms = best_ms(lambda: eng.run("vdp", "euler", [1.0, 0.5], t, [0.0, 0.0], nx=2, npaths=P, seed=3, X=X, want_time=True))
+        steps = P * (nt - 1)
+        emit("c3_vdp_traj_philox", paths=P, nt=nt, ms=ms, path_steps_per_s=steps / ms * 1e3, gbs=16.0 * steps / ms / 1e6,
+             hbm_frac=16.0 * steps / ms / 1e6 / hbm, bytes_per_step=16)
+        chk = X.view(P, 2, nt)[:4, :, :3].cpu().numpy().tolist()
+        emit("c3_check", first=chk[0])
+        # supplied-B variant: 8 B read + 16 B written per path-step
+        P2 = P // 2
+        B = torch.empty(P2 * nt, dtype=torch.float64, device=dev)
+        eng.rvbm(t, P2, B, seed=9)
+        X2 = X[: P2 * 2 * nt]
+        for arith in ("strict", "fast"):
+            ms = best_ms(lambda: eng.run("vdp", "euler", [1.0, 0.5], t, [0.0, 0.0], nx=2, npaths=P2, B=B, arith=arith, X=X2,
+                                         want_time=True))
+            steps = P2 * (nt - 1)
+            emit(f"c3_vdp_traj_suppliedB_{arith}", paths=P2, nt=nt, ms=ms, path_steps_per_s=steps / ms * 1e3,
+                 gbs=24.0 * steps / ms / 1e6, hbm_frac=24.0 * steps / ms / 1e6 / hbm, bytes_per_step=24)
+        del X, X2, B
+        torch.cuda.empty_cache()
+
+    # C5 per-GPU share: OU euler, terminal moments + 512-bin histogram (FP64/issue bound; 71 flops per path-step)
+    if want("c5"):
+        P = (1 << 22) if args.quick else 50_000_000
+        n = 1000
+        t = np.arange(n + 1) * 1e-3
+        ps = torch.zeros(5, dtype=torch.float64, device=dev)
+        hc = torch.zeros(515, dtype=torch.int64, device=dev)
+        ms = best_ms(lambda: eng.run("ou", "euler", [1.3, 0.7, 0.9], t, [2.0], nx=1, npaths=P, seed=0x5DE70005, power_sums=ps,
+                                     center=[1.05], hist_counts=hc, hist=(-2.2, 4.3, 512), want_time=True))
+        steps = P * n
+        emit("c5_ou_euler_terminal", paths=P, nsteps=n, ms=ms, path_steps_per_s=steps / ms * 1e3,
+             tflops_conv=71.0 * steps / ms / 1e9, fp64_peak=fp64, frac=71.0 * steps / ms / 1e9 / fp64)
+
+    # integrals: stochint l/r/c on stored paths (16 B read, 24 B written per element)
+    if want("integrals"):
+        n, nc = 1001, (1 << 16 if args.quick else 1 << 19)
+        f = torch.randn(nc * n, dtype=torch.float64, device=dev)
+        g = torch.randn(nc * n, dtype=torch.float64, device=dev).cumsum(0) * 0.01
+        l, r, c = (torch.empty_like(f) for _ in range(3))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.use_torch_stream()
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(3):
+                ev0.record()
+                fn()
+                ev1.record()
+                torch.cuda.synchronize()
+                best = min(best, ev0.elapsed_time(ev1))
+            return best
+        ms = timed(lambda: eng.stochint(f, g, n, nc, l, r, c))
+        emit("stochint_lrc", n=n, ncols=nc, ms=ms, elems_per_s=n * nc / ms * 1e3, gbs=40.0 * n * nc / ms / 1e6,
+             hbm_frac=40.0 * n * nc / ms / 1e6 / hbm)
+        ms = timed(lambda: eng.itointegral(f, g, n, nc, l))
+        emit("itointegral", n=n, ncols=nc, ms=ms, elems_per_s=n * nc / ms * 1e3, gbs=24.0 * n * nc / ms / 1e6,
+             hbm_frac=24.0 * n * nc / ms / 1e6 / hbm)
+        ms = timed(lambda: eng.qv(g, n, nc, l))
+        emit("quadratic_variation", n=n, ncols=nc, ms=ms, elems_per_s=n * nc / ms * 1e3, gbs=16.0 * n * nc / ms / 1e6,
+             hbm_frac=16.0 * n * nc / ms / 1e6 / hbm)
+        eng.use_own_stream()
+        del f, g, l, r, c
+        torch.cuda.empty_cache()
+
+    # C4: linear SDE d = 256 (A x as a GEMM over paths); 2d^2+4d flops per path-step
+    if want("c4"):
+        d = 256
+        P = 1 << (10 if args.quick else 14)
+        n = 100 if args.quick else 1000
+        rng = np.random.default_rng(256)
+        R = rng.standard_normal((d, d))
+        A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
+        G = np.eye(d)
+        params = np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
+        x0 = np.zeros(d)
+        x0[0] = 1.0
+        XT = torch.empty(P * d, dtype=torch.float64, device=dev)
+        ms = best_ms(lambda: eng.run("linear", "euler", params, np.arange(n + 1) * (1.0 / n), x0, nx=d, nB=d, npaths=P, seed=4,
+                                     XT=XT, want_time=True), reps=2)
+        steps = P * n
+        fl = 2.0 * d * d + 4 * d
+        emit("c4_linear_d256", paths=P, nsteps=n, ms=ms, path_steps_per_s=steps / ms * 1e3, tflops=fl * steps / ms / 1e9,
+             fp64_peak=fp64, frac=fl * steps / ms / 1e9 / fp64)
+        xt = XT.view(P, d)
+        emit("c4_check", mean0=float(xt[:, 0].mean()), var_mean=float(xt.var(dim=0).mean()), var_expected=1 - np.exp(-1.0))
+
+
+if __name__ == "__main__":
+    main()
