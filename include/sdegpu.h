@@ -124,8 +124,10 @@ SDEGPU_API const char *sdegpu_last_error(void);
 SDEGPU_API int sdegpu_create(int device, sdegpu_ctx **ctx);
 SDEGPU_API int sdegpu_destroy(sdegpu_ctx *ctx);
 SDEGPU_API int sdegpu_device_info(sdegpu_ctx *ctx, sdegpu_devinfo *info);
-/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream. */
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream; NULL = CUDA's default stream);
+ * sdegpu_reset_stream goes back to the context's own non-blocking stream. */
 SDEGPU_API int sdegpu_set_stream(sdegpu_ctx *ctx, void *cuda_stream);
+SDEGPU_API int sdegpu_reset_stream(sdegpu_ctx *ctx);
 SDEGPU_API int sdegpu_synchronize(sdegpu_ctx *ctx);
 
 /* Replaces sapply/replicate around euler() (R/sdetools.R:375-470) or heun() (:240-338).

@@ -55,6 +55,7 @@ SYMBOLS = {
     "sdegpu_destroy": (C.c_int, [_vp]),
     "sdegpu_device_info": (C.c_int, [_vp, C.POINTER(DevInfo)]),
     "sdegpu_set_stream": (C.c_int, [_vp, _vp]),
+    "sdegpu_reset_stream": (C.c_int, [_vp]),
     "sdegpu_synchronize": (C.c_int, [_vp]),
     "sdegpu_run": (C.c_int, [_vp, C.POINTER(Problem), C.POINTER(Output)]),
     "sdegpu_stochint": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _u32]),

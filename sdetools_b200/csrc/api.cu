@@ -162,7 +162,14 @@ int sdegpu_device_info(sdegpu_ctx *c, sdegpu_devinfo *info)
 int sdegpu_set_stream(sdegpu_ctx *c, void *s)
 {
     if (!c) return fail(SDEGPU_ERR_ARG, "sdegpu_set_stream: ctx is NULL");
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;          // NULL is CUDA's default stream, a valid choice
+    return SDEGPU_OK;
+}
+
+int sdegpu_reset_stream(sdegpu_ctx *c)
+{
+    if (!c) return fail(SDEGPU_ERR_ARG, "sdegpu_reset_stream: ctx is NULL");
+    c->stream = c->own_stream;
     return SDEGPU_OK;
 }
 

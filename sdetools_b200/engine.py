@@ -54,7 +54,7 @@ class Engine:
         check(self.lib.sdegpu_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
     def use_own_stream(self):
-        check(self.lib.sdegpu_set_stream(self._h, None))
+        check(self.lib.sdegpu_reset_stream(self._h))
 
     def synchronize(self):
         check(self.lib.sdegpu_synchronize(self._h))
