@@ -17,10 +17,10 @@ namespace sdegpu {
 
 constexpr int MAX_NX = 2;           // catalogue models handled here have nx <= 2
 #ifndef SDEGPU_TERMINAL_THREADS
-#define SDEGPU_TERMINAL_THREADS 768
+#define SDEGPU_TERMINAL_THREADS 640
 #endif
 #ifndef SDEGPU_TERMINAL_MIN_BLOCKS
-#define SDEGPU_TERMINAL_MIN_BLOCKS 2
+#define SDEGPU_TERMINAL_MIN_BLOCKS 1
 #endif
 constexpr int TERMINAL_THREADS = SDEGPU_TERMINAL_THREADS;
 constexpr int TILE_PATHS = 128;     // paths (= threads) per block in k_tiled
@@ -164,20 +164,24 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 
 // ---- full-trajectory kernel, fused generator (HBM-write bound) ----------------
 // X[(p*nx+j)*nt + i] is time-fastest per path (the reference's column-major nt x nx matrix), so the
-// 32 paths of a warp write 32 rows that are nt*8 bytes apart.  Each thread therefore pairs two
-// consecutive time points of its own row in registers and writes them with one 16-byte store on
-// 16-byte-aligned element pairs (2m, 2m+1); rows of odd length shift the pairing per row, the odd
-// element at either end of a row is written alone.  Half-sector stores from a warp's 32 rows meet in
-// L2 (active set = npaths*nx sectors, far below the 126 MB L2) and reach HBM as full sectors.
+// 32 paths of a warp write 32 rows that are nt*8 bytes apart and nothing coalesces across lanes.
+// Partial-sector stores make L2 fetch the rest of the sector from HBM (measured: 0.43 B read per B
+// written with 16-byte stores), so each thread keeps four consecutive time points of its own row in
+// registers and writes them as ONE aligned 32-byte sector (sm_100 256-bit store, STG.E.256).  Rows
+// start at arbitrary element offsets (nt is usually odd), so the sector grid is shifted per row by
+// d = (row start + 1) mod 4: the sector that completes in a 4-step group is made of the last d values
+// of the previous group and the first 4-d of this one.  Paths are dealt to lanes with stride Q
+// (Q*nx*nt = 0 mod 4) so that d is warp-uniform and the four-way switch does not diverge.  Only the
+// first/last partial sector of a row is written element by element.
 constexpr int TRAJ_THREADS = 512;
 
-__device__ __forceinline__ void st_pair(double *p, double a, double b)
+__device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d)
 {
-    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 template <class M, int SCHEME, int PROJ>
-__global__ void __launch_bounds__(TRAJ_THREADS, 2) k_traj(const RunArgs a, const int pair_ok)
+__global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const int vec_ok, const int Q)
 {
     constexpr int NX = M::NX;
     extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
@@ -192,46 +196,79 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) k_traj(const RunArgs a, const
 #pragma unroll
         for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
 
-    const int nsteps = a.nt - 1;
+    const int nsteps = a.nt - 1, ngroups = nsteps >> 2;
     const uint64_t stride = (uint64_t)gridDim.x * TRAJ_THREADS;
-    for (uint64_t p = (uint64_t)blockIdx.x * TRAJ_THREADS + threadIdx.x; p < a.npaths; p += stride) {
-        double x[NX], held[NX];
-        uint64_t e[NX];                                          // global element index of the next write
+    const uint64_t W = 32u * (unsigned)Q;                        // paths per lane-interleaved group of Q warps
+    for (uint64_t T = (uint64_t)blockIdx.x * TRAJ_THREADS + threadIdx.x;; T += stride) {
+        const uint64_t within = T % W, p = (T - within) + (within >> 5) + (uint64_t)Q * (within & 31);
+        if (T - within >= a.npaths) break;                       // whole group out of range (uniform)
+        if (p >= a.npaths) continue;
+        double x[NX], v[NX][4], pv[NX][4];
+        double *row[NX];                                         // &X[row start + 1]: stream position 0
+        int d[NX];
         load_x0<NX>(a, p, x);
 #pragma unroll
-        for (int j = 0; j < NX; ++j) {                            // X[1,] <- x0  (:441)
-            e[j] = (p * NX + j) * (uint64_t)a.nt;
-            if (!pair_ok || (e[j] & 1)) a.X[e[j]] = x[j];
-            held[j] = x[j];
-            ++e[j];
+        for (int j = 0; j < NX; ++j) {
+            const uint64_t e0 = (p * NX + j) * (uint64_t)a.nt;
+            row[j] = a.X + e0 + 1;
+            d[j] = vec_ok ? (int)((e0 + 1) & 3) : 4;             // 4: element-wise stores only
+            if (d[j] != 1) a.X[e0] = x[j];                       // X[1,] <- x0 (:441); with d = 1 it opens the first sector
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pv[j][k] = x[j];
         }
         const uint64_t gp = a.path_offset + p;
-        uint32_t r0, r1, r2, r3;
-        philox_block(a.seed, gp, 0u, 0u, r0, r1, r2, r3);
-        for (int i = 0; i < nsteps; i += 2) {
-            uint32_t n0, n1, n2, n3;
-            philox_block(a.seed, gp, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
-            const double z0 = icdf_normal(r0, r1, sh_tab), z1 = icdf_normal(r2, r3, sh_tab);
+        uint32_t ra[4], rb[4];
+        philox_block(a.seed, gp, 0u, 0u, ra[0], ra[1], ra[2], ra[3]);
+        philox_block(a.seed, gp, 1u, 0u, rb[0], rb[1], rb[2], rb[3]);
+        for (int m = 0; m < ngroups; ++m) {
+            uint32_t na[4], nb[4];                               // next group's bits, generated under this group's FP64 chain
+            philox_block(a.seed, gp, 2u * (uint32_t)m + 2u, 0u, na[0], na[1], na[2], na[3]);
+            philox_block(a.seed, gp, 2u * (uint32_t)m + 3u, 0u, nb[0], nb[1], nb[2], nb[3]);
+            const double z[4] = {icdf_normal(ra[0], ra[1], sh_tab), icdf_normal(ra[2], ra[3], sh_tab),
+                                 icdf_normal(rb[0], rb[1], sh_tab), icdf_normal(rb[2], rb[3], sh_tab)};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (i + h < nsteps) {
-                    const double2 d = __ldg(&a.dtsq[i + h]);
-                    sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d.x, d.y * (h ? z1 : z0));
+            for (int k = 0; k < 4; ++k) {
+                const double2 dt = __ldg(&a.dtsq[4 * m + k]);
+                sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * z[k]);
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) {
-                        if (!pair_ok) a.X[e[j]] = x[j];
-                        else if (e[j] & 1) st_pair(a.X + e[j] - 1, held[j], x[j]);      // closes the pair (e-1, e)
-                        held[j] = x[j];
-                        ++e[j];
-                    }
-                }
+                for (int j = 0; j < NX; ++j) v[j][k] = x[j];
             }
-            r0 = n0; r1 = n1; r2 = n2; r3 = n3;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                double *g = row[j] + 4 * (int64_t)m;             // stream position 4m
+                if (d[j] == 4 || (m == 0 && d[j] >= 2)) {        // no vector store possible: the sector starts before the row
+                    const int n = d[j] == 4 ? 4 : 4 - d[j];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < n) g[k] = v[j][k];
+                } else if (d[j] == 0) st_sector(g, v[j][0], v[j][1], v[j][2], v[j][3]);
+                else if (d[j] == 1) st_sector(g - 1, pv[j][3], v[j][0], v[j][1], v[j][2]);
+                else if (d[j] == 2) st_sector(g - 2, pv[j][2], pv[j][3], v[j][0], v[j][1]);
+                else st_sector(g - 3, pv[j][1], pv[j][2], pv[j][3], v[j][0]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pv[j][k] = v[j][k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { ra[k] = na[k]; rb[k] = nb[k]; }
         }
-        if (pair_ok) {
+        // values of the last group that opened a sector the row does not complete in a full group
+        if (ngroups > 0) {
 #pragma unroll
             for (int j = 0; j < NX; ++j)
-                if (e[j] & 1) a.X[e[j] - 1] = held[j];            // last element opened a pair that the next row owns
+                if (d[j] >= 1 && d[j] <= 3) {
+#pragma unroll
+                    for (int k = 1; k < 4; ++k)
+                        if (k >= 4 - d[j]) row[j][4 * (int64_t)(ngroups - 1) + k] = pv[j][k];
+                }
+        }
+        for (int i = 4 * ngroups; i < nsteps; ++i) {              // up to three trailing steps, element-wise
+            const int k = i & 3;
+            const double zz = k == 0 ? icdf_normal(ra[0], ra[1], sh_tab)
+                            : (k == 1 ? icdf_normal(ra[2], ra[3], sh_tab) : icdf_normal(rb[0], rb[1], sh_tab));
+            const double2 dt = __ldg(&a.dtsq[i]);
+            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * zz);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) row[j][i] = x[j];
         }
         if (a.XT) {
 #pragma unroll

@@ -42,8 +42,10 @@ static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     const size_t smem = ICDF_TABLE_BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + TRAJ_THREADS - 1) / TRAJ_THREADS;
     const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TRAJ_THREADS, smem, c.sm_count, work);
-    const int pair_ok = (reinterpret_cast<uintptr_t>(a.X) & 15) == 0;
-    kernel<<<grid, TRAJ_THREADS, smem, c.stream>>>(a, pair_ok);
+    const int vec_ok = (reinterpret_cast<uintptr_t>(a.X) & 31) == 0;
+    const unsigned long long span = (unsigned long long)M::NX * (unsigned long long)a.nt;
+    const int Q = (span % 4 == 0) ? 1 : ((span % 2 == 0) ? 2 : 4);   // lanes take every Q-th path: uniform sector phase
+    kernel<<<grid, TRAJ_THREADS, smem, c.stream>>>(a, vec_ok, Q);
     *grid_used = grid;
     return (int)cudaGetLastError();
 }
