@@ -174,11 +174,15 @@ int oracle_ensemble(int scheme, int model, const double *params, int nx, int nB,
                     const double *b = B + ((size_t)p * nB + k) * nt;
                     dB[k] = b[i + 1] - b[i];
                 }
-            } else {                                                                     /* fused generator */
-                if ((i & 1) == 0)
-                    for (int k = 0; k < nB; ++k) normal_pair(seed, path_offset + p, (uint32_t)(i >> 1), (uint32_t)k, zbuf[k]);
+            } else if (nB == 1) {                                                        /* fused generator: one block = 2 steps */
+                if ((i & 1) == 0) normal_pair(seed, path_offset + p, (uint32_t)(i >> 1), 0u, zbuf[0]);
+                dB[0] = sqrt(dt) * zbuf[0][i & 1];
+            } else {                                                   /* matrix-valued g: one block = one step, 2 channels */
                 double sq = sqrt(dt);
-                for (int k = 0; k < nB; ++k) dB[k] = sq * zbuf[k][i & 1];
+                for (int k = 0; k < nB; ++k) {
+                    if ((k & 1) == 0) normal_pair(seed, path_offset + p, (uint32_t)i, 0x80000000u + (uint32_t)(k >> 1), zbuf[0]);
+                    dB[k] = sq * zbuf[0][k & 1];
+                }
             }
             drift(model, params, nx, x, fX);                                             /* :450 */
             diffusion(model, params, nx, nB, x, gX);                                     /* :451 */

@@ -82,7 +82,7 @@ struct sdegpu_ctx {
     cudaDeviceProp prop;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params;
+    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch;
     const double *icdf = nullptr;
     int max_grid = 0;
 };
@@ -135,7 +135,7 @@ int sdegpu_destroy(sdegpu_ctx *c)
     if (!c) return SDEGPU_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params};
+    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch};
     for (DevBuf *b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -356,7 +356,11 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         CU(cudaMemcpyAsync(c->out2.p, hc.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         la.center = (const double *)c->out2.p;
-        cuerr = launch_linear(la, c->prop.multiProcessorCount, c->stream);
+        if (dmma_eligible(la, pr->params + (size_t)nx * nx)) {
+            CU(c->scratch.reserve(sizeof(double) * ((size_t)nx * nx + nx)));
+            cuerr = launch_linear_dmma(la, (double *)c->scratch.p, c->prop.multiProcessorCount, c->stream);
+        } else
+            cuerr = launch_linear(la, c->prop.multiProcessorCount, c->stream);
         if (cuerr) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: linear kernel launch: %s", cudaGetErrorString((cudaError_t)cuerr));
     }
     CU(cudaEventRecord(c->ev1, c->stream));

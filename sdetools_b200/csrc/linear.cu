@@ -50,12 +50,12 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
                 if (a.B) {
                     const double *b = a.B + ((p0 + q) * nB + k) * (uint64_t)a.nt + i;
                     dBs[e] = __dsub_rn(b[1], b[0]);                           // dB <- apply(B,2,diff) (:437)
-                } else if ((i & 1) == 0) {
+                } else {
+                    // matrix-valued g: one Philox block per (path, step, channel pair), shared with the DMMA kernel
                     double z0, z1;
-                    normal_pair(a.seed, a.path_offset + p0 + q, (uint32_t)(i >> 1), (uint32_t)k, sh_tab, z0, z1);
-                    zs[e] = z1;
-                    dBs[e] = ds.y * z0;
-                } else dBs[e] = ds.y * zs[e];
+                    normal_pair(a.seed, a.path_offset + p0 + q, (uint32_t)i, 0x80000000u + (uint32_t)(k >> 1), sh_tab, z0, z1);
+                    dBs[e] = ds.y * ((k & 1) ? z1 : z0);
+                }
             }
             __syncthreads();
             // Y = (x + (A x) dt) + G dB        (euler :453 / heun predictor :318)

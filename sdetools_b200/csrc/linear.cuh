@@ -25,5 +25,8 @@ struct LinearArgs {
 };
 
 int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream);
+// FP64 tensor-core (DMMA) path: euler, fused generator, nB = d, diagonal G, d a multiple of 32 up to 256
+bool dmma_eligible(const LinearArgs &a, const double *hostG);
+int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream);
 
 }  // namespace sdegpu

@@ -1,0 +1,186 @@
+// High-dimensional linear SDE  dX = A X dt + diag(g) dB  (BASELINE.json config 4: d = 256, 10^6 paths).
+// Across a tile of paths the drift `A %*% x` (R/sdetools.R:360-368, vignettes/NoisyOscillator.Rmd:38-54)
+// is a GEMM  Y[d x P] = A[d x d] . X[d x P], so it runs on the FP64 tensor path:
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  tcgen05 has no FP64 kind, so this legacy-encoded DMMA *is*
+// Blackwell's FP64 tensor instruction.
+//
+//  * one CTA owns 64 paths for all time steps; X (d x 64, padded to 68) stays in shared memory,
+//    the accumulators Y stay in registers (4 x 8 DMMA tiles = 32 rows x 64 paths per warp);
+//  * A is re-laid out once per run into per-warp fragment order, so each k-step is four fully
+//    coalesced 256-byte loads per warp that stream from L2 (512 KB per CTA per step), prefetched
+//    one k-step ahead under 32 DMMAs;
+//  * the Euler update  X' = (X + Y dt) + g sqrt(dt) Z  (R/sdetools.R:453) is the epilogue of the GEMM;
+//    Z comes from the fused Philox generator, one block per (path, step, channel pair), the two
+//    rows of a pair live in lanes L and L^4 and swap one normal each by shuffle.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sdegpu.h"
+#include "linear.cuh"
+
+namespace sdegpu {
+
+constexpr int DM_PT = 64;            // paths per CTA
+constexpr int DM_LDX = DM_PT + 4;    // leading dimension of the X tile: 4 mod 16 keeps B-fragment loads conflict-free
+constexpr int DM_MA = 4, DM_NB = 8;  // DMMA tiles per warp: 32 rows x 64 paths
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// A (d x d, column-major) -> fragment order: Apk[((w*KK + kk)*MA + mi)*32 + lane] = A[32w + 8mi + lane/4, 4kk + lane%4]
+__global__ void k_pack_A(const double *__restrict__ A, double *__restrict__ Apk, int d)
+{
+    const int KK = d / 4;
+    const size_t n = (size_t)d * d;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int lane = (int)(idx & 31);
+        size_t t = idx >> 5;
+        const int mi = (int)(t % DM_MA); t /= DM_MA;
+        const int kk = (int)(t % KK);
+        const int w = (int)(t / KK);
+        const int row = 32 * w + 8 * mi + (lane >> 2), col = 4 * kk + (lane & 3);
+        Apk[idx] = A[(size_t)col * d + row];
+    }
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs a, const double *__restrict__ Apk,
+                                                                const double *__restrict__ gdiag)
+{
+    constexpr int D = 32 * NWARPS, KK = D / 4;
+    extern __shared__ __align__(16) double sm[];
+    double *sh_tab = sm;                                         // quantile table
+    double *xs = sm + ICDF_TABLE_DOUBLES;                        // X tile, xs[k*DM_LDX + n]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    icdf_stage(sh_tab, a.icdf, tid, 32 * NWARPS);
+    const int nsteps = a.nt - 1;
+    const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
+    const double *Aw = Apk + (size_t)w * KK * DM_MA * 32 + lane;
+    double grow[DM_MA];                                          // diffusion intensity of this lane's rows
+#pragma unroll
+    for (int mi = 0; mi < DM_MA; ++mi) grow[mi] = gdiag[32 * w + 8 * mi + gid];
+
+    for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const uint64_t p0 = grp * DM_PT;
+        const int np = (int)((a.npaths - p0 < (uint64_t)DM_PT) ? (a.npaths - p0) : DM_PT);
+        __syncthreads();
+        for (int e = tid; e < D * DM_PT; e += 32 * NWARPS) {
+            const int n = e / D, k = e - n * D;                  // consecutive threads walk one path's state vector
+            xs[k * DM_LDX + n] = n < np ? (a.x0 ? a.x0[(p0 + n) * D + k] : a.x0_shared[k]) : 0.0;
+        }
+        __syncthreads();
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 ds = __ldg(&a.dtsq[i]);
+            double acc[DM_MA][DM_NB][2];
+#pragma unroll
+            for (int mi = 0; mi < DM_MA; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            double an[DM_MA];
+#pragma unroll
+            for (int mi = 0; mi < DM_MA; ++mi) an[mi] = __ldg(Aw + mi * 32);
+#pragma unroll 2
+            for (int kk = 0; kk < KK; ++kk) {
+                double ac[DM_MA], b[DM_NB];
+#pragma unroll
+                for (int mi = 0; mi < DM_MA; ++mi) ac[mi] = an[mi];
+                if (kk + 1 < KK) {
+#pragma unroll
+                    for (int mi = 0; mi < DM_MA; ++mi) an[mi] = __ldg(Aw + ((size_t)(kk + 1) * DM_MA + mi) * 32);
+                }
+                const double *xb = xs + (4 * kk + tig) * DM_LDX + gid;
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) b[ni] = xb[8 * ni];
+#pragma unroll
+                for (int mi = 0; mi < DM_MA; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < DM_NB; ++ni) dmma884(acc[mi][ni], ac[mi], b[ni]);
+            }
+            __syncthreads();                                     // every warp is done reading X_i
+            // epilogue: X_{i+1} = (X_i + Y dt) + g sqrt(dt) Z      rows 32w+8mi+gid, paths 8ni+2tig+{0,1}
+#pragma unroll
+            for (int mi = 0; mi < DM_MA; ++mi) {
+                const int r = 32 * w + 8 * mi + gid;
+                const double gs = grow[mi] * ds.y;
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) {
+                    const int c = 8 * ni + 2 * tig;
+                    // channel pair (r & ~1, r | 1): even-row lane draws for path c, odd-row lane for path c+1
+                    double za, zb;
+                    normal_pair(a.seed, a.path_offset + p0 + c + (gid & 1), (uint32_t)i, 0x80000000u + (uint32_t)(r >> 1), sh_tab, za, zb);
+                    // even lane holds {z(r,c), z(r+1,c)}, odd lane holds {z(r-1,c+1), z(r,c+1)}
+                    const double send = (gid & 1) ? za : zb;
+                    const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                    const double z0 = (gid & 1) ? recv : za;     // this lane's row, path c
+                    const double z1 = (gid & 1) ? zb : recv;     // this lane's row, path c+1
+                    double2 xo = *reinterpret_cast<double2 *>(xs + r * DM_LDX + c);
+                    xo.x = (xo.x + acc[mi][ni][0] * ds.x) + gs * z0;
+                    xo.y = (xo.y + acc[mi][ni][1] * ds.x) + gs * z1;
+                    *reinterpret_cast<double2 *>(xs + r * DM_LDX + c) = xo;
+                }
+            }
+            __syncthreads();
+        }
+        // terminal state and per-component power sums
+        for (int e = tid; e < D * np; e += 32 * NWARPS) {
+            const int n = e / D, k = e - n * D;
+            const double v = xs[k * DM_LDX + n];
+            if (a.XT) a.XT[(p0 + n) * D + k] = v;
+        }
+        if (a.moments) {
+            for (int k = tid; k < D; k += 32 * NWARPS) {
+                double s[5] = {0, 0, 0, 0, 0};
+                const double cen = a.center[k];
+                for (int n = 0; n < np; ++n) {
+                    const double dd = xs[k * DM_LDX + n] - cen;
+                    if (isfinite(dd)) {
+                        const double d2 = dd * dd;
+                        s[0] += 1.0; s[1] += dd; s[2] += d2; s[3] += d2 * dd; s[4] += d2 * d2;
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < 5; ++m) atomicAdd(&a.moments[k * 5 + m], s[m]);
+            }
+        }
+    }
+}
+
+bool dmma_eligible(const LinearArgs &a, const double *hostG)
+{
+    if (a.B || a.scheme != SDEGPU_EULER || a.X || a.nB != a.d || a.d % 32 != 0 || a.d < 32 || a.d > 256) return false;
+    for (int c = 0; c < a.d; ++c)
+        for (int r = 0; r < a.d; ++r)
+            if (r != c && hostG[(size_t)c * a.d + r] != 0.0) return false;
+    return true;
+}
+
+// scratch: d*d + d doubles (packed A, diagonal of G)
+int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream)
+{
+    const int d = a.d;
+    double *Apk = scratch, *gdiag = scratch + (size_t)d * d;
+    k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d);
+    cudaMemcpy2DAsync(gdiag, sizeof(double), a.G, sizeof(double) * (d + 1), sizeof(double), d, cudaMemcpyDeviceToDevice, stream);
+    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * d, stream);
+    const size_t smem = sizeof(double) * ((size_t)ICDF_TABLE_DOUBLES + (size_t)d * DM_LDX);
+    const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
+    const int grid = (int)(ngroups < (uint64_t)sm_count ? ngroups : (uint64_t)sm_count);
+#define SDEGPU_DMMA_CASE(NW)                                                                                   \
+    case NW: {                                                                                                 \
+        auto k = k_linear_dmma<NW>;                                                                            \
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
+        k<<<grid, 32 * NW, smem, stream>>>(a, Apk, gdiag);                                                     \
+    } break;
+    switch (d / 32) {
+        SDEGPU_DMMA_CASE(1) SDEGPU_DMMA_CASE(2) SDEGPU_DMMA_CASE(3) SDEGPU_DMMA_CASE(4)
+        SDEGPU_DMMA_CASE(5) SDEGPU_DMMA_CASE(6) SDEGPU_DMMA_CASE(7) SDEGPU_DMMA_CASE(8)
+    default: return (int)cudaErrorInvalidValue;
+    }
+#undef SDEGPU_DMMA_CASE
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sdegpu

@@ -329,3 +329,54 @@ def test_argument_errors(sde, eng):
         sde.euler(f, g, [0.0, 1.0, 2.0], 0.0, h=lambda t, x: 1)
     assert sde.euler(f, g, [0.0, 1.0], 0.5, np.array([0.0, 2.0]))["X"].tolist() == [[0.5], [0.5 + -0.5 * 1.0 + 2.0]]   # nt = 2
     eng.run("ou", "euler", [1, 0, 1], [0.0, 1.0, 2.0], [0.0], nx=1, npaths=0)                  # empty ensemble is a no-op
+
+
+# ---- high-dimensional linear SDE on the FP64 tensor path (DMMA) ------------------------------------------
+@pytest.mark.parametrize("d", [32, 96, 256])
+def test_linear_dmma_matches_generic_kernel_and_oracle(eng, d):
+    """Config C4 at test size: dX = AX dt + diag(g) dB, euler, fused generator.  The DMMA kernel (terminal
+    output) must agree with the generic kernel (taken when the trajectory is requested) to summation
+    order, and with the CPU oracle's own fused generator to the quantile table's accuracy."""
+    rng = np.random.default_rng(d)
+    R = rng.standard_normal((d, d))
+    A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
+    g = rng.uniform(0.5, 1.5, d)
+    params = np.concatenate([A.ravel(order="F"), np.diag(g).ravel(order="F")])
+    P, nt, seed, off = 150, 41, 77, 12345                       # 150 paths: two full 64-path tiles + a ragged one
+    t = O.r_seq(0, (nt - 1) * 0.01, 0.01)
+    x0 = rng.standard_normal(d)
+    XT = np.empty((d, P), order="F")
+    eng.run("linear", "euler", params, t, x0, nx=d, nB=d, npaths=P, seed=seed, path_offset=off, XT=XT)
+    X = np.empty((nt, d, P), order="F")
+    eng.run("linear", "euler", params, t, x0, nx=d, nB=d, npaths=P, seed=seed, path_offset=off, X=X)
+    assert np.allclose(XT, X[-1], rtol=1e-11, atol=1e-12)
+    _, XTc = c_oracle.ensemble(0, 6, params, d, d, 0, t, x0, seed=seed, path_offset=off, npaths=P, full=False, nthreads=8)
+    assert np.allclose(XT, XTc.T, rtol=1e-7, atol=1e-8)
+    # per-path x0 and power sums through the same kernel
+    x0p = rng.standard_normal((P, d))
+    ps = np.zeros((5, d), order="F")
+    eng.run("linear", "euler", params, t, np.ascontiguousarray(x0p), nx=d, nB=d, npaths=P, seed=seed, XT=XT, power_sums=ps,
+            center=np.zeros(d))
+    assert np.allclose(ps[1], XT.sum(axis=1), rtol=1e-10, atol=1e-10) and np.all(ps[0] == P)
+
+
+def test_linear_dmma_covariance_matches_lyapunov_law(eng):
+    """A + A' = -I, G = s I  =>  lyap(A, s^2 I) = s^2 I and St = s^2 (1 - exp(-t)) I (SURVEY.md §8d, C4);
+    the ensemble is compared with the exact Euler-discrete covariance (MC error only)."""
+    d, s, n, h, P = 64, 0.7, 200, 0.005, 1 << 15
+    rng = np.random.default_rng(1)
+    R = rng.standard_normal((d, d))
+    A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
+    G = s * np.eye(d)
+    x0 = np.zeros(d)
+    x0[0] = 1.0
+    XT = np.empty((d, P), order="F")
+    eng.run("linear", "euler", np.concatenate([A.ravel(order="F"), G.ravel(order="F")]), np.arange(n + 1) * h, x0, nx=d, nB=d,
+            npaths=P, seed=5, XT=XT)
+    m, S = laws.linear_discrete_law(A, G, x0, h, n)
+    C = np.cov(XT)
+    sd = np.sqrt(np.diag(S))
+    assert np.all(np.abs(XT.mean(axis=1) - m) < 5.5 * sd / np.sqrt(P))
+    assert np.max(np.abs(C - S) / np.outer(sd, sd)) < 6 * np.sqrt(2 / P)
+    assert np.allclose(np.diag(S), s * s * (1 - np.exp(-n * h)), rtol=0.02)         # dLinSDE/lyap closed form, O(h) bias
+    assert np.allclose(laws.lyap(A[:4, :4] * 0 - 0.5 * np.eye(4), s * s * np.eye(4)), s * s * np.eye(4))
