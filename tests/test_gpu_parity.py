@@ -310,7 +310,7 @@ def test_linear_oscillator_covariance_vs_dLinSDE(sde):
     assert np.all(np.abs(XT.mean(axis=1) - m) < 5 * np.sqrt(np.diag(S) / N))
     assert np.all(np.abs(np.cov(XT) - S) < 5 * np.sqrt(2 / N) * np.sqrt(np.outer(np.diag(S), np.diag(S))) + 1e-12)
     ref = laws.dLinSDE(A, G, n * h, x0=x0)
-    assert np.allclose(XT.mean(axis=1), ref["EX"], atol=0.01) and np.allclose(np.cov(XT), ref["St"], atol=0.01)
+    assert np.allclose(XT.mean(axis=1), ref["EX"], atol=0.02) and np.allclose(np.cov(XT), ref["St"], atol=0.02)   # O(h) Euler bias
 
 
 # ---- error behaviour ----------------------------------------------------------------------------------
