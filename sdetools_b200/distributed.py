@@ -55,7 +55,7 @@ def run_sharded(engine, model, scheme, params, times, x0, *, nx, npaths_total, p
     import torch
     lo, hi = shard_range(npaths_total, rank, world)
     nb = hist[2] if hist is not None else 0
-    dev = torch.device("cuda", engine.device)
+    dev = engine.torch_device() if hasattr(engine, "torch_device") else torch.device("cuda", engine.device)
     ps = torch.zeros(5 * nx, dtype=torch.float64, device=dev)
     hc = torch.zeros(nb + 3, dtype=torch.int64, device=dev) if nb else None
     ms = engine.run(model, scheme, params, times, x0, nx=nx, npaths=hi - lo, projection=projection, seed=seed,

@@ -147,3 +147,14 @@ def test_icdf_table_matches_qnorm():
     assert t.max() < nseg and np.max(np.abs(r)) <= 2.0 ** -(21 - shift)
     assert np.max(np.abs(a - want)) < 1e-9
     assert np.all(a > -1e-9)          # next to u = 1 the true value (~1e-16) is below the table's error
+
+
+def test_r_shim_compiles_against_mock_r_headers():
+    """R is not installed: the .Call shim (r/src/sdegpu_shim.c) is type-checked against a mock of R's C API."""
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "mock_r"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "sdegpu_shim.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "r", "src", "sdegpu_shim.c")).read()
+    used = set(re.findall(r"\b(sdegpu_[a-z0-9_]+)\s*\(", src))
+    assert used <= set(_lib.SYMBOLS), used - set(_lib.SYMBOLS)
