@@ -173,7 +173,10 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 // of the previous group and the first 4-d of this one.  Paths are dealt to lanes with stride Q
 // (Q*nx*nt = 0 mod 4) so that d is warp-uniform and the four-way switch does not diverge.  Only the
 // first/last partial sector of a row is written element by element.
-constexpr int TRAJ_THREADS = 512;
+#ifndef SDEGPU_TRAJ_THREADS
+#define SDEGPU_TRAJ_THREADS 512
+#endif
+constexpr int TRAJ_THREADS = SDEGPU_TRAJ_THREADS;
 
 __device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d)
 {
@@ -217,21 +220,19 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
             for (int k = 0; k < 4; ++k) pv[j][k] = x[j];
         }
         const uint64_t gp = a.path_offset + p;
-        uint32_t ra[4], rb[4];
-        philox_block(a.seed, gp, 0u, 0u, ra[0], ra[1], ra[2], ra[3]);
-        philox_block(a.seed, gp, 1u, 0u, rb[0], rb[1], rb[2], rb[3]);
         for (int m = 0; m < ngroups; ++m) {
-            uint32_t na[4], nb[4];                               // next group's bits, generated under this group's FP64 chain
-            philox_block(a.seed, gp, 2u * (uint32_t)m + 2u, 0u, na[0], na[1], na[2], na[3]);
-            philox_block(a.seed, gp, 2u * (uint32_t)m + 3u, 0u, nb[0], nb[1], nb[2], nb[3]);
-            const double z[4] = {icdf_normal(ra[0], ra[1], sh_tab), icdf_normal(ra[2], ra[3], sh_tab),
-                                 icdf_normal(rb[0], rb[1], sh_tab), icdf_normal(rb[2], rb[3], sh_tab)};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double2 dt = __ldg(&a.dtsq[4 * m + k]);
-                sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * z[k]);
+            for (int h = 0; h < 2; ++h) {                        // one Philox block per two steps
+                double z[2];
+                normal_pair(a.seed, gp, 2u * (uint32_t)m + (uint32_t)h, 0u, sh_tab, z[0], z[1]);
 #pragma unroll
-                for (int j = 0; j < NX; ++j) v[j][k] = x[j];
+                for (int q = 0; q < 2; ++q) {
+                    const int k = 2 * h + q;
+                    const double2 dt = __ldg(&a.dtsq[4 * m + k]);
+                    sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * z[q]);
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) v[j][k] = x[j];
+                }
             }
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
@@ -248,8 +249,6 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
 #pragma unroll
                 for (int k = 0; k < 4; ++k) pv[j][k] = v[j][k];
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { ra[k] = na[k]; rb[k] = nb[k]; }
         }
         // values of the last group that opened a sector the row does not complete in a full group
         if (ngroups > 0) {
@@ -262,9 +261,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
                 }
         }
         for (int i = 4 * ngroups; i < nsteps; ++i) {              // up to three trailing steps, element-wise
-            const int k = i & 3;
-            const double zz = k == 0 ? icdf_normal(ra[0], ra[1], sh_tab)
-                            : (k == 1 ? icdf_normal(ra[2], ra[3], sh_tab) : icdf_normal(rb[0], rb[1], sh_tab));
+            double z0, z1;
+            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
+            const double zz = (i & 1) ? z1 : z0;
             const double2 dt = __ldg(&a.dtsq[i]);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * zz);
 #pragma unroll
