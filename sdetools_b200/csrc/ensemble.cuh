@@ -4,8 +4,9 @@
 //
 //   k_terminal : increments from the fused Philox generator, nothing but terminal
 //                state / power sums / histogram leaves the SM   (FP64-pipe bound)
-//   k_tiled    : supplied B read through shared-memory tiles and/or the full
-//                trajectory X written through shared-memory tiles (HBM bound)
+//   k_traj     : fused generator, full trajectory X written as 32-byte sectors (HBM-write bound)
+//   k_stream   : supplied B read, X written, both as per-thread 32-byte sectors (HBM bound; the
+//                bit-exact STRICT path)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,9 +24,6 @@ constexpr int MAX_NX = 2;           // catalogue models handled here have nx <= 
 #define SDEGPU_TERMINAL_MIN_BLOCKS 1
 #endif
 constexpr int TERMINAL_THREADS = SDEGPU_TERMINAL_THREADS;
-constexpr int TILE_PATHS = 128;     // paths (= threads) per block in k_tiled
-constexpr int TILE_STEPS = 32;      // time steps staged per tile
-constexpr int TILE_LD = TILE_STEPS + 1;   // odd leading dimension: conflict-free column walks
 
 struct RunArgs {
     KParams P;
@@ -278,26 +276,43 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
     flush_block_stats<NX, TRAJ_THREADS>(a, acc, sh_hist);
 }
 
-// ---- tiled kernel: supplied B in, and/or full trajectory out ----------------
-// Shared memory (dynamic): [quantile table]                               if !SRC_B
-//                          [hist: nbins+3 u32, padded to 16 B]
-//                          [sB: TILE_PATHS x TILE_LD doubles]            if SRC_B
-//                          [sX: NX x TILE_PATHS x TILE_LD doubles]       if a.X
-template <class M, int SCHEME, int PROJ, class A, bool SRC_B>
-__global__ void __launch_bounds__(TILE_PATHS) k_tiled(const RunArgs a, const int hist_words)
+// ---- supplied-B kernel: Brownian paths in, trajectory and/or terminal state out ----------------
+// Same streaming pattern as k_traj, on both sides of the step: each thread walks its own row of B
+// (B[p*nt + i], time fastest) with aligned 256-bit loads — one 32-byte sector = four increments — and
+// writes X through the sector writer.  No shared memory, no barrier: rows are private to a thread.
+// dB_i = B[i+1] - B[i] is formed from the same doubles the reference subtracts (:437); with A = Strict
+// every operation is individually rounded in the reference's order, so X is bit-identical to it.
+constexpr int STREAM_THREADS = 256;
+
+__device__ __forceinline__ void ld_sector(const double *p, double (&s)[4])
+{
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(s[0]), "=d"(s[1]), "=d"(s[2]), "=d"(s[3]) : "l"(p));
+}
+
+// Writes the sector that completes in a 4-value group: g = address of the group's first value, d = its
+// position in the 32-byte grid (4 = element-wise only), pv = previous group's values.
+__device__ __forceinline__ void store_group(double *g, int d, bool before_row, const double (&v)[4], double (&pv)[4])
+{
+    if (d == 4 || before_row) {                                  // element-wise: the sector would start before the row
+        const int n = d == 4 ? 4 : 4 - d;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < n) g[k] = v[k];
+    } else if (d == 0) st_sector(g, v[0], v[1], v[2], v[3]);
+    else if (d == 1) st_sector(g - 1, pv[3], v[0], v[1], v[2]);
+    else if (d == 2) st_sector(g - 2, pv[2], pv[3], v[0], v[1]);
+    else st_sector(g - 3, pv[1], pv[2], pv[3], v[0]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pv[k] = v[k];
+}
+
+template <class M, int SCHEME, int PROJ, class A>
+__global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, const int vec_in, const int vec_out)
 {
     constexpr int NX = M::NX;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const double *sh_tab = reinterpret_cast<const double *>(smem_raw);
-    unsigned char *after_tab = smem_raw + (SRC_B ? 0 : ICDF_TABLE_BYTES);
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(after_tab);
-    double *sB = reinterpret_cast<double *>(after_tab + (size_t)hist_words * 4);
-    double *sX = sB + (SRC_B ? TILE_PATHS * TILE_LD : 0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (!SRC_B) icdf_stage(reinterpret_cast<double *>(smem_raw), a.icdf, tid, TILE_PATHS);
-    if (a.hist) {
-        for (int i = tid; i < a.hist_nbins + 3; i += TILE_PATHS) sh_hist[i] = 0u;
-    }
+    extern __shared__ __align__(16) unsigned int sh_hist[];
+    if (a.hist)
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += STREAM_THREADS) sh_hist[i] = 0u;
     __syncthreads();
     double acc[NX][5];
 #pragma unroll
@@ -306,72 +321,83 @@ __global__ void __launch_bounds__(TILE_PATHS) k_tiled(const RunArgs a, const int
         for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
 
     const int nsteps = a.nt - 1;
-    const uint64_t ntiles = (a.npaths + TILE_PATHS - 1) / TILE_PATHS;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t p0 = tile * TILE_PATHS, p = p0 + tid;
-        const bool valid = p < a.npaths;
-        const int rows = (int)((a.npaths - p0 < (uint64_t)TILE_PATHS) ? (a.npaths - p0) : TILE_PATHS);
-        double x[NX];
-        if (valid) load_x0<NX>(a, p, x);
-        else {
+    const uint64_t stride = (uint64_t)gridDim.x * STREAM_THREADS;
+    for (uint64_t p = (uint64_t)blockIdx.x * STREAM_THREADS + threadIdx.x; p < a.npaths; p += stride) {
+        double x[NX], v[NX][4], pv[NX][4];
+        const double *brow = a.B + p * (uint64_t)a.nt;           // B[i] of this path
+        double *xrow[NX];                                        // &X[i = 1] of each component
+        load_x0<NX>(a, p, x);
+        // steps taken one by one until B[s+1] starts an aligned sector (all of them if B is unaligned)
+        int sa = vec_in ? (int)((4 - ((p * (uint64_t)a.nt + 1) & 3)) & 3) : nsteps;
+        if (sa > nsteps) sa = nsteps;
+        const int ngroups = (nsteps - sa) >> 2;
+        int d[NX];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) x[j] = 0.0;
-        }
-        if (a.X && valid) {
+        for (int j = 0; j < NX; ++j) {
+            const uint64_t e0 = (p * NX + j) * (uint64_t)a.nt;
+            xrow[j] = a.X ? a.X + e0 + 1 : nullptr;
+            d[j] = vec_out ? (int)((e0 + 1 + sa) & 3) : 4;       // grid position of the first grouped value
+            if (a.X) a.X[e0] = x[j];                             // X[1,] <- x0 (:441)
 #pragma unroll
-            for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt] = x[j];      // X[1,] <- x0  (:441)
+            for (int k = 0; k < 4; ++k) pv[j][k] = x[j];
         }
-        const uint64_t gp = a.path_offset + p;
-        double z0 = 0.0, z1 = 0.0;
-        for (int i0 = 0; i0 < nsteps; i0 += TILE_STEPS) {
-            const int nc = (nsteps - i0 < TILE_STEPS) ? (nsteps - i0) : TILE_STEPS;
-            if (SRC_B) {
-                // rows of the B tile are contiguous in time: one warp streams one row at a time
-                for (int r = warp; r < rows; r += TILE_PATHS / 32) {
-                    const double *src = a.B + (p0 + r) * (uint64_t)a.nt + i0;
-                    for (int c = lane; c <= nc; c += 32) sB[r * TILE_LD + c] = __ldg(src + c);
-                }
-                __syncthreads();
+        double prev = __ldg(brow);
+        int s = 0;
+        for (; s < sa; ++s) {                                    // head: at most three steps
+            const double cur = __ldg(brow + s + 1);
+            const double2 dt = __ldg(&a.dtsq[s]);
+            sde_step<M, SCHEME, PROJ, A>(a.P, x, dt.x, A::sub(cur, prev));
+            prev = cur;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                if (a.X) xrow[j][s] = x[j];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pv[j][k] = pv[j][k + 1];
+                pv[j][3] = x[j];
             }
-            if (valid) {
-#pragma unroll 2
-                for (int c = 0; c < nc; ++c) {
-                    const int i = i0 + c;
-                    const double2 d = __ldg(&a.dtsq[i]);
-                    double dB;
-                    if (SRC_B) {
-                        dB = A::sub(sB[tid * TILE_LD + c + 1], sB[tid * TILE_LD + c]);   // dB = diff(B)  (:437)
-                    } else {
-                        if ((c & 1) == 0) normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
-                        dB = d.y * ((c & 1) ? z1 : z0);
-                    }
-                    sde_step<M, SCHEME, PROJ, A>(a.P, x, d.x, dB);
-                    if (a.X) {
+        }
+        for (int m = 0; m < ngroups; ++m, s += 4) {
+            double b[4];
+            ld_sector(brow + s + 1, b);
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) sX[(j * TILE_PATHS + tid) * TILE_LD + c] = x[j];
-                    }
-                }
+            for (int k = 0; k < 4; ++k) {
+                const double2 dt = __ldg(&a.dtsq[s + k]);
+                sde_step<M, SCHEME, PROJ, A>(a.P, x, dt.x, A::sub(b[k], prev));      // dB = diff(B)  (:437)
+                prev = b[k];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) v[j][k] = x[j];
             }
             if (a.X) {
-                __syncthreads();
-                for (int r = warp; r < rows * NX; r += TILE_PATHS / 32) {
-                    const int row = r / NX, j = r - row * NX;
-                    double *dst = a.X + ((p0 + row) * NX + j) * (uint64_t)a.nt + i0 + 1;
-                    const double *srow = sX + (j * TILE_PATHS + row) * TILE_LD;
-                    for (int c = lane; c < nc; c += 32) dst[c] = srow[c];
-                }
-            }
-            __syncthreads();
-        }
-        if (valid) {
-            if (a.XT) {
 #pragma unroll
-                for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+                for (int j = 0; j < NX; ++j) store_group(xrow[j] + s, d[j], m == 0 && d[j] > sa + 1, v[j], pv[j]);
             }
-            accumulate_terminal<NX>(a, x, acc, sh_hist);
         }
+        if (a.X && ngroups > 0) {                                // values that opened a sector no full group completes
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                if (d[j] >= 1 && d[j] <= 3) {
+#pragma unroll
+                    for (int k = 1; k < 4; ++k)
+                        if (k >= 4 - d[j]) xrow[j][s - 4 + k] = pv[j][k];
+                }
+        }
+        for (; s < nsteps; ++s) {                                // tail: at most three steps
+            const double cur = __ldg(brow + s + 1);
+            const double2 dt = __ldg(&a.dtsq[s]);
+            sde_step<M, SCHEME, PROJ, A>(a.P, x, dt.x, A::sub(cur, prev));
+            prev = cur;
+            if (a.X) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j) xrow[j][s] = x[j];
+            }
+        }
+        if (a.XT) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+        }
+        accumulate_terminal<NX>(a, x, acc, sh_hist);
     }
-    flush_block_stats<NX, TILE_PATHS>(a, acc, sh_hist);
+    flush_block_stats<NX, STREAM_THREADS>(a, acc, sh_hist);
 }
 
 // ---- host-side launch signature shared by the per-model translation units ---

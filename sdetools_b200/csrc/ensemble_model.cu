@@ -50,17 +50,16 @@ static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     return (int)cudaGetLastError();
 }
 
-template <int SCHEME, int PROJ, class A, bool SRC_B>
-static int launch_tiled(const RunArgs &a, const LaunchCfg &c, int *grid_used)
+template <int SCHEME, int PROJ, class A>
+static int launch_stream(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
-    auto kernel = k_tiled<M, SCHEME, PROJ, A, SRC_B>;
-    const int hist_words = a.hist ? ((a.hist_nbins + 3 + 3) / 4) * 4 : 0;
-    const size_t smem = (SRC_B ? 0 : ICDF_TABLE_BYTES) + (size_t)hist_words * 4 +
-                        sizeof(double) * TILE_PATHS * TILE_LD * ((SRC_B ? 1 : 0) + (a.X ? M::NX : 0));
-    const uint64_t work = (a.npaths + TILE_PATHS - 1) / TILE_PATHS;
-    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TILE_PATHS, smem, c.sm_count, work);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, TILE_PATHS, smem, c.stream>>>(a, hist_words);
+    auto kernel = k_stream<M, SCHEME, PROJ, A>;
+    const size_t smem = a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0;
+    const uint64_t work = (a.npaths + STREAM_THREADS - 1) / STREAM_THREADS;
+    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, STREAM_THREADS, smem, c.sm_count, work);
+    const int vec_in = (reinterpret_cast<uintptr_t>(a.B) & 31) == 0;
+    const int vec_out = a.X && (reinterpret_cast<uintptr_t>(a.X) & 31) == 0;
+    kernel<<<grid, STREAM_THREADS, smem, c.stream>>>(a, vec_in, vec_out);
     *grid_used = grid;
     return (int)cudaGetLastError();
 }
@@ -69,8 +68,8 @@ template <int SCHEME, int PROJ>
 static int dispatch_mode(const RunArgs &a, const LaunchCfg &c, int *g)
 {
     if (c.src_b)
-        return c.arith == SDEGPU_ARITH_STRICT ? launch_tiled<SCHEME, PROJ, Strict, true>(a, c, g)
-                                              : launch_tiled<SCHEME, PROJ, Fast, true>(a, c, g);
+        return c.arith == SDEGPU_ARITH_STRICT ? launch_stream<SCHEME, PROJ, Strict>(a, c, g)
+                                              : launch_stream<SCHEME, PROJ, Fast>(a, c, g);
     if (c.want_x) return launch_traj<SCHEME, PROJ>(a, c, g);
     return launch_terminal<SCHEME, PROJ>(a, c, g);
 }

@@ -7,8 +7,7 @@
 //
 // A prefix sum with R's rounding is a strict recurrence per column, so the
 // parallel axis is the column (= path): one thread per column, 80-bit
-// accumulator in registers (float80.cuh), columns staged through shared-memory
-// tiles so that global traffic stays coalesced along time.
+// accumulator in registers (float80.cuh).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -17,9 +16,10 @@
 
 namespace sdegpu {
 
-constexpr int IT_COLS = 128;     // columns (= threads) per block
-constexpr int IT_STEPS = 32;     // increments staged per tile
+constexpr int IT_COLS = 128;     // columns (= threads) per block in k_rvbm
+constexpr int IT_STEPS = 32;     // increments staged per tile in k_rvbm
 constexpr int IT_LD = IT_STEPS + 1;
+constexpr int INT_THREADS = 256;
 
 struct IntegralArgs {
     const double *a, *b;         // stochint: f, g       crossvar: X, Y
@@ -27,63 +27,75 @@ struct IntegralArgs {
     uint64_t n, ncols;
 };
 
-template <int MODE>              // 0 stochint, 1 cross-variation
-__global__ void __launch_bounds__(IT_COLS) k_integral(const IntegralArgs q)
+__device__ __forceinline__ void ld_sector(const double *p, double (&s)[4])
 {
-    extern __shared__ __align__(16) double sm[];
-    double *sA = sm, *sB = sm + IT_COLS * IT_LD, *sC = sB + IT_COLS * IT_LD;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t ntiles = (q.ncols + IT_COLS - 1) / IT_COLS;
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(s[0]), "=d"(s[1]), "=d"(s[2]), "=d"(s[3]) : "l"(p));
+}
+__device__ __forceinline__ void st_sector(double *p, const double (&s)[4])
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(s[0]), "d"(s[1]), "d"(s[2]), "d"(s[3]) : "memory");
+}
+
+// One thread per column; the column is streamed as aligned 32-byte sectors (256-bit loads/stores, four
+// elements each) straight between HBM and registers: columns are private to a thread, so there is no
+// shared memory and no barrier.  All arrays have the same shape, hence the same sector phase.
+template <int MODE>              // 0 stochint, 1 cross-variation
+__global__ void __launch_bounds__(INT_THREADS) k_integral(const IntegralArgs q, const int vec_ok)
+{
     const uint64_t nsteps = q.n - 1;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t c0 = tile * IT_COLS, col = c0 + tid;
-        const bool valid = col < q.ncols;
-        const int rows = (int)((q.ncols - c0 < (uint64_t)IT_COLS) ? (q.ncols - c0) : IT_COLS);
+    const bool need_l = MODE == 1 || q.l || q.c, need_r = MODE == 0 && (q.r || q.c);
+    const uint64_t stride = (uint64_t)gridDim.x * INT_THREADS;
+    for (uint64_t col = (uint64_t)blockIdx.x * INT_THREADS + threadIdx.x; col < q.ncols; col += stride) {
+        const uint64_t base = col * q.n;
+        const double *pa = q.a + base, *pb = q.b + base;
         F80 accl = f80_zero(), accr = f80_zero();
-        if (valid) {                                            // c(0, ...)
-            if (q.l) q.l[col * q.n] = 0.0;
-            if (MODE == 0 && q.r) q.r[col * q.n] = 0.0;
-            if (MODE == 0 && q.c) q.c[col * q.n] = 0.0;
+        if (q.l) q.l[base] = 0.0;                                // c(0, ...)
+        if (MODE == 0 && q.r) q.r[base] = 0.0;
+        if (MODE == 0 && q.c) q.c[base] = 0.0;
+        double a0 = __ldg(pa), b0 = __ldg(pb);
+        uint64_t sa = vec_ok ? ((4 - ((base + 1) & 3)) & 3) : nsteps;
+        if (sa > nsteps) sa = nsteps;
+        const uint64_t ngroups = (nsteps - sa) >> 2;
+        double ol, orr, oc;
+        auto element = [&](double a1, double b1) {               // consumes (a0,b0)->(a1,b1), produces out[s+1]
+            if (MODE == 0) {
+                const double dg = __dsub_rn(b1, b0);
+                if (need_l) f80_add(accl, __dmul_rn(a0, dg));
+                if (need_r) f80_add(accr, __dmul_rn(a1, dg));
+                ol = f80_to_double(accl);
+                orr = f80_to_double(accr);
+                oc = __dmul_rn(0.5, __dadd_rn(ol, orr));
+            } else {
+                f80_add(accl, __dmul_rn(__dsub_rn(a1, a0), __dsub_rn(b1, b0)));
+                ol = f80_to_double(accl);
+            }
+            a0 = a1; b0 = b1;
+        };
+        uint64_t s = 0;
+        for (; s < sa; ++s) {
+            element(__ldg(pa + s + 1), __ldg(pb + s + 1));
+            if (q.l) q.l[base + s + 1] = ol;
+            if (MODE == 0 && q.r) q.r[base + s + 1] = orr;
+            if (MODE == 0 && q.c) q.c[base + s + 1] = oc;
         }
-        for (uint64_t i0 = 0; i0 < nsteps; i0 += IT_STEPS) {
-            const int nc = (int)((nsteps - i0 < (uint64_t)IT_STEPS) ? (nsteps - i0) : IT_STEPS);
-            for (int rr = warp; rr < rows; rr += IT_COLS / 32) {
-                const double *pa = q.a + (c0 + rr) * q.n + i0, *pb = q.b + (c0 + rr) * q.n + i0;
-                for (int k = lane; k <= nc; k += 32) {
-                    sA[rr * IT_LD + k] = __ldg(pa + k);
-                    sB[rr * IT_LD + k] = __ldg(pb + k);
-                }
+        for (uint64_t m = 0; m < ngroups; ++m, s += 4) {
+            double va[4], vb[4], vl[4], vr[4], vc[4];
+            ld_sector(pa + s + 1, va);
+            if (pb != pa) ld_sector(pb + s + 1, vb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                element(va[k], pb != pa ? vb[k] : va[k]);
+                vl[k] = ol; vr[k] = orr; vc[k] = oc;
             }
-            __syncthreads();
-            if (valid) {
-                double a0 = sA[tid * IT_LD], b0 = sB[tid * IT_LD];
-                for (int k = 0; k < nc; ++k) {
-                    const double a1 = sA[tid * IT_LD + k + 1], b1 = sB[tid * IT_LD + k + 1];
-                    if (MODE == 0) {
-                        const double dg = __dsub_rn(b1, b0);
-                        f80_add(accl, __dmul_rn(a0, dg));
-                        f80_add(accr, __dmul_rn(a1, dg));
-                        const double lv = f80_to_double(accl), rv = f80_to_double(accr);
-                        sA[tid * IT_LD + k] = lv;
-                        sB[tid * IT_LD + k] = rv;
-                        sC[tid * IT_LD + k] = __dmul_rn(0.5, __dadd_rn(lv, rv));
-                    } else {
-                        f80_add(accl, __dmul_rn(__dsub_rn(a1, a0), __dsub_rn(b1, b0)));
-                        sA[tid * IT_LD + k] = f80_to_double(accl);
-                    }
-                    a0 = a1; b0 = b1;
-                }
-            }
-            __syncthreads();
-            for (int rr = warp; rr < rows; rr += IT_COLS / 32) {
-                const uint64_t off = (c0 + rr) * q.n + i0 + 1;
-                for (int k = lane; k < nc; k += 32) {
-                    if (q.l) q.l[off + k] = sA[rr * IT_LD + k];
-                    if (MODE == 0 && q.r) q.r[off + k] = sB[rr * IT_LD + k];
-                    if (MODE == 0 && q.c) q.c[off + k] = sC[rr * IT_LD + k];
-                }
-            }
-            __syncthreads();
+            if (q.l) st_sector(q.l + base + s + 1, vl);
+            if (MODE == 0 && q.r) st_sector(q.r + base + s + 1, vr);
+            if (MODE == 0 && q.c) st_sector(q.c + base + s + 1, vc);
+        }
+        for (; s < nsteps; ++s) {
+            element(__ldg(pa + s + 1), __ldg(pb + s + 1));
+            if (q.l) q.l[base + s + 1] = ol;
+            if (MODE == 0 && q.r) q.r[base + s + 1] = orr;
+            if (MODE == 0 && q.c) q.c[base + s + 1] = oc;
         }
     }
 }
@@ -91,18 +103,18 @@ __global__ void __launch_bounds__(IT_COLS) k_integral(const IntegralArgs q)
 int launch_integral(int mode, const IntegralArgs &q, int sm_count, cudaStream_t stream)
 {
     if (q.n == 0 || q.ncols == 0) return 0;
-    const size_t smem = sizeof(double) * IT_COLS * IT_LD * 3;
-    const uint64_t ntiles = (q.ncols + IT_COLS - 1) / IT_COLS;
+    const uint64_t nblk = (q.ncols + INT_THREADS - 1) / INT_THREADS;
     auto k0 = k_integral<0>;
     auto k1 = k_integral<1>;
-    cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode == 0 ? k0 : k1, IT_COLS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode == 0 ? k0 : k1, INT_THREADS, 0);
     uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
-    if (grid > ntiles) grid = ntiles;
-    if (mode == 0) k0<<<(int)grid, IT_COLS, smem, stream>>>(q);
-    else k1<<<(int)grid, IT_COLS, smem, stream>>>(q);
+    if (grid > nblk) grid = nblk;
+    uintptr_t bits = reinterpret_cast<uintptr_t>(q.a) | reinterpret_cast<uintptr_t>(q.b) | reinterpret_cast<uintptr_t>(q.l) |
+                     reinterpret_cast<uintptr_t>(q.r) | reinterpret_cast<uintptr_t>(q.c);
+    const int vec_ok = (bits & 31) == 0;
+    if (mode == 0) k0<<<(int)grid, INT_THREADS, 0, stream>>>(q, vec_ok);
+    else k1<<<(int)grid, INT_THREADS, 0, stream>>>(q, vec_ok);
     return (int)cudaGetLastError();
 }
 
