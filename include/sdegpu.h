@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDEGPU_ABI_VERSION 1
+#define SDEGPU_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SDEGPU_API __attribute__((visibility("default")))
@@ -67,6 +67,23 @@ typedef enum { SDEGPU_PROJ_IDENTITY = 0, SDEGPU_PROJ_ABS = 1, SDEGPU_PROJ_RELU =
  * FAST:   FMA contraction and algebraically equivalent regrouping allowed. */
 typedef enum { SDEGPU_ARITH_STRICT = 0, SDEGPU_ARITH_FAST = 1 } sdegpu_arith;
 
+/* Killing rate r(x) and stopping function h(t,x) of euler()/heun() (R/sdetools.R:397-416,455-457;
+ * vignettes/Killing.Rmd:152-190), again from a catalogue; `comp` selects the state component.
+ *   survival  S_{i+1} = S_i * exp(-r(X_i) * dt_i), evaluated at the OLD state; the path is killed when S < Stau
+ *   stopping  the path stops at the first i with h(t_{i+1}, X_{i+1}) <= 0 (S is then not updated: it reads 0) */
+typedef enum {
+    SDEGPU_KILL_NONE = 0,
+    SDEGPU_KILL_CONST = 1,     /* r = a */
+    SDEGPU_KILL_EXP = 2,       /* r = a * exp(b * x)        (Killing.Rmd: 0.5*exp(2*x)) */
+    SDEGPU_KILL_QUAD = 3       /* r = a * (x - b) * (x - b) */
+} sdegpu_kill;
+typedef enum {
+    SDEGPU_STOP_NONE = 0,
+    SDEGPU_STOP_BELOW = 1,     /* h = x - lo          stop when x <= lo */
+    SDEGPU_STOP_ABOVE = 2,     /* h = hi - x          stop when x >= hi */
+    SDEGPU_STOP_OUTSIDE = 3    /* h = (x - lo) * (hi - x)   stop on leaving (lo, hi) */
+} sdegpu_stop;
+
 enum {
     SDEGPU_DEVICE_PTRS = 1u,  /* B, per-path x0 and every output buffer are device pointers */
     SDEGPU_ACCUMULATE = 2u    /* add into power_sums / hist_counts instead of overwriting */
@@ -93,6 +110,14 @@ typedef struct {
     uint64_t seed;
     uint32_t flags;
     uint32_t reserved;
+    /* --- ABI 2: mortality and stopping (`r`, `h`, `S0`, `Stau` arguments) --- */
+    int32_t kill_kind, kill_comp;   /* sdegpu_kill */
+    double kill_a, kill_b;
+    int32_t stop_kind, stop_comp;   /* sdegpu_stop */
+    double stop_lo, stop_hi;
+    double S0;                /* initial survival (reference default 1) */
+    const double *Stau;       /* per-path thresholds Stau[p] (the reference draws runif(1) per call), or NULL: drawn
+                                 in-kernel from Philox, counter (path, 0, 0xC0000000) */
 } sdegpu_problem;
 
 /* Caller-allocated outputs; any pointer may be NULL. */
@@ -109,6 +134,9 @@ typedef struct {
     int32_t hist_nbins;
     int32_t reserved;
     float *elapsed_ms;        /* host: CUDA-event time of the kernels of this call (no copies) */
+    /* --- ABI 2: with kill_kind/stop_kind set, XT is the state at tau and X holds NaN after tau --- */
+    double *tau;              /* npaths: times[i+1] at the stop/kill step, or times[nt-1] (R/sdetools.R:467) */
+    double *S_tau;            /* npaths: survival S at tau (0 after an h-stop, like the reference's S vector) */
 } sdegpu_output;
 
 typedef struct {

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libsdegpu.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 DEVICE_PTRS = 1
 ACCUMULATE = 2
 
@@ -16,6 +16,8 @@ MODEL = {"ou": 0, "cir": 1, "vdp": 2, "logistic": 3, "gbm": 4, "doublewell": 5, 
 SCHEME = {"euler": 0, "heun": 1}
 PROJ = {"identity": 0, "abs": 1, "relu": 2}
 ARITH = {"strict": 0, "fast": 1}
+KILL = {"none": 0, "const": 1, "exp": 2, "quad": 3}
+STOP = {"none": 0, "below": 1, "above": 2, "outside": 3}
 
 _dp = C.POINTER(C.c_double)
 
@@ -25,14 +27,17 @@ class Problem(C.Structure):
                 ("projection", C.c_int32), ("nx", C.c_int32), ("nB", C.c_int32), ("nparams", C.c_int32),
                 ("params", C.c_void_p), ("nt", C.c_int32), ("x0_stride", C.c_int32), ("times", C.c_void_p),
                 ("x0", C.c_void_p), ("B", C.c_void_p), ("npaths", C.c_uint64), ("path_offset", C.c_uint64),
-                ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("kill_kind", C.c_int32), ("kill_comp", C.c_int32), ("kill_a", C.c_double), ("kill_b", C.c_double),
+                ("stop_kind", C.c_int32), ("stop_comp", C.c_int32), ("stop_lo", C.c_double), ("stop_hi", C.c_double),
+                ("S0", C.c_double), ("Stau", C.c_void_p)]
 
 
 class Output(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("hist_component", C.c_int32), ("X", C.c_void_p), ("XT", C.c_void_p),
                 ("power_sums", C.c_void_p), ("center", C.c_void_p), ("hist_counts", C.c_void_p),
                 ("hist_lo", C.c_double), ("hist_hi", C.c_double), ("hist_nbins", C.c_int32), ("reserved", C.c_int32),
-                ("elapsed_ms", C.c_void_p)]
+                ("elapsed_ms", C.c_void_p), ("tau", C.c_void_p), ("S_tau", C.c_void_p)]
 
 
 class DevInfo(C.Structure):

@@ -32,8 +32,10 @@ def _catalogue_model(f, g):
 
 def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith,
               device, path_offset):
-    if h is not None or r is not None:
-        raise NotImplementedError("stopping (h) and killing (r) are not in the device catalogue yet")
+    if h is not None and not hasattr(h, "sdegpu_stop"):
+        raise TypeError("h must be a catalogue stop rule (catalogue.stop_below/stop_above/stop_outside)")
+    if r is not None and not hasattr(r, "sdegpu_kill"):
+        raise TypeError("r must be a catalogue killing rate (catalogue.kill_const/kill_exp/kill_quad)")
     model, params, nx, nB = _catalogue_model(f, g)
     proj = _cat.projection_id(p)
     times = np.ascontiguousarray(times, dtype=np.float64)
@@ -80,9 +82,22 @@ def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, outpu
     XT = np.empty((nx, npaths), order="F") if output in ("path", "terminal") else None
     ps = np.zeros((5, nx), order="F") if moments else None
     hc = np.zeros(hist[2] + 3, dtype=np.uint64) if hist is not None else None
+    killed = h is not None or r is not None
+    tau = np.empty(npaths) if killed else None
+    S_tau = np.empty(npaths) if r is not None else None
+    Stau_arr = None
+    if killed and Stau is not None:              # one threshold per path (the reference: one runif(1) per call)
+        Stau_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(Stau, dtype=np.float64), (npaths,)))
     eng.run(model, scheme, params, times, x0c, nx=nx, nB=nB, npaths=npaths, B=Bdev, projection=proj, arith=arith,
-            seed=seed, path_offset=path_offset, X=X, XT=XT, power_sums=ps, center=center, hist_counts=hc, hist=hist)
+            seed=seed, path_offset=path_offset, X=X, XT=XT, power_sums=ps, center=center, hist_counts=hc, hist=hist,
+            kill=r, stop=h, S0=S0, Stau=Stau_arr, tau=tau, S_tau=S_tau)
     res = {"times": times}
+    if killed:
+        # with mortality the reference returns tau = times[i+1] and truncates (:466-468); an ensemble keeps
+        # the full grid with NaN rows after each path's tau (the r = NULL convention, :439,:464) plus tau/S
+        res["tau"] = tau if ensemble else float(tau[0])
+        if S_tau is not None:
+            res["S"] = S_tau if ensemble else float(S_tau[0])
     if want_path:
         res["X"] = X if ensemble else X[:, :, 0]
     if XT is not None:

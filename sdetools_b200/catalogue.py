@@ -78,6 +78,57 @@ def linear(A, G):
     return _pair("linear", params, lambda x: A @ x, lambda x: G, nx=d, nB=G.shape[1])
 
 
+class KillRate:
+    """Killing rate r(x) for the `r` argument of euler/heun (R/sdetools.R:405-416,456; Killing.Rmd:152-190)."""
+
+    def __init__(self, kind, a, b=0.0, component=0, fn=None):
+        self.sdegpu_kill, self.a, self.b, self.component, self.fn = kind, float(a), float(b), int(component), fn
+
+    def __call__(self, *args):          # r(x) or r(t,x)
+        x = np.atleast_1d(np.asarray(args[-1], dtype=np.float64))
+        return self.fn(x[self.component])
+
+
+class StopRule:
+    """Stopping function h(t,x) for the `h` argument: the path stops when h <= 0 (R/sdetools.R:455)."""
+
+    def __init__(self, kind, lo=0.0, hi=0.0, component=0, fn=None):
+        self.sdegpu_stop, self.lo, self.hi, self.component, self.fn = kind, float(lo), float(hi), int(component), fn
+
+    def __call__(self, t, x):
+        x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        return self.fn(x[self.component])
+
+
+def kill_const(a):
+    return KillRate("const", a, fn=lambda v: a + 0.0 * v)
+
+
+def kill_exp(a, b, component=0):
+    """r = a*exp(b*x)   (Killing.Rmd: r <- function(x) 0.5*exp(2*x))."""
+    return KillRate("exp", a, b, component, fn=lambda v: a * np.exp(b * v))
+
+
+def kill_quad(a, b=0.0, component=0):
+    """r = a*(x-b)*(x-b)."""
+    return KillRate("quad", a, b, component, fn=lambda v: a * ((v - b) * (v - b)))
+
+
+def stop_below(lo, component=0):
+    """h = x - lo: stop when x <= lo."""
+    return StopRule("below", lo=lo, component=component, fn=lambda v: v - lo)
+
+
+def stop_above(hi, component=0):
+    """h = hi - x: stop when x >= hi."""
+    return StopRule("above", hi=hi, component=component, fn=lambda v: hi - v)
+
+
+def stop_outside(lo, hi, component=0):
+    """h = (x-lo)*(hi-x): stop on leaving (lo, hi)."""
+    return StopRule("outside", lo=lo, hi=hi, component=component, fn=lambda v: (v - lo) * (hi - v))
+
+
 def relu(x):
     """Projection pmax(x, 0)."""
     return np.where(np.asarray(x) < 0, 0.0, x)

@@ -82,7 +82,7 @@ struct sdegpu_ctx {
     cudaDeviceProp prop;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch;
+    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill;
     const double *icdf = nullptr;
     int max_grid = 0;
 };
@@ -135,7 +135,7 @@ int sdegpu_destroy(sdegpu_ctx *c)
     if (!c) return SDEGPU_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch};
+    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch, &c->times, &c->kill};
     for (DevBuf *b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -222,7 +222,15 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
     if (pr->nt < 2) return fail(SDEGPU_ERR_ARG, "sdegpu_run: need at least 2 time points, got %d", pr->nt);
     if (!pr->times || !pr->x0 || !pr->params) return fail(SDEGPU_ERR_ARG, "sdegpu_run: times/x0/params must not be NULL");
     if (pr->x0_stride != 0 && pr->x0_stride != pr->nx) return fail(SDEGPU_ERR_ARG, "sdegpu_run: x0_stride must be 0 or nx");
-    if (!pr->B && pr->arith == SDEGPU_ARITH_STRICT)
+    const bool killed = pr->kill_kind != SDEGPU_KILL_NONE || pr->stop_kind != SDEGPU_STOP_NONE;
+    if (pr->kill_kind < 0 || pr->kill_kind > SDEGPU_KILL_QUAD || pr->stop_kind < 0 || pr->stop_kind > SDEGPU_STOP_OUTSIDE)
+        return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown kill/stop kind (%d, %d)", pr->kill_kind, pr->stop_kind);
+    if (killed && (pr->kill_comp < 0 || pr->kill_comp >= pr->nx || pr->stop_comp < 0 || pr->stop_comp >= pr->nx))
+        return fail(SDEGPU_ERR_ARG, "sdegpu_run: kill/stop component out of range");
+    if (killed && pr->model == SDEGPU_MODEL_LINEAR)
+        return fail(SDEGPU_ERR_ARG, "sdegpu_run: killing/stopping is not available for the linear model");
+    if ((out->tau || out->S_tau) && !killed) return fail(SDEGPU_ERR_ARG, "sdegpu_run: tau/S_tau outputs need a kill or stop rule");
+    if (!pr->B && pr->arith == SDEGPU_ARITH_STRICT && !killed)
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: STRICT arithmetic is defined for a supplied B; fused-generator runs are FAST");
     for (int i = 0; i + 1 < pr->nt; ++i)
         if (!(pr->times[i + 1] >= pr->times[i])) return fail(SDEGPU_ERR_ARG, "sdegpu_run: times must be non-decreasing (index %d)", i);
@@ -314,7 +322,27 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         a.hist_invw = dh ? (double)out->hist_nbins / (out->hist_hi - out->hist_lo) : 0.0;
         a.npaths = pr->npaths; a.path_offset = pr->path_offset; a.seed = make_philox_key(pr->seed);
         a.nt = nt; a.hist_nbins = out->hist_nbins; a.hist_comp = out->hist_component;
+        if (killed) {
+            a.kill_kind = pr->kill_kind; a.kill_comp = pr->kill_comp; a.kill_a = pr->kill_a; a.kill_b = pr->kill_b;
+            a.stop_kind = pr->stop_kind; a.stop_comp = pr->stop_comp; a.stop_lo = pr->stop_lo; a.stop_hi = pr->stop_hi;
+            a.S0 = pr->S0;
+            CU(c->times.reserve(sizeof(double) * nt));
+            CU(cudaMemcpyAsync(c->times.p, pr->times, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
+            a.times = (const double *)c->times.p;
+            if (dev) { a.Stau = pr->Stau; a.tau = out->tau; a.S_tau = out->S_tau; }
+            else {
+                CU(c->kill.reserve(sizeof(double) * 3 * pr->npaths));
+                double *kb = (double *)c->kill.p;
+                if (pr->Stau) {
+                    CU(cudaMemcpyAsync(kb, pr->Stau, sizeof(double) * pr->npaths, cudaMemcpyHostToDevice, c->stream));
+                    a.Stau = kb;
+                }
+                if (out->tau) a.tau = kb + pr->npaths;
+                if (out->S_tau) a.S_tau = kb + 2 * pr->npaths;
+            }
+        }
         LaunchCfg cfg;
+        cfg.killed = killed;
         cfg.scheme = pr->scheme; cfg.proj = pr->projection; cfg.arith = pr->B ? pr->arith : SDEGPU_ARITH_FAST;
         cfg.src_b = pr->B != nullptr; cfg.want_x = out->X != nullptr;
         cfg.grid = 0; cfg.sm_count = c->prop.multiProcessorCount; cfg.stream = c->stream;
@@ -370,6 +398,8 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         if (out->XT) CU(cudaMemcpyAsync(out->XT, dXT, bytesXT, cudaMemcpyDeviceToHost, c->stream));
         if (out->power_sums) CU(cudaMemcpyAsync(out->power_sums, dps, sizeof(double) * nps, cudaMemcpyDeviceToHost, c->stream));
         if (out->hist_counts) CU(cudaMemcpyAsync(out->hist_counts, dh, sizeof(unsigned long long) * nh, cudaMemcpyDeviceToHost, c->stream));
+        if (out->tau) CU(cudaMemcpyAsync(out->tau, (double *)c->kill.p + pr->npaths, sizeof(double) * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
+        if (out->S_tau) CU(cudaMemcpyAsync(out->S_tau, (double *)c->kill.p + 2 * pr->npaths, sizeof(double) * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
     }
     if (!dev || out->elapsed_ms) {
         CU(cudaStreamSynchronize(c->stream));

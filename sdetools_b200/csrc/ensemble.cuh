@@ -41,6 +41,12 @@ struct RunArgs {
     uint64_t npaths, path_offset;
     PhiloxKey seed;                 // round keys of the run's seed
     int nt, hist_nbins, hist_comp;
+    // mortality / stopping (k_killed only)
+    int kill_kind, kill_comp, stop_kind, stop_comp;
+    double kill_a, kill_b, stop_lo, stop_hi, S0;
+    const double *Stau;             // per-path thresholds or nullptr (drawn from Philox)
+    const double *times;            // device copy of the time grid (tau = times[i+1])
+    double *tau, *S_tau;
 };
 
 // ---- terminal statistics ---------------------------------------------------
@@ -400,10 +406,116 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, cons
     flush_block_stats<NX, STREAM_THREADS>(a, acc, sh_hist);
 }
 
+// ---- mortality and stopping (R/sdetools.R:397-416,455-469; vignettes/Killing.Rmd:152-190) ----------
+// Per step, in the reference's order: the new state is tested against h (stop: S is not updated and
+// reads 0); otherwise S <- S * exp(-r(X_i) * dt_i) with the OLD state, and the path is killed when
+// S < Stau.  tau = times[i+1] of the break, or the last grid time.  Paths leave the loop individually.
+// Arithmetic is STRICT for both increment sources; Stau[p] defaults to a Philox uniform per path
+// (the reference draws one runif() per euler() call).
+constexpr int KILLED_THREADS = 256;
+
+template <int NX>
+__device__ __forceinline__ double kill_rate(const RunArgs &a, const double (&x)[NX])
+{
+    const double v = x[a.kill_comp < NX ? a.kill_comp : 0];
+    if (a.kill_kind == SDEGPU_KILL_CONST) return a.kill_a;
+    if (a.kill_kind == SDEGPU_KILL_EXP) return __dmul_rn(a.kill_a, exp(__dmul_rn(a.kill_b, v)));
+    if (a.kill_kind == SDEGPU_KILL_QUAD) { const double t = __dsub_rn(v, a.kill_b); return __dmul_rn(a.kill_a, __dmul_rn(t, t)); }
+    return 0.0;
+}
+
+template <int NX>
+__device__ __forceinline__ double stop_value(const RunArgs &a, const double (&x)[NX])
+{
+    const double v = x[a.stop_comp < NX ? a.stop_comp : 0];
+    if (a.stop_kind == SDEGPU_STOP_BELOW) return __dsub_rn(v, a.stop_lo);
+    if (a.stop_kind == SDEGPU_STOP_ABOVE) return __dsub_rn(a.stop_hi, v);
+    if (a.stop_kind == SDEGPU_STOP_OUTSIDE) return __dmul_rn(__dsub_rn(v, a.stop_lo), __dsub_rn(a.stop_hi, v));
+    return 1.0;
+}
+
+template <class M, int SCHEME, int PROJ>
+__global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
+{
+    constexpr int NX = M::NX;
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table (if no B)][histogram]
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + (a.B ? 0 : ICDF_TABLE_DOUBLES));
+    if (!a.B) icdf_stage(sh_tab, a.icdf, threadIdx.x, KILLED_THREADS);
+    if (a.hist)
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += KILLED_THREADS) sh_hist[i] = 0u;
+    __syncthreads();
+    double acc[NX][5];
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
+
+    const int nsteps = a.nt - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * KILLED_THREADS;
+    for (uint64_t p = (uint64_t)blockIdx.x * KILLED_THREADS + threadIdx.x; p < a.npaths; p += stride) {
+        double x[NX], xo[NX];
+        load_x0<NX>(a, p, x);
+        const uint64_t gp = a.path_offset + p;
+        double Stau;
+        if (a.Stau) Stau = a.Stau[p];
+        else {                                                   // runif(1): 52-bit uniform in [0,1)
+            uint32_t r0, r1, r2, r3;
+            philox_block(a.seed, gp, 0u, 0xC0000000u, r0, r1, r2, r3);
+            Stau = __hiloint2double((int)(0x3FF00000u | (r1 >> 12)), (int)((r1 << 20) | (r0 >> 12))) - 1.0;
+        }
+        if (a.X) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt] = x[j];
+        }
+        const double *brow = a.B ? a.B + p * (uint64_t)a.nt : nullptr;
+        double S = a.S0, Sout = a.S0, z0 = 0.0, z1 = 0.0;
+        int last = nsteps;                                       // index of the last valid row of X
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 dt = __ldg(&a.dtsq[i]);
+            double dB;
+            if (brow) dB = __dsub_rn(__ldg(brow + i + 1), __ldg(brow + i));
+            else {
+                if ((i & 1) == 0) normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
+                dB = __dmul_rn(dt.y, (i & 1) ? z1 : z0);
+            }
+#pragma unroll
+            for (int j = 0; j < NX; ++j) xo[j] = x[j];
+            sde_step<M, SCHEME, PROJ, Strict>(a.P, x, dt.x, dB);
+            if (a.X) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt + i + 1] = x[j];
+            }
+            if (a.stop_kind != SDEGPU_STOP_NONE && !(stop_value<NX>(a, x) > 0.0)) {      // h(...) <= 0  (:455)
+                last = i + 1; Sout = 0.0;
+                break;
+            }
+            if (a.kill_kind != SDEGPU_KILL_NONE) {
+                S = __dmul_rn(S, exp(__dmul_rn(-kill_rate<NX>(a, xo), dt.x)));           // :456, old state
+                Sout = S;
+                if (S < Stau) { last = i + 1; break; }                                    // :457
+            }
+        }
+        if (a.X) {                                               // rows after the break stay NA in the reference (:439)
+            const double nan = __longlong_as_double(0x7FF8000000000000ll);
+            for (int i = last + 1; i <= nsteps; ++i)
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt + i] = nan;
+        }
+        if (a.tau) a.tau[p] = a.times[last];                     // tau <- times[i+1]  (:467)
+        if (a.S_tau) a.S_tau[p] = Sout;
+        if (a.XT) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+        }
+        accumulate_terminal<NX>(a, x, acc, sh_hist);
+    }
+    flush_block_stats<NX, KILLED_THREADS>(a, acc, sh_hist);
+}
+
 // ---- host-side launch signature shared by the per-model translation units ---
 struct LaunchCfg {
     int scheme, proj, arith;
-    bool src_b, want_x;
+    bool src_b, want_x, killed;
     int grid;            // 0: choose from occupancy
     int sm_count;
     cudaStream_t stream;

@@ -65,8 +65,21 @@ static int launch_stream(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 }
 
 template <int SCHEME, int PROJ>
+static int launch_killed(const RunArgs &a, const LaunchCfg &c, int *grid_used)
+{
+    auto kernel = k_killed<M, SCHEME, PROJ>;
+    const size_t smem = (a.B ? 0 : ICDF_TABLE_BYTES) + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    const uint64_t work = (a.npaths + KILLED_THREADS - 1) / KILLED_THREADS;
+    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, KILLED_THREADS, smem, c.sm_count, work);
+    kernel<<<grid, KILLED_THREADS, smem, c.stream>>>(a);
+    *grid_used = grid;
+    return (int)cudaGetLastError();
+}
+
+template <int SCHEME, int PROJ>
 static int dispatch_mode(const RunArgs &a, const LaunchCfg &c, int *g)
 {
+    if (c.killed) return launch_killed<SCHEME, PROJ>(a, c, g);
     if (c.src_b)
         return c.arith == SDEGPU_ARITH_STRICT ? launch_stream<SCHEME, PROJ, Strict>(a, c, g)
                                               : launch_stream<SCHEME, PROJ, Fast>(a, c, g);

@@ -325,7 +325,7 @@ def test_argument_errors(sde, eng):
         sde.euler(f, g, [0.0, 1.0, 2.0], 0.0, arith="strict")
     with pytest.raises(ValueError):
         sde.euler(f, g, [0.0, 1.0, 2.0], [0.0, 1.0])
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):
         sde.euler(f, g, [0.0, 1.0, 2.0], 0.0, h=lambda t, x: 1)
     assert sde.euler(f, g, [0.0, 1.0], 0.5, np.array([0.0, 2.0]))["X"].tolist() == [[0.5], [0.5 + -0.5 * 1.0 + 2.0]]   # nt = 2
     eng.run("ou", "euler", [1, 0, 1], [0.0, 1.0, 2.0], [0.0], nx=1, npaths=0)                  # empty ensemble is a no-op
@@ -380,3 +380,59 @@ def test_linear_dmma_covariance_matches_lyapunov_law(eng):
     assert np.max(np.abs(C - S) / np.outer(sd, sd)) < 6 * np.sqrt(2 / P)
     assert np.allclose(np.diag(S), s * s * (1 - np.exp(-n * h)), rtol=0.02)         # dLinSDE/lyap closed form, O(h) bias
     assert np.allclose(laws.lyap(A[:4, :4] * 0 - 0.5 * np.eye(4), s * s * np.eye(4)), s * s * np.eye(4))
+
+
+# ---- mortality and stopping (R/sdetools.R:397-416,455-469; Killing.Rmd:152-207) ---------
+def test_killing_matches_reference_loop(sde):
+    """euler(f, g, times, x0, B, r=r, Stau=Stau) path by path against the numpy restatement of R's loop:
+    tau and the trajectory up to tau are bit-identical, S agrees to exp()'s last ulp."""
+    t, B = brownian(601, 1, 96, 21)
+    f, g = sde.catalogue.ou(1.0, 0.0, 1.0)                   # Killing.Rmd: f = -x, g = 1, r = 0.5*exp(2x)
+    r = sde.catalogue.kill_exp(0.5, 2.0)
+    Stau = np.random.default_rng(3).random(96)
+    got = sde.euler(f, g, t, 0.0, B, r=r, Stau=Stau)
+    fo, go, _, _ = O.catalogue("ou", [1.0, 0.0, 1.0])
+    ro = lambda x: 0.5 * np.exp(2.0 * x[0])
+    assert got["X"].shape == (601, 1, 96) and got["tau"].shape == (96,)
+    n_killed = 0
+    for p in range(96):
+        ref = O.euler(fo, go, t, 0.0, B=B[:, :, p], r=ro, Stau=Stau[p])
+        k = ref["times"].size                                 # rows kept by the reference (1:(i+1))
+        assert got["tau"][p] == ref["tau"]
+        assert np.array_equal(got["X"][:k, 0, p], np.atleast_1d(ref["X"]).ravel())
+        assert np.all(np.isnan(got["X"][k:, 0, p]))
+        assert got["S"][p] == pytest.approx(ref["S"][-1], rel=1e-13)
+        assert got["XT"][0, p] == np.atleast_1d(ref["X"]).ravel()[-1]
+        n_killed += ref["tau"] < t[-1]
+    assert 20 < n_killed < 96                                 # both outcomes are exercised
+
+
+def test_stopping_rule_matches_reference_loop(sde):
+    t, B = brownian(301, 1, 64, 22)
+    f, g = sde.catalogue.gbm(0.1, 0.6)
+    h = sde.catalogue.stop_outside(0.7, 1.5)
+    got = sde.heun(f, g, t, 1.0, B, h=h)
+    fo, go, _, _ = O.catalogue("gbm", [0.1, 0.6])
+    stops = 0
+    for p in range(64):
+        ref = O.heun(fo, go, t, 1.0, B=B[:, :, p], h=lambda tt, x: (x[0] - 0.7) * (1.5 - x[0]))
+        X = ref["X"][:, 0]                                    # r = NULL: full length, NA after the stop (:439,:464)
+        k = int(np.sum(~np.isnan(X)))
+        assert np.array_equal(got["X"][:k, 0, p], X[:k]) and np.all(np.isnan(got["X"][k:, 0, p]))
+        assert got["tau"][p] == t[k - 1]
+        stops += k < t.size
+    assert 10 < stops <= 64 and "S" not in got
+
+
+def test_constant_killing_rate_gives_exponential_lifetimes(sde):
+    a, T, n, N = 0.7, 2.0, 200, 1 << 18
+    t = np.arange(n + 1) * (T / n)
+    res = sde.euler(*sde.catalogue.ou(1.0, 0.0, 1.0), t, 0.0, r=sde.catalogue.kill_const(a), npaths=N, seed=9,
+                    output="terminal")
+    tau = res["tau"]
+    for tk in (0.5, 1.0, 1.5):
+        pk = np.exp(-a * tk)                                  # P(tau > t_k) = P(Stau <= exp(-a t_k))
+        assert abs(np.mean(tau > tk + 1e-12) - pk) < 4.5 * np.sqrt(pk * (1 - pk) / N)
+    alive = tau == t[-1]
+    assert abs(alive.mean() - np.exp(-a * T)) < 4.5 * np.sqrt(np.exp(-a * T) / N)
+    assert np.all(res["S"][~alive] < 1) and res["XT"].shape == (1, N)
