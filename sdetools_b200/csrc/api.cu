@@ -82,7 +82,7 @@ struct sdegpu_ctx {
     cudaDeviceProp prop;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill;
+    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill, coef;
     const double *icdf = nullptr;
     int max_grid = 0;
 };
@@ -135,7 +135,7 @@ int sdegpu_destroy(sdegpu_ctx *c)
     if (!c) return SDEGPU_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch, &c->times, &c->kill};
+    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch, &c->times, &c->kill, &c->coef};
     for (DevBuf *b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -312,6 +312,20 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         for (int i = 0; i < pr->nparams; ++i) a.P.p[i] = pr->params[i];
         a.dtsq = dtsq;
         a.icdf = c->icdf;
+        if (!pr->B && !out->X && !killed) {                       // k_terminal: folded step coefficients (FAST only)
+            std::vector<double> hc((size_t)(nt - 1) * FAST_NCOEF);
+            bool folded = true;
+            for (int i = 0; i + 1 < nt && folded; ++i) {
+                const double dt = pr->times[i + 1] - pr->times[i];
+                folded = fast_step_coefficients(pr->model, pr->params, dt, sqrt(dt), &hc[(size_t)i * FAST_NCOEF]);
+            }
+            if (folded) {
+                CU(c->coef.reserve(sizeof(double) * hc.size()));
+                CU(cudaMemcpyAsync(c->coef.p, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                a.coef = (const double *)c->coef.p;
+            }
+        }
         a.x0 = dx0;
         if (!pr->x0_stride) for (int j = 0; j < nx; ++j) a.x0s[j] = pr->x0[j];
         a.B = dB; a.X = dX; a.XT = dXT;

@@ -29,6 +29,7 @@ struct RunArgs {
     KParams P;
     const double2 *dtsq;            // [nt-1] {dt_i, sqrt(dt_i)},  dt_i = times[i+1]-times[i]  (:446)
     const double *icdf;             // device, half-normal quantile table (philox.cuh)
+    const double *coef;             // [nt-1][FAST_NCOEF] folded step coefficients (models.cuh FastStep) or nullptr
     const double *x0;               // per-path x0 (device) or nullptr
     double x0s[MAX_NX];             // shared x0
     const double *B;                // device, B[p*nt+i]  (nB = 1)
@@ -120,6 +121,7 @@ template <class M, int SCHEME, int PROJ>
 __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) k_terminal(const RunArgs a)
 {
     constexpr int NX = M::NX;
+    using FS = FastStep<M, SCHEME, PROJ>;
     extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
     unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_TABLE_DOUBLES);
     icdf_stage(sh_tab, a.icdf, threadIdx.x, TERMINAL_THREADS);
@@ -147,15 +149,16 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
             uint32_t n0, n1, n2, n3;
             philox_block(a.seed, gp, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
             const double z0 = icdf_normal(r0, r1, sh_tab), z1 = icdf_normal(r2, r3, sh_tab);
-            const double2 d0 = __ldg(&a.dtsq[i]), d1 = __ldg(&a.dtsq[i + 1]);
-            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
-            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d1.x, d1.y * z1);
+            double2 d0 = make_double2(0.0, 0.0), d1 = d0;
+            if (!FS::uses_coef) { d0 = __ldg(&a.dtsq[i]); d1 = __ldg(&a.dtsq[i + 1]); }
+            FS::apply(a.P, x, d0, a.coef + (size_t)i * FAST_NCOEF, z0);
+            FS::apply(a.P, x, d1, a.coef + (size_t)(i + 1) * FAST_NCOEF, z1);
             r0 = n0; r1 = n1; r2 = n2; r3 = n3;
         }
         if (i < nsteps) {
             const double z0 = icdf_normal(r0, r1, sh_tab);
             const double2 d0 = __ldg(&a.dtsq[i]);
-            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, d0.x, d0.y * z0);
+            FS::apply(a.P, x, d0, a.coef + (size_t)i * FAST_NCOEF, z0);
         }
         if (a.XT) {
 #pragma unroll
