@@ -18,7 +18,10 @@ namespace sdegpu {
 
 constexpr int MAX_NX = 2;           // catalogue models handled here have nx <= 2
 #ifndef SDEGPU_TERMINAL_THREADS
-#define SDEGPU_TERMINAL_THREADS 640
+#define SDEGPU_TERMINAL_THREADS 512
+#endif
+#ifndef SDEGPU_TERMINAL_NP
+#define SDEGPU_TERMINAL_NP 2
 #endif
 #ifndef SDEGPU_TERMINAL_MIN_BLOCKS
 #define SDEGPU_TERMINAL_MIN_BLOCKS 1
@@ -135,36 +138,54 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
         for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
 
     const int nsteps = a.nt - 1;
+    constexpr int NP = SDEGPU_TERMINAL_NP;                       // independent paths advanced together by one thread (ILP)
     const uint64_t stride = (uint64_t)gridDim.x * TERMINAL_THREADS;
-    for (uint64_t p = (uint64_t)blockIdx.x * TERMINAL_THREADS + threadIdx.x; p < a.npaths; p += stride) {
-        double x[NX];
-        load_x0<NX>(a, p, x);
-        const uint64_t gp = a.path_offset + p;
-        // Software-pipelined: the Philox block of steps (i+2, i+3) is generated while steps (i, i+1)
-        // integrate, so the integer rounds issue in the shadow of the dependent FP64 chain.
+    for (uint64_t pb = (uint64_t)blockIdx.x * TERMINAL_THREADS + threadIdx.x; pb < a.npaths; pb += stride * NP) {
+        double x[NP][NX];
+        uint64_t pq[NP];
+        uint32_t r[NP][4];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            pq[q] = pb + (uint64_t)q * stride;
+            const uint64_t pl = pq[q] < a.npaths ? pq[q] : pb;   // a missing partner recomputes path pb and is discarded
+            load_x0<NX>(a, pl, x[q]);
+            // Software-pipelined: the Philox block of steps (i+2, i+3) is generated while steps (i, i+1)
+            // integrate, so the integer rounds issue in the shadow of the dependent FP64 chain.
+            philox_block(a.seed, a.path_offset + pl, 0u, 0u, r[q][0], r[q][1], r[q][2], r[q][3]);
+        }
         int i = 0;
-        uint32_t r0, r1, r2, r3;
-        philox_block(a.seed, gp, 0u, 0u, r0, r1, r2, r3);
         for (; i + 1 < nsteps; i += 2) {
-            uint32_t n0, n1, n2, n3;
-            philox_block(a.seed, gp, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
-            const double z0 = icdf_normal(r0, r1, sh_tab), z1 = icdf_normal(r2, r3, sh_tab);
             double2 d0 = make_double2(0.0, 0.0), d1 = d0;
             if (!FS::uses_coef) { d0 = __ldg(&a.dtsq[i]); d1 = __ldg(&a.dtsq[i + 1]); }
-            FS::apply(a.P, x, d0, a.coef + (size_t)i * FAST_NCOEF, z0);
-            FS::apply(a.P, x, d1, a.coef + (size_t)(i + 1) * FAST_NCOEF, z1);
-            r0 = n0; r1 = n1; r2 = n2; r3 = n3;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const uint64_t pl = pq[q] < a.npaths ? pq[q] : pb;
+                uint32_t n0, n1, n2, n3;
+                philox_block(a.seed, a.path_offset + pl, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
+                const double z0 = icdf_normal(r[q][0], r[q][1], sh_tab), z1 = icdf_normal(r[q][2], r[q][3], sh_tab);
+                FS::apply(a.P, x[q], d0, a.coef + (size_t)i * FAST_NCOEF, z0);
+                FS::apply(a.P, x[q], d1, a.coef + (size_t)(i + 1) * FAST_NCOEF, z1);
+                r[q][0] = n0; r[q][1] = n1; r[q][2] = n2; r[q][3] = n3;
+            }
         }
         if (i < nsteps) {
-            const double z0 = icdf_normal(r0, r1, sh_tab);
             const double2 d0 = __ldg(&a.dtsq[i]);
-            FS::apply(a.P, x, d0, a.coef + (size_t)i * FAST_NCOEF, z0);
-        }
-        if (a.XT) {
 #pragma unroll
-            for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+            for (int q = 0; q < NP; ++q) {
+                const double z0 = icdf_normal(r[q][0], r[q][1], sh_tab);
+                FS::apply(a.P, x[q], d0, a.coef + (size_t)i * FAST_NCOEF, z0);
+            }
         }
-        accumulate_terminal<NX>(a, x, acc, sh_hist);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (pq[q] < a.npaths) {
+                if (a.XT) {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) a.XT[pq[q] * NX + j] = x[q][j];
+                }
+                accumulate_terminal<NX>(a, x[q], acc, sh_hist);
+            }
+        }
     }
     flush_block_stats<NX, TERMINAL_THREADS>(a, acc, sh_hist);
 }
