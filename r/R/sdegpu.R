@@ -33,6 +33,16 @@ sde.linear <- function(A, G) {
   .catalogue("linear", c(as.numeric(A), as.numeric(G)), function(x) A %*% x, function(x) G, nx = nrow(A), nB = ncol(G))
 }
 
+## Killing rates r(x) and stopping functions h(t,x) (R/sdetools.R:397-416,455-457; Killing.Rmd:152-190):
+## ordinary closures again, tagged so the device can evaluate them.
+.tag_rule <- function(fn, what, kind, ...) { attr(fn, what) <- c(list(kind = kind), list(...)); fn }
+sde.kill.const <- function(a) .tag_rule(function(x) a, "sdegpu_kill", 1L, a = a, b = 0, comp = 0L)
+sde.kill.exp <- function(a, b, comp = 1L) .tag_rule(function(x) a * exp(b * x[comp]), "sdegpu_kill", 2L, a = a, b = b, comp = comp - 1L)
+sde.kill.quad <- function(a, b = 0, comp = 1L) .tag_rule(function(x) a * ((x[comp] - b) * (x[comp] - b)), "sdegpu_kill", 3L, a = a, b = b, comp = comp - 1L)
+sde.stop.below <- function(lo, comp = 1L) .tag_rule(function(t, x) x[comp] - lo, "sdegpu_stop", 1L, lo = lo, hi = 0, comp = comp - 1L)
+sde.stop.above <- function(hi, comp = 1L) .tag_rule(function(t, x) hi - x[comp], "sdegpu_stop", 2L, lo = 0, hi = hi, comp = comp - 1L)
+sde.stop.outside <- function(lo, hi, comp = 1L) .tag_rule(function(t, x) (x[comp] - lo) * (hi - x[comp]), "sdegpu_stop", 3L, lo = lo, hi = hi, comp = comp - 1L)
+
 .projection_id <- function(p) {
   if (is.null(p)) return(0L)
   if (identical(p, abs)) return(1L)
@@ -45,7 +55,8 @@ sde.linear <- function(A, G) {
                              npaths, seed, output, moments, center, hist, arith) {
   proj <- .projection_id(p)
   on.device <- !is.null(attr(f, "sdegpu_model")) && identical(attr(f, "sdegpu_model"), attr(g, "sdegpu_model")) &&
-    identical(attr(f, "sdegpu_params"), attr(g, "sdegpu_params")) && !is.na(proj) && is.null(h) && is.null(r)
+    identical(attr(f, "sdegpu_params"), attr(g, "sdegpu_params")) && !is.na(proj) &&
+    (is.null(h) || !is.null(attr(h, "sdegpu_stop"))) && (is.null(r) || !is.null(attr(r, "sdegpu_kill")))
   if (!on.device) return(fallback(f, g, times, x0, B, p = if (is.null(p)) function(x) x else p, h = h, r = r, S0 = S0, Stau = Stau))
   force(Stau)                       # the reference consumes one runif() per call (lazy default forced at :457/:327)
   nx <- attr(f, "sdegpu_nx"); nB <- attr(f, "sdegpu_nB"); nt <- length(times)
@@ -56,6 +67,9 @@ sde.linear <- function(A, G) {
   opts <- list(npaths = npaths, nx = nx, nB = nB, projection = proj, output = match(output, c("none", "terminal", "path")) - 1L,
                moments = as.numeric(moments), center = center, hist = hist, seed = seed)
   if (!is.null(arith)) opts$arith <- match(arith, c("strict", "fast")) - 1L
+  if (!is.null(r)) { k <- attr(r, "sdegpu_kill"); opts <- c(opts, list(kill_kind = k$kind, kill_comp = k$comp, kill_a = k$a, kill_b = k$b)) }
+  if (!is.null(h)) { k <- attr(h, "sdegpu_stop"); opts <- c(opts, list(stop_kind = k$kind, stop_comp = k$comp, stop_lo = k$lo, stop_hi = k$hi)) }
+  if (!is.null(r) || !is.null(h)) opts <- c(opts, list(S0 = S0, Stau = rep_len(as.numeric(Stau), npaths)))
   res <- .Call(C_sdegpu_run, scheme, .sdegpu_models[[attr(f, "sdegpu_model")]], attr(f, "sdegpu_params"),
                as.numeric(times), as.numeric(x0), B, opts[!vapply(opts, is.null, TRUE)])
   X <- res$X
@@ -63,7 +77,12 @@ sde.linear <- function(A, G) {
     if (npaths == 1L) { X <- matrix(X, nrow = nt, ncol = nx); colnames(X) <- names(x0) }       # list(times=, X=)  :464
     else dimnames(X) <- list(NULL, names(x0), NULL)
   }
-  c(list(times = times, X = X), res[c("XT", "power_sums", "hist", "seed")][!vapply(res[c("XT", "power_sums", "hist", "seed")], is.null, TRUE)])
+  if (!is.null(r) && npaths == 1L) {                          # the reference truncates at tau with mortality (:466-468)
+    k <- which(times == res$tau)[1]
+    return(list(times = times[1:k], X = if (nx == 1L) X[1:k, 1] else X[1:k, , drop = FALSE], S = res$S, tau = res$tau))
+  }
+  extra <- res[c("XT", "power_sums", "hist", "seed", "tau", "S")]
+  c(list(times = times, X = X), extra[!vapply(extra, is.null, TRUE)])
 }
 
 euler <- function(f, g, times, x0, B = NULL, p = function(x) x, h = NULL, r = NULL, S0 = 1, Stau = runif(1),

@@ -57,7 +57,9 @@ static uint64_t seed_from(SEXP opts)
  *   x0      length nx (shared) or nx x npaths;  B: NULL, or nt x nB x npaths (the `B` argument, :431-437)
  *   opts    list(npaths, nx, nB, projection, arith, seed, output = 0 none/1 terminal/2 path, moments, center,
  *                hist = c(lo, hi, nbins, component))
- * returns list(X = nt x nx x npaths | NULL, XT = nx x npaths | NULL, power_sums = 5 x nx | NULL, hist = counts | NULL, seed) */
+ *                kill_kind/kill_comp/kill_a/kill_b, stop_kind/stop_comp/stop_lo/stop_hi, S0, Stau)
+ * returns list(X = nt x nx x npaths | NULL, XT = nx x npaths | NULL, power_sums = 5 x nx | NULL, hist = counts | NULL, seed,
+ *              tau, S)   — with a kill/stop rule X holds NA after each path's tau and XT is the state at tau */
 SEXP C_sdegpu_run(SEXP scheme, SEXP model, SEXP params, SEXP times, SEXP x0, SEXP B, SEXP opts)
 {
     sdegpu_problem pr;
@@ -82,12 +84,23 @@ SEXP C_sdegpu_run(SEXP scheme, SEXP model, SEXP params, SEXP times, SEXP x0, SEX
     pr.npaths = (uint64_t)npaths;
     pr.path_offset = (uint64_t)opt_real(opts, "path_offset", 0);
     pr.seed = seed_from(opts);
+    /* mortality / stopping: catalogue r(x), h(t,x) (R/sdetools.R:397-416,455-457) */
+    pr.kill_kind = (int)opt_real(opts, "kill_kind", SDEGPU_KILL_NONE);
+    pr.kill_comp = (int)opt_real(opts, "kill_comp", 0);
+    pr.kill_a = opt_real(opts, "kill_a", 0); pr.kill_b = opt_real(opts, "kill_b", 0);
+    pr.stop_kind = (int)opt_real(opts, "stop_kind", SDEGPU_STOP_NONE);
+    pr.stop_comp = (int)opt_real(opts, "stop_comp", 0);
+    pr.stop_lo = opt_real(opts, "stop_lo", 0); pr.stop_hi = opt_real(opts, "stop_hi", 0);
+    pr.S0 = opt_real(opts, "S0", 1);
+    SEXP stau = list_get(opts, "Stau");
+    pr.Stau = Rf_isNull(stau) ? NULL : REAL(stau);              /* one threshold per path */
+    const int killed = pr.kill_kind != SDEGPU_KILL_NONE || pr.stop_kind != SDEGPU_STOP_NONE;
 
     int np = 0;
-    SEXP res = PROTECT(Rf_allocVector(VECSXP, 5)); ++np;
-    SEXP nms = PROTECT(Rf_allocVector(STRSXP, 5)); ++np;
-    const char *names[5] = {"X", "XT", "power_sums", "hist", "seed"};
-    for (int i = 0; i < 5; ++i) SET_STRING_ELT(nms, i, Rf_mkChar(names[i]));
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 7)); ++np;
+    SEXP nms = PROTECT(Rf_allocVector(STRSXP, 7)); ++np;
+    const char *names[7] = {"X", "XT", "power_sums", "hist", "seed", "tau", "S"};
+    for (int i = 0; i < 7; ++i) SET_STRING_ELT(nms, i, Rf_mkChar(names[i]));
     Rf_setAttrib(res, R_NamesSymbol, nms);
     if (output == 2) {
         SEXP X = PROTECT(Rf_alloc3DArray(REALSXP, nt, nx, (int)npaths)); ++np;      /* nt x nx x npaths, column-major */
@@ -105,6 +118,14 @@ SEXP C_sdegpu_run(SEXP scheme, SEXP model, SEXP params, SEXP times, SEXP x0, SEX
         out.power_sums = REAL(ps);
         SEXP cen = list_get(opts, "center");
         out.center = Rf_isNull(cen) ? NULL : REAL(cen);
+    }
+    if (killed) {                                                   /* tau <- times[i+1], S at tau  (:467-468) */
+        SEXP tau = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)npaths)); ++np;
+        SEXP S = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)npaths)); ++np;
+        SET_VECTOR_ELT(res, 5, tau);
+        SET_VECTOR_ELT(res, 6, S);
+        out.tau = REAL(tau);
+        out.S_tau = REAL(S);
     }
     uint64_t *counts = NULL;
     SEXP h = list_get(opts, "hist");

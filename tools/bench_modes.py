@@ -40,7 +40,9 @@ def main():
 
     # C3: van der Pol, full trajectory, fused generator (HBM-write bound; 16 B per path-step)
     if want("c3"):
-        P = 1 << (15 if args.quick else 17)
+        # two full waves of the trajectory kernel (one 512-thread CTA per SM): equal-length paths cannot fill a
+        # partial wave, so sizes that are not a multiple of 148*512 lose the remainder (2^17 paths: 86 %)
+        P = (1 << 15) if args.quick else 2 * eng.info["sm_count"] * 512
         nt = 10001
         t = np.arange(nt) * 0.01
         X = torch.empty(P * 2 * nt, dtype=torch.float64, device=dev)
@@ -51,7 +53,7 @@ def main():
         chk = X.view(P, 2, nt)[:4, :, :3].cpu().numpy().tolist()
         emit("c3_check", first=chk[0])
         # supplied-B variant: 8 B read + 16 B written per path-step
-        P2 = P // 2
+        P2 = (P // 2) if args.quick else eng.info["sm_count"] * 512
         B = torch.empty(P2 * nt, dtype=torch.float64, device=dev)
         eng.rvbm(t, P2, B, seed=9)
         X2 = X[: P2 * 2 * nt]
@@ -113,7 +115,7 @@ def main():
     # C4: linear SDE d = 256 (A x as a GEMM over paths); 2d^2+4d flops per path-step
     if want("c4"):
         d = 256
-        P = 1 << (10 if args.quick else 14)
+        P = (1 << 10) if args.quick else 2 * eng.info["sm_count"] * 64      # two full waves of 64-path CTAs
         n = 100 if args.quick else 1000
         rng = np.random.default_rng(256)
         R = rng.standard_normal((d, d))
