@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 {
     constexpr int NX = M::NX;
     using FS = FastStep<M, SCHEME, PROJ>;
-    extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_TABLE_DOUBLES);
-    icdf_stage(sh_tab, a.icdf, threadIdx.x, TERMINAL_THREADS);
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table, hot layout][histogram]
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_HOT_TABLE_DOUBLES);
+    icdf_stage_hot(sh_tab, a.icdf, threadIdx.x, TERMINAL_THREADS);
     if (a.hist)
         for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TERMINAL_THREADS) sh_hist[i] = 0u;
     __syncthreads();
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
                 const uint64_t pl = pq[q] < a.npaths ? pq[q] : pb;
                 uint32_t n0, n1, n2, n3;
                 philox_block(a.seed, a.path_offset + pl, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
-                const double z0 = icdf_normal(r[q][0], r[q][1], sh_tab), z1 = icdf_normal(r[q][2], r[q][3], sh_tab);
+                const double z0 = icdf_normal<true>(r[q][0], r[q][1], sh_tab), z1 = icdf_normal<true>(r[q][2], r[q][3], sh_tab);
                 FS::apply(a.P, x[q], d0, a.coef + (size_t)i * FAST_NCOEF, z0);
                 FS::apply(a.P, x[q], d1, a.coef + (size_t)(i + 1) * FAST_NCOEF, z1);
                 r[q][0] = n0; r[q][1] = n1; r[q][2] = n2; r[q][3] = n3;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
             const double2 d0 = __ldg(&a.dtsq[i]);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                const double z0 = icdf_normal(r[q][0], r[q][1], sh_tab);
+                const double z0 = icdf_normal<true>(r[q][0], r[q][1], sh_tab);
                 FS::apply(a.P, x[q], d0, a.coef + (size_t)i * FAST_NCOEF, z0);
             }
         }

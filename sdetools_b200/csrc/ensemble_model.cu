@@ -27,7 +27,7 @@ template <int SCHEME, int PROJ>
 static int launch_terminal(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
     auto kernel = k_terminal<M, SCHEME, PROJ>;
-    const size_t smem = ICDF_TABLE_BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    const size_t smem = ICDF_HOT_TABLE_BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + TERMINAL_THREADS - 1) / TERMINAL_THREADS;
     const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TERMINAL_THREADS, smem, c.sm_count, work);
     kernel<<<grid, TERMINAL_THREADS, smem, c.stream>>>(a);

@@ -56,6 +56,19 @@ __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32
     }
 }
 
+// Shared-memory layouts of the quantile table.
+//   plain : three planes of ICDF_NSEG words, 39 KB — every kernel that draws a few normals per step.
+//   hot   : the same planes, each followed by a 16-way replica of the top ICDF_HOT_SEG segments (the six
+//           highest octaves, 98.4 % of all draws): lane L reads replica L%16, whose 8-byte words sit in bank
+//           pair L%16, so a half-warp's 64-bit loads are conflict-free unless it holds a tail draw.
+//           Measured: the plain layout costs 5.4 wavefronts per LDS.64 (random segments collide in 16 bank
+//           pairs) and the LSU — shared by the four sub-partitions — was the busiest unit of k_terminal.
+constexpr int ICDF_HOT_SEG = 6 * 32;
+constexpr int ICDF_HOT_T0 = ICDF_NSEG - ICDF_HOT_SEG;
+constexpr int ICDF_HOT_STRIDE = ICDF_NSEG + 16 * ICDF_HOT_SEG;           // words per plane in the hot layout
+constexpr int ICDF_HOT_TABLE_DOUBLES = 3 * ICDF_HOT_STRIDE;
+constexpr int ICDF_HOT_TABLE_BYTES = ICDF_HOT_TABLE_DOUBLES * 8;
+
 // cooperative copy of the quantile table into shared memory (call before __syncthreads)
 __device__ __forceinline__ void icdf_stage(double *sh_tab, const double *__restrict__ g_tab, int tid, int nthreads)
 {
@@ -64,22 +77,37 @@ __device__ __forceinline__ void icdf_stage(double *sh_tab, const double *__restr
     for (int i = tid; i < ICDF_TABLE_DOUBLES / 2; i += nthreads) dst[i] = __ldg(src + i);
 }
 
-// one standard normal from 64 random bits
+__device__ __forceinline__ void icdf_stage_hot(double *sh_tab, const double *__restrict__ g_tab, int tid, int nthreads)
+{
+    for (int i = tid; i < ICDF_HOT_TABLE_DOUBLES; i += nthreads) {
+        const int plane = i / ICDF_HOT_STRIDE, j = i - plane * ICDF_HOT_STRIDE;
+        const int t = j < ICDF_NSEG ? j : ICDF_HOT_T0 + ((j - ICDF_NSEG) >> 4);
+        sh_tab[i] = __ldg(g_tab + plane * ICDF_NSEG + t);
+    }
+}
+
+// one standard normal from 64 random bits; HOT selects the shared-memory layout staged above
+template <bool HOT = false>
 __device__ __forceinline__ double icdf_normal(uint32_t lo, uint32_t hi, const double *sh_tab)
 {
+    constexpr int STRIDE = HOT ? ICDF_HOT_STRIDE : ICDF_NSEG;
     const double y0 = __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
     const double u = y0 - 1.0;                                   // [0,1): exponent = octave, mantissa = position
     const uint32_t uh = (uint32_t)__double2hiint(u);
     int t = (int)(uh >> ICDF_SHIFT) - ICDF_BASE;
     t = t < 0 ? 0 : t;                                           // u < 2^-52 (incl. 0) -> last segment
+    if (HOT) {
+        const int lane16 = (int)(threadIdx.x & 15u);
+        t = t >= ICDF_HOT_T0 ? ICDF_NSEG + ((t - ICDF_HOT_T0) << 4) + lane16 : t;
+    }
     const uint32_t yh = (uh & 0x000FFFFFu) | 0x3FF00000u;        // y = u * 2^(k+1) in [1,2)
     const double y = __hiloint2double((int)yh, __double2loint(u));
     const double c = __hiloint2double((int)((yh & ~((1u << ICDF_SHIFT) - 1u)) | (1u << (ICDF_SHIFT - 1))), 0);   // segment centre
     const double r = y - c;
     const double *p = sh_tab + t;
-    const float2 c23 = *reinterpret_cast<const float2 *>(p + 2 * ICDF_NSEG);
-    double a = fma((double)c23.y, r, (double)c23.x);
-    a = fma(a, r, p[ICDF_NSEG]);
+    const int2 c23 = *reinterpret_cast<const int2 *>(p + 2 * STRIDE);     // high words of c2, c3
+    double a = fma(__hiloint2double(c23.y, 0), r, __hiloint2double(c23.x, 0));
+    a = fma(a, r, p[STRIDE]);
     a = fma(a, r, p[0]);
     return __hiloint2double(__double2hiint(a) ^ (int)((lo << 20) & 0x80000000u), __double2loint(a));
 }
@@ -98,8 +126,8 @@ __device__ __forceinline__ void normal_pair(const PhiloxKey &key, uint64_t path,
 {
     uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32), c2 = block, c3 = channel;
     philox4x32_10(c0, c1, c2, c3, key);
-    z0 = icdf_normal(c0, c1, sh_tab);
-    z1 = icdf_normal(c2, c3, sh_tab);
+    z0 = icdf_normal<false>(c0, c1, sh_tab);
+    z1 = icdf_normal<false>(c2, c3, sh_tab);
 }
 
 }  // namespace sdegpu

@@ -129,8 +129,8 @@ def test_icdf_table_matches_qnorm():
     body = txt[txt.index("] = {") + 5:txt.index("};")]
     words =np.array([int(v.strip().rstrip("ul"), 16) for v in body.split(",") if v.strip()], dtype=np.uint64).reshape(3, nseg)
     c0, c1 = words[0].view(np.float64), words[1].view(np.float64)
-    c2 = (words[2] & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32).astype(np.float64)
-    c3 = (words[2] >> np.uint64(32)).astype(np.uint32).view(np.float32).astype(np.float64)
+    c2 = ((words[2] & np.uint64(0xFFFFFFFF)) << np.uint64(32)).view(np.float64)      # high words of the doubles
+    c3 = (words[2] & np.uint64(0xFFFFFFFF00000000)).view(np.float64)
     rng = np.random.default_rng(0)
     m = np.concatenate([rng.integers(0, 2 ** 52, 400000), 2 ** rng.integers(0, 52, 2000) + rng.integers(0, 3, 2000),
                         np.arange(0, 4), 2 ** 52 - 1 - np.arange(0, 4)]).astype(np.uint64)
