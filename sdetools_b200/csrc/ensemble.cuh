@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
 {
     constexpr int NX = M::NX;
     extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_TABLE_DOUBLES);
-    icdf_stage(sh_tab, a.icdf, threadIdx.x, TRAJ_THREADS);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_HOT_TABLE_DOUBLES);
+    icdf_stage_hot(sh_tab, a.icdf, threadIdx.x, TRAJ_THREADS);
     if (a.hist)
         for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TRAJ_THREADS) sh_hist[i] = 0u;
     __syncthreads();
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
 #pragma unroll
             for (int h = 0; h < 2; ++h) {                        // one Philox block per two steps
                 double z[2];
-                normal_pair(a.seed, gp, 2u * (uint32_t)m + (uint32_t)h, 0u, sh_tab, z[0], z[1]);
+                normal_pair<true>(a.seed, gp, 2u * (uint32_t)m + (uint32_t)h, 0u, sh_tab, z[0], z[1]);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int k = 2 * h + q;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
         }
         for (int i = 4 * ngroups; i < nsteps; ++i) {              // up to three trailing steps, element-wise
             double z0, z1;
-            normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
+            normal_pair<true>(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
             const double zz = (i & 1) ? z1 : z0;
             const double2 dt = __ldg(&a.dtsq[i]);
             sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * zz);

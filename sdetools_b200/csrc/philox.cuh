@@ -121,13 +121,14 @@ __device__ __forceinline__ void philox_block(const PhiloxKey &key, uint64_t path
 }
 
 // Two independent standard normals for (path, block, channel).
+template <bool HOT = false>
 __device__ __forceinline__ void normal_pair(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
                                             const double *sh_tab, double &z0, double &z1)
 {
     uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32), c2 = block, c3 = channel;
     philox4x32_10(c0, c1, c2, c3, key);
-    z0 = icdf_normal<false>(c0, c1, sh_tab);
-    z1 = icdf_normal<false>(c2, c3, sh_tab);
+    z0 = icdf_normal<HOT>(c0, c1, sh_tab);
+    z1 = icdf_normal<HOT>(c2, c3, sh_tab);
 }
 
 }  // namespace sdegpu
