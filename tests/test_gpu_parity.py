@@ -436,3 +436,68 @@ def test_constant_killing_rate_gives_exponential_lifetimes(sde):
     alive = tau == t[-1]
     assert abs(alive.mean() - np.exp(-a * T)) < 4.5 * np.sqrt(np.exp(-a * T) / N)
     assert np.all(res["S"][~alive] < 1) and res["XT"].shape == (1, N)
+
+
+# ---- BASELINE.json full sizes, through size-independent properties ---------------------------------------
+def test_c2_full_size_histogram_and_moments(sde):
+    """Config C2 as benchmarked: CIR heun(), 10^7 paths x 10^4 steps.  Properties: every path is counted once,
+    terminal mean/variance match the Stratonovich CIR law (noncentral chi-square) within MC error (the O(h)
+    bias at h = 1e-4 is below it), the histogram passes a chi-square test against pCIR(Stratonovich=TRUE)."""
+    from scipy import stats
+    N, n = 10 ** 7, 10 ** 4
+    t = np.arange(n + 1) * (1.0 / n)
+    res = sde.heun(*sde.catalogue.cir(1.0, 1.0, 1.0), t, 1.0, p=abs, npaths=N, seed=0x5DE70015, output="none", moments=True,
+                   center=[1.0], hist=(0.0, 8.0, 256))
+    h = res["hist"]
+    assert int(h["counts"].sum()) + h["under"] + h["over"] + h["nan"] == N and h["nan"] == 0 and h["under"] == 0
+    c, nu, dof = laws.cir_parameters(1.0, 1.0, 1.0, 1.0, 1.0, Stratonovich=True)
+    mean, var = (dof + nu) / (2 * c), 2 * (dof + 2 * nu) / (2 * c) ** 2
+    assert abs(res["moments"]["mean"][0] - mean) < 5 * np.sqrt(var / N)
+    assert abs(res["moments"]["var"][0] / var - 1) < 5 * np.sqrt((res["moments"]["kurtosis"][0] - 1) / N) + 2e-4
+    prob = np.diff(laws.pCIR(h["breaks"], 1.0, 1.0, 1.0, 1.0, 1.0, Stratonovich=True))
+    keep = prob * N > 200
+    chi2 = (((h["counts"] - prob * N) ** 2 / (prob * N))[keep]).sum()
+    assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-4, chi2
+
+
+def test_c5_share_ou_against_exact_discrete_law(sde):
+    """One GPU's share of config C5 (OU euler, 10^3 steps): 5*10^7 paths against the scheme's exact Gaussian law
+     — at this N the variance is resolved to 2e-4, far finer than the lambda*h/2 = 6.5e-4
+    bias against dOU, which must therefore be visible with the right sign and size."""
+    lam, xi, sig, x0, n, T, N = 1.3, 0.7, 0.9, 2.0, 1000, 1.0, 5 * 10 ** 7
+    m, s = laws.ou_discrete_law("euler", x0, lam, xi, sig, T / n, n)
+    res = sde.euler(*sde.catalogue.ou(lam, xi, sig), np.arange(n + 1) * (T / n), x0, npaths=N, seed=0x5DE70005, output="none",
+                    moments=True, center=[m], hist=(m - 6 * s, m + 6 * s, 512))
+    mom = res["moments"]
+    assert mom["n"][0] == N
+    assert abs(mom["mean"][0] - m) < 5 * s / np.sqrt(N)
+    assert abs(mom["var"][0] / s ** 2 - 1) < 5 * np.sqrt(2 / N)
+    assert abs(mom["skewness"][0]) < 5 * np.sqrt(6 / N) and abs(mom["kurtosis"][0] - 3) < 5 * np.sqrt(24 / N)
+    s0 = laws.ou_parameters(x0, lam, xi, sig, T)[1]
+    assert mom["var"][0] / s0 ** 2 - 1 == pytest.approx(lam * (T / n) / 2, abs=2.5e-4)
+    from scipy import stats
+    prob = np.diff(stats.norm.cdf(res["hist"]["breaks"], m, s))
+    keep = prob * N > 200
+    chi2 = (((res["hist"]["counts"] - prob * N) ** 2 / (prob * N))[keep]).sum()
+    assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-4, chi2
+
+
+def test_c3_trajectory_properties_at_scale(eng):
+    """Config C3 at 2 GB: the trajectory kernel's last row equals the register-resident kernel's terminal
+    state, the first row is x0, and an arbitrary sub-range run with path_offset reproduces its slice."""
+    import torch
+    P, nt = 13000, 10001                                       # odd nt, ragged last wave
+    t = np.arange(nt) * 0.01
+    dev = torch.device("cuda", 0)
+    X = torch.empty(P * 2 * nt, dtype=torch.float64, device=dev)
+    XT = torch.empty(P * 2, dtype=torch.float64, device=dev)
+    eng.run("vdp", "euler", [1.0, 0.5], t, [0.3, -0.2], nx=2, npaths=P, seed=11, X=X)
+    eng.run("vdp", "euler", [1.0, 0.5], t, [0.3, -0.2], nx=2, npaths=P, seed=11, XT=XT)
+    eng.synchronize()
+    Xv = X.view(P, 2, nt)
+    assert torch.all(Xv[:, 0, 0] == 0.3) and torch.all(Xv[:, 1, 0] == -0.2) and bool(torch.isfinite(Xv).all())
+    assert torch.allclose(Xv[:, :, -1], XT.view(P, 2), rtol=1e-13, atol=0)
+    sub = torch.empty(37 * 2 * nt, dtype=torch.float64, device=dev)
+    eng.run("vdp", "euler", [1.0, 0.5], t, [0.3, -0.2], nx=2, npaths=37, seed=11, path_offset=5003, X=sub)
+    eng.synchronize()
+    assert torch.equal(sub.view(37, 2, nt), Xv[5003:5040])
