@@ -25,7 +25,7 @@ namespace sdegpu {
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
-constexpr int ICDF_TABLE_DOUBLES = 3 * ICDF_NSEG;      // three 64-bit planes: c0, c1, {c2,c3 as floats}
+constexpr int ICDF_TABLE_DOUBLES = 4 * ICDF_NSEG;      // two planes of 16-byte entries: {c0,c1} and {c2,c3}
 constexpr int ICDF_TABLE_BYTES = ICDF_TABLE_DOUBLES * 8;
 
 // The ten round keys of a seed, expanded once on the host: as kernel parameters they sit in the
@@ -56,17 +56,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32
     }
 }
 
-// Shared-memory layouts of the quantile table.
-//   plain : three planes of ICDF_NSEG words, 39 KB — every kernel that draws a few normals per step.
-//   hot   : the same planes, each followed by a 16-way replica of the top ICDF_HOT_SEG segments (the six
-//           highest octaves, 98.4 % of all draws): lane L reads replica L%16, whose 8-byte words sit in bank
-//           pair L%16, so a half-warp's 64-bit loads are conflict-free unless it holds a tail draw.
-//           Measured: the plain layout costs 5.4 wavefronts per LDS.64 (random segments collide in 16 bank
-//           pairs) and the LSU — shared by the four sub-partitions — was the busiest unit of k_terminal.
+// Shared-memory layouts of the quantile table (entries are double2; plane B follows plane A).
+//   plain : 2 x ICDF_NSEG entries, 52 KB — kernels that draw a few normals per step.
+//   hot   : each plane followed by a 16-way replica of its top ICDF_HOT_SEG segments (the six highest
+//           octaves, 98.4 % of all draws): lane L reads replica L%16, so the eight lanes a 128-bit load
+//           serves per wavefront sit in eight different bank quads and never conflict unless a lane holds
+//           a tail draw.  Measured on the first layout (three 8-byte planes, random segments): 5.4
+//           wavefronts per LDS.64, and the LSU — shared by the four sub-partitions — was the busiest unit
+//           of k_terminal (65 of 118 cycles per warp-step); after replication 42.
 constexpr int ICDF_HOT_SEG = 6 * 32;
 constexpr int ICDF_HOT_T0 = ICDF_NSEG - ICDF_HOT_SEG;
-constexpr int ICDF_HOT_STRIDE = ICDF_NSEG + 16 * ICDF_HOT_SEG;           // words per plane in the hot layout
-constexpr int ICDF_HOT_TABLE_DOUBLES = 3 * ICDF_HOT_STRIDE;
+constexpr int ICDF_HOT_STRIDE = ICDF_NSEG + 16 * ICDF_HOT_SEG;           // entries per plane in the hot layout
+constexpr int ICDF_HOT_TABLE_DOUBLES = 4 * ICDF_HOT_STRIDE;
 constexpr int ICDF_HOT_TABLE_BYTES = ICDF_HOT_TABLE_DOUBLES * 8;
 
 // cooperative copy of the quantile table into shared memory (call before __syncthreads)
@@ -74,15 +75,17 @@ __device__ __forceinline__ void icdf_stage(double *sh_tab, const double *__restr
 {
     const double2 *src = reinterpret_cast<const double2 *>(g_tab);
     double2 *dst = reinterpret_cast<double2 *>(sh_tab);
-    for (int i = tid; i < ICDF_TABLE_DOUBLES / 2; i += nthreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < 2 * ICDF_NSEG; i += nthreads) dst[i] = __ldg(src + i);
 }
 
 __device__ __forceinline__ void icdf_stage_hot(double *sh_tab, const double *__restrict__ g_tab, int tid, int nthreads)
 {
-    for (int i = tid; i < ICDF_HOT_TABLE_DOUBLES; i += nthreads) {
+    const double2 *src = reinterpret_cast<const double2 *>(g_tab);
+    double2 *dst = reinterpret_cast<double2 *>(sh_tab);
+    for (int i = tid; i < 2 * ICDF_HOT_STRIDE; i += nthreads) {
         const int plane = i / ICDF_HOT_STRIDE, j = i - plane * ICDF_HOT_STRIDE;
         const int t = j < ICDF_NSEG ? j : ICDF_HOT_T0 + ((j - ICDF_NSEG) >> 4);
-        sh_tab[i] = __ldg(g_tab + plane * ICDF_NSEG + t);
+        dst[i] = __ldg(src + plane * ICDF_NSEG + t);
     }
 }
 
@@ -100,15 +103,17 @@ __device__ __forceinline__ double icdf_normal(uint32_t lo, uint32_t hi, const do
         const int lane16 = (int)(threadIdx.x & 15u);
         t = t >= ICDF_HOT_T0 ? ICDF_NSEG + ((t - ICDF_HOT_T0) << 4) + lane16 : t;
     }
-    const uint32_t yh = (uh & 0x000FFFFFu) | 0x3FF00000u;        // y = u * 2^(k+1) in [1,2)
-    const double y = __hiloint2double((int)yh, __double2loint(u));
-    const double c = __hiloint2double((int)((yh & ~((1u << ICDF_SHIFT) - 1u)) | (1u << (ICDF_SHIFT - 1))), 0);   // segment centre
-    const double r = y - c;
-    const double *p = sh_tab + t;
-    const int2 c23 = *reinterpret_cast<const int2 *>(p + 2 * STRIDE);     // high words of c2, c3
-    double a = fma(__hiloint2double(c23.y, 0), r, __hiloint2double(c23.x, 0));
-    a = fma(a, r, p[STRIDE]);
-    a = fma(a, r, p[0]);
+    // r = y - c with y = u*2^(k+1) in [1,2) and c the segment centre; both share the exponent and the top
+    // mantissa bits, so r is the low mantissa of u re-based at 1 minus half a segment: one LOP3 + one DADD
+    // against an immediate (1 + 2^-6), exact.
+    constexpr uint32_t LOWMASK = (1u << ICDF_SHIFT) - 1u;
+    const double d = __hiloint2double((int)((uh & LOWMASK) | 0x3FF00000u), __double2loint(u));
+    const double r = d - (1.0 + 1.0 / (double)(1u << (21 - ICDF_SHIFT)));
+    const double2 *p = reinterpret_cast<const double2 *>(sh_tab) + t;
+    const double2 c01 = p[0], c23 = p[STRIDE];
+    double a = fma(c23.y, r, c23.x);
+    a = fma(a, r, c01.y);
+    a = fma(a, r, c01.x);
     return __hiloint2double(__double2hiint(a) ^ (int)((lo << 20) & 0x80000000u), __double2loint(a));
 }
 

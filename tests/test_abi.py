@@ -127,10 +127,9 @@ def test_icdf_table_matches_qnorm():
     shift = int(re.search(r"#define ICDF_SHIFT (\d+)", txt).group(1))
     base = int(re.search(r"#define ICDF_BASE (\d+)", txt).group(1))
     body = txt[txt.index("] = {") + 5:txt.index("};")]
-    words =np.array([int(v.strip().rstrip("ul"), 16) for v in body.split(",") if v.strip()], dtype=np.uint64).reshape(3, nseg)
-    c0, c1 = words[0].view(np.float64), words[1].view(np.float64)
-    c2 = ((words[2] & np.uint64(0xFFFFFFFF)) << np.uint64(32)).view(np.float64)      # high words of the doubles
-    c3 = (words[2] & np.uint64(0xFFFFFFFF00000000)).view(np.float64)
+    words = np.array([int(v.strip().rstrip("ul"), 16) for v in body.split(",") if v.strip()], dtype=np.uint64)
+    planes = words.view(np.float64).reshape(2, nseg, 2)          # plane A = {c0,c1}, plane B = {c2,c3}
+    c0, c1, c2, c3 = planes[0, :, 0], planes[0, :, 1], planes[1, :, 0], planes[1, :, 1]
     rng = np.random.default_rng(0)
     m = np.concatenate([rng.integers(0, 2 ** 52, 400000), 2 ** rng.integers(0, 52, 2000) + rng.integers(0, 3, 2000),
                         np.arange(0, 4), 2 ** 52 - 1 - np.arange(0, 4)]).astype(np.uint64)
@@ -138,10 +137,9 @@ def test_icdf_table_matches_qnorm():
     bits = u.view(np.uint64)
     uh = (bits >> np.uint64(32)).astype(np.int64)
     t = np.maximum((uh >> shift) - base, 0)
-    yh = (uh & 0x000FFFFF) | 0x3FF00000
-    y = ((yh.astype(np.uint64) << np.uint64(32)) | (bits & np.uint64(0xFFFFFFFF))).view(np.float64)
-    c = (((yh & ~((1 << shift) - 1)) | (1 << (shift - 1))).astype(np.uint64) << np.uint64(32)).view(np.float64)
-    r = y - c
+    dh = (uh & ((1 << shift) - 1)) | 0x3FF00000                  # low mantissa of u re-based at 1
+    d = ((dh.astype(np.uint64) << np.uint64(32)) | (bits & np.uint64(0xFFFFFFFF))).view(np.float64)
+    r = d - (1.0 + 2.0 ** -(21 - shift))
     a = ((c3[t] * r + c2[t]) * r + c1[t]) * r + c0[t]
     want = -ndtri(0.5 * np.where(m == 0, 2.0 ** -52, u))
     assert t.max() < nseg and np.max(np.abs(r)) <= 2.0 ** -(21 - shift)
