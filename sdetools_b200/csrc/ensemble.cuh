@@ -249,6 +249,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
         }
         const uint64_t gp = a.path_offset + p;
         for (int m = 0; m < ngroups; ++m) {
+            double2 dts[4];                                      // issued before the generator: their latency (behind this
+#pragma unroll                                                   // SM's store traffic in the LSU queue) hides under Philox
+            for (int k = 0; k < 4; ++k) dts[k] = __ldg(&a.dtsq[4 * m + k]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {                        // one Philox block per two steps
                 double z[2];
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int k = 2 * h + q;
-                    const double2 dt = __ldg(&a.dtsq[4 * m + k]);
+                    const double2 dt = dts[k];
                     sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * z[q]);
 #pragma unroll
                     for (int j = 0; j < NX; ++j) v[j][k] = x[j];
@@ -386,13 +389,20 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, cons
                 pv[j][3] = x[j];
             }
         }
-        for (int m = 0; m < ngroups; ++m, s += 4) {
+        // register pipeline two sectors deep: DRAM latency is ~1 us and a thread owns one row, so while group m
+        // integrates the sectors of groups m+1 and m+2 are already in flight (two buffers, loop unrolled by two)
+        double bA[4], bB[4];
+        if (ngroups > 0) ld_sector(brow + s + 1, bA);
+        if (ngroups > 1) ld_sector(brow + s + 5, bB);
+        auto group = [&](double (&buf)[4], int m) {
             double b[4];
-            ld_sector(brow + s + 1, b);
+            double2 dts[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { b[k] = buf[k]; dts[k] = __ldg(&a.dtsq[s + k]); }
+            if (m + 2 < ngroups) ld_sector(brow + s + 9, buf);   // refill this buffer for group m+2
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double2 dt = __ldg(&a.dtsq[s + k]);
-                sde_step<M, SCHEME, PROJ, A>(a.P, x, dt.x, A::sub(b[k], prev));      // dB = diff(B)  (:437)
+                sde_step<M, SCHEME, PROJ, A>(a.P, x, dts[k].x, A::sub(b[k], prev));      // dB = diff(B)  (:437)
                 prev = b[k];
 #pragma unroll
                 for (int j = 0; j < NX; ++j) v[j][k] = x[j];
@@ -401,7 +411,11 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, cons
 #pragma unroll
                 for (int j = 0; j < NX; ++j) store_group(xrow[j] + s, d[j], m == 0 && d[j] > sa + 1, v[j], pv[j]);
             }
-        }
+            s += 4;
+        };
+        int m = 0;
+        for (; m + 1 < ngroups; m += 2) { group(bA, m); group(bB, m + 1); }
+        if (m < ngroups) group(bA, m);
         if (a.X && ngroups > 0) {                                // values that opened a sector no full group completes
 #pragma unroll
             for (int j = 0; j < NX; ++j)
