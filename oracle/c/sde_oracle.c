@@ -134,6 +134,27 @@ static double bits_to_normal(uint32_t lo, uint32_t hi)
     return (lo & 0x800u) ? -a : a;
 }
 
+/* one Brownian channel: four normals per block from 32-bit words; draws beyond 2^-12 in the tail take 21 more
+ * mantissa bits from the extension block (channel | 0x40000000) so the tail keeps 52-bit resolution */
+static void normal_quad(uint64_t seed, uint64_t path, uint32_t block, uint32_t channel, double z[4])
+{
+    uint32_t c[4] = { (uint32_t)path, (uint32_t)(path >> 32), block, channel };
+    uint32_t e[4] = { (uint32_t)path, (uint32_t)(path >> 32), block, channel | 0x40000000u };
+    int have_ext = 0;
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int s = 0; s < 4; ++s) {
+        uint64_t m = (uint64_t)(c[s] & 0x7FFFFFFFu) << 21;
+        if ((c[s] & 0x7FFFFFFFu) < (1u << 19)) {
+            if (!have_ext) { philox4x32_10(e, (uint32_t)seed, (uint32_t)(seed >> 32)); have_ext = 1; }
+            m |= e[s] >> 11;
+        }
+        double u = m ? (double)m * 0x1p-52 : 0x1p-52;
+        double a = -as241_qnorm(0.5 * u);
+        z[s] = (c[s] & 0x80000000u) ? -a : a;
+    }
+}
+
+/* matrix-valued g: two normals per block (one channel pair), 52-bit uniforms */
 static void normal_pair(uint64_t seed, uint64_t path, uint32_t block, uint32_t channel, double z[2])
 {
     uint32_t c[4] = { (uint32_t)path, (uint32_t)(path >> 32), block, channel };
@@ -164,7 +185,7 @@ int oracle_ensemble(int scheme, int model, const double *params, int nx, int nB,
         double x[MAXD], xn[MAXD], Y[MAXD], fX[MAXD], fY[MAXD], dB[MAXD];
         double *gX = (double *)malloc(sizeof(double) * 3 * (size_t)nx * nB), *gY = gX + (size_t)nx * nB,
                *gS = gY + (size_t)nx * nB;
-        double zbuf[MAXD][2];
+        double zbuf[MAXD][2], zquad[4];
         for (int j = 0; j < nx; ++j) x[j] = x0[(size_t)p * x0_stride + j];
         if (X) for (int j = 0; j < nx; ++j) X[((size_t)p * nx + j) * nt] = x[j];         /* X[1,] <- x0 :441 */
         for (int i = 0; i < nt - 1; ++i) {
@@ -174,9 +195,9 @@ int oracle_ensemble(int scheme, int model, const double *params, int nx, int nB,
                     const double *b = B + ((size_t)p * nB + k) * nt;
                     dB[k] = b[i + 1] - b[i];
                 }
-            } else if (nB == 1) {                                                        /* fused generator: one block = 2 steps */
-                if ((i & 1) == 0) normal_pair(seed, path_offset + p, (uint32_t)(i >> 1), 0u, zbuf[0]);
-                dB[0] = sqrt(dt) * zbuf[0][i & 1];
+            } else if (nB == 1) {                                                        /* fused generator: one block = 4 steps */
+                if ((i & 3) == 0) normal_quad(seed, path_offset + p, (uint32_t)(i >> 2), 0u, zquad);
+                dB[0] = sqrt(dt) * zquad[i & 3];
             } else {                                                   /* matrix-valued g: one block = one step, 2 channels */
                 double sq = sqrt(dt);
                 for (int k = 0; k < nB; ++k) {
@@ -210,10 +231,10 @@ int oracle_ensemble(int scheme, int model, const double *params, int nx, int nB,
 /* normals the fused generator hands to steps 0..nsteps-1 of one path/channel */
 void oracle_normals(uint64_t seed, uint64_t path, uint32_t channel, int nsteps, double *z)
 {
-    double zz[2];
+    double zz[4];
     for (int i = 0; i < nsteps; ++i) {
-        if ((i & 1) == 0) normal_pair(seed, path, (uint32_t)(i >> 1), channel, zz);
-        z[i] = zz[i & 1];
+        if ((i & 3) == 0) normal_quad(seed, path, (uint32_t)(i >> 2), channel, zz);
+        z[i] = zz[i & 3];
     }
 }
 

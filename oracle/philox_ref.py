@@ -8,14 +8,16 @@ draw is a pure function of (seed, global path id, step, channel).  This file sta
 generator exactly so the device stream can be checked draw by draw:
 
   key      = (seed & 0xffffffff, seed >> 32)
-  counter  = (path & 0xffffffff, path >> 32, block, channel)      one block = two steps
-  r0..r3   = philox4x32_10(counter, key)
-  step 2*block uses (lo,hi) = (r0,r1); step 2*block+1 uses (r2,r3):
-    m    = top 52 bits of hi:lo;  u = m * 2^-52  (u = 2^-52 if m == 0)
-    z    = (-1)^(bit 11 of lo) * -qnorm(u/2)
+  counter  = (path & 0xffffffff, path >> 32, block, channel)      one block = FOUR steps
+  r0..r3   = philox4x32_10(counter, key);  step 4*block+s uses word r_s:
+    sign = bit 31, m31 = low 31 bits, m = m31 << 21
+    if m31 < 2^19: m |= e_s >> 11 with e = philox4x32_10((path, block, channel | 0x40000000), key)
+    u    = m * 2^-52  (u = 2^-52 if m == 0);   z = (-1)^sign * -qnorm(u/2)
   dB[i,k]  = sqrt(dt[i]) * z[i]   for channel k
-The device evaluates -qnorm(u/2) from a table of piecewise degree-5 polynomials with
-|error| < 2e-12 (tools/gen_icdf_table.py); here it is scipy's ndtri.
+(The linear model's matrix-valued g uses one block per (path, step, channel pair) with 52-bit uniforms;
+only the C oracle restates that variant.)
+The device evaluates -qnorm(u/2) from a table of piecewise cubics with |error| < 8e-10
+(tools/gen_icdf_table.py); here it is scipy's ndtri.
 """
 from __future__ import annotations
 
@@ -44,24 +46,23 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def bits_to_normal(lo, hi):
-    from scipy.special import ndtri
-    lo = np.asarray(lo, dtype=np.uint64)
-    hi = np.asarray(hi, dtype=np.uint64)
-    m = ((hi << np.uint64(32)) | lo) >> np.uint64(12)
-    u = np.where(m == 0, 2.0 ** -52, m.astype(np.float64) * 2.0 ** -52)
-    a = -ndtri(0.5 * u)
-    return np.where((lo & np.uint64(0x800)) != 0, -a, a)
-
-
 def normals(paths, nsteps, channel, seed):
     """z[(step, path)] for steps 0..nsteps-1 — float64 array (nsteps, npaths)."""
+    from scipy.special import ndtri
     paths = np.asarray(paths, dtype=np.uint64)
-    nblk = (nsteps + 1) // 2
+    nblk = (nsteps + 3) // 4
     blk = np.arange(nblk, dtype=np.uint64)[:, None]
-    r0, r1, r2, r3 = philox4x32_10(paths[None, :] & MASK, paths[None, :] >> np.uint64(32), blk, channel,
-                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    z = np.empty((2 * nblk, paths.shape[0]))
-    z[0::2] = bits_to_normal(r0, r1)
-    z[1::2] = bits_to_normal(r2, r3)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    plo, phi = paths[None, :] & MASK, paths[None, :] >> np.uint64(32)
+    r = philox4x32_10(plo, phi, blk, channel, k0, k1)
+    e = philox4x32_10(plo, phi, blk, channel | 0x40000000, k0, k1)
+    z = np.empty((4 * nblk, paths.shape[0]))
+    for s_ in range(4):
+        w = np.broadcast_to(r[s_], (nblk, paths.shape[0]))
+        m31 = w & np.uint64(0x7FFFFFFF)
+        m = m31 << np.uint64(21)
+        m = np.where(m31 < np.uint64(1 << 19), m | (np.broadcast_to(e[s_], m.shape) >> np.uint64(11)), m)
+        u = np.where(m == 0, 2.0 ** -52, m.astype(np.float64) * 2.0 ** -52)
+        a = -ndtri(0.5 * u)
+        z[s_::4] = np.where((w >> np.uint64(31)) != 0, -a, a)
     return z[:nsteps]

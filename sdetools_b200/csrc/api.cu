@@ -538,11 +538,12 @@ __global__ void k_normals(const double *icdf, const PhiloxKey seed, uint64_t pat
     __syncthreads();
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npaths) return;
-    for (int i = 0; i < nsteps; i += 2) {
-        double z0, z1;
-        normal_pair(seed, path_offset + p, (uint32_t)(i >> 1), channel, sh_tab, z0, z1);
-        z[(size_t)i * npaths + p] = z0;
-        if (i + 1 < nsteps) z[(size_t)(i + 1) * npaths + p] = z1;
+    for (int i = 0; i < nsteps; i += 4) {
+        double zq[4];
+        normal_quad(seed, path_offset + p, (uint32_t)(i >> 2), channel, sh_tab, zq);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k < nsteps) z[(size_t)(i + k) * npaths + p] = zq[k];
     }
 }
 

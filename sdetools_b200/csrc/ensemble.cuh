@@ -149,31 +149,38 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
             pq[q] = pb + (uint64_t)q * stride;
             const uint64_t pl = pq[q] < a.npaths ? pq[q] : pb;   // a missing partner recomputes path pb and is discarded
             load_x0<NX>(a, pl, x[q]);
-            // Software-pipelined: the Philox block of steps (i+2, i+3) is generated while steps (i, i+1)
+            // Software-pipelined: the Philox block of steps i+4..i+7 is generated while steps i..i+3
             // integrate, so the integer rounds issue in the shadow of the dependent FP64 chain.
             philox_block(a.seed, a.path_offset + pl, 0u, 0u, r[q][0], r[q][1], r[q][2], r[q][3]);
         }
         int i = 0;
-        for (; i + 1 < nsteps; i += 2) {
-            double2 d0 = make_double2(0.0, 0.0), d1 = d0;
-            if (!FS::uses_coef) { d0 = __ldg(&a.dtsq[i]); d1 = __ldg(&a.dtsq[i + 1]); }
+        for (; i + 3 < nsteps; i += 4) {
+            double2 dts[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dts[k] = FS::uses_coef ? make_double2(0.0, 0.0) : __ldg(&a.dtsq[i + k]);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                const uint64_t pl = pq[q] < a.npaths ? pq[q] : pb;
-                uint32_t n0, n1, n2, n3;
-                philox_block(a.seed, a.path_offset + pl, (uint32_t)(i >> 1) + 1u, 0u, n0, n1, n2, n3);
-                const double z0 = icdf_normal<true>(r[q][0], r[q][1], sh_tab), z1 = icdf_normal<true>(r[q][2], r[q][3], sh_tab);
-                FS::apply(a.P, x[q], d0, a.coef + (size_t)i * FAST_NCOEF, z0);
-                FS::apply(a.P, x[q], d1, a.coef + (size_t)(i + 1) * FAST_NCOEF, z1);
-                r[q][0] = n0; r[q][1] = n1; r[q][2] = n2; r[q][3] = n3;
+                const uint64_t gp = a.path_offset + (pq[q] < a.npaths ? pq[q] : pb);
+                uint32_t n[4];
+                philox_block(a.seed, gp, (uint32_t)(i >> 2) + 1u, 0u, n[0], n[1], n[2], n[3]);
+                double z[4];
+                normals_from_block<true>(a.seed, gp, (uint32_t)(i >> 2), 0u, r[q], sh_tab, z);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    FS::apply(a.P, x[q], dts[k], a.coef + (size_t)(i + k) * FAST_NCOEF, z[k]);
+                    r[q][k] = n[k];
+                }
             }
         }
-        if (i < nsteps) {
-            const double2 d0 = __ldg(&a.dtsq[i]);
+        if (i < nsteps) {                                        // up to three trailing steps of the last block
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                const double z0 = icdf_normal<true>(r[q][0], r[q][1], sh_tab);
-                FS::apply(a.P, x[q], d0, a.coef + (size_t)i * FAST_NCOEF, z0);
+                const uint64_t gp = a.path_offset + (pq[q] < a.npaths ? pq[q] : pb);
+                double z[4];
+                normals_from_block<true>(a.seed, gp, (uint32_t)(i >> 2), 0u, r[q], sh_tab, z);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (i + k < nsteps) FS::apply(a.P, x[q], __ldg(&a.dtsq[i + k]), a.coef + (size_t)(i + k) * FAST_NCOEF, z[k]);
             }
         }
 #pragma unroll
@@ -252,18 +259,13 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
             double2 dts[4];                                      // issued before the generator: their latency (behind this
 #pragma unroll                                                   // SM's store traffic in the LSU queue) hides under Philox
             for (int k = 0; k < 4; ++k) dts[k] = __ldg(&a.dtsq[4 * m + k]);
+            double z[4];                                         // one Philox block per group of four steps
+            normal_quad<true>(a.seed, gp, (uint32_t)m, 0u, sh_tab, z);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                        // one Philox block per two steps
-                double z[2];
-                normal_pair<true>(a.seed, gp, 2u * (uint32_t)m + (uint32_t)h, 0u, sh_tab, z[0], z[1]);
+            for (int k = 0; k < 4; ++k) {
+                sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dts[k].x, dts[k].y * z[k]);
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int k = 2 * h + q;
-                    const double2 dt = dts[k];
-                    sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * z[q]);
-#pragma unroll
-                    for (int j = 0; j < NX; ++j) v[j][k] = x[j];
-                }
+                for (int j = 0; j < NX; ++j) v[j][k] = x[j];
             }
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
@@ -291,14 +293,19 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
                         if (k >= 4 - d[j]) row[j][4 * (int64_t)(ngroups - 1) + k] = pv[j][k];
                 }
         }
-        for (int i = 4 * ngroups; i < nsteps; ++i) {              // up to three trailing steps, element-wise
-            double z0, z1;
-            normal_pair<true>(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
-            const double zz = (i & 1) ? z1 : z0;
-            const double2 dt = __ldg(&a.dtsq[i]);
-            sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * zz);
+        if (4 * ngroups < nsteps) {                               // up to three trailing steps, element-wise
+            double z[4];
+            normal_quad<true>(a.seed, gp, (uint32_t)ngroups, 0u, sh_tab, z);
 #pragma unroll
-            for (int j = 0; j < NX; ++j) row[j][i] = x[j];
+            for (int k = 0; k < 3; ++k) {
+                const int i = 4 * ngroups + k;
+                if (i < nsteps) {
+                    const double2 dt = __ldg(&a.dtsq[i]);
+                    sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * z[k]);
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) row[j][i] = x[j];
+                }
+            }
         }
         if (a.XT) {
 #pragma unroll
@@ -506,15 +513,16 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
             for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt] = x[j];
         }
         const double *brow = a.B ? a.B + p * (uint64_t)a.nt : nullptr;
-        double S = a.S0, Sout = a.S0, z0 = 0.0, z1 = 0.0;
+        double S = a.S0, Sout = a.S0, zq[4] = {0.0, 0.0, 0.0, 0.0};
         int last = nsteps;                                       // index of the last valid row of X
         for (int i = 0; i < nsteps; ++i) {
             const double2 dt = __ldg(&a.dtsq[i]);
             double dB;
             if (brow) dB = __dsub_rn(__ldg(brow + i + 1), __ldg(brow + i));
             else {
-                if ((i & 1) == 0) normal_pair(a.seed, gp, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
-                dB = __dmul_rn(dt.y, (i & 1) ? z1 : z0);
+                if ((i & 3) == 0) normal_quad(a.seed, gp, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+                const int k = i & 3;
+                dB = __dmul_rn(dt.y, k == 0 ? zq[0] : (k == 1 ? zq[1] : (k == 2 ? zq[2] : zq[3])));
             }
 #pragma unroll
             for (int j = 0; j < NX; ++j) xo[j] = x[j];

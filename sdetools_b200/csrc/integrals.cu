@@ -143,16 +143,18 @@ __global__ void __launch_bounds__(IT_COLS) k_rvbm(const BMArgs q)
         const bool valid = col < q.ncols;
         const int rows = (int)((q.ncols - c0 < (uint64_t)IT_COLS) ? (q.ncols - c0) : IT_COLS);
         F80 acc = f80_zero();
-        double z0 = 0.0, z1 = 0.0;
+        double zq[4] = {0.0, 0.0, 0.0, 0.0};
         for (int i0 = 0; i0 < q.nt; i0 += IT_STEPS) {
             const int nc = (q.nt - i0 < IT_STEPS) ? (q.nt - i0) : IT_STEPS;
             if (valid) {
                 for (int k = 0; k < nc; ++k) {
                     const int i = i0 + k;
-                    if ((i & 1) == 0) normal_pair(q.seed, q.path_offset + col, (uint32_t)(i >> 1), 0u, sh_tab, z0, z1);
+                    if ((i & 3) == 0) normal_quad(q.seed, q.path_offset + col, (uint32_t)(i >> 2), 0u, sh_tab, zq);
                     const double2 d = __ldg(&q.dtsq[i]);
+                    const int s4 = i & 3;
+                    const double z = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
                     // rnorm(mean=u*dt, sd=sigma*sqrt(dt)) = mean + sd*Z
-                    const double dB = __dadd_rn(__dmul_rn(q.u, d.x), __dmul_rn(__dmul_rn(q.sigma, d.y), (i & 1) ? z1 : z0));
+                    const double dB = __dadd_rn(__dmul_rn(q.u, d.x), __dmul_rn(__dmul_rn(q.sigma, d.y), z));
                     f80_add(acc, dB);
                     sm[tid * IT_LD + k] = __dadd_rn(q.B0, f80_to_double(acc));
                 }

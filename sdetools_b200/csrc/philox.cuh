@@ -5,17 +5,21 @@
 // (seed, global path id, step, channel).
 //
 //   key     = (seed lo, seed hi)
-//   counter = (path lo, path hi, block, channel)        one block = two consecutive steps
-//   r0..r3  = Philox4x32-10 (Salmon et al. SC'11; KATs in SURVEY.md App. F)
-//   step 2*block   uses (r0, r1), step 2*block+1 uses (r2, r3):
-//     u    = [1,2)-double built from the top 52 bits of hi:lo, minus 1      in [0,1)
-//     sign = bit 11 of lo
-//     z    = sign * a(u),   a(u) = -qnorm(u/2)  (half-normal quantile)
-//   a(u) is a table of cubics on 52 octaves x 32 mantissa sub-intervals (tools/gen_icdf_table.py,
-//   |error| < 8e-10: a Kolmogorov distance ~3e-10 from the exact normal law, three orders of
-//   magnitude below the 1/sqrt(N) resolution of even a 10^13-draw ensemble), 39 KB staged in
-//   shared memory: the transform costs 2 DADD + 3 DFMA + 3 LDS.64 and has no transcendental,
-//   no branch and no divergence.
+//   r0..r3  = Philox4x32-10(counter, key)   (Salmon et al. SC'11; KATs in SURVEY.md App. F)
+//
+//   One Brownian channel (every catalogue model with a vector-valued g):
+//     counter = (path lo, path hi, block, channel), one block = FOUR consecutive steps, step 4*block+s uses r_s:
+//       sign = bit 31, m = low 31 bits, u = m * 2^-31                               (P(octave k) = 2^-(k+1) exactly)
+//       if m < 2^19 (probability 2^-12: the draw lies beyond 2^-12 in the tail) the 21 low mantissa bits of u
+//       are filled from word s of the extension block, counter (path, block, channel | 0x40000000): tail draws
+//       keep full 52-bit resolution down to u = 2^-52 (|z| up to 8.2) while the bulk spends 32 bits per normal.
+//   Matrix-valued g (linear model, nB channels):
+//     counter = (path lo, path hi, step, 0x80000000 + pair), channel 2*pair uses (r0,r1), 2*pair+1 uses (r2,r3):
+//       52-bit u from the top 52 bits of hi:lo, sign = bit 11 of lo.
+//   z = sign * a(u), a(u) = -qnorm(u/2) (half-normal quantile): a table of cubics on 52 octaves x 32 mantissa
+//   sub-intervals indexed straight from the exponent/mantissa bits of u (tools/gen_icdf_table.py, |error| < 8e-10:
+//   a Kolmogorov distance ~3e-10 from the normal law, three orders below the 1/sqrt(N) resolution of a 10^13-draw
+//   ensemble), staged in shared memory: 2 DADD + 3 DFMA + 2 LDS.128, no transcendental, no conversion, no branch.
 #pragma once
 #include <stdint.h>
 
@@ -89,13 +93,12 @@ __device__ __forceinline__ void icdf_stage_hot(double *sh_tab, const double *__r
     }
 }
 
-// one standard normal from 64 random bits; HOT selects the shared-memory layout staged above
-template <bool HOT = false>
-__device__ __forceinline__ double icdf_normal(uint32_t lo, uint32_t hi, const double *sh_tab)
+// a(u) with sign, from the two words of y0 = 1 + u (a [1,2) double) — HOT selects the layout staged above
+template <bool HOT>
+__device__ __forceinline__ double icdf_eval(uint32_t y0hi, uint32_t y0lo, uint32_t signbit, const double *sh_tab)
 {
     constexpr int STRIDE = HOT ? ICDF_HOT_STRIDE : ICDF_NSEG;
-    const double y0 = __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
-    const double u = y0 - 1.0;                                   // [0,1): exponent = octave, mantissa = position
+    const double u = __hiloint2double((int)y0hi, (int)y0lo) - 1.0;   // [0,1): exponent = octave, mantissa = position
     const uint32_t uh = (uint32_t)__double2hiint(u);
     int t = (int)(uh >> ICDF_SHIFT) - ICDF_BASE;
     t = t < 0 ? 0 : t;                                           // u < 2^-52 (incl. 0) -> last segment
@@ -114,7 +117,21 @@ __device__ __forceinline__ double icdf_normal(uint32_t lo, uint32_t hi, const do
     double a = fma(c23.y, r, c23.x);
     a = fma(a, r, c01.y);
     a = fma(a, r, c01.x);
-    return __hiloint2double(__double2hiint(a) ^ (int)((lo << 20) & 0x80000000u), __double2loint(a));
+    return __hiloint2double(__double2hiint(a) ^ (int)signbit, __double2loint(a));
+}
+
+// one standard normal from 64 random bits (matrix-valued g: two per Philox block)
+template <bool HOT = false>
+__device__ __forceinline__ double icdf_normal(uint32_t lo, uint32_t hi, const double *sh_tab)
+{
+    return icdf_eval<HOT>(0x3FF00000u | (hi >> 12), (hi << 20) | (lo >> 12), (lo << 20) & 0x80000000u, sh_tab);
+}
+
+// one standard normal from a 32-bit word plus the (usually zero) 21 extension bits
+template <bool HOT = false>
+__device__ __forceinline__ double icdf_normal32(uint32_t w, uint32_t ext21, const double *sh_tab)
+{
+    return icdf_eval<HOT>(0x3FF00000u | ((w >> 11) & 0x000FFFFFu), (w << 21) | ext21, w & 0x80000000u, sh_tab);
 }
 
 // The 128 random bits of (path, block, channel).
@@ -125,7 +142,36 @@ __device__ __forceinline__ void philox_block(const PhiloxKey &key, uint64_t path
     philox4x32_10(r0, r1, r2, r3, key);
 }
 
-// Two independent standard normals for (path, block, channel).
+// Four standard normals (steps 4*block .. 4*block+3 of one channel) from the words of a Philox block.
+// The tail extension is evaluated once per block and taken by ~1 block in 1000.
+template <bool HOT = false>
+__device__ __forceinline__ void normals_from_block(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
+                                                   const uint32_t (&r)[4], const double *sh_tab, double (&z)[4])
+{
+    uint32_t ext[4] = {0u, 0u, 0u, 0u};
+    const uint32_t m0 = r[0] & 0x7FFFFFFFu, m1 = r[1] & 0x7FFFFFFFu, m2 = r[2] & 0x7FFFFFFFu, m3 = r[3] & 0x7FFFFFFFu;
+    if (min(min(m0, m1), min(m2, m3)) < (1u << 19)) {
+        uint32_t e[4];
+        philox_block(key, path, block, channel | 0x40000000u, e[0], e[1], e[2], e[3]);
+        ext[0] = m0 < (1u << 19) ? e[0] >> 11 : 0u;
+        ext[1] = m1 < (1u << 19) ? e[1] >> 11 : 0u;
+        ext[2] = m2 < (1u << 19) ? e[2] >> 11 : 0u;
+        ext[3] = m3 < (1u << 19) ? e[3] >> 11 : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = icdf_normal32<HOT>(r[k], ext[k], sh_tab);
+}
+
+template <bool HOT = false>
+__device__ __forceinline__ void normal_quad(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
+                                            const double *sh_tab, double (&z)[4])
+{
+    uint32_t r[4];
+    philox_block(key, path, block, channel, r[0], r[1], r[2], r[3]);
+    normals_from_block<HOT>(key, path, block, channel, r, sh_tab, z);
+}
+
+// Two standard normals for a channel pair of the matrix-valued-g generator (52-bit uniforms).
 template <bool HOT = false>
 __device__ __forceinline__ void normal_pair(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
                                             const double *sh_tab, double &z0, double &z1)
