@@ -142,6 +142,23 @@ __device__ __forceinline__ void philox_block(const PhiloxKey &key, uint64_t path
     philox4x32_10(r0, r1, r2, r3, key);
 }
 
+// Extension block of the tail draws, out of line on purpose: it runs for ~1 block in 1000 and, inlined, its
+// twenty round keys would be copied into vector registers at the top of every iteration of the hot loop.
+__device__ __noinline__ uint4 philox_extension(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+                                               uint32_t block, uint32_t channel)
+{
+    uint32_t c0 = path_lo, c1 = path_hi, c2 = block, c3 = channel | 0x40000000u, k0 = seed_lo, k1 = seed_hi;
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // Four standard normals (steps 4*block .. 4*block+3 of one channel) from the words of a Philox block.
 // The tail extension is evaluated once per block and taken by ~1 block in 1000.
 template <bool HOT = false>
@@ -151,12 +168,11 @@ __device__ __forceinline__ void normals_from_block(const PhiloxKey &key, uint64_
     uint32_t ext[4] = {0u, 0u, 0u, 0u};
     const uint32_t m0 = r[0] & 0x7FFFFFFFu, m1 = r[1] & 0x7FFFFFFFu, m2 = r[2] & 0x7FFFFFFFu, m3 = r[3] & 0x7FFFFFFFu;
     if (min(min(m0, m1), min(m2, m3)) < (1u << 19)) {
-        uint32_t e[4];
-        philox_block(key, path, block, channel | 0x40000000u, e[0], e[1], e[2], e[3]);
-        ext[0] = m0 < (1u << 19) ? e[0] >> 11 : 0u;
-        ext[1] = m1 < (1u << 19) ? e[1] >> 11 : 0u;
-        ext[2] = m2 < (1u << 19) ? e[2] >> 11 : 0u;
-        ext[3] = m3 < (1u << 19) ? e[3] >> 11 : 0u;
+        const uint4 e = philox_extension(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel);
+        ext[0] = m0 < (1u << 19) ? e.x >> 11 : 0u;
+        ext[1] = m1 < (1u << 19) ? e.y >> 11 : 0u;
+        ext[2] = m2 < (1u << 19) ? e.z >> 11 : 0u;
+        ext[3] = m3 < (1u << 19) ? e.w >> 11 : 0u;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) z[k] = icdf_normal32<HOT>(r[k], ext[k], sh_tab);
