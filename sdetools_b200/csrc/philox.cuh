@@ -144,7 +144,7 @@ __device__ __forceinline__ void philox_block(const PhiloxKey &key, uint64_t path
 
 // Extension block of the tail draws, out of line on purpose: it runs for ~1 block in 1000 and, inlined, its
 // twenty round keys would be copied into vector registers at the top of every iteration of the hot loop.
-__device__ __noinline__ uint4 philox_extension(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+static __device__ __noinline__ uint4 philox_extension(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
                                                uint32_t block, uint32_t channel)
 {
     uint32_t c0 = path_lo, c1 = path_hi, c2 = block, c3 = channel | 0x40000000u, k0 = seed_lo, k1 = seed_hi;
