@@ -18,10 +18,10 @@ namespace sdegpu {
 
 constexpr int MAX_NX = 2;           // catalogue models handled here have nx <= 2
 #ifndef SDEGPU_TERMINAL_THREADS
-#define SDEGPU_TERMINAL_THREADS 512
+#define SDEGPU_TERMINAL_THREADS 768
 #endif
 #ifndef SDEGPU_TERMINAL_NP
-#define SDEGPU_TERMINAL_NP 2
+#define SDEGPU_TERMINAL_NP 1
 #endif
 #ifndef SDEGPU_TERMINAL_MIN_BLOCKS
 #define SDEGPU_TERMINAL_MIN_BLOCKS 1
