@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 // of the previous group and the first 4-d of this one.  Paths are dealt to lanes with stride Q
 // (Q*nx*nt = 0 mod 4) so that d is warp-uniform and the four-way switch does not diverge.  Only the
 // first/last partial sector of a row is written element by element.
+constexpr int TRAJ_CHUNK = 1024;    // steps of the {dt, sqrt dt} table staged in shared memory at a time (16 KB)
 #ifndef SDEGPU_TRAJ_THREADS
 #define SDEGPU_TRAJ_THREADS 512
 #endif
@@ -223,7 +224,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
 {
     constexpr int NX = M::NX;
     extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_HOT_TABLE_DOUBLES);
+    // [quantile table, hot layout][step table chunk: TRAJ_CHUNK x {dt, sqrt dt}][histogram]
+    double2 *sh_dt = reinterpret_cast<double2 *>(sh_tab + ICDF_HOT_TABLE_DOUBLES);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_dt + TRAJ_CHUNK);
     icdf_stage_hot(sh_tab, a.icdf, threadIdx.x, TRAJ_THREADS);
     if (a.hist)
         for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TRAJ_THREADS) sh_hist[i] = 0u;
@@ -237,28 +240,37 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
     const int nsteps = a.nt - 1, ngroups = nsteps >> 2;
     const uint64_t stride = (uint64_t)gridDim.x * TRAJ_THREADS;
     const uint64_t W = 32u * (unsigned)Q;                        // paths per lane-interleaved group of Q warps
-    for (uint64_t T = (uint64_t)blockIdx.x * TRAJ_THREADS + threadIdx.x;; T += stride) {
-        const uint64_t within = T % W, p = (T - within) + (within >> 5) + (uint64_t)Q * (within & 31);
-        if (T - within >= a.npaths) break;                       // whole group out of range (uniform)
-        if (p >= a.npaths) continue;
+    const uint64_t Tmax = (a.npaths + W - 1) / W * W, nrounds = (Tmax + stride - 1) / stride;
+    for (uint64_t round = 0; round < nrounds; ++round) {         // every thread of the CTA runs every round: the step
+        const uint64_t T = round * stride + (uint64_t)blockIdx.x * TRAJ_THREADS + threadIdx.x;    // table is staged
+        const uint64_t within = T % W, p = (T - within) + (within >> 5) + (uint64_t)Q * (within & 31);        // cooperatively
+        const bool valid = p < a.npaths;
         double x[NX], v[NX][4], pv[NX][4];
         double *row[NX];                                         // &X[row start + 1]: stream position 0
         int d[NX];
-        load_x0<NX>(a, p, x);
+        load_x0<NX>(a, valid ? p : 0, x);
 #pragma unroll
         for (int j = 0; j < NX; ++j) {
             const uint64_t e0 = (p * NX + j) * (uint64_t)a.nt;
             row[j] = a.X + e0 + 1;
             d[j] = vec_ok ? (int)((e0 + 1) & 3) : 4;             // 4: element-wise stores only
-            if (d[j] != 1) a.X[e0] = x[j];                       // X[1,] <- x0 (:441); with d = 1 it opens the first sector
+            if (valid && d[j] != 1) a.X[e0] = x[j];              // X[1,] <- x0 (:441); with d = 1 it opens the first sector
 #pragma unroll
             for (int k = 0; k < 4; ++k) pv[j][k] = x[j];
         }
         const uint64_t gp = a.path_offset + p;
         for (int m = 0; m < ngroups; ++m) {
-            double2 dts[4];                                      // issued before the generator: their latency (behind this
-#pragma unroll                                                   // SM's store traffic in the LSU queue) hides under Philox
-            for (int k = 0; k < 4; ++k) dts[k] = __ldg(&a.dtsq[4 * m + k]);
+            // {dt_i, sqrt dt_i} through shared memory, TRAJ_CHUNK steps at a time: global loads of the table queue
+            // behind this SM's scattered sector stores in the LSU (measured: 29 % long-scoreboard stalls)
+            if ((m & (TRAJ_CHUNK / 4 - 1)) == 0) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < TRAJ_CHUNK && 4 * m + i < nsteps; i += TRAJ_THREADS) sh_dt[i] = __ldg(&a.dtsq[4 * m + i]);
+                __syncthreads();
+            }
+            if (!valid) continue;
+            double2 dts[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dts[k] = sh_dt[4 * (m & (TRAJ_CHUNK / 4 - 1)) + k];
             double z[4];                                         // one Philox block per group of four steps
             normal_quad<true>(a.seed, gp, (uint32_t)m, 0u, sh_tab, z);
 #pragma unroll
@@ -283,6 +295,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
                 for (int k = 0; k < 4; ++k) pv[j][k] = v[j][k];
             }
         }
+        if (!valid) continue;
         // values of the last group that opened a sector the row does not complete in a full group
         if (ngroups > 0) {
 #pragma unroll

@@ -39,7 +39,7 @@ template <int SCHEME, int PROJ>
 static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
     auto kernel = k_traj<M, SCHEME, PROJ>;
-    const size_t smem = ICDF_HOT_TABLE_BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    const size_t smem = ICDF_HOT_TABLE_BYTES + sizeof(double2) * TRAJ_CHUNK + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + TRAJ_THREADS - 1) / TRAJ_THREADS;
     const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TRAJ_THREADS, smem, c.sm_count, work);
     const int vec_ok = (reinterpret_cast<uintptr_t>(a.X) & 31) == 0;

@@ -78,13 +78,22 @@ __global__ void __launch_bounds__(INT_THREADS) k_integral(const IntegralArgs q, 
             if (MODE == 0 && q.r) q.r[base + s + 1] = orr;
             if (MODE == 0 && q.c) q.c[base + s + 1] = oc;
         }
+        double na[4], nb[4];                                     // next sectors, in flight while this group is summed
+        if (ngroups > 0) {
+            ld_sector(pa + s + 1, na);
+            if (pb != pa) ld_sector(pb + s + 1, nb);
+        }
         for (uint64_t m = 0; m < ngroups; ++m, s += 4) {
             double va[4], vb[4], vl[4], vr[4], vc[4];
-            ld_sector(pa + s + 1, va);
-            if (pb != pa) ld_sector(pb + s + 1, vb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { va[k] = na[k]; vb[k] = pb != pa ? nb[k] : na[k]; }
+            if (m + 1 < ngroups) {
+                ld_sector(pa + s + 5, na);
+                if (pb != pa) ld_sector(pb + s + 5, nb);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                element(va[k], pb != pa ? vb[k] : va[k]);
+                element(va[k], vb[k]);
                 vl[k] = ol; vr[k] = orr; vc[k] = oc;
             }
             if (q.l) st_sector(q.l + base + s + 1, vl);
