@@ -117,7 +117,7 @@ def run_reference(args):
 def workload_config(args):
     return {"workload": f"C2 CIR heun() {args.paths:.0e} paths x {args.nsteps} steps per GPU, fused Philox increments, "
                         "terminal 256-bin histogram + power sums",
-            "model": "cir", "scheme": "heun", "projection": "abs", "paths_per_gpu": args.paths, "nsteps": args.nsteps,
+            "sde": "cir", "scheme": "heun", "projection": "abs", "paths_per_gpu": args.paths, "nsteps": args.nsteps,
             "params": {"lambda": CIR["lam"], "xi": CIR["xi"], "gamma": CIR["gamma"], "x0": CIR["x0"], "T": CIR["T"]},
             "flops_per_path_step": FLOPS_PER_PATH_STEP,
             "l2": "no HBM-resident input (state in registers); 256 MiB L2 flush written between timed passes",
@@ -228,12 +228,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(16 * nsteps + 8 * 5),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((16 + 48) * nsteps + 8 * 5),
                     "d2h_bytes_per_step": int(8 * (nb + 3) + 8 * 5), "steps": e2e_steps,
                     "api": "sdetools_b200.heun(f, g, times, x0, p=abs, npaths=..., hist=..., moments=True) with host buffers"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None,
+                         "traffic": 607232, "traffic_source": "ncu --set full dram__bytes_read+write per launch "
+                                                              "(profiles/r1_ncu_k_terminal_cir_heun.txt): tables only, no path data",
                          "kernel": "k_terminal<cir,heun,abs>", "kernel_ms": k_ms,
                          "peak_source": "sdegpu_measure_fp64_peak: DFMA stream measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_convention": "85 algorithmic FP64 flops per path-step (SURVEY.md §8d)",
