@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 // first/last partial sector of a row is written element by element.
 constexpr int TRAJ_CHUNK = 1024;    // steps of the {dt, sqrt dt} table staged in shared memory at a time (16 KB)
 #ifndef SDEGPU_TRAJ_THREADS
-#define SDEGPU_TRAJ_THREADS 512
+#define SDEGPU_TRAJ_THREADS 256     // tuned on the device: 128: 2.85, 192: 3.5, 256: 4.6, 320: 4.35, 384: 4.3, 512: 4.15 TB/s (C3)
 #endif
 constexpr int TRAJ_THREADS = SDEGPU_TRAJ_THREADS;
 

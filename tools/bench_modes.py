@@ -18,6 +18,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--c3-paths", type=int, default=0, help="override the C3 path count (tuning runs)")
+    ap.add_argument("--c3b-paths", type=int, default=0, help="override the supplied-B path count (tuning runs)")
     args = ap.parse_args()
     import torch
     import sdetools_b200 as sde
@@ -42,7 +44,7 @@ def main():
     if want("c3"):
         # two full waves of the trajectory kernel (one 512-thread CTA per SM): equal-length paths cannot fill a
         # partial wave, so sizes that are not a multiple of 148*512 lose the remainder (2^17 paths: 86 %)
-        P = (1 << 15) if args.quick else 2 * eng.info["sm_count"] * 512
+        P = (1 << 15) if args.quick else (args.c3_paths or 2 * eng.info["sm_count"] * 512)
         nt = 10001
         t = np.arange(nt) * 0.01
         X = torch.empty(P * 2 * nt, dtype=torch.float64, device=dev)
@@ -53,7 +55,7 @@ def main():
         chk = X.view(P, 2, nt)[:4, :, :3].cpu().numpy().tolist()
         emit("c3_check", first=chk[0])
         # supplied-B variant: 8 B read + 16 B written per path-step
-        P2 = (P // 2) if args.quick else eng.info["sm_count"] * 512
+        P2 = (P // 2) if args.quick else (args.c3b_paths or eng.info["sm_count"] * 512)
         B = torch.empty(P2 * nt, dtype=torch.float64, device=dev)
         eng.rvbm(t, P2, B, seed=9)
         X2 = X[: P2 * 2 * nt]
