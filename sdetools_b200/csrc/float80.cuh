@@ -177,4 +177,81 @@ SDEGPU_HD double f80_to_double(const F80 &acc)
     return f80_bitsd(sbit | bits);
 }
 
+
+// ---- floating-point fast path ------------------------------------------------------------------
+// The same accumulator as a pair of doubles: S = h + l with h = RN53(S), so that (double)S — what
+// cumsum stores — is h itself.  S has a 64-bit significand, hence l (at most 11 bits) is exact.
+// S' = RN64(S + x) is formed without integer arithmetic on the significand:
+//   three TwoSums give V = S + x = a + b + c exactly (|b| <= ulp(a)/2, |c| <= ulp(b)/2);
+//   the 64-bit grid q = 2^(e-63) follows from a's exponent (one binade lower when a is a power of
+//   two and the remainder points back towards zero); b is rounded to that grid, ties to even, with
+//   the add-and-subtract constant 1.5 * 2^52 * q, c only ever deciding an exact tie;
+//   S' = a + r is split back into (h, l) by FastTwoSum.
+// Every operation is an individually rounded IEEE add/subtract (no products, nothing to contract).
+// Returns false — state untouched — when the case is left to the integer path: non-finite values,
+// magnitudes whose 64-bit grid or sum leaves the double range (|.| < 2^-895 or >= 2^992).
+// tests/native/float80_check.cpp compares it with f80_add and with the x87 FPU.
+#ifndef SDEGPU_F80P_COUNT
+#define SDEGPU_F80P_COUNT(k)          // host test hook: counts tie-broken / lower-binade / exact-tie cases
+#endif
+
+SDEGPU_HD void f80p_two_sum(double x, double y, double &s, double &e)
+{
+    s = x + y;
+    const double t = s - x;
+    e = (x - (s - t)) + (y - t);
+}
+
+SDEGPU_HD bool f80p_add(double &h, double &l, double x)
+{
+    const uint64_t xb = f80_dbits(x), hb = f80_dbits(h);
+    const uint32_t xe = (uint32_t)(xb >> 52) & 0x7FFu, he = (uint32_t)(hb >> 52) & 0x7FFu;
+    if (xe >= 0x7DFu || he >= 0x7DFu) return false;            // Inf/NaN, or close enough to overflow a TwoSum
+    if ((xb << 1) == 0) {                                      // x = +-0: only the sign of a zero sum can change
+        if ((hb << 1) == 0) h = h + x;
+        return true;
+    }
+    double s1, e1, s2, e2, a, b0, b, c;
+    f80p_two_sum(h, x, s1, e1);
+    f80p_two_sum(e1, l, s2, e2);
+    f80p_two_sum(s1, s2, a, b0);
+    f80p_two_sum(b0, e2, b, c);
+    const uint64_t ab = f80_dbits(a);
+    const uint32_t ae = (uint32_t)(ab >> 52) & 0x7FFu;
+    if ((ab << 1) == 0) {                                      // exact cancellation: +0 in round-to-nearest
+        if (b != 0.0 || c != 0.0) return false;
+        h = 0.0; l = 0.0;
+        return true;
+    }
+    if (ae < 0x080u) return false;                             // 64-bit grid would leave the double range
+    const bool pow2 = (ab & 0x000FFFFFFFFFFFFFull) == 0;
+    const bool back = pow2 && b != 0.0 && ((f80_dbits(b) ^ ab) >> 63) != 0;   // V lies in the binade below a
+    const uint64_t qe = (uint64_t)ae - 63u - (back ? 1u : 0u);  // biased exponent of the grid q = ulp64(V)
+    const double half_q = f80_bitsd((qe - 1u) << 52);
+    const double C = f80_bitsd(((qe + 52u) << 52) | 0x0008000000000000ull);   // 1.5 * 2^52 * q
+    double r = (b + C) - C;                                    // b to a multiple of q, ties to even
+    const double d = b - r;                                    // exact
+    if (c != 0.0 && (d == half_q || d == -half_q)) {           // b sat on a tie and c breaks it
+        if ((d > 0.0) == (c > 0.0)) r = r + (d + d);
+        SDEGPU_F80P_COUNT(0);
+    }
+    if (back) SDEGPU_F80P_COUNT(1);
+    if (c == 0.0 && (d == half_q || d == -half_q)) SDEGPU_F80P_COUNT(2);
+    const double hn = a + r;                                   // FastTwoSum, |a| >= |r|
+    l = r - (hn - a);
+    h = hn;
+    return true;
+}
+
+// S = h + l as an F80 (both conversions and the add are exact: S has 64 significant bits)
+SDEGPU_HD F80 f80_from_pair(double h, double l)
+{
+    F80 acc = f80_zero();
+    const uint64_t hb = f80_dbits(h);
+    if (((hb >> 52) & 0x7FF) == 0x7FF) { acc.special = 1; acc.sp = h; return acc; }
+    f80_from_double(h, acc.mant, acc.exp, acc.sign);
+    if (l != 0.0) f80_add(acc, l);
+    return acc;
+}
+
 }  // namespace sdegpu

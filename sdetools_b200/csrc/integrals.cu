@@ -6,8 +6,8 @@
 // plus rvBM (R/sdetools.R:16-22,40-46) whose B0+cumsum(dB) uses the same accumulator.
 //
 // A prefix sum with R's rounding is a strict recurrence per column, so the
-// parallel axis is the column (= path): one thread per column, 80-bit
-// accumulator in registers (float80.cuh).
+// parallel axis is the column (= path): one thread per column, the 80-bit
+// accumulator in registers as a pair of doubles (float80.cuh).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -20,6 +20,30 @@ constexpr int IT_COLS = 128;     // columns (= threads) per block in k_rvbm
 constexpr int IT_STEPS = 32;     // increments staged per tile in k_rvbm
 constexpr int IT_LD = IT_STEPS + 1;
 constexpr int INT_THREADS = 256;
+
+// R's cumsum accumulator on the device: the floating-point pair of float80.cuh while the column stays in
+// its range (always, for data that is not within 2^-895 of underflow or 2^992 of overflow), the integer
+// emulation — out of line, its state in local memory — from the first element that is not, for the rest of
+// the column.  add() returns (double)sum, the value cumsum stores.
+__device__ __noinline__ double f80_slow_add(F80 *big, bool first, double h, double l, double x)
+{
+    if (first) *big = f80_from_pair(h, l);
+    f80_add(*big, x);
+    return f80_to_double(*big);
+}
+
+struct CumsumAcc {
+    double h = 0.0, l = 0.0;
+    bool slow = false;
+    F80 big;
+    __device__ __forceinline__ double add(double x)
+    {
+        if (!slow && f80p_add(h, l, x)) return h;
+        const double out = f80_slow_add(&big, !slow, h, l, x);
+        slow = true;
+        return out;
+    }
+};
 
 struct IntegralArgs {
     const double *a, *b;         // stochint: f, g       crossvar: X, Y
@@ -48,7 +72,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_integral(const IntegralArgs q, 
     for (uint64_t col = (uint64_t)blockIdx.x * INT_THREADS + threadIdx.x; col < q.ncols; col += stride) {
         const uint64_t base = col * q.n;
         const double *pa = q.a + base, *pb = q.b + base;
-        F80 accl = f80_zero(), accr = f80_zero();
+        CumsumAcc accl, accr;
         if (q.l) q.l[base] = 0.0;                                // c(0, ...)
         if (MODE == 0 && q.r) q.r[base] = 0.0;
         if (MODE == 0 && q.c) q.c[base] = 0.0;
@@ -60,14 +84,11 @@ __global__ void __launch_bounds__(INT_THREADS) k_integral(const IntegralArgs q, 
         auto element = [&](double a1, double b1) {               // consumes (a0,b0)->(a1,b1), produces out[s+1]
             if (MODE == 0) {
                 const double dg = __dsub_rn(b1, b0);
-                if (need_l) f80_add(accl, __dmul_rn(a0, dg));
-                if (need_r) f80_add(accr, __dmul_rn(a1, dg));
-                ol = f80_to_double(accl);
-                orr = f80_to_double(accr);
+                ol = need_l ? accl.add(__dmul_rn(a0, dg)) : 0.0;
+                orr = need_r ? accr.add(__dmul_rn(a1, dg)) : 0.0;
                 oc = __dmul_rn(0.5, __dadd_rn(ol, orr));
             } else {
-                f80_add(accl, __dmul_rn(__dsub_rn(a1, a0), __dsub_rn(b1, b0)));
-                ol = f80_to_double(accl);
+                ol = accl.add(__dmul_rn(__dsub_rn(a1, a0), __dsub_rn(b1, b0)));
             }
             a0 = a1; b0 = b1;
         };
@@ -151,7 +172,7 @@ __global__ void __launch_bounds__(IT_COLS) k_rvbm(const BMArgs q)
         const uint64_t c0 = tile * IT_COLS, col = c0 + tid;
         const bool valid = col < q.ncols;
         const int rows = (int)((q.ncols - c0 < (uint64_t)IT_COLS) ? (q.ncols - c0) : IT_COLS);
-        F80 acc = f80_zero();
+        CumsumAcc acc;
         double zq[4] = {0.0, 0.0, 0.0, 0.0};
         for (int i0 = 0; i0 < q.nt; i0 += IT_STEPS) {
             const int nc = (q.nt - i0 < IT_STEPS) ? (q.nt - i0) : IT_STEPS;
@@ -164,8 +185,7 @@ __global__ void __launch_bounds__(IT_COLS) k_rvbm(const BMArgs q)
                     const double z = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
                     // rnorm(mean=u*dt, sd=sigma*sqrt(dt)) = mean + sd*Z
                     const double dB = __dadd_rn(__dmul_rn(q.u, d.x), __dmul_rn(__dmul_rn(q.sigma, d.y), z));
-                    f80_add(acc, dB);
-                    sm[tid * IT_LD + k] = __dadd_rn(q.B0, f80_to_double(acc));
+                    sm[tid * IT_LD + k] = __dadd_rn(q.B0, acc.add(dB));
                 }
             }
             __syncthreads();

@@ -245,6 +245,58 @@ def test_integrals_edge_cases(sde):
     assert sde.itointegral(G, np.arange(5.0))[-1] == 2.0 ** -59 and np.cumsum(G)[-2] == 0.0
 
 
+def test_cumsum_accumulator_adversarial_columns(sde):
+    """The accumulator's floating-point fast path and its integer fallback (float80.cuh) on columns built to
+    hit exact 64-bit ties, sums just below powers of two, cancellation, subnormals, near-overflow and
+    Inf/NaN — against numpy's long double cumsum (the x87 FPU), bit for bit.  G*dB with B = 0,1,2,.. is G."""
+    rng = np.random.default_rng(80)
+    n = 600
+    cols = []
+    for kind in range(12):
+        v = rng.standard_normal(n)
+        if kind == 1: v = np.ldexp(v, rng.integers(-60, 60, n))
+        if kind == 2: v = np.ldexp(v, rng.integers(-1070, 1000, n))                 # leaves the fast path's range
+        if kind == 3: v[1::2] = -v[0::2] * (1 + 2.0 ** -52 * rng.integers(0, 9, n // 2))
+        if kind == 4: v = np.ldexp(rng.integers(1, 2 ** 53, n).astype(float), rng.integers(-113, 7, n)) * rng.choice([-1, 1], n)
+        if kind == 5: v = np.where(rng.random(n) < 0.2, rng.choice([0.0, -0.0], n), np.ldexp(1.0, rng.integers(-60, 60, n)))
+        if kind == 6: v = np.ldexp(1.0, -(np.arange(n) % 120)) * np.where(np.arange(n) % 3, 1.0, -1.0)
+        if kind == 7: v = v * v * 1e-4
+        if kind == 8:                                                                # ties of the running sum, broken or not
+            cur = np.longdouble(0)
+            for i in range(n):
+                if i % 3 == 0 or cur == 0:
+                    x = float(np.ldexp(float(rng.integers(1, 2 ** 53) | 1), int(rng.integers(-70, -30))))
+                else:
+                    e = int(np.frexp(np.float64(cur))[1])
+                    x = float(np.ldexp(1.0, e - 65)) * float(2 * rng.integers(0, 9) - 7)
+                    x += [0.0, 1.0, -1.0][int(rng.integers(0, 3))] * float(np.ldexp(1.0, e - 65 - 20 - int(rng.integers(0, 30))))
+                v[i] = x
+                cur = cur + np.longdouble(x)
+        if kind == 9:                                                                # crossing powers of two
+            cur = np.longdouble(0)
+            for i in range(n):
+                if i % 4 == 0 or cur == 0:
+                    x = float(np.ldexp(1.0 + float(rng.integers(0, 4096)) * 2.0 ** -52, int(rng.integers(-20, 20))))
+                else:
+                    e = int(np.frexp(np.float64(cur))[1])
+                    p2 = np.ldexp(np.longdouble(1), e - 1 + int(rng.integers(0, 2)))
+                    tgt = (-p2 if cur < 0 else p2) + np.ldexp(np.longdouble(int(rng.integers(-3, 4))), e - 66 + int(rng.integers(0, 3)))
+                    x = float(tgt - cur)
+                v[i] = x
+                cur = cur + np.longdouble(x)
+        if kind == 10: v[[50, 300]] = [np.inf, -np.inf]
+        if kind == 11: v = np.concatenate(([5e-324, 5e-324, -5e-324, 1e308, 1e308, 1e308, -1e308, 4.9e-324], v[8:]))
+        cols.append(v)
+    G = np.stack(cols, axis=1)                                   # (n, 12)
+    G = np.concatenate([G, np.zeros((1, G.shape[1]))])           # itointegral uses G[:-1]
+    Bt = np.repeat(np.arange(n + 1.0)[:, None], G.shape[1], axis=1)
+    with np.errstate(all="ignore"):
+        got = sde.itointegral(G, Bt)
+        want = np.stack([O.itointegral(G[:, c], Bt[:, c]) for c in range(G.shape[1])], axis=1)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.isinf(want[:, 2]).any() or np.abs(want[:, 2]).max() > 1e290          # the wide column did leave the fast range
+
+
 def test_vignette_identities_on_device(sde):
     """vignettes/ItoIntegrals.Rmd:82-115,143-153 end to end on the GPU path."""
     t, B = brownian(101, 1, 64, 7)
