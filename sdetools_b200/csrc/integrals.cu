@@ -19,7 +19,16 @@ namespace sdegpu {
 constexpr int IT_COLS = 128;     // columns (= threads) per block in k_rvbm
 constexpr int IT_STEPS = 32;     // increments staged per tile in k_rvbm
 constexpr int IT_LD = IT_STEPS + 1;
-constexpr int INT_THREADS = 256;
+#ifndef SDEGPU_INT_THREADS
+#define SDEGPU_INT_THREADS 256
+#endif
+#ifndef SDEGPU_INT_MIN_BLOCKS
+#define SDEGPU_INT_MIN_BLOCKS 1
+#endif
+#ifndef SDEGPU_INT_MAX_BLOCKS_PER_SM
+#define SDEGPU_INT_MAX_BLOCKS_PER_SM 0         // 0: as many as fit
+#endif
+constexpr int INT_THREADS = SDEGPU_INT_THREADS;
 
 // R's cumsum accumulator on the device: the floating-point pair of float80.cuh while the column stays in
 // its range (always, for data that is not within 2^-895 of underflow or 2^992 of overflow), the integer
@@ -64,7 +73,7 @@ __device__ __forceinline__ void st_sector(double *p, const double (&s)[4])
 // elements each) straight between HBM and registers: columns are private to a thread, so there is no
 // shared memory and no barrier.  All arrays have the same shape, hence the same sector phase.
 template <int MODE>              // 0 stochint, 1 cross-variation
-__global__ void __launch_bounds__(INT_THREADS) k_integral(const IntegralArgs q, const int vec_ok)
+__global__ void __launch_bounds__(INT_THREADS, SDEGPU_INT_MIN_BLOCKS) k_integral(const IntegralArgs q, const int vec_ok)
 {
     const uint64_t nsteps = q.n - 1;
     const bool need_l = MODE == 1 || q.l || q.c, need_r = MODE == 0 && (q.r || q.c);
@@ -138,7 +147,9 @@ int launch_integral(int mode, const IntegralArgs &q, int sm_count, cudaStream_t 
     auto k1 = k_integral<1>;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode == 0 ? k0 : k1, INT_THREADS, 0);
-    uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
+    if (per_sm < 1) per_sm = 1;
+    if (SDEGPU_INT_MAX_BLOCKS_PER_SM > 0 && per_sm > SDEGPU_INT_MAX_BLOCKS_PER_SM) per_sm = SDEGPU_INT_MAX_BLOCKS_PER_SM;
+    uint64_t grid = (uint64_t)per_sm * sm_count;
     if (grid > nblk) grid = nblk;
     uintptr_t bits = reinterpret_cast<uintptr_t>(q.a) | reinterpret_cast<uintptr_t>(q.b) | reinterpret_cast<uintptr_t>(q.l) |
                      reinterpret_cast<uintptr_t>(q.r) | reinterpret_cast<uintptr_t>(q.c);
