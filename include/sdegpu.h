@@ -184,6 +184,20 @@ SDEGPU_API int sdegpu_crossvar(sdegpu_ctx *ctx, const double *X, const double *Y
 SDEGPU_API int sdegpu_rvbm(sdegpu_ctx *ctx, const double *times, int32_t nt, uint64_t ncols, double sigma, double B0,
                 double u, uint64_t seed, uint64_t path_offset, double *B, uint32_t flags);
 
+/* Exact transition-law samplers and their recursive use:
+ *   law = SDEGPU_LAW_OU   rOU(n,x0,lambda,xi,sigma,t)                R/sdetools.R:784-791 (ou.parameters :706-712)
+ *   law = SDEGPU_LAW_CIR  rCIR(n,x0,lambda,xi,gamma,t,Stratonovich)  R/sdetools.R:695-702 (cir.parameters :606-617)
+ * params = {lambda, xi, sigma|gamma}.  Draw p starts at x0[p*x0_stride] (x0_stride 0: one shared start, as the
+ * reference's scalar x0) and takes `nsteps` transitions of length t, X_{k+1} ~ law(. | X_k, t)
+ * (vignettes/CoxIngersollRoss.Rmd:76-84; nsteps = 1 is the reference call).  out[p] = final state;
+ * path (optional) [p*(nsteps+1)+i] = state after i transitions.  Randomness is a pure function of
+ * (seed, path_offset+p, transition index); the OU normals are those euler()/heun() hand to the same path
+ * and step under the same seed.  x0, out, path are host pointers unless SDEGPU_DEVICE_PTRS. */
+typedef enum { SDEGPU_LAW_OU = 0, SDEGPU_LAW_CIR = 1 } sdegpu_law;
+SDEGPU_API int sdegpu_rlaw(sdegpu_ctx *ctx, int32_t law, const double params[3], double t, int32_t stratonovich,
+                const double *x0, int64_t x0_stride, uint64_t n, int32_t nsteps, uint64_t seed, uint64_t path_offset,
+                double *out, double *path, uint32_t flags);
+
 /* Generator introspection (tests / known-answer vectors). */
 SDEGPU_API int sdegpu_philox4x32_10(sdegpu_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* z[i*npaths + p] = standard normal handed to step i, channel `channel`, of path path_offset+p (host ptr). */

@@ -39,6 +39,13 @@ def qOU(ps, x0, lam, xi, sigma, t):
     return stats.norm.ppf(ps, m, s)
 
 
+def rOU(n, x0, lam, xi, sigma, t, rng=None, z=None):
+    """R/sdetools.R:784-791: rnorm(n, mean, sd) = mean + sd*Z (z: supplied standard normals)."""
+    m, s = ou_parameters(np.asarray(x0, dtype=float), lam, xi, sigma, t)
+    z = (rng or np.random.default_rng()).standard_normal(n) if z is None else np.asarray(z, dtype=float)
+    return m + s * z
+
+
 # ---- Cox-Ingersoll-Ross ---------------------------------------------------
 def cir_parameters(x0, lam, xi, gamma, t, Stratonovich=False):
     """R/sdetools.R:606-617."""
@@ -73,6 +80,18 @@ def qCIR(ps, x0, lam, xi, gamma, t, Stratonovich=False):
     c, nu, n = cir_parameters(x0, lam, xi, gamma, t, Stratonovich)
     d = stats.chi2(n) if np.isinf(t) else stats.ncx2(n, nu)
     return d.ppf(ps) / 2 / c
+
+
+def rCIR(n, x0, lam, xi, gamma, t, Stratonovich=False, rng=None):
+    """R/sdetools.R:695-702: rchisq(n, df, ncp)/2/c; R's rchisq with ncp is the Poisson mixture
+    rpois(ncp/2) -> rchisq(2 r) + rgamma(df/2, scale 2) (nmath/rnchisq.c), restated with numpy draws."""
+    rng = rng or np.random.default_rng()
+    c, nu, df = cir_parameters(np.broadcast_to(np.asarray(x0, dtype=float), (n,)), lam, xi, gamma, t, Stratonovich)
+    r = rng.poisson(nu / 2).astype(float)
+    chi = np.where(r > 0, 2.0 * rng.standard_gamma(np.maximum(r, 1e-300)), 0.0)
+    if df > 0:
+        chi = chi + 2.0 * rng.standard_gamma(df / 2, n)
+    return chi / 2 / c
 
 
 # ---- linear SDE -----------------------------------------------------------

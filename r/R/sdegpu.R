@@ -108,3 +108,14 @@ CrossVariation <- function(X, Y) .Call(C_sdegpu_crossvar, X + 0, Y + 0)
 
 rvBM.gpu <- function(times, n = 1, sigma = 1, B0 = 0, u = 0, seed = NULL)
   .Call(C_sdegpu_rvbm, as.numeric(times), as.integer(n), sigma, B0, u, if (is.null(seed)) list() else list(seed = seed))
+
+## Exact transition-law samplers on the device.  Like rvBM.gpu they keep their own names: the draws come
+## from Philox, not from R's stream, so they are the same law as rOU/rCIR (R/sdetools.R:784-791, :695-702)
+## but not the same numbers.  steps > 1: X_{k+1} ~ law(. | X_k, t), the vignette's recursive sampling.
+rOU.gpu <- function(n, x0, lambda, xi, sigma, t, steps = 1, seed = NULL)
+  .Call(C_sdegpu_rlaw, 0L, as.integer(n), as.numeric(x0), c(lambda, xi, sigma), t,
+        c(list(steps = steps), if (is.null(seed)) list() else list(seed = seed)))
+
+rCIR.gpu <- function(n, x0, lambda, xi, gamma, t, Stratonovich = FALSE, steps = 1, seed = NULL)
+  .Call(C_sdegpu_rlaw, 1L, as.integer(n), as.numeric(x0), c(lambda, xi, gamma), t,
+        c(list(steps = steps, stratonovich = as.numeric(Stratonovich)), if (is.null(seed)) list() else list(seed = seed)))

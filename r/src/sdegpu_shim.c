@@ -239,6 +239,27 @@ SEXP C_sdegpu_rvbm(SEXP times, SEXP n, SEXP sigma, SEXP B0, SEXP u, SEXP opts)
     return res;
 }
 
+/* rOU(n,x0,lambda,xi,sigma,t) R/sdetools.R:784-791 and rCIR(n,x0,lambda,xi,gamma,t,Stratonovich) :695-702;
+ * x0 is recycled to length n as R's rnorm/rchisq recycle their parameters; opts$steps > 1 applies the
+ * transition repeatedly (vignettes/CoxIngersollRoss.Rmd:76-84). */
+SEXP C_sdegpu_rlaw(SEXP law, SEXP n, SEXP x0, SEXP params, SEXP t, SEXP opts)
+{
+    const int nn = Rf_asInteger(n);
+    const R_xlen_t nx0 = XLENGTH(x0);
+    if (nn < 0 || nx0 < 1 || XLENGTH(params) != 3) Rf_error("sdegpu_rlaw: bad arguments");
+    SEXP res = PROTECT(Rf_allocVector(REALSXP, nn));
+    SEXP start = PROTECT(Rf_allocVector(REALSXP, nn > 0 ? nn : 1));
+    for (int i = 0; i < nn; ++i) REAL(start)[i] = REAL(x0)[i % nx0];
+    if (sdegpu_rlaw(ctx(), Rf_asInteger(law), REAL(params), Rf_asReal(t), (int)opt_real(opts, "stratonovich", 0), REAL(start),
+                    nx0 == 1 ? 0 : 1, (uint64_t)nn, (int)opt_real(opts, "steps", 1), seed_from(opts),
+                    (uint64_t)opt_real(opts, "path_offset", 0), REAL(res), NULL, 0) != SDEGPU_OK) {
+        UNPROTECT(2);
+        Rf_error("sdegpu_rlaw: %s", sdegpu_last_error());
+    }
+    UNPROTECT(2);
+    return res;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_sdegpu_run", (DL_FUNC)&C_sdegpu_run, 7},
     {"C_sdegpu_stochint", (DL_FUNC)&C_sdegpu_stochint, 3},
@@ -246,6 +267,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_sdegpu_qv", (DL_FUNC)&C_sdegpu_qv, 1},
     {"C_sdegpu_crossvar", (DL_FUNC)&C_sdegpu_crossvar, 2},
     {"C_sdegpu_rvbm", (DL_FUNC)&C_sdegpu_rvbm, 6},
+    {"C_sdegpu_rlaw", (DL_FUNC)&C_sdegpu_rlaw, 6},
     {NULL, NULL, 0}};
 
 void R_init_SDEtools(DllInfo *dll)

@@ -6,8 +6,8 @@ and an sm_100 GPU every compute call raises.
 """
 from . import catalogue
 from .api import (CrossVariation, QuadraticVariation, euler, heun, itointegral, moments_from_power_sums, rBM,
-                  rBrownianBridge, rvBM, stochint)
+                  rBrownianBridge, rCIR, rOU, rvBM, stochint)
 from .engine import Engine, default_engine
 
 __all__ = ["catalogue", "euler", "heun", "stochint", "itointegral", "QuadraticVariation", "CrossVariation", "rBM",
-           "rvBM", "rBrownianBridge", "Engine", "default_engine", "moments_from_power_sums"]
+           "rvBM", "rBrownianBridge", "rOU", "rCIR", "Engine", "default_engine", "moments_from_power_sums"]

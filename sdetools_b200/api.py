@@ -221,6 +221,30 @@ def rvBM(times, n=1, sigma=1.0, B0=0.0, u=0.0, *, seed=None, device=None, path_o
     return out
 
 
+def _rlaw(law, n, x0, params, t, stratonovich, steps, path, seed, device, path_offset):
+    if seed is None:
+        seed = int(np.random.default_rng().integers(0, 2 ** 63))
+    n = int(n)
+    out = np.empty(n)
+    traj = np.empty((steps + 1, n), order="F") if path else None
+    default_engine(device).rlaw(law, params, t, x0, n, out, nsteps=steps, path=traj, stratonovich=stratonovich, seed=seed,
+                                path_offset=path_offset)
+    return traj if path else out
+
+
+def rOU(n, x0, lam, xi, sigma, t, *, steps=1, path=False, seed=None, device=None, path_offset=0):
+    """R/sdetools.R:784-791: n draws of X_t | X_0 = x0 for dX = lambda (xi - X) dt + sigma dB.
+    `steps` > 1 applies the transition repeatedly (X_{k+1} ~ law(. | X_k, t)); `path=True` returns the
+    (steps+1) x n states.  The normals are the ones euler()/heun() give the same path and step under `seed`."""
+    return _rlaw("ou", n, x0, (lam, xi, sigma), t, False, steps, path, seed, device, path_offset)
+
+
+def rCIR(n, x0, lam, xi, gamma, t, Stratonovich=False, *, steps=1, path=False, seed=None, device=None, path_offset=0):
+    """R/sdetools.R:695-702: n draws of X_t | X_0 = x0 for dX = lambda (xi - X) dt + gamma sqrt(X) dB, a scaled
+    non-central chi-square.  `steps`/`path` as in rOU: the recursive sampling of vignettes/CoxIngersollRoss.Rmd:76-84."""
+    return _rlaw("cir", n, x0, (lam, xi, gamma), t, Stratonovich, steps, path, seed, device, path_offset)
+
+
 def rBM(times, sigma=1.0, B0=0.0, u=0.0, *, seed=None, device=None):
     """R/sdetools.R:16-22."""
     return rvBM(times, 1, sigma, B0, u, seed=seed, device=device)[:, 0]

@@ -12,6 +12,7 @@
 #define ICDF_TABLE_DEFINE __device__ const unsigned long long g_icdf_table
 #include "../../include/sdegpu.h"
 #include "ensemble.cuh"
+#include "laws.cuh"
 #include "linear.cuh"
 
 namespace sdegpu {
@@ -512,6 +513,61 @@ int sdegpu_rvbm(sdegpu_ctx *c, const double *times, int32_t nt, uint64_t ncols, 
     if (e) return fail(SDEGPU_ERR_CUDA, "sdegpu_rvbm: kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     if (!dev) {
         CU(cudaMemcpyAsync(B, q.B, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return SDEGPU_OK;
+}
+
+int sdegpu_rlaw(sdegpu_ctx *c, int32_t law, const double params[3], double t, int32_t stratonovich, const double *x0,
+                int64_t x0_stride, uint64_t n, int32_t nsteps, uint64_t seed, uint64_t path_offset, double *out, double *path,
+                uint32_t flags)
+{
+    if (!c || !params || !x0 || !out) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: NULL argument");
+    if (law != SDEGPU_LAW_OU && law != SDEGPU_LAW_CIR) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: unknown law %d", law);
+    if (nsteps < 0 || x0_stride < 0) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: nsteps and x0_stride must be >= 0");
+    if (!(t >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: t must be >= 0");
+    const double lambda = params[0], xi = params[1], s = params[2];
+    if (!(s >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: noise intensity must be >= 0");
+    if (law == SDEGPU_LAW_CIR && (!(lambda > 0) || !(s > 0) || !(t > 0)))
+        return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: CIR needs lambda > 0, gamma > 0, t > 0");
+    if (n == 0) return SDEGPU_OK;
+    CU(cudaSetDevice(c->device));
+    const bool dev = (flags & SDEGPU_DEVICE_PTRS) != 0;
+    LawArgs q;
+    q.icdf = c->icdf; q.n = n; q.path_offset = path_offset; q.seed = make_philox_key(seed); q.law = law; q.nsteps = nsteps;
+    q.decay = exp(-lambda * t);                                  // ou.parameters :708 / cir.parameters :613-614
+    q.xi = xi;
+    q.sd = lambda == 0 ? s * sqrt(t) : s * sqrt((1 - exp(-2 * lambda * t)) / 2 / lambda);            // :709
+    const double xi_ito = stratonovich ? xi + s * s / 4 / lambda : xi;                                 // :610
+    q.two_c = law == SDEGPU_LAW_CIR ? 2 * (2 * lambda / (s * s) / (1 - q.decay)) : 1.0;             // :613
+    q.df = law == SDEGPU_LAW_CIR ? 4 * lambda * xi_ito / (s * s) : 0.0;                               // :615
+    if (law == SDEGPU_LAW_CIR && !(q.df >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: CIR needs xi >= 0");
+    const size_t out_bytes = sizeof(double) * n, path_bytes = path ? sizeof(double) * n * ((size_t)nsteps + 1) : 0;
+    q.x0 = nullptr; q.x0s = 0.0; q.x0_stride = (uint64_t)x0_stride;
+    if (x0_stride == 0) {
+        if (dev) {
+            CU(cudaMemcpyAsync(&q.x0s, x0, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        } else q.x0s = x0[0];
+    } else if (dev) q.x0 = x0;
+    else {
+        const size_t bytes = sizeof(double) * ((n - 1) * (size_t)x0_stride + 1);
+        CU(c->in0.reserve(bytes));
+        CU(cudaMemcpyAsync(c->in0.p, x0, bytes, cudaMemcpyHostToDevice, c->stream));
+        q.x0 = (const double *)c->in0.p;
+    }
+    if (dev) { q.out = out; q.path = path; }
+    else {
+        CU(c->out0.reserve(out_bytes));
+        q.out = (double *)c->out0.p;
+        q.path = nullptr;
+        if (path) { CU(c->out1.reserve(path_bytes)); q.path = (double *)c->out1.p; }
+    }
+    int e = launch_rlaw(q, c->prop.multiProcessorCount, c->stream);
+    if (e) return fail(SDEGPU_ERR_CUDA, "sdegpu_rlaw: kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+    if (!dev) {
+        CU(cudaMemcpyAsync(out, q.out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (path) CU(cudaMemcpyAsync(path, q.path, path_bytes, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     }
     return SDEGPU_OK;

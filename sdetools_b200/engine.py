@@ -147,6 +147,20 @@ class Engine:
         check(self.lib.sdegpu_rvbm(self._h, _ptr(times), int(times.size), int(ncols), float(sigma), float(B0), float(u),
                                    int(seed) & 0xFFFFFFFFFFFFFFFF, int(path_offset), _ptr(out), self._flags(out)))
 
+    def rlaw(self, law, params, t, x0, n, out, nsteps=1, path=None, stratonovich=False, seed=0, path_offset=0):
+        """Exact-law sampler (sdegpu_rlaw): law "ou" | "cir", params = (lambda, xi, sigma|gamma); x0 scalar or one per draw."""
+        p = (C.c_double * 3)(*[float(v) for v in params])
+        if _is_torch(x0):
+            stride = 0 if x0.numel() == 1 else 1
+        else:
+            x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+            stride = 0 if x0.size == 1 else 1
+            if stride and x0.size != n:
+                raise ValueError("x0 must be a scalar or have one entry per draw")
+        check(self.lib.sdegpu_rlaw(self._h, {"ou": 0, "cir": 1}[law], p, float(t), int(bool(stratonovich)), _ptr(x0), stride, int(n),
+                                   int(nsteps), int(seed) & 0xFFFFFFFFFFFFFFFF, int(path_offset), _ptr(out), _ptr(path),
+                                   self._flags(x0, out, path)))
+
     # -- introspection ------------------------------------------------------------
     def philox4x32_10(self, ctr, key):
         a = (C.c_uint32 * 4)(*ctr)

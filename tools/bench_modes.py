@@ -114,6 +114,35 @@ def main():
         del f, g, l, r, c
         torch.cuda.empty_cache()
 
+    # next-2: exact transition-law samplers, device-resident output (draws = transitions)
+    if want("laws"):
+        n = (1 << 20) if args.quick else 1 << 24
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        x0 = torch.full((1,), 1.0, dtype=torch.float64, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.use_torch_stream()
+
+        def timed_law(fn):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(3):
+                ev0.record()
+                fn()
+                ev1.record()
+                torch.cuda.synchronize()
+                best = min(best, ev0.elapsed_time(ev1))
+            return best
+        for name, law, params, t, steps in (("rOU_100_transitions", "ou", (1.3, 0.7, 0.9), 0.01, 100),
+                                             ("rCIR_df4_t0.5", "cir", (1.0, 1.0, 1.0), 0.5, 10),
+                                             ("rCIR_df4_dt1e-3_ptrs", "cir", (1.0, 1.0, 1.0), 1e-3, 10),
+                                             ("rCIR_df0.18", "cir", (0.5, 0.2, 1.5), 1.0, 10)):
+            ms = timed_law(lambda: eng.rlaw(law, params, t, x0, n, out, nsteps=steps, seed=1))
+            emit(name, draws=n, transitions=steps, ms=ms, transitions_per_s=n * steps / ms * 1e3)
+        eng.use_own_stream()
+        del out
+        torch.cuda.empty_cache()
+
     # C4: linear SDE d = 256 (A x as a GEMM over paths); 2d^2+4d flops per path-step
     if want("c4"):
         d = 256
