@@ -8,6 +8,7 @@ from . import catalogue
 from .api import (CrossVariation, QuadraticVariation, euler, heun, itointegral, moments_from_power_sums, rBM,
                   rBrownianBridge, rCIR, rOU, rvBM, stochint)
 from .engine import Engine, default_engine
+from .laws import dLinSDE, linear_exact, lyap
 
 __all__ = ["catalogue", "euler", "heun", "stochint", "itointegral", "QuadraticVariation", "CrossVariation", "rBM",
-           "rvBM", "rBrownianBridge", "rOU", "rCIR", "Engine", "default_engine", "moments_from_power_sums"]
+           "rvBM", "rBrownianBridge", "rOU", "rCIR", "dLinSDE", "lyap", "linear_exact", "Engine", "default_engine", "moments_from_power_sums"]

@@ -28,6 +28,49 @@ def test_oracle_rCIR_follows_pCIR(lam, xi, gam, t, x0, strat):
     assert ks.pvalue > 1e-3, ks
 
 
+# ---- CPU: host-side dLinSDE / lyap of the product (O(d^3)) against the oracle's restatement of the reference ----
+def test_product_dLinSDE_reproduces_reference_known_answers_and_oracle():
+    from sdetools_b200 import laws as P                      # host logic: importable without the GPU library
+    tol = 1.5e-8
+    sol = P.dLinSDE(-1, 1, 1, S0=0.5)                        # tests/testthat/test_solvers.R:20-36
+    assert sol["eAt"].item() == pytest.approx(np.exp(-1), rel=tol) and sol["St"].item() == pytest.approx(0.5, rel=tol)
+    A = np.array([[0.0, 1.0], [-1.0, 0.0]])
+    sol = P.dLinSDE(A, np.eye(2), 2 * np.pi, x0=[1, 0])     # singular Lyapunov equation: Van Loan route
+    assert np.allclose(sol["EX"], [1, 0], atol=tol) and np.allclose(sol["St"], 2 * np.pi * np.eye(2), atol=10 * tol)
+    assert P.dLinSDE(-1, 1, 2, x0=1, u=1)["EX"][0] == pytest.approx(1, rel=tol)
+    assert P.dLinSDE(0, 1, 2, x0=1, u=np.array([[1.0, 3.0]]))["EX"][0] == pytest.approx(5, rel=tol)
+    assert P.lyap(-1, 1).item() == pytest.approx(0.5)       # R/sdetools.R:587-590
+    Ao = np.array([[0.0, 1.0], [-1.0, -0.1]])
+    assert np.allclose(P.lyap(Ao, np.diag([0.0, 1.0])), 5 * np.eye(2))
+    with pytest.raises(np.linalg.LinAlgError):
+        P.lyap(A, np.eye(2))
+    rng = np.random.default_rng(3)
+    for d in (1, 3, 7):
+        Ar = -np.eye(d) + 0.4 * rng.standard_normal((d, d))
+        Gr = rng.standard_normal((d, max(1, d - 1)))
+        S0 = np.diag(rng.uniform(0, 1, d))
+        x0, u1, u2 = rng.standard_normal(d), rng.standard_normal(d), rng.standard_normal((d, 2))
+        for kw in ({}, {"x0": x0}, {"x0": x0, "u": u1}, {"x0": x0, "u": u2}, {"S0": S0}):
+            a, b = P.dLinSDE(Ar, Gr, 0.7, **kw), laws.dLinSDE(Ar, Gr, 0.7, **kw)
+            assert a.keys() == b.keys()
+            for k in a:
+                assert np.allclose(a[k], b[k], rtol=1e-10, atol=1e-12), (d, kw.keys(), k)
+        assert np.allclose(P.lyap(Ar, Gr @ Gr.T), laws.lyap(Ar, Gr @ Gr.T), rtol=1e-10, atol=1e-12)
+
+
+def test_product_dLinSDE_at_d256_matches_closed_form():
+    """C4's matrix: A + A' = -I and A normal, so S_t = sigma^2 (1 - e^{-t}) I — out of reach of the
+    reference's 65536 x 65536 Kronecker solve."""
+    from sdetools_b200 import laws as P
+    d = 256
+    R = np.random.default_rng(256).standard_normal((d, d))
+    A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
+    sol = P.dLinSDE(A, np.eye(d), 1.0)
+    assert np.allclose(sol["St"], (1 - np.exp(-1.0)) * np.eye(d), atol=1e-10)
+    assert np.allclose(sol["eAt"] @ sol["eAt"].T, np.exp(-1.0) * np.eye(d), atol=1e-10)
+    assert np.allclose(P.lyap(A, np.eye(d)), np.eye(d), atol=1e-10)
+
+
 # ---- GPU -----------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def sde(gpu):
@@ -125,3 +168,25 @@ def test_rlaw_argument_errors(sde):
     with pytest.raises(ValueError):
         sde.rOU(10, np.ones(7), 1.0, 1.0, 1.0, 1.0)
     assert sde.rOU(0, 1.0, 1.0, 1.0, 1.0, 1.0).shape == (0,)
+
+
+@pytest.mark.gpu
+def test_linear_exact_stepping_has_no_discretisation_error(sde):
+    """vignettes/NoisyOscillator.Rmd:70-80 as an ensemble: X_{k+1} = e^{A dt} X_k + chol(S_dt) Z on a coarse grid
+    reproduces the law at T exactly, where plain Euler on the same grid is visibly biased."""
+    rng = np.random.default_rng(6)
+    d, n, nsteps, T = 4, 200000, 10, 2.0
+    A = np.array([[-0.2, 1.0, 0, 0], [-1.0, -0.2, 0, 0], [0.3, 0, -0.5, 0.2], [0, 0.1, 0, -1.0]])
+    G = rng.standard_normal((d, 2))
+    x0 = np.array([1.0, 0.0, -1.0, 0.5])
+    t = np.arange(nsteps + 1) * (T / nsteps)
+    want = sde.dLinSDE(A, G, T, x0=x0)
+    fe, ge = sde.linear_exact(A, G, T / nsteps)
+    XT = sde.euler(fe, ge, t, x0, npaths=n, seed=4, output="terminal")["XT"]          # (d, n)
+    se = np.sqrt(np.diag(want["St"]) / n)
+    assert np.all(np.abs(XT.mean(axis=1) - want["EX"]) < 5 * se)
+    C = np.cov(XT)
+    assert np.max(np.abs(C - want["St"])) < 5 * np.max(np.diag(want["St"])) * np.sqrt(2.0 / n)
+    f, g = sde.catalogue.linear(A, G)
+    XE = sde.euler(f, g, t, x0, npaths=n, seed=4, output="terminal")["XT"]
+    assert np.max(np.abs(np.cov(XE) - want["St"])) > 20 * np.max(np.diag(want["St"])) * np.sqrt(2.0 / n)   # dt = 0.2: biased
