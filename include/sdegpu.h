@@ -184,6 +184,16 @@ SDEGPU_API int sdegpu_crossvar(sdegpu_ctx *ctx, const double *X, const double *Y
 SDEGPU_API int sdegpu_rvbm(sdegpu_ctx *ctx, const double *times, int32_t nt, uint64_t ncols, double sigma, double B0,
                 double u, uint64_t seed, uint64_t path_offset, double *B, uint32_t flags);
 
+/* Path functionals of the rvBM ensemble without storing it (apply(rvBM(0:Nt,Np),2,max),
+ * vignettes/BrownianMotion.Rmd:101-144).  Column c is regenerated exactly as sdegpu_rvbm builds it (same
+ * arguments, same seed => same doubles), so each output equals the functional of the stored matrix bit for bit:
+ * vmax/vmin = max/min over the grid, tmax/tmin = times[] of the first maximum/minimum (which.max), thit = first
+ * times[i] with B_i >= level (level >= B0) or B_i <= level (level < B0), NaN if the level is never reached.
+ * Any output may be NULL. */
+SDEGPU_API int sdegpu_bm_functionals(sdegpu_ctx *ctx, const double *times, int32_t nt, uint64_t ncols, double sigma,
+                double B0, double u, double level, uint64_t seed, uint64_t path_offset, double *vmax, double *vmin,
+                double *tmax, double *tmin, double *thit, uint32_t flags);
+
 /* Exact transition-law samplers and their recursive use:
  *   law = SDEGPU_LAW_OU   rOU(n,x0,lambda,xi,sigma,t)                R/sdetools.R:784-791 (ou.parameters :706-712)
  *   law = SDEGPU_LAW_CIR  rCIR(n,x0,lambda,xi,gamma,t,Stratonovich)  R/sdetools.R:695-702 (cir.parameters :606-617)

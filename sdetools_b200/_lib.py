@@ -68,6 +68,8 @@ SYMBOLS = {
     "sdegpu_qv": (C.c_int, [_vp, _vp, _u64, _u64, _vp, _u32]),
     "sdegpu_crossvar": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _vp, _u32]),
     "sdegpu_rvbm": (C.c_int, [_vp, _vp, _i32, _u64, C.c_double, C.c_double, C.c_double, _u64, _u64, _vp, _u32]),
+    "sdegpu_bm_functionals": (C.c_int, [_vp, _vp, _i32, _u64, C.c_double, C.c_double, C.c_double, C.c_double, _u64, _u64,
+                                        _vp, _vp, _vp, _vp, _vp, _u32]),
     "sdegpu_rlaw": (C.c_int, [_vp, _i32, _dp, C.c_double, _i32, _vp, C.c_int64, _u64, _i32, _u64, _u64, _vp, _vp, _u32]),
     "sdegpu_philox4x32_10": (C.c_int, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "sdegpu_normals": (C.c_int, [_vp, _u64, _u64, _u64, _u32, _i32, _vp]),

@@ -245,15 +245,34 @@ def rCIR(n, x0, lam, xi, gamma, t, Stratonovich=False, *, steps=1, path=False, s
     return _rlaw("cir", n, x0, (lam, xi, gamma), t, Stratonovich, steps, path, seed, device, path_offset)
 
 
+def rvBM_functionals(times, n=1, sigma=1.0, B0=0.0, u=0.0, level=None, *, seed=None, device=None, path_offset=0):
+    """max / min / which.max / which.min / first passage of each column of rvBM(times, n, sigma, B0, u) without
+    storing the n paths (vignettes/BrownianMotion.Rmd:101-144: `apply(rvBM(0:Nt,Np),2,max)`).  With the same
+    `seed` the values equal those computed from rvBM()'s matrix bit for bit.  Returns a dict of length-n
+    arrays: max, min, tmax, tmin and, when `level` is given, thit (NaN where the level is not reached)."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    if seed is None:
+        seed = int(np.random.default_rng().integers(0, 2 ** 63))
+    out = {k: np.empty(n) for k in ("max", "min", "tmax", "tmin")}
+    if level is not None:
+        out["thit"] = np.empty(n)
+    default_engine(device).bm_functionals(times, n, sigma, B0, u, 0.0 if level is None else level, seed, path_offset,
+                                          vmax=out["max"], vmin=out["min"], tmax=out["tmax"], tmin=out["tmin"],
+                                          thit=out.get("thit"))
+    return out
+
+
 def rBM(times, sigma=1.0, B0=0.0, u=0.0, *, seed=None, device=None):
     """R/sdetools.R:16-22."""
     return rvBM(times, 1, sigma, B0, u, seed=seed, device=device)[:, 0]
 
 
-def rBrownianBridge(times, B0T=(0.0, 0.0), sigma=1.0, *, seed=None, device=None):
-    """R/sdetools.R:62-73: linear detrending of one rBM path."""
+def rBrownianBridge(times, B0T=(0.0, 0.0), sigma=1.0, *, n=None, seed=None, device=None):
+    """R/sdetools.R:62-73: linear detrending of an rBM path.  `n` gives the nt x n matrix that
+    `replicate(n, rBrownianBridge(...))` builds (vignettes/BrownianMotion.Rmd:78-98), one device ensemble."""
     times = np.asarray(times, dtype=np.float64)
-    B = rBM(times, sigma=sigma, seed=seed, device=device)
-    n = times.size
-    slope = (B0T[1] - B0T[0] - B[n - 1] + B[0]) / (times[n - 1] - times[0])
-    return B + B0T[0] - B[0] + slope * (times - times[0])
+    B = rvBM(times, 1 if n is None else n, sigma=sigma, seed=seed, device=device)
+    nt = times.size
+    slope = (B0T[1] - B0T[0] - B[nt - 1] + B[0]) / (times[nt - 1] - times[0])
+    BB = B + B0T[0] - B[0] + slope * (times - times[0])[:, None]
+    return BB[:, 0] if n is None else BB

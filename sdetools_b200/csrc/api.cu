@@ -39,6 +39,13 @@ struct BMArgs {
     int nt;
 };
 int launch_rvbm(const BMArgs &q, int sm_count, cudaStream_t stream);
+struct BMFuncArgs {
+    BMArgs bm;
+    double level;
+    double *vmax, *vmin, *tmax, *tmin, *thit;
+    const double *times;
+};
+int launch_bm_functionals(const BMFuncArgs &q, int sm_count, cudaStream_t stream);
 }  // namespace sdegpu
 
 using namespace sdegpu;
@@ -515,6 +522,43 @@ int sdegpu_rvbm(sdegpu_ctx *c, const double *times, int32_t nt, uint64_t ncols, 
         CU(cudaMemcpyAsync(B, q.B, bytes, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     }
+    return SDEGPU_OK;
+}
+
+int sdegpu_bm_functionals(sdegpu_ctx *c, const double *times, int32_t nt, uint64_t ncols, double sigma, double B0, double u,
+                           double level, uint64_t seed, uint64_t path_offset, double *vmax, double *vmin, double *tmax,
+                           double *tmin, double *thit, uint32_t flags)
+{
+    if (!c || !times) return fail(SDEGPU_ERR_ARG, "sdegpu_bm_functionals: NULL argument");
+    if (nt < 1) return fail(SDEGPU_ERR_ARG, "sdegpu_bm_functionals: nt must be >= 1");
+    if (ncols == 0) return SDEGPU_OK;
+    if (times[0] < 0) return fail(SDEGPU_ERR_ARG, "sdegpu_bm_functionals: times[0] must be >= 0 (first increment spans [0,times[0]])");
+    for (int i = 0; i + 1 < nt; ++i)
+        if (!(times[i + 1] >= times[i])) return fail(SDEGPU_ERR_ARG, "sdegpu_bm_functionals: times must be non-decreasing (index %d)", i);
+    CU(cudaSetDevice(c->device));
+    const bool dev = (flags & SDEGPU_DEVICE_PTRS) != 0;
+    const double2 *dtsq = nullptr;
+    int rc = upload_dtsq(c, times, nt, true, &dtsq);
+    if (rc) return rc;
+    CU(c->times.reserve(sizeof(double) * (size_t)nt));
+    CU(cudaMemcpyAsync(c->times.p, times, sizeof(double) * (size_t)nt, cudaMemcpyHostToDevice, c->stream));
+    BMFuncArgs q;
+    q.bm.dtsq = dtsq; q.bm.icdf = c->icdf; q.bm.B = nullptr; q.bm.sigma = sigma; q.bm.B0 = B0; q.bm.u = u; q.bm.ncols = ncols;
+    q.bm.path_offset = path_offset; q.bm.seed = make_philox_key(seed); q.bm.nt = nt;
+    q.level = level; q.times = (const double *)c->times.p;
+    double *host[5] = {vmax, vmin, tmax, tmin, thit};
+    double **dst[5] = {&q.vmax, &q.vmin, &q.tmax, &q.tmin, &q.thit};
+    if (dev) for (int k = 0; k < 5; ++k) *dst[k] = host[k];
+    else {
+        CU(c->out0.reserve(sizeof(double) * 5 * ncols));
+        for (int k = 0; k < 5; ++k) *dst[k] = host[k] ? (double *)c->out0.p + (size_t)k * ncols : nullptr;
+    }
+    int e = launch_bm_functionals(q, c->prop.multiProcessorCount, c->stream);
+    if (e) return fail(SDEGPU_ERR_CUDA, "sdegpu_bm_functionals: kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+    if (!dev)
+        for (int k = 0; k < 5; ++k)
+            if (host[k]) CU(cudaMemcpyAsync(host[k], *dst[k], sizeof(double) * ncols, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));                        // the staged `times` is read by the kernel
     return SDEGPU_OK;
 }
 

@@ -221,4 +221,62 @@ int launch_rvbm(const BMArgs &q, int sm_count, cudaStream_t stream)
     return (int)cudaGetLastError();
 }
 
+// ---- path functionals of Brownian ensembles -----------------------------
+// apply(rvBM(times, n), 2, max) and friends (vignettes/BrownianMotion.Rmd:101-144) without storing the paths:
+// column c is regenerated exactly as k_rvbm builds it (same normals, same 80-bit cumsum, same B0 + ...), so
+// every functional is bit-identical to the one computed from the stored rvBM matrix.  One thread per column.
+struct BMFuncArgs {
+    BMArgs bm;                   // bm.B unused
+    double level;                // first passage level
+    double *vmax, *vmin;         // [ncols] max_i B_i, min_i B_i           (any may be null)
+    double *tmax, *tmin;         // [ncols] times[i] of the first maximum / minimum
+    double *thit;                // [ncols] first times[i] with B_i >= level (level >= B0) or <= level (level < B0); NaN: never
+    const double *times;         // device [nt]
+};
+
+__global__ void __launch_bounds__(INT_THREADS) k_bm_functionals(const BMFuncArgs q)
+{
+    extern __shared__ __align__(16) double sh_tab[];
+    icdf_stage(sh_tab, q.bm.icdf, threadIdx.x, INT_THREADS);
+    __syncthreads();
+    const bool up = q.level >= q.bm.B0;
+    const uint64_t stride = (uint64_t)gridDim.x * INT_THREADS;
+    for (uint64_t col = (uint64_t)blockIdx.x * INT_THREADS + threadIdx.x; col < q.bm.ncols; col += stride) {
+        CumsumAcc acc;
+        double zq[4] = {0.0, 0.0, 0.0, 0.0};
+        double vmax = 0.0, vmin = 0.0;
+        int imax = 0, imin = 0, ihit = -1;
+        for (int i = 0; i < q.bm.nt; ++i) {
+            if ((i & 3) == 0) normal_quad(q.bm.seed, q.bm.path_offset + col, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+            const double2 d = __ldg(&q.bm.dtsq[i]);
+            const int s4 = i & 3;
+            const double z = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
+            const double dB = __dadd_rn(__dmul_rn(q.bm.u, d.x), __dmul_rn(__dmul_rn(q.bm.sigma, d.y), z));
+            const double b = __dadd_rn(q.bm.B0, acc.add(dB));
+            if (i == 0 || b > vmax) { vmax = b; imax = i; }      // which.max / which.min: first occurrence
+            if (i == 0 || b < vmin) { vmin = b; imin = i; }
+            if (ihit < 0 && (up ? b >= q.level : b <= q.level)) ihit = i;
+        }
+        if (q.vmax) q.vmax[col] = vmax;
+        if (q.vmin) q.vmin[col] = vmin;
+        if (q.tmax) q.tmax[col] = __ldg(&q.times[imax]);
+        if (q.tmin) q.tmin[col] = __ldg(&q.times[imin]);
+        if (q.thit) q.thit[col] = ihit >= 0 ? __ldg(&q.times[ihit]) : __longlong_as_double(0x7FF8000000000000ll);
+    }
+}
+
+int launch_bm_functionals(const BMFuncArgs &q, int sm_count, cudaStream_t stream)
+{
+    if (q.bm.ncols == 0 || q.bm.nt == 0) return 0;
+    const size_t smem = ICDF_TABLE_BYTES;
+    cudaFuncSetAttribute(k_bm_functionals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bm_functionals, INT_THREADS, smem);
+    uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
+    const uint64_t nblk = (q.bm.ncols + INT_THREADS - 1) / INT_THREADS;
+    if (grid > nblk) grid = nblk;
+    k_bm_functionals<<<(int)grid, INT_THREADS, smem, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace sdegpu

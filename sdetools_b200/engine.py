@@ -147,6 +147,14 @@ class Engine:
         check(self.lib.sdegpu_rvbm(self._h, _ptr(times), int(times.size), int(ncols), float(sigma), float(B0), float(u),
                                    int(seed) & 0xFFFFFFFFFFFFFFFF, int(path_offset), _ptr(out), self._flags(out)))
 
+    def bm_functionals(self, times, ncols, sigma=1.0, B0=0.0, u=0.0, level=0.0, seed=0, path_offset=0, vmax=None, vmin=None,
+                       tmax=None, tmin=None, thit=None):
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        check(self.lib.sdegpu_bm_functionals(self._h, _ptr(times), int(times.size), int(ncols), float(sigma), float(B0), float(u),
+                                             float(level), int(seed) & 0xFFFFFFFFFFFFFFFF, int(path_offset), _ptr(vmax),
+                                             _ptr(vmin), _ptr(tmax), _ptr(tmin), _ptr(thit),
+                                             self._flags(vmax, vmin, tmax, tmin, thit)))
+
     def rlaw(self, law, params, t, x0, n, out, nsteps=1, path=None, stratonovich=False, seed=0, path_offset=0):
         """Exact-law sampler (sdegpu_rlaw): law "ou" | "cir", params = (lambda, xi, sigma|gamma); x0 scalar or one per draw."""
         p = (C.c_double * 3)(*[float(v) for v in params])

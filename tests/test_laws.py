@@ -190,3 +190,53 @@ def test_linear_exact_stepping_has_no_discretisation_error(sde):
     f, g = sde.catalogue.linear(A, G)
     XE = sde.euler(f, g, t, x0, npaths=n, seed=4, output="terminal")["XT"]
     assert np.max(np.abs(np.cov(XE) - want["St"])) > 20 * np.max(np.diag(want["St"])) * np.sqrt(2.0 / n)   # dt = 0.2: biased
+
+
+# ---- next-3: Brownian ensembles and their path functionals -------------------------------------
+@pytest.mark.gpu
+def test_bm_functionals_equal_those_of_the_stored_ensemble(sde):
+    t = np.concatenate(([0.0], np.cumsum(np.random.default_rng(1).uniform(0.01, 0.2, 333))))
+    n, seed = 2000, 17
+    B = sde.rvBM(t, n, sigma=1.3, B0=0.4, u=-0.1, seed=seed, path_offset=5)                   # (nt, n)
+    F = sde.rvBM_functionals(t, n, sigma=1.3, B0=0.4, u=-0.1, level=1.5, seed=seed, path_offset=5)
+    assert np.array_equal(F["max"], B.max(axis=0)) and np.array_equal(F["min"], B.min(axis=0))
+    assert np.array_equal(F["tmax"], t[B.argmax(axis=0)]) and np.array_equal(F["tmin"], t[B.argmin(axis=0)])
+    hit = B >= 1.5
+    want = np.where(hit.any(axis=0), t[hit.argmax(axis=0)], np.nan)
+    assert np.array_equal(F["thit"], want, equal_nan=True) and 0.05 < np.isnan(want).mean() < 0.95
+    down = sde.rvBM_functionals(t, n, sigma=1.3, B0=0.4, u=-0.1, level=-1.0, seed=seed, path_offset=5)["thit"]
+    hit = B <= -1.0
+    assert np.array_equal(down, np.where(hit.any(axis=0), t[hit.argmax(axis=0)], np.nan), equal_nan=True)
+    assert "thit" not in sde.rvBM_functionals(t, 3, seed=1)
+
+
+@pytest.mark.gpu
+def test_maximum_of_brownian_motion_reflection_principle(sde):
+    """vignettes/BrownianMotion.Rmd:101-144: P(S_t >= x) = 2 P(B_t >= x); on a grid the maximum is short by
+    about 0.5826 sqrt(dt) (the vignette's Nt = 10 vs 1000 discussion), which the comparison allows for."""
+    Nt, Np = 4000, 400000
+    t = np.arange(Nt + 1, dtype=float)
+    m = sde.rvBM_functionals(t, Np, seed=23)["max"]
+    assert np.all(m >= 0)                                                       # B_0 = 0 is on the grid
+    shift = 0.5826
+    for x in (0.5, 1.0, 2.0):
+        lvl = x * np.sqrt(Nt)
+        emp = np.mean(m + shift >= lvl)
+        assert abs(emp - 2 * stats.norm.sf(x)) < 4 * np.sqrt(0.25 / Np) + 2e-3
+    coarse = sde.rvBM_functionals(np.arange(11.0), Np, seed=23)["max"]
+    assert np.mean(coarse >= np.sqrt(10.0)) < 2 * stats.norm.sf(1.0) - 0.05    # Nt = 10: visibly too few crossings
+
+
+@pytest.mark.gpu
+def test_brownian_bridge_ensemble(sde):
+    """vignettes/BrownianMotion.Rmd:78-98: mean on the chord, variance sigma^2 (t-t0)(1-(t-t0)/(T-t0))."""
+    tv, n, sigma, B0T = np.arange(10.0, 21.0), 100000, 2.0, (15.0, 5.0)
+    BB = sde.rBrownianBridge(tv, B0T, sigma, n=n, seed=8)
+    assert BB.shape == (tv.size, n)
+    assert np.allclose(BB[0], 15.0) and np.allclose(BB[-1], 5.0)
+    s = tv - tv[0]
+    var = sigma ** 2 * s * (1 - s / s[-1])
+    assert np.max(np.abs(BB.mean(axis=1) - (15.0 - s))) < 5 * np.sqrt(var.max() / n)
+    assert np.max(np.abs(BB.var(axis=1) - var)) < 5 * var.max() * np.sqrt(2.0 / n)
+    one = sde.rBrownianBridge(tv, B0T, sigma, seed=8)
+    assert one.shape == (tv.size,) and np.array_equal(one, BB[:, 0])
