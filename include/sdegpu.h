@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDEGPU_ABI_VERSION 2
+#define SDEGPU_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SDEGPU_API __attribute__((visibility("default")))
@@ -137,6 +137,11 @@ typedef struct {
     /* --- ABI 2: with kill_kind/stop_kind set, XT is the state at tau and X holds NaN after tau --- */
     double *tau;              /* npaths: times[i+1] at the stop/kill step, or times[nt-1] (R/sdetools.R:467) */
     double *S_tau;            /* npaths: survival S at tau (0 after an h-stop, like the reference's S vector) */
+    /* --- ABI 3: integrals along each path, accumulated in the step loop (no trajectory stored; X must be NULL) --- */
+    double *path_integrals;   /* 4*nx*npaths, [(p*nx+j)*4 + k]: the terminal entries of
+                                 k=0 QuadraticVariation(X_j) (R/sdetools.R:134-137), k=1 itointegral(X_j,B) (:155-158),
+                                 k=2 stochint(X_j,B,"c") (:105-113), k=3 itointegral(X_j,times); 80-bit cumsum each.
+                                 With a supplied B bit-identical to those functions run on the stored path. */
 } sdegpu_output;
 
 typedef struct {

@@ -52,7 +52,7 @@ sde.stop.outside <- function(lo, hi, comp = 1L) .tag_rule(function(t, x) (x[comp
 }
 
 .sdegpu_dispatch <- function(scheme, fallback, f, g, times, x0, B, p, h, r, S0, Stau,
-                             npaths, seed, output, moments, center, hist, arith) {
+                             npaths, seed, output, moments, center, hist, arith, integrals = FALSE) {
   proj <- .projection_id(p)
   on.device <- !is.null(attr(f, "sdegpu_model")) && identical(attr(f, "sdegpu_model"), attr(g, "sdegpu_model")) &&
     identical(attr(f, "sdegpu_params"), attr(g, "sdegpu_params")) && !is.na(proj) &&
@@ -64,8 +64,9 @@ sde.stop.outside <- function(lo, hi, comp = 1L) .tag_rule(function(t, x) (x[comp
     if (!is.array(B) || length(dim(B)) < 3) B <- array(matrix(B, nrow = nt, ncol = nB), c(nt, nB, 1L))   # :435
     npaths <- dim(B)[3]
   } else if (is.null(npaths)) npaths <- if (is.matrix(x0)) ncol(x0) else 1L
+  if (integrals && output == "path") output <- "terminal"    # integrals accumulate in the step loop, no path is stored
   opts <- list(npaths = npaths, nx = nx, nB = nB, projection = proj, output = match(output, c("none", "terminal", "path")) - 1L,
-               moments = as.numeric(moments), center = center, hist = hist, seed = seed)
+               moments = as.numeric(moments), center = center, hist = hist, seed = seed, integrals = as.numeric(integrals))
   if (!is.null(arith)) opts$arith <- match(arith, c("strict", "fast")) - 1L
   if (!is.null(r)) { k <- attr(r, "sdegpu_kill"); opts <- c(opts, list(kill_kind = k$kind, kill_comp = k$comp, kill_a = k$a, kill_b = k$b)) }
   if (!is.null(h)) { k <- attr(h, "sdegpu_stop"); opts <- c(opts, list(stop_kind = k$kind, stop_comp = k$comp, stop_lo = k$lo, stop_hi = k$hi)) }
@@ -81,17 +82,20 @@ sde.stop.outside <- function(lo, hi, comp = 1L) .tag_rule(function(t, x) (x[comp
     k <- which(times == res$tau)[1]
     return(list(times = times[1:k], X = if (nx == 1L) X[1:k, 1] else X[1:k, , drop = FALSE], S = res$S, tau = res$tau))
   }
-  extra <- res[c("XT", "power_sums", "hist", "seed", "tau", "S")]
+  if (!is.null(res$integrals)) dimnames(res$integrals) <- list(c("QV", "ito", "strat", "time"), names(x0), NULL)
+  extra <- res[c("XT", "power_sums", "hist", "seed", "tau", "S", "integrals")]
   c(list(times = times, X = X), extra[!vapply(extra, is.null, TRUE)])
 }
 
 euler <- function(f, g, times, x0, B = NULL, p = function(x) x, h = NULL, r = NULL, S0 = 1, Stau = runif(1),
-                  npaths = NULL, seed = NULL, output = "path", moments = FALSE, center = NULL, hist = NULL, arith = NULL)
-  .sdegpu_dispatch(0L, euler.R, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith)
+                  npaths = NULL, seed = NULL, output = "path", moments = FALSE, center = NULL, hist = NULL, arith = NULL,
+                  integrals = FALSE)
+  .sdegpu_dispatch(0L, euler.R, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith, integrals)
 
 heun <- function(f, g, times, x0, B = NULL, p = function(x) x, h = NULL, r = NULL, S0 = 1, Stau = runif(1),
-                 npaths = NULL, seed = NULL, output = "path", moments = FALSE, center = NULL, hist = NULL, arith = NULL)
-  .sdegpu_dispatch(1L, heun.R, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith)
+                 npaths = NULL, seed = NULL, output = "path", moments = FALSE, center = NULL, hist = NULL, arith = NULL,
+                 integrals = FALSE)
+  .sdegpu_dispatch(1L, heun.R, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith, integrals)
 
 ## Integrals: same results bit for bit (the device emulates cumsum's 80-bit accumulator); matrices are
 ## integrated column by column in one launch.

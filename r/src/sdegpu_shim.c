@@ -59,7 +59,7 @@ static uint64_t seed_from(SEXP opts)
  *                hist = c(lo, hi, nbins, component))
  *                kill_kind/kill_comp/kill_a/kill_b, stop_kind/stop_comp/stop_lo/stop_hi, S0, Stau)
  * returns list(X = nt x nx x npaths | NULL, XT = nx x npaths | NULL, power_sums = 5 x nx | NULL, hist = counts | NULL, seed,
- *              tau, S)   — with a kill/stop rule X holds NA after each path's tau and XT is the state at tau */
+ *              tau, S, integrals = 4 x nx x npaths | NULL)   — with a kill/stop rule X holds NA after each path's tau and XT is the state at tau */
 SEXP C_sdegpu_run(SEXP scheme, SEXP model, SEXP params, SEXP times, SEXP x0, SEXP B, SEXP opts)
 {
     sdegpu_problem pr;
@@ -97,10 +97,10 @@ SEXP C_sdegpu_run(SEXP scheme, SEXP model, SEXP params, SEXP times, SEXP x0, SEX
     const int killed = pr.kill_kind != SDEGPU_KILL_NONE || pr.stop_kind != SDEGPU_STOP_NONE;
 
     int np = 0;
-    SEXP res = PROTECT(Rf_allocVector(VECSXP, 7)); ++np;
-    SEXP nms = PROTECT(Rf_allocVector(STRSXP, 7)); ++np;
-    const char *names[7] = {"X", "XT", "power_sums", "hist", "seed", "tau", "S"};
-    for (int i = 0; i < 7; ++i) SET_STRING_ELT(nms, i, Rf_mkChar(names[i]));
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 8)); ++np;
+    SEXP nms = PROTECT(Rf_allocVector(STRSXP, 8)); ++np;
+    const char *names[8] = {"X", "XT", "power_sums", "hist", "seed", "tau", "S", "integrals"};
+    for (int i = 0; i < 8; ++i) SET_STRING_ELT(nms, i, Rf_mkChar(names[i]));
     Rf_setAttrib(res, R_NamesSymbol, nms);
     if (output == 2) {
         SEXP X = PROTECT(Rf_alloc3DArray(REALSXP, nt, nx, (int)npaths)); ++np;      /* nt x nx x npaths, column-major */
@@ -126,6 +126,11 @@ SEXP C_sdegpu_run(SEXP scheme, SEXP model, SEXP params, SEXP times, SEXP x0, SEX
         SET_VECTOR_ELT(res, 6, S);
         out.tau = REAL(tau);
         out.S_tau = REAL(S);
+    }
+    if (opt_real(opts, "integrals", 0) != 0) {          /* 4 x nx x npaths: QV, ito, strat, time — terminal entries */
+        SEXP PI = PROTECT(Rf_alloc3DArray(REALSXP, 4, nx, (int)npaths)); ++np;
+        SET_VECTOR_ELT(res, 7, PI);
+        out.path_integrals = REAL(PI);
     }
     uint64_t *counts = NULL;
     SEXP h = list_get(opts, "hist");

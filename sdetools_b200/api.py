@@ -31,7 +31,7 @@ def _catalogue_model(f, g):
 
 
 def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith,
-              device, path_offset):
+              device, path_offset, integrals=False):
     if h is not None and not hasattr(h, "sdegpu_stop"):
         raise TypeError("h must be a catalogue stop rule (catalogue.stop_below/stop_above/stop_outside)")
     if r is not None and not hasattr(r, "sdegpu_kill"):
@@ -75,9 +75,12 @@ def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, outpu
     if seed is None:
         seed = int(np.random.default_rng().integers(0, 2 ** 63))
     eng = default_engine(device)
+    if integrals and output == "path":
+        output = "terminal"                # the integrals are accumulated in the step loop instead of storing the path
     want_path = output == "path"
     if output not in ("path", "terminal", "none"):
         raise ValueError("output must be 'path', 'terminal' or 'none'")
+    PI = np.empty((4, nx, npaths), order="F") if integrals else None
     X = np.empty((nt, nx, npaths), order="F") if want_path else None
     XT = np.empty((nx, npaths), order="F") if output in ("path", "terminal") else None
     ps = np.zeros((5, nx), order="F") if moments else None
@@ -90,8 +93,10 @@ def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, outpu
         Stau_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(Stau, dtype=np.float64), (npaths,)))
     eng.run(model, scheme, params, times, x0c, nx=nx, nB=nB, npaths=npaths, B=Bdev, projection=proj, arith=arith,
             seed=seed, path_offset=path_offset, X=X, XT=XT, power_sums=ps, center=center, hist_counts=hc, hist=hist,
-            kill=r, stop=h, S0=S0, Stau=Stau_arr, tau=tau, S_tau=S_tau)
+            kill=r, stop=h, S0=S0, Stau=Stau_arr, tau=tau, S_tau=S_tau, path_integrals=PI)
     res = {"times": times}
+    if PI is not None:                     # terminal entries of the reference's integral functions on each path
+        res["integrals"] = {k: (PI[i] if ensemble else PI[i, :, 0]) for i, k in enumerate(("QV", "ito", "strat", "time"))}
     if killed:
         # with mortality the reference returns tau = times[i+1] and truncates (:466-468); an ensemble keeps
         # the full grid with NaN rows after each path's tau (the r = NULL convention, :439,:464) plus tau/S
@@ -127,7 +132,7 @@ def moments_from_power_sums(ps, center):
 
 
 def euler(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *, npaths=None, seed=None,
-          output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0):
+          output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0, integrals=False):
     """Euler-Maruyama for the Ito SDE dX = f dt + g dB (R/sdetools.R:375-470).
 
     With the reference's arguments only, returns dict(times=, X=) with X the `nt x nx` matrix of one
@@ -135,16 +140,19 @@ def euler(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *,
     a 2-d `x0` (nx x npaths) turn the call into the ensemble the reference builds with sapply
     (vignettes/Killing.Rmd:183-189): X is then `nt x nx x npaths`.  If B is None the Brownian
     increments are drawn on the device (Philox, `seed`).  `output='terminal'` skips the trajectory;
-    `moments=True` / `hist=(lo, hi, nbins[, component])` reduce the terminal states on the device."""
+    `moments=True` / `hist=(lo, hi, nbins[, component])` reduce the terminal states on the device.
+    `integrals=True` accumulates, in the step loop and without storing the path, the terminal entries of
+    QuadraticVariation(X_j), itointegral(X_j,B), stochint(X_j,B,"c") and itointegral(X_j,times) for every path
+    and component: res["integrals"] = {"QV","ito","strat","time"}, each nx x npaths (nB = 1 models)."""
     return _simulate("euler", f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist,
-                     arith, device, path_offset)
+                     arith, device, path_offset, integrals)
 
 
 def heun(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *, npaths=None, seed=None,
-         output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0):
+         output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0, integrals=False):
     """Heun's method for the Stratonovich SDE dX = f dt + g o dB (R/sdetools.R:240-338); see `euler`."""
     return _simulate("heun", f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist,
-                     arith, device, path_offset)
+                     arith, device, path_offset, integrals)
 
 
 # ---- integrals ------------------------------------------------------------------

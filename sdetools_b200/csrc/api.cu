@@ -237,6 +237,8 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: kill/stop component out of range");
     if (killed && pr->model == SDEGPU_MODEL_LINEAR)
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: killing/stopping is not available for the linear model");
+    if (out->path_integrals && (killed || out->X || pr->model == SDEGPU_MODEL_LINEAR))
+        return fail(SDEGPU_ERR_ARG, "sdegpu_run: path_integrals needs a catalogue model without kill/stop rule and X = NULL");
     if ((out->tau || out->S_tau) && !killed) return fail(SDEGPU_ERR_ARG, "sdegpu_run: tau/S_tau outputs need a kill or stop rule");
     if (!pr->B && pr->arith == SDEGPU_ARITH_STRICT && !killed)
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: STRICT arithmetic is defined for a supplied B; fused-generator runs are FAST");
@@ -320,7 +322,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         for (int i = 0; i < pr->nparams; ++i) a.P.p[i] = pr->params[i];
         a.dtsq = dtsq;
         a.icdf = c->icdf;
-        if (!pr->B && !out->X && !killed) {                       // k_terminal: folded step coefficients (FAST only)
+        if (!pr->B && !out->X && !killed && !out->path_integrals) {   // k_terminal: folded step coefficients (FAST only)
             std::vector<double> hc((size_t)(nt - 1) * FAST_NCOEF);
             bool folded = true;
             for (int i = 0; i + 1 < nt && folded; ++i) {
@@ -363,8 +365,13 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
                 if (out->S_tau) a.S_tau = kb + 2 * pr->npaths;
             }
         }
+        const size_t bytesF = sizeof(double) * 4 * (size_t)nx * pr->npaths;
+        if (out->path_integrals) {
+            if (dev) a.func = out->path_integrals;
+            else { CU(c->out2.reserve(bytesF)); a.func = (double *)c->out2.p; }
+        }
         LaunchCfg cfg;
-        cfg.killed = killed;
+        cfg.killed = killed; cfg.want_func = out->path_integrals != nullptr;
         cfg.scheme = pr->scheme; cfg.proj = pr->projection; cfg.arith = pr->B ? pr->arith : SDEGPU_ARITH_FAST;
         cfg.src_b = pr->B != nullptr; cfg.want_x = out->X != nullptr;
         cfg.grid = 0; cfg.sm_count = c->prop.multiProcessorCount; cfg.stream = c->stream;
@@ -416,6 +423,8 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
     CU(cudaEventRecord(c->ev1, c->stream));
 
     if (!dev) {
+        if (out->path_integrals)
+            CU(cudaMemcpyAsync(out->path_integrals, c->out2.p, sizeof(double) * 4 * (size_t)nx * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
         if (out->X) CU(cudaMemcpyAsync(out->X, dX, bytesX, cudaMemcpyDeviceToHost, c->stream));
         if (out->XT) CU(cudaMemcpyAsync(out->XT, dXT, bytesXT, cudaMemcpyDeviceToHost, c->stream));
         if (out->power_sums) CU(cudaMemcpyAsync(out->power_sums, dps, sizeof(double) * nps, cudaMemcpyDeviceToHost, c->stream));

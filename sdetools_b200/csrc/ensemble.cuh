@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "float80.cuh"
 #include "models.cuh"
 #include "philox.cuh"
 
@@ -51,6 +52,7 @@ struct RunArgs {
     const double *Stau;             // per-path thresholds or nullptr (drawn from Philox)
     const double *times;            // device copy of the time grid (tau = times[i+1])
     double *tau, *S_tau;
+    double *func;                   // device, path integrals func[(p*nx+j)*4 + {QV, ito, strat, time}] (k_functionals)
 };
 
 // ---- terminal statistics ---------------------------------------------------
@@ -464,6 +466,86 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, cons
     flush_block_stats<NX, STREAM_THREADS>(a, acc, sh_hist);
 }
 
+// ---- running integrals along the path, nothing stored (SURVEY build-plan step 5) ------------------------
+// For every path and component j the terminal entries of the reference's integral functions on that path:
+//   QV    QuadraticVariation(X_j)[nt]      = sum (X_{i+1}-X_i)^2                    R/sdetools.R:134-137
+//   ito   itointegral(X_j, B)[nt]          = sum X_i dB_i                           :155-158
+//   strat stochint(X_j, B, "c")[nt]        = 0.5 (sum X_i dB_i + sum X_{i+1} dB_i)   :105-113
+//   time  itointegral(X_j, times)[nt]      = sum X_i dt_i
+// each sum in cumsum's 80-bit accumulator (float80.cuh) and each term formed with the same individually
+// rounded operations k_integral uses, so with a supplied B they are bit-identical to running the
+// integral kernels on the stored trajectory.  Without B, dB_i is the generator's increment sqrt(dt_i) Z_i.
+constexpr int FUNC_THREADS = 128;
+constexpr int FUNC_PER_COMP = 4;
+
+template <class M, int SCHEME, int PROJ, class A>
+__global__ void __launch_bounds__(FUNC_THREADS) k_functionals(const RunArgs a)
+{
+    constexpr int NX = M::NX;
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table (generator source only)][histogram]
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + (a.B ? 0 : ICDF_TABLE_DOUBLES));
+    if (!a.B) icdf_stage(sh_tab, a.icdf, threadIdx.x, FUNC_THREADS);
+    if (a.hist)
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += FUNC_THREADS) sh_hist[i] = 0u;
+    __syncthreads();
+    double acc[NX][5];
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
+    const int nsteps = a.nt - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * FUNC_THREADS;
+    for (uint64_t p = (uint64_t)blockIdx.x * FUNC_THREADS + threadIdx.x; p < a.npaths; p += stride) {
+        double x[NX];
+        load_x0<NX>(a, p, x);
+        CumsumAcc qv[NX], il[NX], ir[NX], it[NX];
+        double out[NX][FUNC_PER_COMP];
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+#pragma unroll
+            for (int k = 0; k < FUNC_PER_COMP; ++k) out[j][k] = 0.0;
+        const double *brow = a.B ? a.B + p * (uint64_t)a.nt : nullptr;
+        double prev = brow ? __ldg(brow) : 0.0;
+        double z[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 dt = __ldg(&a.dtsq[i]);
+            double dB;
+            if (brow) {
+                const double cur = __ldg(brow + i + 1);
+                dB = A::sub(cur, prev);                          // dB = diff(B)  (:437)
+                prev = cur;
+            } else {
+                if ((i & 3) == 0) normal_quad(a.seed, a.path_offset + p, (uint32_t)(i >> 2), 0u, sh_tab, z);
+                const int s4 = i & 3;
+                dB = dt.y * (s4 == 0 ? z[0] : (s4 == 1 ? z[1] : (s4 == 2 ? z[2] : z[3])));
+            }
+            double xo[NX];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) xo[j] = x[j];
+            sde_step<M, SCHEME, PROJ, A>(a.P, x, dt.x, dB);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                const double dx = __dsub_rn(x[j], xo[j]);
+                out[j][0] = qv[j].add(__dmul_rn(dx, dx));
+                out[j][1] = il[j].add(__dmul_rn(xo[j], dB));
+                out[j][2] = ir[j].add(__dmul_rn(x[j], dB));
+                out[j][3] = it[j].add(__dmul_rn(xo[j], dt.x));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            double *f = a.func + (p * NX + j) * FUNC_PER_COMP;
+            f[0] = out[j][0];
+            f[1] = out[j][1];
+            f[2] = __dmul_rn(0.5, __dadd_rn(out[j][1], out[j][2]));
+            f[3] = out[j][3];
+            if (a.XT) a.XT[p * NX + j] = x[j];
+        }
+        accumulate_terminal<NX>(a, x, acc, sh_hist);
+    }
+    flush_block_stats<NX, FUNC_THREADS>(a, acc, sh_hist);
+}
+
 // ---- mortality and stopping (R/sdetools.R:397-416,455-469; vignettes/Killing.Rmd:152-190) ----------
 // Per step, in the reference's order: the new state is tested against h (stop: S is not updated and
 // reads 0); otherwise S <- S * exp(-r(X_i) * dt_i) with the OLD state, and the path is killed when
@@ -574,7 +656,7 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
 // ---- host-side launch signature shared by the per-model translation units ---
 struct LaunchCfg {
     int scheme, proj, arith;
-    bool src_b, want_x, killed;
+    bool src_b, want_x, killed, want_func;
     int grid;            // 0: choose from occupancy
     int sm_count;
     cudaStream_t stream;

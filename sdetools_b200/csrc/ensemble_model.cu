@@ -76,10 +76,25 @@ static int launch_killed(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     return (int)cudaGetLastError();
 }
 
+template <int SCHEME, int PROJ, class A>
+static int launch_functionals(const RunArgs &a, const LaunchCfg &c, int *grid_used)
+{
+    auto kernel = k_functionals<M, SCHEME, PROJ, A>;
+    const size_t smem = (a.B ? 0 : ICDF_TABLE_BYTES) + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    const uint64_t work = (a.npaths + FUNC_THREADS - 1) / FUNC_THREADS;
+    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, FUNC_THREADS, smem, c.sm_count, work);
+    kernel<<<grid, FUNC_THREADS, smem, c.stream>>>(a);
+    *grid_used = grid;
+    return (int)cudaGetLastError();
+}
+
 template <int SCHEME, int PROJ>
 static int dispatch_mode(const RunArgs &a, const LaunchCfg &c, int *g)
 {
     if (c.killed) return launch_killed<SCHEME, PROJ>(a, c, g);
+    if (c.want_func)
+        return c.src_b && c.arith == SDEGPU_ARITH_STRICT ? launch_functionals<SCHEME, PROJ, Strict>(a, c, g)
+                                                         : launch_functionals<SCHEME, PROJ, Fast>(a, c, g);
     if (c.src_b)
         return c.arith == SDEGPU_ARITH_STRICT ? launch_stream<SCHEME, PROJ, Strict>(a, c, g)
                                               : launch_stream<SCHEME, PROJ, Fast>(a, c, g);

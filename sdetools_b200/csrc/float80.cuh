@@ -254,4 +254,30 @@ SDEGPU_HD F80 f80_from_pair(double h, double l)
     return acc;
 }
 
+#if defined(__CUDACC__)
+// R's cumsum accumulator on the device: the floating-point pair while the column stays in its range (always,
+// for data that is not within 2^-895 of underflow or 2^992 of overflow), the integer emulation — out of line,
+// its state in local memory — from the first element that is not, for the rest of the column.
+// add() returns (double)sum, the value cumsum stores.
+static __device__ __noinline__ double f80_slow_add(F80 *big, bool first, double h, double l, double x)
+{
+    if (first) *big = f80_from_pair(h, l);
+    f80_add(*big, x);
+    return f80_to_double(*big);
+}
+
+struct CumsumAcc {
+    double h = 0.0, l = 0.0;
+    bool slow = false;
+    F80 big;
+    __device__ __forceinline__ double add(double x)
+    {
+        if (!slow && f80p_add(h, l, x)) return h;
+        const double out = f80_slow_add(&big, !slow, h, l, x);
+        slow = true;
+        return out;
+    }
+};
+#endif
+
 }  // namespace sdegpu

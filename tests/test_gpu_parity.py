@@ -554,3 +554,55 @@ def test_c3_trajectory_properties_at_scale(eng):
     eng.run("vdp", "euler", [1.0, 0.5], t, [0.3, -0.2], nx=2, npaths=37, seed=11, path_offset=5003, X=sub)
     eng.synchronize()
     assert torch.equal(sub.view(37, 2, nt), Xv[5003:5040])
+
+
+# ---- integrals accumulated in the step loop (no trajectory stored) -------------------------------------
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+@pytest.mark.parametrize("model,params,x0,proj", [CASES[1], CASES[3], CASES[6]])
+def test_fused_path_integrals_equal_integral_functions_on_the_stored_path(sde, scheme, model, params, x0, proj):
+    """With a supplied B the fused functionals are the terminal entries of QuadraticVariation / itointegral /
+    stochint(.., "c") / itointegral(X, times) evaluated on the stored trajectory — bit for bit (same terms, same
+    80-bit accumulator), for both arithmetic modes."""
+    fn = sde.euler if scheme == "euler" else sde.heun
+    f, g = getattr(sde.catalogue, model)(*params)
+    p = {"identity": None, "abs": abs, "relu": "relu"}[proj]
+    t, B = brownian(157, 1, 70, 12)
+    for arith in ("strict", "fast"):
+        path = fn(f, g, t, x0, B, p=p, arith=arith)["X"]                      # (nt, nx, P)
+        got = fn(f, g, t, x0, B, p=p, arith=arith, integrals=True)
+        assert "X" not in got and np.array_equal(got["XT"], path[-1])
+        nx, P = path.shape[1], path.shape[2]
+        for j in range(nx):
+            Xj, Bj = path[:, j, :], B[:, 0, :]
+            T = np.repeat(t[:, None], P, axis=1)
+            assert np.array_equal(got["integrals"]["QV"][j], sde.QuadraticVariation(Xj)[-1])
+            assert np.array_equal(got["integrals"]["ito"][j], sde.itointegral(Xj, Bj)[-1])
+            assert np.array_equal(got["integrals"]["strat"][j], sde.stochint(Xj, Bj, "c")[-1])
+            assert np.array_equal(got["integrals"]["time"][j], sde.itointegral(Xj, T)[-1])
+
+
+def test_fused_path_integrals_with_the_generator(sde):
+    """Fused generator (no B to compare with): the ensemble means of the four functionals of an OU path against
+    their closed forms — E[QV] = sigma^2 T, E[strat - ito] = sigma T / 2 (half the cross-variation [X,B]_T,
+    vignettes/ItoIntegrals.Rmd:143-153) and E int X dt."""
+    lam, xi, sig, x0, n, nsteps = 1.3, 0.7, 0.9, 2.0, 50000, 1000
+    t = np.arange(nsteps + 1) / nsteps
+    f, g = sde.catalogue.ou(lam, xi, sig)
+    r = sde.euler(f, g, t, x0, npaths=n, seed=31, integrals=True)
+    I, XT = r["integrals"], r["XT"][0]
+    assert abs(I["QV"][0].mean() - sig ** 2) < 5 * I["QV"][0].std() / np.sqrt(n) + 2e-3      # E QV = sigma^2 T (+ O(dt))
+    assert np.all(I["QV"][0] > 0)
+    # Stratonovich - Ito = 0.5 [X,B]_T = 0.5 sigma T in expectation (additive noise)
+    diff = I["strat"][0] - I["ito"][0]
+    assert abs(diff.mean() - 0.5 * sig) < 5 * diff.std() / np.sqrt(n) + 1e-3
+    # E int X dt for OU started at x0
+    want = xi + (x0 - xi) * (1 - np.exp(-lam)) / lam
+    assert abs(I["time"][0].mean() - want) < 5 * I["time"][0].std() / np.sqrt(n) + 2e-3
+    assert np.isfinite(XT).all()
+
+
+def test_path_integrals_argument_errors(sde):
+    from sdetools_b200._lib import SdeGpuError
+    f, g = sde.catalogue.ou()
+    with pytest.raises(SdeGpuError, match="path_integrals"):
+        sde.euler(f, g, [0.0, 0.5, 1.0], 0.0, npaths=4, seed=1, integrals=True, r=sde.catalogue.kill_const(1.0))
