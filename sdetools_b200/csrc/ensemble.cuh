@@ -653,6 +653,102 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
     flush_block_stats<NX, KILLED_THREADS>(a, acc, sh_hist);
 }
 
+// ---- mortality and stopping without a trajectory: lane-level refill ----------------------------------
+// Lifetimes differ from path to path, so with one path per thread a warp runs until its longest-lived lane
+// ends (measured: 19-29 % of the lanes' steps useful).  Here every warp owns a contiguous chunk of paths and
+// a lane whose path has ended takes the chunk's next path; new paths start only on warp iterations that are
+// multiples of four, so all lanes stay in the same phase of the four-normals-per-Philox-block stream.
+// No atomics: which lane runs which path depends only on the lifetimes, so results — including the order of
+// every floating-point accumulation — are reproducible.  Per-path results are those of k_killed bit for bit.
+template <class M, int SCHEME, int PROJ>
+__global__ void __launch_bounds__(KILLED_THREADS) k_killed_refill(const RunArgs a)
+{
+    constexpr int NX = M::NX;
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table (if no B)][histogram]
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + (a.B ? 0 : ICDF_TABLE_DOUBLES));
+    if (!a.B) icdf_stage(sh_tab, a.icdf, threadIdx.x, KILLED_THREADS);
+    if (a.hist)
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += KILLED_THREADS) sh_hist[i] = 0u;
+    __syncthreads();
+    double acc[NX][5];
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
+
+    const int nsteps = a.nt - 1, lane = threadIdx.x & 31;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (KILLED_THREADS / 32);
+    const uint64_t warp = (uint64_t)blockIdx.x * (KILLED_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t chunk = (a.npaths + nwarps - 1) / nwarps;
+    uint64_t next = warp * chunk;                                // warp-uniform: first unclaimed path of the chunk
+    const uint64_t end = next + chunk < a.npaths ? next + chunk : a.npaths;
+
+    bool active = false;
+    uint64_t p = 0;
+    int i = 0;
+    double x[NX], xo[NX], S = 0.0, Sout = 0.0, Stau = 0.0, zq[4] = {0.0, 0.0, 0.0, 0.0};
+    const double *brow = nullptr;
+    for (uint32_t k = 0;; ++k) {
+        if ((k & 3u) == 0u) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (idle) {
+                if (!active) {
+                    const uint64_t cand = next < end ? next + (uint64_t)__popc(idle & ((1u << lane) - 1u)) : end;
+                    if (cand < end) {
+                        p = cand; active = true; i = 0;
+                        load_x0<NX>(a, p, x);
+                        if (a.Stau) Stau = a.Stau[p];
+                        else {                                   // runif(1): 52-bit uniform in [0,1)
+                            uint32_t r0, r1, r2, r3;
+                            philox_block(a.seed, a.path_offset + p, 0u, 0xC0000000u, r0, r1, r2, r3);
+                            Stau = __hiloint2double((int)(0x3FF00000u | (r1 >> 12)), (int)((r1 << 20) | (r0 >> 12))) - 1.0;
+                        }
+                        brow = a.B ? a.B + p * (uint64_t)a.nt : nullptr;
+                        S = a.S0; Sout = a.S0;
+                    }
+                }
+                if (next < end) { const uint64_t left = end - next, want = (uint64_t)__popc(idle); next += want < left ? want : left; }
+                if (!__any_sync(0xffffffffu, active)) break;     // chunk exhausted and every lane done
+            }
+            if (active && !brow) normal_quad(a.seed, a.path_offset + p, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+        }
+        if (!active) continue;
+        int last = -1;
+        if (i < nsteps) {
+            const double2 dt = __ldg(&a.dtsq[i]);
+            double dB;
+            if (brow) dB = __dsub_rn(__ldg(brow + i + 1), __ldg(brow + i));
+            else {
+                const int q = i & 3;
+                dB = __dmul_rn(dt.y, q == 0 ? zq[0] : (q == 1 ? zq[1] : (q == 2 ? zq[2] : zq[3])));
+            }
+#pragma unroll
+            for (int j = 0; j < NX; ++j) xo[j] = x[j];
+            sde_step<M, SCHEME, PROJ, Strict>(a.P, x, dt.x, dB);
+            if (a.stop_kind != SDEGPU_STOP_NONE && !(stop_value<NX>(a, x) > 0.0)) {      // h(...) <= 0  (:455)
+                last = i + 1; Sout = 0.0;
+            } else if (a.kill_kind != SDEGPU_KILL_NONE) {
+                S = __dmul_rn(S, exp(__dmul_rn(-kill_rate<NX>(a, xo), dt.x)));           // :456, old state
+                Sout = S;
+                if (S < Stau) last = i + 1;                                               // :457
+            }
+            ++i;
+            if (last < 0 && i == nsteps) last = nsteps;
+        } else last = nsteps;                                    // nt = 1 never happens (nt >= 2), kept for safety
+        if (last >= 0) {
+            if (a.tau) a.tau[p] = a.times[last];                 // tau <- times[i+1]  (:467)
+            if (a.S_tau) a.S_tau[p] = Sout;
+            if (a.XT) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+            }
+            accumulate_terminal<NX>(a, x, acc, sh_hist);
+            active = false;
+        }
+    }
+    flush_block_stats<NX, KILLED_THREADS>(a, acc, sh_hist);
+}
+
 // ---- host-side launch signature shared by the per-model translation units ---
 struct LaunchCfg {
     int scheme, proj, arith;

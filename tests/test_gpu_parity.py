@@ -490,6 +490,36 @@ def test_constant_killing_rate_gives_exponential_lifetimes(sde):
     assert np.all(res["S"][~alive] < 1) and res["XT"].shape == (1, N)
 
 
+def test_lane_refill_kernel_equals_one_path_per_thread(sde):
+    """Without a trajectory the kill/stop kernel lets a lane whose path ended take the warp's next path
+    (k_killed_refill).  Per path it must give exactly what the one-path-per-thread kernel (taken when X is
+    requested) gives; the run is reproducible although lanes pick paths dynamically."""
+    f, g = sde.catalogue.ou(1.0, 0.0, 1.0)
+    t = np.arange(301) * 0.01
+    kw = dict(r=sde.catalogue.kill_quad(2.0, 0.0), h=sde.catalogue.stop_above(1.2), seed=44)
+    N = 1_000_000                                               # ~280 paths per warp: every lane refills many times
+    big = sde.euler(f, g, t, 0.3, npaths=N, output="terminal", moments=True, center=[0.0], hist=(-3.0, 3.0, 64), **kw)
+    lifetimes = big["tau"]
+    assert 0.05 < np.mean(lifetimes < t[-1]) < 0.999 and np.unique(lifetimes).size > 100
+    for off in (0, 123_457, N - 500):
+        ref = sde.euler(f, g, t, 0.3, npaths=500, path_offset=off, output="path", **kw)       # k_killed (stores X)
+        sl = slice(off, off + 500)
+        assert np.array_equal(ref["tau"], big["tau"][sl]) and np.array_equal(ref["S"], big["S"][sl])
+        assert np.array_equal(ref["XT"], big["XT"][:, sl])
+    again = sde.euler(f, g, t, 0.3, npaths=N, output="terminal", moments=True, center=[0.0], hist=(-3.0, 3.0, 64), **kw)
+    assert np.array_equal(again["power_sums"], big["power_sums"]) and np.array_equal(again["hist"]["counts"], big["hist"]["counts"])
+    assert big["hist"]["counts"].sum() + big["hist"]["under"] + big["hist"]["over"] + big["hist"]["nan"] == N
+    # supplied B (STRICT): enough paths that a warp's chunk exceeds its 32 lanes
+    rng = np.random.default_rng(5)
+    tb, P = np.arange(102) * 0.02, 400_000
+    B = np.cumsum(np.concatenate([np.zeros((1, P)), rng.standard_normal((101, P)) * np.sqrt(0.02)]), axis=0)[:, None, :]
+    Stau = rng.random(P)
+    a = sde.euler(f, g, tb, 0.3, B, output="terminal", Stau=Stau, r=kw["r"], h=kw["h"])
+    b = sde.euler(f, g, tb, 0.3, B, output="path", Stau=Stau, r=kw["r"], h=kw["h"])
+    assert np.array_equal(a["tau"], b["tau"]) and np.array_equal(a["S"], b["S"]) and np.array_equal(a["XT"], b["XT"])
+    assert np.unique(a["tau"]).size > 50
+
+
 # ---- BASELINE.json full sizes, through size-independent properties ---------------------------------------
 def test_c2_full_size_histogram_and_moments(sde):
     """Config C2 as benchmarked: CIR heun(), 10^7 paths x 10^4 steps.  Properties: every path is counted once,

@@ -114,6 +114,26 @@ def main():
         del f, g, l, r, c
         torch.cuda.empty_cache()
 
+    # next-1: killing / stopping (vignettes/Killing.Rmd:152-207 scaled up): OU with exp killing rate, lifetime only
+    if want("killed"):
+        import sdetools_b200.catalogue as cat
+        P = (1 << 20) if args.quick else 1 << 24
+        n = 1000
+        t = np.arange(n + 1) * 0.01
+        tau = torch.empty(P, dtype=torch.float64, device=dev)
+        S = torch.empty(P, dtype=torch.float64, device=dev)
+        XT = torch.empty(P, dtype=torch.float64, device=dev)
+        for name, kw in (("killed_ou_exp_rate", dict(kill=cat.kill_exp(0.5, 1.0))),
+                         ("stopped_ou_outside", dict(stop=cat.stop_outside(-1.0, 1.5))),
+                         ("killed_and_stopped", dict(kill=cat.kill_quad(1.0, 0.0), stop=cat.stop_above(2.0)))):
+            ms = best_ms(lambda: eng.run("ou", "euler", [1.0, 0.0, 1.0], t, [0.0], nx=1, npaths=P, seed=12, XT=XT, tau=tau,
+                                         S_tau=S if "kill" in kw else None, want_time=True, **kw))
+            alive = float(tau.sum()) / (P * t[-1])          # mean lifetime / horizon = fraction of path-steps actually taken
+            emit(name, paths=P, nsteps=n, ms=ms, grid_path_steps_per_s=P * n / ms * 1e3, mean_lifetime_frac=alive,
+                 taken_path_steps_per_s=alive * P * n / ms * 1e3)
+        del tau, S, XT
+        torch.cuda.empty_cache()
+
     # next-2: exact transition-law samplers, device-resident output (draws = transitions)
     if want("laws"):
         n = (1 << 20) if args.quick else 1 << 24
