@@ -337,7 +337,17 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const
 // writes X through the sector writer.  No shared memory, no barrier: rows are private to a thread.
 // dB_i = B[i+1] - B[i] is formed from the same doubles the reference subtracts (:437); with A = Strict
 // every operation is individually rounded in the reference's order, so X is bit-identical to it.
-constexpr int STREAM_THREADS = 256;
+#ifndef SDEGPU_STREAM_THREADS
+#define SDEGPU_STREAM_THREADS 256
+#endif
+#ifndef SDEGPU_STREAM_BLOCKS_PER_SM
+#define SDEGPU_STREAM_BLOCKS_PER_SM 0          // 0: as many as fit
+#endif
+#ifndef SDEGPU_STREAM_PREFETCH
+#define SDEGPU_STREAM_PREFETCH 2               // sectors of B in flight per thread
+#endif
+constexpr int STREAM_THREADS = SDEGPU_STREAM_THREADS;
+constexpr int STREAM_PREFETCH = SDEGPU_STREAM_PREFETCH;
 
 __device__ __forceinline__ void ld_sector(const double *p, double (&s)[4])
 {
@@ -411,17 +421,18 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, cons
                 pv[j][3] = x[j];
             }
         }
-        // register pipeline two sectors deep: DRAM latency is ~1 us and a thread owns one row, so while group m
-        // integrates the sectors of groups m+1 and m+2 are already in flight (two buffers, loop unrolled by two)
-        double bA[4], bB[4];
-        if (ngroups > 0) ld_sector(brow + s + 1, bA);
-        if (ngroups > 1) ld_sector(brow + s + 5, bB);
+        // register pipeline STREAM_PREFETCH sectors deep: DRAM latency is ~1 us and a thread owns one row, so while
+        // group m integrates, the sectors of the next groups are already in flight (loop unrolled by the depth)
+        double bq[STREAM_PREFETCH][4];
+#pragma unroll
+        for (int k = 0; k < STREAM_PREFETCH; ++k)
+            if (ngroups > k) ld_sector(brow + s + 1 + 4 * k, bq[k]);
         auto group = [&](double (&buf)[4], int m) {
             double b[4];
             double2 dts[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { b[k] = buf[k]; dts[k] = __ldg(&a.dtsq[s + k]); }
-            if (m + 2 < ngroups) ld_sector(brow + s + 9, buf);   // refill this buffer for group m+2
+            if (m + STREAM_PREFETCH < ngroups) ld_sector(brow + s + 1 + 4 * STREAM_PREFETCH, buf);   // refill for group m+depth
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 sde_step<M, SCHEME, PROJ, A>(a.P, x, dts[k].x, A::sub(b[k], prev));      // dB = diff(B)  (:437)
@@ -436,8 +447,13 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, cons
             s += 4;
         };
         int m = 0;
-        for (; m + 1 < ngroups; m += 2) { group(bA, m); group(bB, m + 1); }
-        if (m < ngroups) group(bA, m);
+        for (; m + STREAM_PREFETCH <= ngroups; m += STREAM_PREFETCH) {
+#pragma unroll
+            for (int k = 0; k < STREAM_PREFETCH; ++k) group(bq[k], m + k);
+        }
+#pragma unroll
+        for (int k = 0; k < STREAM_PREFETCH - 1; ++k)
+            if (m + k < ngroups) group(bq[k], m + k);
         if (a.X && ngroups > 0) {                                // values that opened a sector no full group completes
 #pragma unroll
             for (int j = 0; j < NX; ++j)

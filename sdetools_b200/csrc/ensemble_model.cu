@@ -12,12 +12,13 @@ namespace sdegpu {
 using M = Model<SDEGPU_TU_MODEL>;
 
 template <class K>
-static int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, uint64_t work_blocks)
+static int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, uint64_t work_blocks, int max_per_sm = 0)
 {
     int per_sm = 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (per_sm < 1) per_sm = 1;
+    if (max_per_sm > 0 && per_sm > max_per_sm) per_sm = max_per_sm;
     uint64_t g = (uint64_t)per_sm * sm_count;
     if (g > work_blocks) g = work_blocks;
     return (int)(g < 1 ? 1 : g);
@@ -56,7 +57,7 @@ static int launch_stream(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     auto kernel = k_stream<M, SCHEME, PROJ, A>;
     const size_t smem = a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0;
     const uint64_t work = (a.npaths + STREAM_THREADS - 1) / STREAM_THREADS;
-    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, STREAM_THREADS, smem, c.sm_count, work);
+    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, STREAM_THREADS, smem, c.sm_count, work, SDEGPU_STREAM_BLOCKS_PER_SM);
     const int vec_in = (reinterpret_cast<uintptr_t>(a.B) & 31) == 0;
     const int vec_out = a.X && (reinterpret_cast<uintptr_t>(a.X) & 31) == 0;
     kernel<<<grid, STREAM_THREADS, smem, c.stream>>>(a, vec_in, vec_out);
