@@ -213,6 +213,14 @@ SDEGPU_API int sdegpu_rlaw(sdegpu_ctx *ctx, int32_t law, const double params[3],
                 const double *x0, int64_t x0_stride, uint64_t n, int32_t nsteps, uint64_t seed, uint64_t path_offset,
                 double *out, double *path, uint32_t flags);
 
+/* Evaluation of the same laws at n points: what = 0 density dOU/dCIR (R/sdetools.R:745-752, :652-663), what = 1
+ * distribution function pOU/pCIR (:758-765, :669-676; lower tail, not log).  out[p] = law(x[p] | x0[p*x0_stride]).
+ * On device pointers this is the probability integral transform of an ensemble's terminal states without a
+ * round trip through the host. */
+SDEGPU_API int sdegpu_law_eval(sdegpu_ctx *ctx, int32_t law, int32_t what, const double params[3], double t,
+                int32_t stratonovich, const double *x0, int64_t x0_stride, const double *x, uint64_t n, double *out,
+                uint32_t flags);
+
 /* Generator introspection (tests / known-answer vectors). */
 SDEGPU_API int sdegpu_philox4x32_10(sdegpu_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* z[i*npaths + p] = standard normal handed to step i, channel `channel`, of path path_offset+p (host ptr). */

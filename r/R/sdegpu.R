@@ -123,3 +123,11 @@ rOU.gpu <- function(n, x0, lambda, xi, sigma, t, steps = 1, seed = NULL)
 rCIR.gpu <- function(n, x0, lambda, xi, gamma, t, Stratonovich = FALSE, steps = 1, seed = NULL)
   .Call(C_sdegpu_rlaw, 1L, as.integer(n), as.numeric(x0), c(lambda, xi, gamma), t,
         c(list(steps = steps, stratonovich = as.numeric(Stratonovich)), if (is.null(seed)) list() else list(seed = seed)))
+
+## The laws themselves on the device (lower tail, natural scale); the reference's dOU/pOU/dCIR/pCIR stay as they are.
+pOU.gpu <- function(x, x0, lambda, xi, sigma, t) .Call(C_sdegpu_law_eval, 0L, 1L, as.numeric(x), as.numeric(x0), c(lambda, xi, sigma), t, 0L)
+dOU.gpu <- function(x, x0, lambda, xi, sigma, t) .Call(C_sdegpu_law_eval, 0L, 0L, as.numeric(x), as.numeric(x0), c(lambda, xi, sigma), t, 0L)
+pCIR.gpu <- function(x, x0, lambda, xi, gamma, t, Stratonovich = FALSE)
+  .Call(C_sdegpu_law_eval, 1L, 1L, as.numeric(x), as.numeric(x0), c(lambda, xi, gamma), t, as.integer(Stratonovich))
+dCIR.gpu <- function(x, x0, lambda, xi, gamma, t, Stratonovich = FALSE)
+  .Call(C_sdegpu_law_eval, 1L, 0L, as.numeric(x), as.numeric(x0), c(lambda, xi, gamma), t, as.integer(Stratonovich))

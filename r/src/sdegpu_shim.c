@@ -265,6 +265,23 @@ SEXP C_sdegpu_rlaw(SEXP law, SEXP n, SEXP x0, SEXP params, SEXP t, SEXP opts)
     return res;
 }
 
+/* dOU/pOU (R/sdetools.R:745-765) and dCIR/pCIR (:652-676) at the points x; x0 is recycled to length(x) */
+SEXP C_sdegpu_law_eval(SEXP law, SEXP what, SEXP x, SEXP x0, SEXP params, SEXP t, SEXP stratonovich)
+{
+    const R_xlen_t n = XLENGTH(x), nx0 = XLENGTH(x0);
+    if (nx0 < 1 || XLENGTH(params) != 3) Rf_error("sdegpu_law_eval: bad arguments");
+    SEXP res = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP start = PROTECT(Rf_allocVector(REALSXP, n > 0 ? n : 1));
+    for (R_xlen_t i = 0; i < n; ++i) REAL(start)[i] = REAL(x0)[i % nx0];
+    if (sdegpu_law_eval(ctx(), Rf_asInteger(law), Rf_asInteger(what), REAL(params), Rf_asReal(t), Rf_asInteger(stratonovich),
+                        REAL(start), nx0 == 1 ? 0 : 1, REAL(x), (uint64_t)n, REAL(res), 0) != SDEGPU_OK) {
+        UNPROTECT(2);
+        Rf_error("sdegpu_law_eval: %s", sdegpu_last_error());
+    }
+    UNPROTECT(2);
+    return res;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_sdegpu_run", (DL_FUNC)&C_sdegpu_run, 7},
     {"C_sdegpu_stochint", (DL_FUNC)&C_sdegpu_stochint, 3},
@@ -273,6 +290,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_sdegpu_crossvar", (DL_FUNC)&C_sdegpu_crossvar, 2},
     {"C_sdegpu_rvbm", (DL_FUNC)&C_sdegpu_rvbm, 6},
     {"C_sdegpu_rlaw", (DL_FUNC)&C_sdegpu_rlaw, 6},
+    {"C_sdegpu_law_eval", (DL_FUNC)&C_sdegpu_law_eval, 7},
     {NULL, NULL, 0}};
 
 void R_init_SDEtools(DllInfo *dll)

@@ -253,6 +253,33 @@ def rCIR(n, x0, lam, xi, gamma, t, Stratonovich=False, *, steps=1, path=False, s
     return _rlaw("cir", n, x0, (lam, xi, gamma), t, Stratonovich, steps, path, seed, device, path_offset)
 
 
+def _law(law, what, x, x0, params, t, stratonovich, device):
+    xs = np.asarray(x, dtype=np.float64)
+    out = np.empty(xs.size)
+    default_engine(device).law_eval(law, what, params, t, x0, np.ascontiguousarray(xs.reshape(-1)), out, stratonovich)
+    return out.reshape(xs.shape) if xs.ndim else float(out[0])
+
+
+def dOU(x, x0, lam, xi, sigma, t, *, device=None):
+    """R/sdetools.R:745-752, evaluated on the device (x0 scalar or one per point)."""
+    return _law("ou", "d", x, x0, (lam, xi, sigma), t, False, device)
+
+
+def pOU(x, x0, lam, xi, sigma, t, *, device=None):
+    """R/sdetools.R:758-765 (lower tail)."""
+    return _law("ou", "p", x, x0, (lam, xi, sigma), t, False, device)
+
+
+def dCIR(x, x0, lam, xi, gamma, t, Stratonovich=False, *, device=None):
+    """R/sdetools.R:652-663: 2c dchisq(2c x, n, nu)."""
+    return _law("cir", "d", x, x0, (lam, xi, gamma), t, Stratonovich, device)
+
+
+def pCIR(x, x0, lam, xi, gamma, t, Stratonovich=False, *, device=None):
+    """R/sdetools.R:669-676 (lower tail)."""
+    return _law("cir", "p", x, x0, (lam, xi, gamma), t, Stratonovich, device)
+
+
 def rvBM_functionals(times, n=1, sigma=1.0, B0=0.0, u=0.0, level=None, *, seed=None, device=None, path_offset=0):
     """max / min / which.max / which.min / first passage of each column of rvBM(times, n, sigma, B0, u) without
     storing the n paths (vignettes/BrownianMotion.Rmd:101-144: `apply(rvBM(0:Nt,Np),2,max)`).  With the same

@@ -483,6 +483,75 @@ static int run_integral(sdegpu_ctx *c, int mode, const double *a, const double *
     return SDEGPU_OK;
 }
 
+// ou.parameters (R/sdetools.R:706-712) / cir.parameters (:606-617) folded into the kernels' constants
+static int fold_law(int32_t law, const double params[3], double t, int32_t stratonovich, LawArgs *q)
+{
+    if (law != SDEGPU_LAW_OU && law != SDEGPU_LAW_CIR) return fail(SDEGPU_ERR_ARG, "sdegpu law: unknown law %d", law);
+    if (!(t >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu law: t must be >= 0");
+    const double lambda = params[0], xi = params[1], s = params[2];
+    if (!(s >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu law: noise intensity must be >= 0");
+    if (law == SDEGPU_LAW_CIR && (!(lambda > 0) || !(s > 0) || !(t > 0)))
+        return fail(SDEGPU_ERR_ARG, "sdegpu law: CIR needs lambda > 0, gamma > 0, t > 0");
+    memset(q, 0, sizeof *q);
+    q->law = law;
+    q->decay = exp(-lambda * t);                                 // :708 / :613-614
+    q->xi = xi;
+    q->sd = lambda == 0 ? s * sqrt(t) : s * sqrt((1 - exp(-2 * lambda * t)) / 2 / lambda);           // :709
+    const double xi_ito = stratonovich ? xi + s * s / 4 / lambda : xi;                                // :610
+    q->two_c = law == SDEGPU_LAW_CIR ? 2 * (2 * lambda / (s * s) / (1 - q->decay)) : 1.0;           // :613
+    q->df = law == SDEGPU_LAW_CIR ? 4 * lambda * xi_ito / (s * s) : 0.0;                              // :615
+    if (law == SDEGPU_LAW_CIR && !(q->df >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu law: CIR needs xi >= 0");
+    return SDEGPU_OK;
+}
+
+extern "C" {
+
+int sdegpu_law_eval(sdegpu_ctx *c, int32_t law, int32_t what, const double params[3], double t, int32_t stratonovich,
+                    const double *x0, int64_t x0_stride, const double *x, uint64_t n, double *out, uint32_t flags)
+{
+    if (!c || !params || !x0 || !x || !out) return fail(SDEGPU_ERR_ARG, "sdegpu_law_eval: NULL argument");
+    if (what != 0 && what != 1) return fail(SDEGPU_ERR_ARG, "sdegpu_law_eval: what must be 0 (density) or 1 (distribution)");
+    if (x0_stride < 0) return fail(SDEGPU_ERR_ARG, "sdegpu_law_eval: x0_stride must be >= 0");
+    LawArgs q;
+    int rc = fold_law(law, params, t, stratonovich, &q);
+    if (rc) return rc;
+    if (law == SDEGPU_LAW_OU && !(q.sd > 0)) return fail(SDEGPU_ERR_ARG, "sdegpu_law_eval: degenerate OU law (sd = 0)");
+    if (n == 0) return SDEGPU_OK;
+    CU(cudaSetDevice(c->device));
+    const bool dev = (flags & SDEGPU_DEVICE_PTRS) != 0;
+    q.n = n; q.x0_stride = (uint64_t)x0_stride;
+    const double *dx = x;
+    double *dout = out;
+    if (x0_stride == 0) {
+        if (dev) {
+            CU(cudaMemcpyAsync(&q.x0s, x0, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        } else q.x0s = x0[0];
+    } else if (dev) q.x0 = x0;
+    else {
+        const size_t bytes = sizeof(double) * ((n - 1) * (size_t)x0_stride + 1);
+        CU(c->in0.reserve(bytes));
+        CU(cudaMemcpyAsync(c->in0.p, x0, bytes, cudaMemcpyHostToDevice, c->stream));
+        q.x0 = (const double *)c->in0.p;
+    }
+    if (!dev) {
+        CU(c->in1.reserve(sizeof(double) * n));
+        CU(cudaMemcpyAsync(c->in1.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        dx = (const double *)c->in1.p;
+        CU(c->out0.reserve(sizeof(double) * n));
+        dout = (double *)c->out0.p;
+    }
+    int e = launch_law_eval(q, what, dx, dout, c->prop.multiProcessorCount, c->stream);
+    if (e) return fail(SDEGPU_ERR_CUDA, "sdegpu_law_eval: kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+    if (!dev) {
+        CU(cudaMemcpyAsync(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return SDEGPU_OK;
+}
+
+}  // extern "C"
+
 extern "C" {
 
 int sdegpu_stochint(sdegpu_ctx *c, const double *f, const double *g, uint64_t n, uint64_t ncols, double *l, double *r,
@@ -579,22 +648,13 @@ int sdegpu_rlaw(sdegpu_ctx *c, int32_t law, const double params[3], double t, in
     if (law != SDEGPU_LAW_OU && law != SDEGPU_LAW_CIR) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: unknown law %d", law);
     if (nsteps < 0 || x0_stride < 0) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: nsteps and x0_stride must be >= 0");
     if (!(t >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: t must be >= 0");
-    const double lambda = params[0], xi = params[1], s = params[2];
-    if (!(s >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: noise intensity must be >= 0");
-    if (law == SDEGPU_LAW_CIR && (!(lambda > 0) || !(s > 0) || !(t > 0)))
-        return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: CIR needs lambda > 0, gamma > 0, t > 0");
+    LawArgs q;
+    int rc = fold_law(law, params, t, stratonovich, &q);
+    if (rc) return rc;
     if (n == 0) return SDEGPU_OK;
     CU(cudaSetDevice(c->device));
     const bool dev = (flags & SDEGPU_DEVICE_PTRS) != 0;
-    LawArgs q;
-    q.icdf = c->icdf; q.n = n; q.path_offset = path_offset; q.seed = make_philox_key(seed); q.law = law; q.nsteps = nsteps;
-    q.decay = exp(-lambda * t);                                  // ou.parameters :708 / cir.parameters :613-614
-    q.xi = xi;
-    q.sd = lambda == 0 ? s * sqrt(t) : s * sqrt((1 - exp(-2 * lambda * t)) / 2 / lambda);            // :709
-    const double xi_ito = stratonovich ? xi + s * s / 4 / lambda : xi;                                 // :610
-    q.two_c = law == SDEGPU_LAW_CIR ? 2 * (2 * lambda / (s * s) / (1 - q.decay)) : 1.0;             // :613
-    q.df = law == SDEGPU_LAW_CIR ? 4 * lambda * xi_ito / (s * s) : 0.0;                               // :615
-    if (law == SDEGPU_LAW_CIR && !(q.df >= 0)) return fail(SDEGPU_ERR_ARG, "sdegpu_rlaw: CIR needs xi >= 0");
+    q.icdf = c->icdf; q.n = n; q.path_offset = path_offset; q.seed = make_philox_key(seed); q.nsteps = nsteps;
     const size_t out_bytes = sizeof(double) * n, path_bytes = path ? sizeof(double) * n * ((size_t)nsteps + 1) : 0;
     q.x0 = nullptr; q.x0s = 0.0; q.x0_stride = (uint64_t)x0_stride;
     if (x0_stride == 0) {

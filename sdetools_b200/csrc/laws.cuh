@@ -22,5 +22,7 @@ struct LawArgs {
 };
 
 int launch_rlaw(const LawArgs &q, int sm_count, cudaStream_t stream);
+// what = 0 density, 1 distribution function of the transition law at xs[p] given x0[p]; uses law/decay/xi/sd/two_c/df, n, x0
+int launch_law_eval(const LawArgs &q, int what, const double *xs, double *out, int sm_count, cudaStream_t stream);
 
 }  // namespace sdegpu

@@ -169,6 +169,20 @@ class Engine:
                                    int(nsteps), int(seed) & 0xFFFFFFFFFFFFFFFF, int(path_offset), _ptr(out), _ptr(path),
                                    self._flags(x0, out, path)))
 
+    def law_eval(self, law, what, params, t, x0, x, out, stratonovich=False):
+        """sdegpu_law_eval: what = "d" density | "p" distribution function of law "ou" | "cir" at x given x0."""
+        p = (C.c_double * 3)(*[float(v) for v in params])
+        n = int(x.numel()) if _is_torch(x) else int(x.size)
+        if _is_torch(x0):
+            stride = 0 if x0.numel() == 1 else 1
+        else:
+            x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+            stride = 0 if x0.size == 1 else 1
+            if stride and x0.size != n:
+                raise ValueError("x0 must be a scalar or have one entry per point")
+        check(self.lib.sdegpu_law_eval(self._h, {"ou": 0, "cir": 1}[law], {"d": 0, "p": 1}[what], p, float(t),
+                                       int(bool(stratonovich)), _ptr(x0), stride, _ptr(x), n, _ptr(out), self._flags(x0, x, out)))
+
     # -- introspection ------------------------------------------------------------
     def philox4x32_10(self, ctr, key):
         a = (C.c_uint32 * 4)(*ctr)

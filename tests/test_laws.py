@@ -240,3 +240,52 @@ def test_brownian_bridge_ensemble(sde):
     assert np.max(np.abs(BB.var(axis=1) - var)) < 5 * var.max() * np.sqrt(2.0 / n)
     one = sde.rBrownianBridge(tv, B0T, sigma, seed=8)
     assert one.shape == (tv.size,) and np.array_equal(one, BB[:, 0])
+
+
+# ---- next-2: the laws themselves on the device ------------------------------------------------------
+@pytest.mark.gpu
+def test_device_laws_match_scipy(sde):
+    """dOU/pOU/dCIR/pCIR evaluated on the device against the oracle's scipy-based restatement of the reference
+    (R/sdetools.R:652-676, :745-765).  Tolerances: 1e-11 absolute on distribution functions, 1e-9 relative on
+    densities that are not denormal."""
+    x = np.linspace(-3, 5, 401)
+    assert np.max(np.abs(sde.pOU(x, 2.0, 1.3, 0.7, 0.9, 0.4) - laws.pOU(x, 2.0, 1.3, 0.7, 0.9, 0.4))) < 1e-14
+    assert np.allclose(sde.dOU(x, 2.0, 1.3, 0.7, 0.9, 0.4), laws.dOU(x, 2.0, 1.3, 0.7, 0.9, 0.4), rtol=1e-12, atol=0)
+    for lam, xi, gam, t, x0, strat in CIR_CASES + [(1.0, 1.0, 0.2, 1e-3, 3.0, False)]:       # last: ncp/2 ~ 75000
+        c, nu, n = laws.cir_parameters(x0, lam, xi, gam, t, strat)
+        mean, sd = (n + nu) / (2 * c), np.sqrt(2 * (n + 2 * nu)) / (2 * c)
+        q = np.concatenate([np.linspace(max(mean - 8 * sd, 1e-12), mean + 10 * sd, 300), [0.0, 1e-9, mean]])
+        P, D = sde.pCIR(q, x0, lam, xi, gam, t, strat), sde.dCIR(q, x0, lam, xi, gam, t, strat)
+        Pw, Dw = laws.pCIR(q, x0, lam, xi, gam, t, strat), laws.dCIR(q, x0, lam, xi, gam, t, strat)
+        assert np.max(np.abs(P - Pw)) < 1e-11, (lam, xi, gam, t)
+        ok = Dw > 1e-250
+        assert np.allclose(D[ok], Dw[ok], rtol=1e-9), (lam, xi, gam, t)
+        assert np.all(np.diff(P[:300]) >= -1e-15) and P[300] == 0.0
+    # per-point x0 and scalars
+    x0v = np.random.default_rng(0).uniform(0.2, 2.0, 50)
+    got = sde.pCIR(np.full(50, 1.0), x0v, 1.0, 1.0, 1.0, 0.5)
+    assert np.allclose(got, [laws.pCIR(1.0, v, 1.0, 1.0, 1.0, 0.5) for v in x0v], atol=1e-12)
+    assert isinstance(sde.pOU(0.3, 0.0, 1.0, 0.0, 1.0, 1.0), float)
+
+
+@pytest.mark.gpu
+def test_probability_integral_transform_stays_on_the_device(sde):
+    """What the device laws are for: u = pCIR(X_T) of an ensemble's terminal states, computed where they live.
+    Exact sampler -> uniform; Heun on a coarse grid -> visibly not."""
+    import torch
+    eng = sde.default_engine(0)
+    n = 400000
+    dev = torch.device("cuda", 0)
+    XT = torch.empty(n, dtype=torch.float64, device=dev)
+    U = torch.empty_like(XT)
+    x0 = torch.full((1,), 1.0, dtype=torch.float64, device=dev)
+    eng.rlaw("cir", (1.0, 1.0, 1.0), 1.0, x0, n, XT, nsteps=1, stratonovich=True, seed=2)
+    eng.law_eval("cir", "p", (1.0, 1.0, 1.0), 1.0, x0, XT, U, stratonovich=True)
+    counts = torch.histc(U, bins=50, min=0.0, max=1.0).cpu().numpy()
+    chi2 = float(((counts - n / 50) ** 2 / (n / 50)).sum())
+    assert stats.chi2.sf(chi2, 49) > 1e-3
+    t = np.arange(11) / 10
+    eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=n, projection="abs", seed=3, XT=XT)
+    eng.law_eval("cir", "p", (1.0, 1.0, 1.0), 1.0, x0, XT, U, stratonovich=True)
+    counts = torch.histc(U, bins=50, min=0.0, max=1.0).cpu().numpy()
+    assert stats.chi2.sf(float(((counts - n / 50) ** 2 / (n / 50)).sum()), 49) < 1e-6
