@@ -16,9 +16,6 @@
 
 namespace sdegpu {
 
-constexpr int IT_COLS = 128;     // columns (= threads) per block in k_rvbm
-constexpr int IT_STEPS = 32;     // increments staged per tile in k_rvbm
-constexpr int IT_LD = IT_STEPS + 1;
 #ifndef SDEGPU_INT_THREADS
 #define SDEGPU_INT_THREADS 256
 #endif
@@ -147,53 +144,62 @@ struct BMArgs {
     int nt;
 };
 
-__global__ void __launch_bounds__(IT_COLS) k_rvbm(const BMArgs q)
+// One thread per column, the column written as aligned 32-byte sectors straight from registers (the k_traj
+// store pattern): columns are dealt to lanes with stride Q (Q*nt = 0 mod 4) so that the sector phase — and with
+// it the position of the four-normal Philox blocks inside a sector — is warp-uniform and nothing diverges.
+// (Round 1 staged tiles through shared memory for coalesced stores: 2.3x slower than this, the barriers and the
+// transposition cost more than the scattered sectors.)
+constexpr int BM_THREADS = 256;
+
+__global__ void __launch_bounds__(BM_THREADS) k_rvbm(const BMArgs q, const int vec_ok, const int Q)
 {
-    extern __shared__ __align__(16) double sh_tab[];             // [quantile table][output tile]
-    double *sm = sh_tab + ICDF_TABLE_DOUBLES;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    icdf_stage(sh_tab, q.icdf, tid, IT_COLS);
+    extern __shared__ __align__(16) double sh_tab[];
+    icdf_stage(sh_tab, q.icdf, threadIdx.x, BM_THREADS);
     __syncthreads();
-    const uint64_t ntiles = (q.ncols + IT_COLS - 1) / IT_COLS;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t c0 = tile * IT_COLS, col = c0 + tid;
-        const bool valid = col < q.ncols;
-        const int rows = (int)((q.ncols - c0 < (uint64_t)IT_COLS) ? (q.ncols - c0) : IT_COLS);
+    const uint64_t stride = (uint64_t)gridDim.x * BM_THREADS, W = 32u * (unsigned)Q;
+    const uint64_t Tmax = (q.ncols + W - 1) / W * W;
+    for (uint64_t T = (uint64_t)blockIdx.x * BM_THREADS + threadIdx.x; T < Tmax; T += stride) {
+        const uint64_t within = T % W, col = (T - within) + (within >> 5) + (uint64_t)Q * (within & 31);
+        if (col >= q.ncols) continue;
+        double *row = q.B + col * (uint64_t)q.nt;
         CumsumAcc acc;
         double zq[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int i0 = 0; i0 < q.nt; i0 += IT_STEPS) {
-            const int nc = (q.nt - i0 < IT_STEPS) ? (q.nt - i0) : IT_STEPS;
-            if (valid) {
-                for (int k = 0; k < nc; ++k) {
-                    const int i = i0 + k;
-                    if ((i & 3) == 0) normal_quad(q.seed, q.path_offset + col, (uint32_t)(i >> 2), 0u, sh_tab, zq);
-                    const double2 d = __ldg(&q.dtsq[i]);
-                    const int s4 = i & 3;
-                    const double z = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
-                    // rnorm(mean=u*dt, sd=sigma*sqrt(dt)) = mean + sd*Z
-                    const double dB = __dadd_rn(__dmul_rn(q.u, d.x), __dmul_rn(__dmul_rn(q.sigma, d.y), z));
-                    sm[tid * IT_LD + k] = __dadd_rn(q.B0, acc.add(dB));
-                }
-            }
-            __syncthreads();
-            for (int rr = warp; rr < rows; rr += IT_COLS / 32)
-                for (int k = lane; k < nc; k += 32) q.B[(c0 + rr) * (uint64_t)q.nt + i0 + k] = sm[rr * IT_LD + k];
-            __syncthreads();
+        auto element = [&](int i) -> double {                    // B[i] of this column
+            if ((i & 3) == 0) normal_quad(q.seed, q.path_offset + col, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+            const double2 d = __ldg(&q.dtsq[i]);
+            const int s4 = i & 3;
+            const double z = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
+            // rnorm(mean=u*dt, sd=sigma*sqrt(dt)) = mean + sd*Z
+            const double dB = __dadd_rn(__dmul_rn(q.u, d.x), __dmul_rn(__dmul_rn(q.sigma, d.y), z));
+            return __dadd_rn(q.B0, acc.add(dB));
+        };
+        int head = vec_ok ? (int)((4 - ((col * (uint64_t)q.nt) & 3)) & 3) : q.nt;   // elements before the first sector boundary
+        if (head > q.nt) head = q.nt;
+        int i = 0;
+        for (; i < head; ++i) row[i] = element(i);
+        for (; i + 3 < q.nt; i += 4) {
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = element(i + k);
+            st_sector(row + i, v);
         }
+        for (; i < q.nt; ++i) row[i] = element(i);
     }
 }
 
 int launch_rvbm(const BMArgs &q, int sm_count, cudaStream_t stream)
 {
     if (q.ncols == 0 || q.nt == 0) return 0;
-    const size_t smem = ICDF_TABLE_BYTES + sizeof(double) * IT_COLS * IT_LD;
-    const uint64_t ntiles = (q.ncols + IT_COLS - 1) / IT_COLS;
+    const size_t smem = ICDF_TABLE_BYTES;
+    const uint64_t nblk = (q.ncols + BM_THREADS - 1) / BM_THREADS;
     int per_sm = 1;
     cudaFuncSetAttribute(k_rvbm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rvbm, IT_COLS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rvbm, BM_THREADS, smem);
     uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
-    if (grid > ntiles) grid = ntiles;
-    k_rvbm<<<(int)grid, IT_COLS, smem, stream>>>(q);
+    if (grid > nblk) grid = nblk;
+    const int vec_ok = (reinterpret_cast<uintptr_t>(q.B) & 31) == 0;
+    const int Q = (q.nt % 4 == 0) ? 1 : ((q.nt % 2 == 0) ? 2 : 4);
+    k_rvbm<<<(int)grid, BM_THREADS, smem, stream>>>(q, vec_ok, Q);
     return (int)cudaGetLastError();
 }
 

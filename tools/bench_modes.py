@@ -114,6 +114,34 @@ def main():
         del f, g, l, r, c
         torch.cuda.empty_cache()
 
+    # rvBM ensemble: 8 B written per element (tiled kernel, coalesced stores) and its functionals (nothing written)
+    if want("rvbm"):
+        nt, nc = 1001, (1 << 16 if args.quick else 1 << 21)
+        t = np.arange(nt) * 0.01
+        Bd = torch.empty(nc * nt, dtype=torch.float64, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.use_torch_stream()
+
+        def timed_bm(fn):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(3):
+                ev0.record()
+                fn()
+                ev1.record()
+                torch.cuda.synchronize()
+                best = min(best, ev0.elapsed_time(ev1))
+            return best
+        ms = timed_bm(lambda: eng.rvbm(t, nc, Bd, seed=9))
+        emit("rvbm", nt=nt, ncols=nc, ms=ms, elems_per_s=nt * nc / ms * 1e3, gbs=8.0 * nt * nc / ms / 1e6, hbm_frac=8.0 * nt * nc / ms / 1e6 / hbm)
+        vmax = torch.empty(nc, dtype=torch.float64, device=dev)
+        ms = timed_bm(lambda: eng.bm_functionals(t, nc, seed=9, vmax=vmax))
+        emit("rvbm_functionals_max", nt=nt, ncols=nc, ms=ms, elems_per_s=nt * nc / ms * 1e3)
+        eng.use_own_stream()
+        del Bd, vmax
+        torch.cuda.empty_cache()
+
     # next-1: killing / stopping (vignettes/Killing.Rmd:152-207 scaled up): OU with exp killing rate, lifetime only
     if want("killed"):
         import sdetools_b200.catalogue as cat
