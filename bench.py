@@ -133,7 +133,6 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -261,10 +260,21 @@ def main():
     ap.add_argument("--nsteps", type=int, default=10_000, help="time steps per path (default: config C2)")
     ap.add_argument("--cpu-paths", type=int, default=0, help="CPU sample size in paths (default 20000 per core; 10000 per core per step for --impl reference)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: everything libraries print while we run (NCCL's version banner, torch
+    # warnings written with printf) is sent to stderr by pointing fd 1 there; the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = sys.stdout
+    sys.stdout = os.fdopen(real_stdout, "w")
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+        sys.stdout.flush()
+    finally:
+        sys.stdout = out
 
 
 if __name__ == "__main__":
