@@ -40,6 +40,23 @@ def main():
 
     want = lambda n: not args.only or n in args.only.split(",")
 
+    # C1: the reference's own CPU-sized case, end to end with HOST buffers (copies inside the timed region)
+    if want("c1"):
+        import time
+        P, nt = 1000, 1001
+        t = np.arange(nt) * 0.01
+        rng = np.random.default_rng(1)
+        Bh = np.asfortranarray(np.cumsum(np.concatenate([np.zeros((1, 1, P)), rng.standard_normal((nt - 1, 1, P)) * 0.1]), axis=0))
+        Xh = np.empty((nt, 1, P), order="F")
+        eng.run("ou", "euler", [1.0, 0.0, 1.0], t, [0.0], nx=1, npaths=P, B=Bh, X=Xh)
+        best = 1e30
+        for _ in range(5):
+            t0 = time.perf_counter()
+            eng.run("ou", "euler", [1.0, 0.0, 1.0], t, [0.0], nx=1, npaths=P, B=Bh, X=Xh)
+            best = min(best, time.perf_counter() - t0)
+        emit("c1_ou_euler_suppliedB_host_buffers", paths=P, nt=nt, wall_ms=best * 1e3, path_steps_per_s=P * (nt - 1) / best,
+             h2d_bytes=Bh.nbytes, d2h_bytes=Xh.nbytes)
+
     # C3: van der Pol, full trajectory, fused generator (HBM-write bound; 16 B per path-step)
     if want("c3"):
         # two full waves of the trajectory kernel (one 512-thread CTA per SM): equal-length paths cannot fill a
