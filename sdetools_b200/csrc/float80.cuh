@@ -182,7 +182,7 @@ SDEGPU_HD double f80_to_double(const F80 &acc)
 // The same accumulator as a pair of doubles: S = h + l with h = RN53(S), so that (double)S — what
 // cumsum stores — is h itself.  S has a 64-bit significand, hence l (at most 11 bits) is exact.
 // S' = RN64(S + x) is formed without integer arithmetic on the significand:
-//   three TwoSums give V = S + x = a + b + c exactly (|b| <= ulp(a)/2, |c| <= ulp(b)/2);
+//   four TwoSums give V = S + x = a + b + c exactly (|b| <= ulp(a)/2, |c| <= ulp(b)/2);
 //   the 64-bit grid q = 2^(e-63) follows from a's exponent (one binade lower when a is a power of
 //   two and the remainder points back towards zero); b is rounded to that grid, ties to even, with
 //   the add-and-subtract constant 1.5 * 2^52 * q, c only ever deciding an exact tie;
