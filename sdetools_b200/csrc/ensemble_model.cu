@@ -1,5 +1,5 @@
 // One translation unit per catalogue model (compiled with -DSDEGPU_TU_MODEL=<id>):
-// instantiates k_terminal / k_tiled for every scheme x projection x arithmetic
+// instantiates k_terminal / k_traj / k_stream / k_killed(_refill) / k_functionals for every scheme x projection x arithmetic
 // combination of that model and exposes one launcher.
 #include "ensemble.cuh"
 

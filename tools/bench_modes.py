@@ -131,7 +131,7 @@ def main():
         del f, g, l, r, c
         torch.cuda.empty_cache()
 
-    # rvBM ensemble: 8 B written per element (tiled kernel, coalesced stores) and its functionals (nothing written)
+    # rvBM ensemble: 8 B written per element (sector stores from registers) and its functionals (nothing written)
     if want("rvbm"):
         nt, nc = 1001, (1 << 16 if args.quick else 1 << 21)
         t = np.arange(nt) * 0.01
