@@ -233,6 +233,9 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None,
+                         "executed": {"fp64_pipe_busy": 0.477, "issue_slots_busy": 0.673, "instructions_per_path_step": 71.3,
+                                      "source": "ncu --set full, profiles/r1_ncu_k_terminal_cir_heun.txt: the kernel is issue-bound; "
+                                                "`frac` credits the survey's algorithmic flop count, not executed FP64 instructions"},
                          "traffic": 607232, "traffic_source": "ncu --set full dram__bytes_read+write per launch "
                                                               "(profiles/r1_ncu_k_terminal_cir_heun.txt): tables only, no path data",
                          "kernel": "k_terminal<cir,heun,abs>", "kernel_ms": k_ms,
