@@ -12,6 +12,7 @@
 #define ICDF_TABLE_DEFINE __device__ const unsigned long long g_icdf_table
 #include "../../include/sdegpu.h"
 #include "ensemble.cuh"
+#include "integrals.cuh"
 #include "laws.cuh"
 #include "linear.cuh"
 
@@ -23,29 +24,6 @@ int launch_model_3(const RunArgs &, const LaunchCfg &, int *);
 int launch_model_4(const RunArgs &, const LaunchCfg &, int *);
 int launch_model_5(const RunArgs &, const LaunchCfg &, int *);
 
-struct IntegralArgs {
-    const double *a, *b;
-    double *l, *r, *c;
-    uint64_t n, ncols;
-};
-int launch_integral(int mode, const IntegralArgs &q, int sm_count, cudaStream_t stream);
-struct BMArgs {
-    const double2 *dtsq;
-    const double *icdf;
-    double *B;
-    double sigma, B0, u;
-    uint64_t ncols, path_offset;
-    PhiloxKey seed;
-    int nt;
-};
-int launch_rvbm(const BMArgs &q, int sm_count, cudaStream_t stream);
-struct BMFuncArgs {
-    BMArgs bm;
-    double level;
-    double *vmax, *vmin, *tmax, *tmin, *thit;
-    const double *times;
-};
-int launch_bm_functionals(const BMFuncArgs &q, int sm_count, cudaStream_t stream);
 }  // namespace sdegpu
 
 using namespace sdegpu;

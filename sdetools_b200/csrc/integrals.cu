@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "float80.cuh"
+#include "integrals.cuh"
 #include "philox.cuh"
 
 namespace sdegpu {
@@ -27,11 +28,6 @@ namespace sdegpu {
 #endif
 constexpr int INT_THREADS = SDEGPU_INT_THREADS;
 
-struct IntegralArgs {
-    const double *a, *b;         // stochint: f, g       crossvar: X, Y
-    double *l, *r, *c;           // stochint outputs (any may be null); crossvar writes `l`
-    uint64_t n, ncols;
-};
 
 __device__ __forceinline__ void ld_sector(const double *p, double (&s)[4])
 {
@@ -133,16 +129,6 @@ int launch_integral(int mode, const IntegralArgs &q, int sm_count, cudaStream_t 
 }
 
 // ---- rvBM ensembles ---------------------------------------------------------
-// Column c: dt <- c(times[1],diff(times)); dB <- u*dt + (sigma*sqrt(dt))*Z; B <- B0+cumsum(dB)
-struct BMArgs {
-    const double2 *dtsq;     // [nt] {dt_i, sqrt(dt_i)} with dt_0 = times[0]
-    const double *icdf;      // device, half-normal quantile table (philox.cuh)
-    double *B;               // B[c*nt+i]
-    double sigma, B0, u;
-    uint64_t ncols, path_offset;
-    PhiloxKey seed;
-    int nt;
-};
 
 // One thread per column, the column written as aligned 32-byte sectors straight from registers (the k_traj
 // store pattern): columns are dealt to lanes with stride Q (Q*nt = 0 mod 4) so that the sector phase — and with
@@ -207,14 +193,6 @@ int launch_rvbm(const BMArgs &q, int sm_count, cudaStream_t stream)
 // apply(rvBM(times, n), 2, max) and friends (vignettes/BrownianMotion.Rmd:101-144) without storing the paths:
 // column c is regenerated exactly as k_rvbm builds it (same normals, same 80-bit cumsum, same B0 + ...), so
 // every functional is bit-identical to the one computed from the stored rvBM matrix.  One thread per column.
-struct BMFuncArgs {
-    BMArgs bm;                   // bm.B unused
-    double level;                // first passage level
-    double *vmax, *vmin;         // [ncols] max_i B_i, min_i B_i           (any may be null)
-    double *tmax, *tmin;         // [ncols] times[i] of the first maximum / minimum
-    double *thit;                // [ncols] first times[i] with B_i >= level (level >= B0) or <= level (level < B0); NaN: never
-    const double *times;         // device [nt]
-};
 
 __global__ void __launch_bounds__(INT_THREADS) k_bm_functionals(const BMFuncArgs q)
 {
