@@ -50,6 +50,13 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
                 if (a.B) {
                     const double *b = a.B + ((p0 + q) * nB + k) * (uint64_t)a.nt + i;
                     dBs[e] = __dsub_rn(b[1], b[0]);                           // dB <- apply(B,2,diff) (:437)
+                } else if (nB == 1) {
+                    // one channel: the scalar models' stream (four normals per block), so a linear model with one
+                    // noise channel sees the same Brownian motion as a catalogue model under the same seed
+                    double zq[4];
+                    normal_quad(a.seed, a.path_offset + p0 + q, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+                    const int s4 = i & 3;
+                    dBs[e] = ds.y * (s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3])));
                 } else {
                     // matrix-valued g: one Philox block per (path, step, channel pair), shared with the DMMA kernel
                     double z0, z1;
@@ -125,9 +132,175 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
     }
 }
 
+// ---- small systems (d, nB <= 4: the noisy oscillator of vignettes/NoisyOscillator.Rmd and its kin) ------------
+// One thread per path with x, A and G in registers — no shared-memory state, no barriers.  Same operations in
+// the same order as k_linear_generic (bit-identical when STRICT) and the same generator stream.
+constexpr int LIN_SMALL_MAX = 4;
+
+template <int D, int NB, bool STRICT>
+__global__ void __launch_bounds__(LIN_THREADS) k_linear_small(const LinearArgs a)
+{
+    extern __shared__ __align__(16) double sh_tab[];
+    if (!a.B) icdf_stage(sh_tab, a.icdf, threadIdx.x, LIN_THREADS);
+    __syncthreads();
+    double Ar[D][D], Gr[D][NB];                                  // Ar[j][k] = A[j,k]
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) Ar[j][k] = __ldg(&a.A[k * D + j]);
+#pragma unroll
+        for (int k = 0; k < NB; ++k) Gr[j][k] = __ldg(&a.G[k * D + j]);
+    }
+    const bool heun = a.scheme == SDEGPU_HEUN;
+    const int nsteps = a.nt - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * LIN_THREADS;
+    const uint64_t rounds = (a.npaths + stride - 1) / stride;
+    double mom[D][5];
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) mom[j][m] = 0.0;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t p = r * stride + (uint64_t)blockIdx.x * LIN_THREADS + threadIdx.x;
+        if (p >= a.npaths) continue;
+        double x[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            x[j] = a.x0 ? a.x0[p * D + j] : a.x0_shared[j];
+            if (a.X) a.X[(p * D + j) * (uint64_t)a.nt] = x[j];                 // X[1,] <- x0 (:441)
+        }
+        double zq[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 ds = __ldg(&a.dtsq[i]);
+            double dB[NB];
+            if (a.B) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    const double *b = a.B + (p * NB + k) * (uint64_t)a.nt + i;
+                    dB[k] = __dsub_rn(__ldg(b + 1), __ldg(b));                  // dB <- apply(B,2,diff) (:437)
+                }
+            } else if (NB == 1) {                                               // the scalar models' stream: 4 normals per block
+                if ((i & 3) == 0) normal_quad(a.seed, a.path_offset + p, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+                const int s4 = i & 3;
+                dB[0] = __dmul_rn(ds.y, s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3])));
+            } else {
+#pragma unroll
+                for (int k = 0; k < NB; k += 2) {                               // one Philox block per channel pair
+                    double z0, z1;
+                    normal_pair(a.seed, a.path_offset + p, (uint32_t)i, 0x80000000u + (uint32_t)(k >> 1), sh_tab, z0, z1);
+                    dB[k] = __dmul_rn(ds.y, z0);
+                    if (k + 1 < NB) dB[k + 1] = __dmul_rn(ds.y, z1);
+                }
+            }
+            double y[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {                                       // (x + (A x) dt) + G dB  (:453 / :318)
+                double f = STRICT ? __dmul_rn(Ar[j][0], x[0]) : Ar[j][0] * x[0];
+#pragma unroll
+                for (int k = 1; k < D; ++k) f = madd<STRICT>(f, Ar[j][k], x[k]);
+                double gdb = STRICT ? __dmul_rn(Gr[j][0], dB[0]) : Gr[j][0] * dB[0];
+#pragma unroll
+                for (int k = 1; k < NB; ++k) gdb = madd<STRICT>(gdb, Gr[j][k], dB[k]);
+                y[j] = STRICT ? __dadd_rn(__dadd_rn(x[j], __dmul_rn(f, ds.x)), gdb) : (x[j] + f * ds.x) + gdb;
+            }
+            if (heun) {                                                         // corrector (:323), gX + gY = G + G
+                double n[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    double fx = STRICT ? __dmul_rn(Ar[j][0], x[0]) : Ar[j][0] * x[0];
+                    double fy = STRICT ? __dmul_rn(Ar[j][0], y[0]) : Ar[j][0] * y[0];
+#pragma unroll
+                    for (int k = 1; k < D; ++k) {
+                        fx = madd<STRICT>(fx, Ar[j][k], x[k]);
+                        fy = madd<STRICT>(fy, Ar[j][k], y[k]);
+                    }
+                    const double g0 = Gr[j][0];
+                    double gdb = STRICT ? __dmul_rn(__dadd_rn(g0, g0), dB[0]) : (g0 + g0) * dB[0];
+#pragma unroll
+                    for (int k = 1; k < NB; ++k) {
+                        const double gk = Gr[j][k];
+                        gdb = madd<STRICT>(gdb, STRICT ? __dadd_rn(gk, gk) : gk + gk, dB[k]);
+                    }
+                    n[j] = STRICT
+                        ? __dadd_rn(__dadd_rn(x[j], __dmul_rn(__dmul_rn(0.5, __dadd_rn(fx, fy)), ds.x)), __dmul_rn(0.5, gdb))
+                        : (x[j] + (0.5 * (fx + fy)) * ds.x) + 0.5 * gdb;
+                }
+#pragma unroll
+                for (int j = 0; j < D; ++j) y[j] = n[j];
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                x[j] = y[j];
+                if (a.X) a.X[(p * D + j) * (uint64_t)a.nt + i + 1] = x[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            if (a.XT) a.XT[p * D + j] = x[j];
+            if (a.moments) {
+                const double dd = x[j] - a.center[j];
+                if (isfinite(dd)) {
+                    const double d2 = dd * dd;
+                    mom[j][0] += 1.0; mom[j][1] += dd; mom[j][2] += d2; mom[j][3] += d2 * dd; mom[j][4] += d2 * d2;
+                }
+            }
+        }
+    }
+    if (a.moments) {                                             // per-thread sums -> warp -> one atomic per warp and moment
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                double v = mom[j][m];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&a.moments[j * 5 + m], v);
+            }
+    }
+}
+
+template <int D, int NB>
+static int launch_small_dn(const LinearArgs &a, int sm_count, cudaStream_t stream)
+{
+    auto ks = k_linear_small<D, NB, true>;
+    auto kf = k_linear_small<D, NB, false>;
+    const size_t smem = a.B ? 0 : (size_t)ICDF_TABLE_BYTES;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, a.strict ? ks : kf, LIN_THREADS, smem);
+    uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
+    const uint64_t nblk = (a.npaths + LIN_THREADS - 1) / LIN_THREADS;
+    if (grid > nblk) grid = nblk;
+    if (a.strict) ks<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
+    else kf<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <int D>
+static int launch_small_d(const LinearArgs &a, int sm_count, cudaStream_t stream)
+{
+    switch (a.nB) {
+    case 1: return launch_small_dn<D, 1>(a, sm_count, stream);
+    case 2: return launch_small_dn<D, 2>(a, sm_count, stream);
+    case 3: return launch_small_dn<D, 3>(a, sm_count, stream);
+    default: return launch_small_dn<D, 4>(a, sm_count, stream);
+    }
+}
+
 int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream)
 {
     if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * a.d, stream);
+    if (a.d <= LIN_SMALL_MAX && a.nB <= LIN_SMALL_MAX && a.npaths > 0) {
+        switch (a.d) {
+        case 1: return launch_small_d<1>(a, sm_count, stream);
+        case 2: return launch_small_d<2>(a, sm_count, stream);
+        case 3: return launch_small_d<3>(a, sm_count, stream);
+        default: return launch_small_d<4>(a, sm_count, stream);
+        }
+    }
     int PT = LIN_THREADS / a.d;                        // paths per block: one thread per (path, row) when d <= 256
     if (PT < 1) PT = 1;
     if (PT > 64) PT = 64;

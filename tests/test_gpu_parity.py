@@ -341,6 +341,38 @@ def test_linear_strict_bit_identical(sde, scheme):
     assert np.allclose(fast, want, rtol=1e-12, atol=1e-13)
 
 
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+@pytest.mark.parametrize("d,nB", [(1, 1), (2, 2), (2, 1), (3, 2), (4, 4), (4, 3)])
+def test_small_linear_systems_register_kernel(sde, eng, scheme, d, nB):
+    """d, nB <= 4 (the noisy oscillator's size) run one thread per path with A, G, x in registers: bit-identical to
+    the oracle with a supplied B, the oracle's own fused generator to the quantile table's accuracy, moments = those
+    of the returned terminal states."""
+    rng = np.random.default_rng(10 * d + nB)
+    A = -0.6 * np.eye(d) + 0.4 * rng.standard_normal((d, d))
+    G = rng.standard_normal((d, nB))
+    x0 = rng.standard_normal(d)
+    t, B = brownian(77, nB, 300, 3)
+    fn = sde.euler if scheme == "euler" else sde.heun
+    want = O.ensemble(scheme, "linear", (A, G), t, x0, B=B)
+    got = fn(*sde.catalogue.linear(A, G), t, x0, B)
+    assert np.array_equal(got["X"], want) and np.array_equal(got["XT"], want[-1])
+    assert np.allclose(fn(*sde.catalogue.linear(A, G), t, x0, B, arith="fast")["X"], want, rtol=1e-12, atol=1e-13)
+    # fused generator against the C oracle's (same Philox stream, libm quantile instead of the table)
+    P, seed, off = 5000, 77, 1 << 34
+    params = np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
+    _, XTc = c_oracle.ensemble(SCH[scheme], 6, params, d, nB, 0, t, x0, seed=seed, path_offset=off, npaths=P, full=False, nthreads=8)
+    XT = np.empty((d, P), order="F")
+    ps = np.zeros((5, d), order="F")
+    eng.run("linear", scheme, params, t, x0, nx=d, nB=nB, npaths=P, seed=seed, path_offset=off, XT=XT, power_sums=ps,
+            center=np.zeros(d))
+    assert np.allclose(XT, XTc.T, rtol=1e-7, atol=1e-7)
+    assert np.array_equal(ps[0], np.full(d, P)) and np.allclose(ps[1], XT.sum(axis=1), rtol=1e-10, atol=1e-9)
+    assert np.allclose(ps[2], (XT ** 2).sum(axis=1), rtol=1e-10)
+    # and the trajectory variant ends where the terminal-only variant does
+    X = fn(*sde.catalogue.linear(A, G), t, x0, npaths=64, seed=seed, path_offset=off)["X"]
+    assert np.allclose(X[-1], XT[:, :64], rtol=1e-13, atol=1e-15)
+
+
 def test_reference_dims_test_on_device(sde):
     """tests/testthat/test_solvers.R:3-18 with catalogue closures: dim(X) = c(nt, nx), nB = 1 and nB = 2."""
     times = np.arange(0, 11, dtype=float)
@@ -636,3 +668,12 @@ def test_path_integrals_argument_errors(sde):
     f, g = sde.catalogue.ou()
     with pytest.raises(SdeGpuError, match="path_integrals"):
         sde.euler(f, g, [0.0, 0.5, 1.0], 0.0, npaths=4, seed=1, integrals=True, r=sde.catalogue.kill_const(1.0))
+
+
+def test_single_channel_linear_model_shares_the_scalar_stream(sde):
+    """A linear model with one noise channel draws from the same stream as the catalogue's scalar models:
+    dX = -lam X dt + sig dB as `linear` and as `ou` give the same paths under one seed (to FMA-level rounding)."""
+    t = np.arange(201) * 0.01
+    a = sde.euler(*sde.catalogue.linear([[-1.3]], [[0.9]]), t, 2.0, npaths=500, seed=8)["X"]
+    b = sde.euler(*sde.catalogue.ou(1.3, 0.0, 0.9), t, 2.0, npaths=500, seed=8)["X"]
+    assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
