@@ -208,6 +208,25 @@ def main():
         del out
         torch.cuda.empty_cache()
 
+    # linear SDE at small and medium d (register kernel for d, nB <= 4, generic kernel above)
+    if want("linear_small"):
+        for d, nB, P, n in ((2, 2, 1 << 20, 1000), (4, 2, 1 << 19, 1000), (8, 8, 1 << 18, 1000), (16, 16, 1 << 17, 500)):
+            if args.quick:
+                P >>= 3
+            rng = np.random.default_rng(d)
+            R = rng.standard_normal((d, d))
+            A = -0.5 * np.eye(d) + 0.5 * (R - R.T) / np.sqrt(d)
+            G = rng.standard_normal((d, nB)) * 0.5
+            params = np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
+            XT = torch.empty(P * d, dtype=torch.float64, device=dev)
+            t = np.arange(n + 1) / n
+            for scheme in ("euler", "heun"):
+                ms = best_ms(lambda: eng.run("linear", scheme, params, t, np.ones(d), nx=d, nB=nB, npaths=P, seed=1, XT=XT,
+                                             want_time=True), reps=2)
+                emit(f"linear_d{d}_nB{nB}_{scheme}", paths=P, nsteps=n, ms=ms, path_steps_per_s=P * n / ms * 1e3)
+            del XT
+        torch.cuda.empty_cache()
+
     # C4: linear SDE d = 256 (A x as a GEMM over paths); 2d^2+4d flops per path-step
     if want("c4"):
         d = 256
