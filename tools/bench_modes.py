@@ -131,6 +131,23 @@ def main():
         del f, g, l, r, c
         torch.cuda.empty_cache()
 
+    # integrals accumulated in the step loop (k_functionals): four 80-bit accumulators per component, nothing stored but 4 doubles
+    if want("functionals"):
+        P, n = ((1 << 18) if args.quick else 1 << 22), 1000
+        t = np.arange(n + 1) * 1e-3
+        PI = torch.empty(P * 4, dtype=torch.float64, device=dev)
+        XT = torch.empty(P, dtype=torch.float64, device=dev)
+        ms = best_ms(lambda: eng.run("ou", "euler", [1.3, 0.7, 0.9], t, [2.0], nx=1, npaths=P, seed=5, XT=XT, path_integrals=PI,
+                                     want_time=True))
+        emit("functionals_ou_euler_generator", paths=P, nsteps=n, ms=ms, path_steps_per_s=P * n / ms * 1e3)
+        PI2 = torch.empty(P * 8, dtype=torch.float64, device=dev)
+        XT2 = torch.empty(P * 2, dtype=torch.float64, device=dev)
+        ms = best_ms(lambda: eng.run("vdp", "heun", [1.0, 0.5], t, [0.1, -0.2], nx=2, npaths=P, seed=5, XT=XT2, path_integrals=PI2,
+                                     want_time=True))
+        emit("functionals_vdp_heun_generator", paths=P, nsteps=n, ms=ms, path_steps_per_s=P * n / ms * 1e3)
+        del PI, XT, PI2, XT2
+        torch.cuda.empty_cache()
+
     # rvBM ensemble: 8 B written per element (sector stores from registers) and its functionals (nothing written)
     if want("rvbm"):
         nt, nc = 1001, (1 << 16 if args.quick else 1 << 21)
