@@ -259,6 +259,145 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_small(const LinearArgs a
     }
 }
 
+// ---- medium systems (4 < d <= 32, nB <= 32): one lane per (path, row), a warp holds 32/DP paths ------------------
+// DP = d rounded up to 8, 16 or 32.  Lane (q, j) keeps x_j, row j of A and row j of G in registers; A x and G dB are
+// accumulated over k in the reference's order with x_k and dB_k fetched from lane (q, k) by shuffle — no shared
+// memory state, no block barriers (k_linear_generic needs three or four per step).  Same operations, same order,
+// same generator stream as the other linear kernels.
+template <int DP, bool STRICT>
+__global__ void __launch_bounds__(LIN_THREADS, DP <= 16 ? 2 : 1) k_linear_warp(const LinearArgs a)
+{
+    extern __shared__ __align__(16) double sh_tab[];
+    if (!a.B) icdf_stage(sh_tab, a.icdf, threadIdx.x, LIN_THREADS);
+    __syncthreads();
+    constexpr int PPW = 32 / DP;                                 // paths per warp
+    const int d = a.d, nB = a.nB, nsteps = a.nt - 1;
+    const int lane = threadIdx.x & 31, q = lane / DP, j = lane - q * DP;
+    const bool row = j < d;                                      // padding lanes compute nothing that is kept
+    double Ar[DP], Gr[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+        Ar[k] = (row && k < d) ? __ldg(&a.A[(size_t)k * d + j]) : 0.0;
+        Gr[k] = (row && k < nB) ? __ldg(&a.G[(size_t)k * d + j]) : 0.0;
+    }
+    const bool heun = a.scheme == SDEGPU_HEUN;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (LIN_THREADS / 32);
+    const uint64_t warp = (uint64_t)blockIdx.x * (LIN_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t ngroups = (a.npaths + PPW - 1) / PPW;
+    double mom[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (uint64_t grp = warp; grp < ngroups; grp += nwarps) {
+        const uint64_t p = grp * PPW + q;
+        const bool valid = p < a.npaths, mine = valid && row;
+        const uint64_t pc = valid ? p : a.npaths - 1;            // padding paths recompute the last one and discard it
+        double x = row ? (a.x0 ? a.x0[pc * d + j] : a.x0_shared[j]) : 0.0;
+        if (mine && a.X) a.X[(p * d + j) * (uint64_t)a.nt] = x;                  // X[1,] <- x0 (:441)
+        double zq[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 ds = __ldg(&a.dtsq[i]);
+            double dBj = 0.0;                                    // increment of channel j (lanes j < nB)
+            if (j < nB) {
+                if (a.B) {
+                    const double *b = a.B + (pc * nB + j) * (uint64_t)a.nt + i;
+                    dBj = __dsub_rn(__ldg(b + 1), __ldg(b));                      // dB <- apply(B,2,diff) (:437)
+                } else if (nB == 1) {
+                    if ((i & 3) == 0) normal_quad(a.seed, a.path_offset + pc, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+                    const int s4 = i & 3;
+                    dBj = __dmul_rn(ds.y, s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3])));
+                }
+            }
+            if (!a.B && nB > 1) {                                // one Philox block per channel pair: the even lane draws
+                double z0 = 0.0, z1 = 0.0;                       // both normals and hands the second to its neighbour
+                if (j < nB && (j & 1) == 0)
+                    normal_pair(a.seed, a.path_offset + pc, (uint32_t)i, 0x80000000u + (uint32_t)(j >> 1), sh_tab, z0, z1);
+                const double zn = __shfl_sync(0xffffffffu, z1, lane & ~1);
+                if (j < nB) dBj = __dmul_rn(ds.y, (j & 1) ? zn : z0);
+            }
+            const int base = q * DP;
+            // Y = (x + (A x) dt) + G dB        (euler :453 / heun predictor :318), accumulation order k = 0..d-1
+            double f = 0.0, gdb = 0.0;
+            if (STRICT) {
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    const double xk = __shfl_sync(0xffffffffu, x, base + k);
+                    if (k == 0) f = __dmul_rn(Ar[0], xk);
+                    else if (k < d) f = madd<true>(f, Ar[k], xk);
+                }
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    const double bk = __shfl_sync(0xffffffffu, dBj, base + k);
+                    if (k == 0) gdb = __dmul_rn(Gr[0], bk);
+                    else if (k < nB) gdb = madd<true>(gdb, Gr[k], bk);
+                }
+            } else {                                             // FAST: four partial sums (padding rows/columns of A, G are 0)
+                double f4[4] = {0.0, 0.0, 0.0, 0.0}, g4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    f4[k & 3] = fma(Ar[k], __shfl_sync(0xffffffffu, x, base + k), f4[k & 3]);
+                    g4[k & 3] = fma(Gr[k], __shfl_sync(0xffffffffu, dBj, base + k), g4[k & 3]);
+                }
+                f = (f4[0] + f4[1]) + (f4[2] + f4[3]);
+                gdb = (g4[0] + g4[1]) + (g4[2] + g4[3]);
+            }
+            double y = STRICT ? __dadd_rn(__dadd_rn(x, __dmul_rn(f, ds.x)), gdb) : (x + f * ds.x) + gdb;
+            if (heun) {                                          // corrector (:323), gX + gY = G + G
+                double fy = 0.0, g2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    const double yk = __shfl_sync(0xffffffffu, y, base + k);
+                    if (k == 0) fy = STRICT ? __dmul_rn(Ar[0], yk) : Ar[0] * yk;
+                    else if (k < d) fy = madd<STRICT>(fy, Ar[k], yk);
+                }
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    const double bk = __shfl_sync(0xffffffffu, dBj, base + k);
+                    const double gk = STRICT ? __dadd_rn(Gr[k], Gr[k]) : Gr[k] + Gr[k];
+                    if (k == 0) g2 = STRICT ? __dmul_rn(gk, bk) : gk * bk;
+                    else if (k < nB) g2 = madd<STRICT>(g2, gk, bk);
+                }
+                y = STRICT ? __dadd_rn(__dadd_rn(x, __dmul_rn(__dmul_rn(0.5, __dadd_rn(f, fy)), ds.x)), __dmul_rn(0.5, g2))
+                           : (x + (0.5 * (f + fy)) * ds.x) + 0.5 * g2;
+            }
+            x = row ? y : 0.0;
+            if (mine && a.X) a.X[(p * d + j) * (uint64_t)a.nt + i + 1] = x;
+        }
+        if (mine) {
+            if (a.XT) a.XT[p * d + j] = x;
+            if (a.moments) {
+                const double dd = x - a.center[j];
+                if (isfinite(dd)) {
+                    const double d2 = dd * dd;
+                    mom[0] += 1.0; mom[1] += dd; mom[2] += d2; mom[3] += d2 * dd; mom[4] += d2 * d2;
+                }
+            }
+        }
+    }
+    if (a.moments && row) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+            if (mom[m] != 0.0) atomicAdd(&a.moments[j * 5 + m], mom[m]);
+    }
+}
+
+template <int DP>
+static int launch_warp_dp(const LinearArgs &a, int sm_count, cudaStream_t stream)
+{
+    auto ks = k_linear_warp<DP, true>;
+    auto kf = k_linear_warp<DP, false>;
+    const size_t smem = a.B ? 0 : (size_t)ICDF_TABLE_BYTES;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, a.strict ? ks : kf, LIN_THREADS, smem);
+    uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
+    const uint64_t ngroups = (a.npaths + (32 / DP) - 1) / (32 / DP), nblk = (ngroups + LIN_THREADS / 32 - 1) / (LIN_THREADS / 32);
+    if (grid > nblk) grid = nblk;
+    if (a.strict) ks<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
+    else kf<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
 template <int D, int NB>
 static int launch_small_dn(const LinearArgs &a, int sm_count, cudaStream_t stream)
 {
@@ -300,6 +439,11 @@ int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream)
         case 3: return launch_small_d<3>(a, sm_count, stream);
         default: return launch_small_d<4>(a, sm_count, stream);
         }
+    }
+    if (a.d <= 32 && a.nB <= a.d && a.npaths > 0) {
+        if (a.d <= 8) return launch_warp_dp<8>(a, sm_count, stream);
+        if (a.d <= 16) return launch_warp_dp<16>(a, sm_count, stream);
+        return launch_warp_dp<32>(a, sm_count, stream);
     }
     int PT = LIN_THREADS / a.d;                        // paths per block: one thread per (path, row) when d <= 256
     if (PT < 1) PT = 1;

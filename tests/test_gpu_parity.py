@@ -342,23 +342,26 @@ def test_linear_strict_bit_identical(sde, scheme):
 
 
 @pytest.mark.parametrize("scheme", ["euler", "heun"])
-@pytest.mark.parametrize("d,nB", [(1, 1), (2, 2), (2, 1), (3, 2), (4, 4), (4, 3)])
-def test_small_linear_systems_register_kernel(sde, eng, scheme, d, nB):
-    """d, nB <= 4 (the noisy oscillator's size) run one thread per path with A, G, x in registers: bit-identical to
-    the oracle with a supplied B, the oracle's own fused generator to the quantile table's accuracy, moments = those
-    of the returned terminal states."""
+@pytest.mark.parametrize("d,nB", [(1, 1), (2, 2), (2, 1), (3, 2), (4, 4), (4, 3),          # k_linear_small
+                                  (5, 1), (7, 7), (8, 8), (12, 5), (16, 16), (20, 7), (32, 32), (32, 1),   # k_linear_warp
+                                  (6, 9), (40, 3)])                                       # k_linear_generic
+def test_small_and_medium_linear_systems(sde, eng, scheme, d, nB):
+    """d, nB <= 4 (the noisy oscillator's size) run one thread per path with A, G, x in registers; d <= 32 one lane
+    per (path, row) with shuffles; the rest in the shared-memory kernel.  Each: bit-identical to the oracle with a
+    supplied B, the oracle's own fused generator to the quantile table's accuracy, moments = those of the returned
+    terminal states."""
     rng = np.random.default_rng(10 * d + nB)
-    A = -0.6 * np.eye(d) + 0.4 * rng.standard_normal((d, d))
+    A = -0.6 * np.eye(d) + 0.4 * rng.standard_normal((d, d)) / np.sqrt(d)
     G = rng.standard_normal((d, nB))
     x0 = rng.standard_normal(d)
-    t, B = brownian(77, nB, 300, 3)
+    t, B = brownian(77, nB, 150, 3)
     fn = sde.euler if scheme == "euler" else sde.heun
     want = O.ensemble(scheme, "linear", (A, G), t, x0, B=B)
     got = fn(*sde.catalogue.linear(A, G), t, x0, B)
     assert np.array_equal(got["X"], want) and np.array_equal(got["XT"], want[-1])
     assert np.allclose(fn(*sde.catalogue.linear(A, G), t, x0, B, arith="fast")["X"], want, rtol=1e-12, atol=1e-13)
     # fused generator against the C oracle's (same Philox stream, libm quantile instead of the table)
-    P, seed, off = 5000, 77, 1 << 34
+    P, seed, off = 1003, 77, 1 << 34
     params = np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
     _, XTc = c_oracle.ensemble(SCH[scheme], 6, params, d, nB, 0, t, x0, seed=seed, path_offset=off, npaths=P, full=False, nthreads=8)
     XT = np.empty((d, P), order="F")
