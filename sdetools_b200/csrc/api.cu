@@ -392,7 +392,8 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         CU(cudaStreamSynchronize(c->stream));
         la.center = (const double *)c->out2.p;
         if (dmma_eligible(la, pr->params + (size_t)nx * nx)) {
-            CU(c->scratch.reserve(sizeof(double) * ((size_t)nx * nx + nx)));
+            const size_t dp = ((size_t)nx + 31) / 32 * 32;          // the kernel pads to a multiple of 32 rows
+            CU(c->scratch.reserve(sizeof(double) * (dp * dp + dp)));
             cuerr = launch_linear_dmma(la, (double *)c->scratch.p, c->prop.multiProcessorCount, c->stream);
         } else
             cuerr = launch_linear(la, c->prop.multiProcessorCount, c->stream);

@@ -30,8 +30,9 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// A (d x d, column-major) -> fragment order: Apk[((w*KK + kk)*MA + mi)*32 + lane] = A[32w + 8mi + lane/4, 4kk + lane%4]
-__global__ void k_pack_A(const double *__restrict__ A, double *__restrict__ Apk, int d)
+// A (dr x dr, column-major), zero-padded to d x d (d a multiple of 32)
+//   -> fragment order: Apk[((w*KK + kk)*MA + mi)*32 + lane] = A[32w + 8mi + lane/4, 4kk + lane%4]
+__global__ void k_pack_A(const double *__restrict__ A, double *__restrict__ Apk, int d, int dr)
 {
     const int KK = d / 4;
     const size_t n = (size_t)d * d;
@@ -42,7 +43,7 @@ __global__ void k_pack_A(const double *__restrict__ A, double *__restrict__ Apk,
         const int kk = (int)(t % KK);
         const int w = (int)(t / KK);
         const int row = 32 * w + 8 * mi + (lane >> 2), col = 4 * kk + (lane & 3);
-        Apk[idx] = A[(size_t)col * d + row];
+        Apk[idx] = (row < dr && col < dr) ? A[(size_t)col * dr + row] : 0.0;
     }
 }
 
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs
     double *xs = sm + ICDF_TABLE_DOUBLES;                        // X tile, xs[k*DM_LDX + n]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
     icdf_stage(sh_tab, a.icdf, tid, 32 * NWARPS);
-    const int nsteps = a.nt - 1;
+    const int nsteps = a.nt - 1, dr = a.d;                       // dr: the system's dimension; rows dr..D-1 are zero padding
     const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
     const double *Aw = Apk + (size_t)w * KK * DM_MA * 32 + lane;
     double grow[DM_MA];                                          // diffusion intensity of this lane's rows
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs
         __syncthreads();
         for (int e = tid; e < D * DM_PT; e += 32 * NWARPS) {
             const int n = e / D, k = e - n * D;                  // consecutive threads walk one path's state vector
-            xs[k * DM_LDX + n] = n < np ? (a.x0 ? a.x0[(p0 + n) * D + k] : a.x0_shared[k]) : 0.0;
+            xs[k * DM_LDX + n] = (n < np && k < dr) ? (a.x0 ? a.x0[(p0 + n) * dr + k] : a.x0_shared[k]) : 0.0;
         }
         __syncthreads();
         for (int i = 0; i < nsteps; ++i) {
@@ -128,10 +129,10 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs
         for (int e = tid; e < D * np; e += 32 * NWARPS) {
             const int n = e / D, k = e - n * D;
             const double v = xs[k * DM_LDX + n];
-            if (a.XT) a.XT[(p0 + n) * D + k] = v;
+            if (a.XT && k < dr) a.XT[(p0 + n) * dr + k] = v;
         }
         if (a.moments) {
-            for (int k = tid; k < D; k += 32 * NWARPS) {
+            for (int k = tid; k < dr; k += 32 * NWARPS) {
                 double s[5] = {0, 0, 0, 0, 0};
                 const double cen = a.center[k];
                 for (int n = 0; n < np; ++n) {
@@ -150,28 +151,34 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs
 
 bool dmma_eligible(const LinearArgs &a, const double *hostG)
 {
-    if (a.B || a.scheme != SDEGPU_EULER || a.X || a.nB != a.d || a.d % 32 != 0 || a.d < 32 || a.d > 256) return false;
+    // any 32 < d <= 256 (rounded up to a multiple of 32 with zero rows); at d <= 32 a one-warp CTA cannot feed the SM
+    if (a.B || a.scheme != SDEGPU_EULER || a.X || a.nB != a.d || a.d <= 32 || a.d > 256) return false;
     for (int c = 0; c < a.d; ++c)
         for (int r = 0; r < a.d; ++r)
             if (r != c && hostG[(size_t)c * a.d + r] != 0.0) return false;
     return true;
 }
 
-// scratch: d*d + d doubles (packed A, diagonal of G)
+// scratch: dp*dp + dp doubles (packed A, diagonal of G), dp = d rounded up to a multiple of 32
 int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream)
 {
-    const int d = a.d;
+    const int dr = a.d, d = (dr + 31) / 32 * 32;
     double *Apk = scratch, *gdiag = scratch + (size_t)d * d;
-    k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d);
-    cudaMemcpy2DAsync(gdiag, sizeof(double), a.G, sizeof(double) * (d + 1), sizeof(double), d, cudaMemcpyDeviceToDevice, stream);
-    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * d, stream);
+    k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d, dr);
+    cudaMemsetAsync(gdiag, 0, sizeof(double) * d, stream);
+    cudaMemcpy2DAsync(gdiag, sizeof(double), a.G, sizeof(double) * (dr + 1), sizeof(double), dr, cudaMemcpyDeviceToDevice, stream);
+    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * dr, stream);
     const size_t smem = sizeof(double) * ((size_t)ICDF_TABLE_DOUBLES + (size_t)d * DM_LDX);
     const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
-    const int grid = (int)(ngroups < (uint64_t)sm_count ? ngroups : (uint64_t)sm_count);
+    // small d leaves room for several CTAs per SM (d = 64: two warps per CTA): as many as registers and shared memory allow
 #define SDEGPU_DMMA_CASE(NW)                                                                                   \
     case NW: {                                                                                                 \
         auto k = k_linear_dmma<NW>;                                                                            \
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
+        int per_sm = 1;                                                                                        \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 32 * NW, smem);                              \
+        const uint64_t cap = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;                                   \
+        const int grid = (int)(ngroups < cap ? ngroups : cap);                                                 \
         k<<<grid, 32 * NW, smem, stream>>>(a, Apk, gdiag);                                                     \
     } break;
     switch (d / 32) {

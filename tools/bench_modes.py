@@ -244,6 +244,25 @@ def main():
             del XT
         torch.cuda.empty_cache()
 
+    # DMMA below and off the d = 256 headline: d = 64, 100 (padded to 128), 128
+    if want("linear_mid"):
+        for d, P, n in ((64, 8 * eng.info["sm_count"] * 64, 500), (100, 4 * eng.info["sm_count"] * 64, 500),
+                        (128, 4 * eng.info["sm_count"] * 64, 500)):
+            rng = np.random.default_rng(d)
+            R = rng.standard_normal((d, d))
+            A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
+            params = np.concatenate([A.ravel(order="F"), np.eye(d).ravel(order="F")])
+            x0 = np.zeros(d)
+            x0[0] = 1.0
+            XT = torch.empty(P * d, dtype=torch.float64, device=dev)
+            ms = best_ms(lambda: eng.run("linear", "euler", params, np.arange(n + 1) * (1.0 / n), x0, nx=d, nB=d, npaths=P, seed=4,
+                                         XT=XT, want_time=True), reps=2)
+            fl = 2.0 * d * d + 4 * d
+            emit(f"linear_dmma_d{d}", paths=P, nsteps=n, ms=ms, path_steps_per_s=P * n / ms * 1e3, tflops=fl * P * n / ms / 1e9,
+                 frac=fl * P * n / ms / 1e9 / fp64)
+            del XT
+        torch.cuda.empty_cache()
+
     # C4: linear SDE d = 256 (A x as a GEMM over paths); 2d^2+4d flops per path-step
     if want("c4"):
         d = 256
