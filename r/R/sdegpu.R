@@ -113,6 +113,12 @@ CrossVariation <- function(X, Y) .Call(C_sdegpu_crossvar, X + 0, Y + 0)
 rvBM.gpu <- function(times, n = 1, sigma = 1, B0 = 0, u = 0, seed = NULL)
   .Call(C_sdegpu_rvbm, as.numeric(times), as.integer(n), sigma, B0, u, if (is.null(seed)) list() else list(seed = seed))
 
+## max / min / which.max / which.min / first passage of every column of rvBM.gpu(times, n, ...) under the same
+## seed, without building the matrix (vignettes/BrownianMotion.Rmd:101-144: apply(rvBM(0:Nt,Np),2,max)).
+rvBM.functionals.gpu <- function(times, n = 1, sigma = 1, B0 = 0, u = 0, level = NULL, seed = NULL)
+  .Call(C_sdegpu_bm_functionals, as.numeric(times), as.integer(n), sigma, B0, u,
+        c(if (is.null(level)) list() else list(level = level), if (is.null(seed)) list() else list(seed = seed)))
+
 ## Exact transition-law samplers on the device.  Like rvBM.gpu they keep their own names: the draws come
 ## from Philox, not from R's stream, so they are the same law as rOU/rCIR (R/sdetools.R:784-791, :695-702)
 ## but not the same numbers.  steps > 1: X_{k+1} ~ law(. | X_k, t), the vignette's recursive sampling.

@@ -244,6 +244,35 @@ SEXP C_sdegpu_rvbm(SEXP times, SEXP n, SEXP sigma, SEXP B0, SEXP u, SEXP opts)
     return res;
 }
 
+/* apply(rvBM(times, n, sigma, B0, u), 2, max) and friends without the n x nt matrix (vignettes/BrownianMotion.Rmd:101-144):
+ * list(max, min, tmax, tmin, thit); opts$level (optional) is the first-passage level */
+SEXP C_sdegpu_bm_functionals(SEXP times, SEXP n, SEXP sigma, SEXP B0, SEXP u, SEXP opts)
+{
+    const int nt = (int)XLENGTH(times), nc = Rf_asInteger(n);
+    SEXP lvl = list_get(opts, "level");
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 5));
+    SEXP nms = PROTECT(Rf_allocVector(STRSXP, 5));
+    const char *names[5] = {"max", "min", "tmax", "tmin", "thit"};
+    double *out[5];
+    for (int i = 0; i < 5; ++i) {
+        SET_STRING_ELT(nms, i, Rf_mkChar(names[i]));
+        SEXP v = PROTECT(Rf_allocVector(REALSXP, nc));
+        SET_VECTOR_ELT(res, i, v);
+        UNPROTECT(1);                                   /* held by res from here on */
+        out[i] = REAL(v);
+    }
+    Rf_setAttrib(res, R_NamesSymbol, nms);
+    if (sdegpu_bm_functionals(ctx(), REAL(times), nt, (uint64_t)nc, Rf_asReal(sigma), Rf_asReal(B0), Rf_asReal(u),
+                              Rf_isNull(lvl) ? 0.0 : Rf_asReal(lvl), seed_from(opts), (uint64_t)opt_real(opts, "path_offset", 0),
+                              out[0], out[1], out[2], out[3], Rf_isNull(lvl) ? NULL : out[4], 0) != SDEGPU_OK) {
+        UNPROTECT(2);
+        Rf_error("sdegpu_bm_functionals: %s", sdegpu_last_error());
+    }
+    if (Rf_isNull(lvl)) SET_VECTOR_ELT(res, 4, R_NilValue);
+    UNPROTECT(2);
+    return res;
+}
+
 /* rOU(n,x0,lambda,xi,sigma,t) R/sdetools.R:784-791 and rCIR(n,x0,lambda,xi,gamma,t,Stratonovich) :695-702;
  * x0 is recycled to length n as R's rnorm/rchisq recycle their parameters; opts$steps > 1 applies the
  * transition repeatedly (vignettes/CoxIngersollRoss.Rmd:76-84). */
@@ -289,6 +318,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_sdegpu_qv", (DL_FUNC)&C_sdegpu_qv, 1},
     {"C_sdegpu_crossvar", (DL_FUNC)&C_sdegpu_crossvar, 2},
     {"C_sdegpu_rvbm", (DL_FUNC)&C_sdegpu_rvbm, 6},
+    {"C_sdegpu_bm_functionals", (DL_FUNC)&C_sdegpu_bm_functionals, 6},
     {"C_sdegpu_rlaw", (DL_FUNC)&C_sdegpu_rlaw, 6},
     {"C_sdegpu_law_eval", (DL_FUNC)&C_sdegpu_law_eval, 7},
     {NULL, NULL, 0}};
