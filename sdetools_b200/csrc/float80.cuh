@@ -195,6 +195,32 @@ SDEGPU_HD double f80_to_double(const F80 &acc)
 #define SDEGPU_F80P_COUNT(k)          // host test hook: counts tie-broken / lower-binade / exact-tie cases
 #endif
 
+// high / low 32-bit words of a double and back (register-pair moves on the device, no 64-bit shifts)
+SDEGPU_HD uint32_t f80_hi(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2hiint(d);
+#else
+    return (uint32_t)(f80_dbits(d) >> 32);
+#endif
+}
+SDEGPU_HD uint32_t f80_lo(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(d);
+#else
+    return (uint32_t)f80_dbits(d);
+#endif
+}
+SDEGPU_HD double f80_from_hi(uint32_t hi)                        // the double with that high word and a zero low word
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, 0);
+#else
+    return f80_bitsd((uint64_t)hi << 32);
+#endif
+}
+
 SDEGPU_HD void f80p_two_sum(double x, double y, double &s, double &e)
 {
     s = x + y;
@@ -204,11 +230,11 @@ SDEGPU_HD void f80p_two_sum(double x, double y, double &s, double &e)
 
 SDEGPU_HD bool f80p_add(double &h, double &l, double x)
 {
-    const uint64_t xb = f80_dbits(x), hb = f80_dbits(h);
-    const uint32_t xe = (uint32_t)(xb >> 52) & 0x7FFu, he = (uint32_t)(hb >> 52) & 0x7FFu;
+    const uint32_t xh = f80_hi(x), hh = f80_hi(h);
+    const uint32_t xe = (xh >> 20) & 0x7FFu, he = (hh >> 20) & 0x7FFu;
     if (xe >= 0x7DFu || he >= 0x7DFu) return false;            // Inf/NaN, or close enough to overflow a TwoSum
-    if ((xb << 1) == 0) {                                      // x = +-0: only the sign of a zero sum can change
-        if ((hb << 1) == 0) h = h + x;
+    if (((xh << 1) | f80_lo(x)) == 0) {                        // x = +-0: only the sign of a zero sum can change
+        if (((hh << 1) | f80_lo(h)) == 0) h = h + x;
         return true;
     }
     double s1, e1, s2, e2, a, b0, b, c;
@@ -216,19 +242,19 @@ SDEGPU_HD bool f80p_add(double &h, double &l, double x)
     f80p_two_sum(e1, l, s2, e2);
     f80p_two_sum(s1, s2, a, b0);
     f80p_two_sum(b0, e2, b, c);
-    const uint64_t ab = f80_dbits(a);
-    const uint32_t ae = (uint32_t)(ab >> 52) & 0x7FFu;
-    if ((ab << 1) == 0) {                                      // exact cancellation: +0 in round-to-nearest
+    const uint32_t ah = f80_hi(a), al = f80_lo(a);
+    const uint32_t ae = (ah >> 20) & 0x7FFu;
+    if (((ah << 1) | al) == 0) {                               // exact cancellation: +0 in round-to-nearest
         if (b != 0.0 || c != 0.0) return false;
         h = 0.0; l = 0.0;
         return true;
     }
     if (ae < 0x080u) return false;                             // 64-bit grid would leave the double range
-    const bool pow2 = (ab & 0x000FFFFFFFFFFFFFull) == 0;
-    const bool back = pow2 && b != 0.0 && ((f80_dbits(b) ^ ab) >> 63) != 0;   // V lies in the binade below a
-    const uint64_t qe = (uint64_t)ae - 63u - (back ? 1u : 0u);  // biased exponent of the grid q = ulp64(V)
-    const double half_q = f80_bitsd((qe - 1u) << 52);
-    const double C = f80_bitsd(((qe + 52u) << 52) | 0x0008000000000000ull);   // 1.5 * 2^52 * q
+    const bool pow2 = ((ah & 0x000FFFFFu) | al) == 0;
+    const bool back = pow2 && b != 0.0 && ((f80_hi(b) ^ ah) >> 31) != 0;      // V lies in the binade below a
+    const uint32_t qe = ae - 63u - (back ? 1u : 0u);           // biased exponent of the grid q = ulp64(V)
+    const double half_q = f80_from_hi((qe - 1u) << 20);
+    const double C = f80_from_hi(((qe + 52u) << 20) | 0x00080000u);           // 1.5 * 2^52 * q
     double r = (b + C) - C;                                    // b to a multiple of q, ties to even
     const double d = b - r;                                    // exact
     if (c != 0.0 && (d == half_q || d == -half_q)) {           // b sat on a tie and c breaks it

@@ -42,7 +42,7 @@ __device__ __forceinline__ void st_sector(double *p, const double (&s)[4])
 // elements each) straight between HBM and registers: columns are private to a thread, so there is no
 // shared memory and no barrier.  All arrays have the same shape, hence the same sector phase.
 template <int MODE>              // 0 stochint, 1 cross-variation
-__global__ void __launch_bounds__(INT_THREADS, SDEGPU_INT_MIN_BLOCKS) k_integral(const IntegralArgs q, const int vec_ok)
+__global__ void __launch_bounds__(INT_THREADS, MODE == 1 ? 3 : SDEGPU_INT_MIN_BLOCKS) k_integral(const IntegralArgs q, const int vec_ok)
 {
     const uint64_t nsteps = q.n - 1;
     const bool need_l = MODE == 1 || q.l || q.c, need_r = MODE == 0 && (q.r || q.c);
