@@ -211,10 +211,17 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 // (Q*nx*nt = 0 mod 4) so that d is warp-uniform and the four-way switch does not diverge.  Only the
 // first/last partial sector of a row is written element by element.
 constexpr int TRAJ_CHUNK = 1024;    // steps of the {dt, sqrt dt} table staged in shared memory at a time (16 KB)
+// Threads per CTA (one CTA per SM), tuned on the device.  Two components (C3, 16 B per step): 128: 2.85, 192: 3.5,
+// 256: 4.6, 320: 4.35, 384: 4.3, 512: 4.15 TB/s — fewer rows in flight suit the memory system.  One component writes
+// half the bytes per generated normal, so there the generator is the cost and more warps win: OU/euler 256: 3.3e11,
+// 512: 4.3e11, 768: 4.3e11 path-steps/s; CIR/heun 1.9e11, 2.7e11, 2.9e11.
 #ifndef SDEGPU_TRAJ_THREADS
-#define SDEGPU_TRAJ_THREADS 256     // tuned on the device: 128: 2.85, 192: 3.5, 256: 4.6, 320: 4.35, 384: 4.3, 512: 4.15 TB/s (C3)
+#define SDEGPU_TRAJ_THREADS 256
 #endif
-constexpr int TRAJ_THREADS = SDEGPU_TRAJ_THREADS;
+#ifndef SDEGPU_TRAJ_THREADS_NX1
+#define SDEGPU_TRAJ_THREADS_NX1 768
+#endif
+template <int NX> struct TrajThreads { static constexpr int value = NX == 1 ? SDEGPU_TRAJ_THREADS_NX1 : SDEGPU_TRAJ_THREADS; };
 
 __device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d)
 {
@@ -222,9 +229,9 @@ __device__ __forceinline__ void st_sector(double *p, double a, double b, double 
 }
 
 template <class M, int SCHEME, int PROJ>
-__global__ void __launch_bounds__(TRAJ_THREADS, 1) k_traj(const RunArgs a, const int vec_ok, const int Q)
+__global__ void __launch_bounds__(TrajThreads<M::NX>::value, 1) k_traj(const RunArgs a, const int vec_ok, const int Q)
 {
-    constexpr int NX = M::NX;
+    constexpr int NX = M::NX, TRAJ_THREADS = TrajThreads<NX>::value;
     extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
     // [quantile table, hot layout][step table chunk: TRAJ_CHUNK x {dt, sqrt dt}][histogram]
     double2 *sh_dt = reinterpret_cast<double2 *>(sh_tab + ICDF_HOT_TABLE_DOUBLES);

@@ -41,6 +41,7 @@ static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
     auto kernel = k_traj<M, SCHEME, PROJ>;
     const size_t smem = ICDF_HOT_TABLE_BYTES + sizeof(double2) * TRAJ_CHUNK + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    constexpr int TRAJ_THREADS = TrajThreads<M::NX>::value;
     const uint64_t work = (a.npaths + TRAJ_THREADS - 1) / TRAJ_THREADS;
     const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TRAJ_THREADS, smem, c.sm_count, work);
     const int vec_ok = (reinterpret_cast<uintptr_t>(a.X) & 31) == 0;

@@ -71,6 +71,17 @@ def main():
              hbm_frac=16.0 * steps / ms / 1e6 / hbm, bytes_per_step=16)
         chk = X.view(P, 2, nt)[:4, :, :3].cpu().numpy().tolist()
         emit("c3_check", first=chk[0])
+        # scalar models through the same kernel (8 B per path-step; 768 threads per SM there)
+        if not args.quick:
+            P1 = 2 * eng.info["sm_count"] * 768
+            X1 = X[: P1 * nt]
+            t1 = np.arange(nt) * 1e-3
+            for name, model, params, scheme, proj in (("traj_ou_euler", "ou", [1.3, 0.7, 0.9], "euler", "identity"),
+                                                      ("traj_cir_heun", "cir", [1.0, 1.0, 1.0], "heun", "abs")):
+                ms = best_ms(lambda: eng.run(model, scheme, params, t1, [1.0], nx=1, npaths=P1, projection=proj, seed=3, X=X1,
+                                             want_time=True))
+                emit(name, paths=P1, nt=nt, ms=ms, path_steps_per_s=P1 * (nt - 1) / ms * 1e3, gbs=8.0 * P1 * (nt - 1) / ms / 1e6,
+                     hbm_frac=8.0 * P1 * (nt - 1) / ms / 1e6 / hbm, bytes_per_step=8)
         # supplied-B variant: 8 B read + 16 B written per path-step
         P2 = (P // 2) if args.quick else (args.c3b_paths or eng.info["sm_count"] * 512)
         B = torch.empty(P2 * nt, dtype=torch.float64, device=dev)
