@@ -65,7 +65,7 @@ class Engine:
             hist_counts=None, hist=None, accumulate=False, want_time=False, kill=None, stop=None, S0=1.0,
             Stau=None, tau=None, S_tau=None, path_integrals=None):
         """Thin, allocation-free call of sdegpu_run.  B / per-path x0 / outputs are either all numpy
-        (host pointers) or all torch CUDA tensors (device pointers, work is only enqueued).
+        (host pointers) or all torch CUDA tensors (device pointers: work is only enqueued, on torch's current stream).
         Layouts are the reference's: B[(p*nB+k)*nt+i], X[(p*nx+j)*nt+i], XT[p*nx+j]."""
         bufs = [b for b in (B, X, XT, power_sums, hist_counts, Stau, tau, S_tau, path_integrals) if b is not None]
         on_dev = any(_is_torch(b) for b in bufs)
@@ -98,6 +98,8 @@ class Engine:
         pr.x0, pr.x0_stride = _ptr(x0_keep), (int(nx) if per_path_x0 else 0)
         pr.B = _ptr(B)
         pr.npaths, pr.path_offset, pr.seed = int(npaths), int(path_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
+        if on_dev:
+            self._follow_torch_stream()
         pr.flags = (_lib.DEVICE_PTRS if on_dev else 0) | (_lib.ACCUMULATE if accumulate else 0)
         if kill is not None:                 # catalogue.KillRate
             pr.kill_kind, pr.kill_comp, pr.kill_a, pr.kill_b = _lib.KILL[kill.sdegpu_kill], kill.component, kill.a, kill.b
@@ -128,7 +130,14 @@ class Engine:
         dev = [_is_torch(b) for b in bufs if b is not None]
         if any(dev) and not all(dev):
             raise TypeError("mixing host and device buffers in one call is not supported")
+        if any(dev):
+            self._follow_torch_stream()
         return _lib.DEVICE_PTRS if any(dev) else 0
+
+    def _follow_torch_stream(self):
+        """Calls on torch tensors are only enqueued; they go to torch's current stream so that they are ordered
+        with the torch operations that produce and consume those tensors."""
+        self.use_torch_stream()
 
     def stochint(self, f, g, n, ncols, l=None, r=None, c=None):
         check(self.lib.sdegpu_stochint(self._h, _ptr(f), _ptr(g), n, ncols, _ptr(l), _ptr(r), _ptr(c), self._flags(f, g, l, r, c)))

@@ -681,3 +681,42 @@ def test_single_channel_linear_model_shares_the_scalar_stream(sde):
     a = sde.euler(*sde.catalogue.linear([[-1.3]], [[0.9]]), t, 2.0, npaths=500, seed=8)["X"]
     b = sde.euler(*sde.catalogue.ou(1.3, 0.0, 0.9), t, 2.0, npaths=500, seed=8)["X"]
     assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
+
+
+def test_device_buffers_at_8_byte_offsets_take_the_elementwise_paths(eng):
+    """The sector (256-bit) loads/stores need 32-byte aligned buffers; device tensors that start 8 bytes into an
+    allocation must fall back to element-wise access and give the same bits (k_traj, k_stream, k_integral, k_rvbm)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    eng.use_torch_stream()                                      # device-pointer calls are only enqueued: share torch's stream
+
+    def off8(n):                                                # n doubles starting 8 bytes past an aligned address
+        return torch.empty(n + 1, dtype=torch.float64, device=dev)[1:]
+
+    P, nt = 333, 205
+    t = np.arange(nt) * 0.01
+    # fused generator trajectory (k_traj), two components
+    Xa = torch.empty(P * 2 * nt, dtype=torch.float64, device=dev)
+    Xo = off8(P * 2 * nt)
+    assert Xo.data_ptr() % 32 == 8 and Xa.data_ptr() % 32 == 0
+    for X in (Xa, Xo):
+        eng.run("vdp", "heun", [1.0, 0.5], t, [0.1, -0.2], nx=2, npaths=P, seed=6, X=X)
+    assert torch.equal(Xa, Xo)
+    # supplied B (k_stream): misaligned input and output
+    Ba = torch.empty(P * nt, dtype=torch.float64, device=dev)
+    eng.rvbm(t, P, Ba, seed=4)
+    Bo = off8(P * nt)
+    Bo.copy_(Ba)
+    X1a = torch.empty(P * nt, dtype=torch.float64, device=dev)
+    X1o = off8(P * nt)
+    eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=P, B=Ba, projection="abs", X=X1a)
+    eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=P, B=Bo, projection="abs", X=X1o)
+    assert torch.equal(X1a, X1o)
+    # integrals and rvBM
+    la, lo = torch.empty(P * nt, dtype=torch.float64, device=dev), off8(P * nt)
+    eng.itointegral(X1a, Ba, nt, P, la)
+    eng.itointegral(X1o, Bo, nt, P, lo)
+    assert torch.equal(la, lo)
+    eng.rvbm(t, P, Bo, seed=4)
+    assert torch.equal(Ba, Bo)
+    eng.use_own_stream()
