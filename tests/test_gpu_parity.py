@@ -720,3 +720,39 @@ def test_device_buffers_at_8_byte_offsets_take_the_elementwise_paths(eng):
     eng.rvbm(t, P, Bo, seed=4)
     assert torch.equal(Ba, Bo)
     eng.use_own_stream()
+
+
+def test_output_options_agree_across_kernels(eng):
+    """One ensemble, every way of asking for its terminal statistics: trajectory kernel, register-resident kernel and
+    fused-integral kernel must report the same terminal states, histogram (on the second component) and power sums;
+    per-path x0 with the generator; the ACCUMULATE flag adds a second shard to the first."""
+    P, nt, seed = 3001, 130, 19
+    t = np.arange(nt) * 0.02
+    rng = np.random.default_rng(3)
+    x0 = np.ascontiguousarray(rng.uniform(-1, 1, (P, 2)))                         # x0[p*nx+j]
+    kw = dict(nx=2, npaths=P, seed=seed, center=[0.1, -0.2], hist=(-4.0, 4.0, 37, 1))
+    out = {}
+    for name, extra in (("traj", dict(X=np.empty((nt, 2, P), order="F"))), ("terminal", {}),
+                        ("functionals", dict(path_integrals=np.empty((4, 2, P), order="F")))):
+        XT, ps, hc = np.empty((2, P), order="F"), np.zeros((5, 2), order="F"), np.zeros(40, np.uint64)
+        eng.run("vdp", "heun", [1.0, 0.5], t, x0, XT=XT, power_sums=ps, hist_counts=hc, **kw, **extra)
+        out[name] = (XT, ps, hc, extra)
+    XT0, ps0, hc0, ex0 = out["traj"]
+    assert np.array_equal(ex0["X"][0].T, x0) and np.array_equal(ex0["X"][-1], XT0)
+    assert int(hc0.sum()) == P
+    for name in ("terminal", "functionals"):
+        XT, ps, hc, _ = out[name]
+        assert np.allclose(XT, XT0, rtol=1e-12, atol=1e-14), name
+        assert np.array_equal(hc, hc0), name
+        assert np.allclose(ps, ps0, rtol=1e-10, atol=1e-9), name
+    d = XT0 - np.array([[0.1], [-0.2]])
+    assert np.array_equal(ps0[0], [P, P]) and np.allclose(ps0[1], d.sum(axis=1), rtol=1e-10, atol=1e-9)
+    assert np.allclose(ps0[4], (d ** 4).sum(axis=1), rtol=1e-10)
+    want_h = O.hist_counts(XT0[1], -4.0, 4.0, 37)
+    assert np.array_equal(hc0, want_h)
+    # ACCUMULATE: shard A then shard B on top == the whole ensemble
+    ps, hc = np.zeros((5, 2), order="F"), np.zeros(40, np.uint64)
+    kw2 = dict(nx=2, seed=seed, center=[0.1, -0.2], hist=(-4.0, 4.0, 37, 1), power_sums=ps, hist_counts=hc)
+    eng.run("vdp", "heun", [1.0, 0.5], t, np.ascontiguousarray(x0[:1000]), npaths=1000, **kw2)
+    eng.run("vdp", "heun", [1.0, 0.5], t, np.ascontiguousarray(x0[1000:]), npaths=P - 1000, path_offset=1000, accumulate=True, **kw2)
+    assert np.array_equal(hc, hc0) and np.allclose(ps, ps0, rtol=1e-10, atol=1e-9)
