@@ -756,3 +756,16 @@ def test_output_options_agree_across_kernels(eng):
     eng.run("vdp", "heun", [1.0, 0.5], t, np.ascontiguousarray(x0[:1000]), npaths=1000, **kw2)
     eng.run("vdp", "heun", [1.0, 0.5], t, np.ascontiguousarray(x0[1000:]), npaths=P - 1000, path_offset=1000, accumulate=True, **kw2)
     assert np.array_equal(hc, hc0) and np.allclose(ps, ps0, rtol=1e-10, atol=1e-9)
+
+
+def test_c_abi_from_plain_c(gpu, tmp_path):
+    """tests/native/abi_smoke.c: the library driven from C with host pointers, as the R shim would."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "abi_smoke"
+    lib = os.path.join(root, "sdetools_b200")
+    subprocess.run(["/usr/bin/gcc", "-O1", "-std=c11", "-I", os.path.join(root, "include"), "-o", str(exe),
+                    os.path.join(root, "tests", "native", "abi_smoke.c"), "-L", lib, "-lsdegpu", "-lm", f"-Wl,-rpath,{lib}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi smoke ok" in r.stdout, r.stdout + r.stderr
