@@ -289,3 +289,37 @@ def test_probability_integral_transform_stays_on_the_device(sde):
     eng.law_eval("cir", "p", (1.0, 1.0, 1.0), 1.0, x0, XT, U, stratonovich=True)
     counts = torch.histc(U, bins=50, min=0.0, max=1.0).cpu().numpy()
     assert stats.chi2.sf(float(((counts - n / 50) ** 2 / (n / 50)).sum()), 49) < 1e-6
+
+
+@pytest.mark.gpu
+def test_edge_cases_of_the_law_and_brownian_entry_points(sde):
+    from sdetools_b200._lib import SdeGpuError
+    # zero transitions: the start comes back; one draw; a start beyond 2^32 draws
+    x0 = np.array([0.3, 1.7, 2.2])
+    assert np.array_equal(sde.rCIR(3, x0, 1.0, 1.0, 1.0, 0.5, steps=0), x0)
+    assert sde.rOU(1, 1.0, 1.0, 0.0, 1.0, 0.1, seed=3, path_offset=(1 << 40)).shape == (1,)
+    a = sde.rCIR(64, 1.0, 1.0, 1.0, 1.0, 0.1, seed=5, path_offset=(1 << 33))
+    b = sde.rCIR(64, 1.0, 1.0, 1.0, 1.0, 0.1, seed=5, path_offset=(1 << 33) + 32)
+    assert np.array_equal(a[32:], b[:32]) and not np.array_equal(a[:32], b[:32])
+    # CIR started at 0 stays non-negative and leaves 0 (df = 4 > 0); with xi = 0 it is absorbed (ncp = 0 and df = 0)
+    z = sde.rCIR(1000, 0.0, 1.0, 1.0, 1.0, 0.1, seed=1)
+    assert np.all(z >= 0) and z.max() > 0
+    assert np.all(sde.rCIR(100, 0.0, 1.0, 0.0, 1.0, 0.1, seed=1) == 0.0)
+    # OU with sigma = 0 is the deterministic relaxation; its density/distribution are refused (sd = 0)
+    assert np.allclose(sde.rOU(4, 2.0, 1.0, 0.5, 0.0, 1.0, seed=1), 0.5 + 1.5 * np.exp(-1.0))
+    with pytest.raises(SdeGpuError, match="degenerate"):
+        sde.pOU(0.0, 1.0, 1.0, 0.0, 0.0, 1.0)
+    # distribution functions at and beyond the ends
+    assert sde.pCIR(np.array([-1.0, 0.0]), 1.0, 1.0, 1.0, 1.0, 0.5).tolist() == [0.0, 0.0]
+    assert sde.pCIR(1e6, 1.0, 1.0, 1.0, 1.0, 0.5) == 1.0 and sde.dCIR(-0.5, 1.0, 1.0, 1.0, 1.0, 0.5) == 0.0
+    assert sde.pOU(np.array([-1e3, 1e3]), 0.0, 1.0, 0.0, 1.0, 1.0).tolist() == [0.0, 1.0]
+    # Brownian motion on a single time point: B = B0 + N(u t0, sigma^2 t0); functionals of a one-point path
+    one = sde.rvBM([0.25], 5, sigma=2.0, B0=1.0, seed=9)
+    F = sde.rvBM_functionals([0.25], 5, sigma=2.0, B0=1.0, level=1.0, seed=9)
+    assert one.shape == (1, 5) and np.array_equal(F["max"], one[0]) and np.array_equal(F["min"], one[0])
+    assert np.all(F["tmax"] == 0.25) and np.array_equal(np.isnan(F["thit"]), one[0] < 1.0)
+    # times[0] = 0: the first increment has zero length, so B starts at B0 exactly
+    W = sde.rvBM([0.0, 1.0, 2.0], 3, B0=-2.0, seed=2)
+    assert np.all(W[0] == -2.0)
+    with pytest.raises(SdeGpuError, match="non-decreasing"):
+        sde.rvBM_functionals([0.0, 2.0, 1.0], 3, seed=1)
