@@ -295,6 +295,31 @@ def main():
              fp64_peak=fp64, frac=fl * steps / ms / 1e9 / fp64)
         xt = XT.view(P, d)
         emit("c4_check", mean0=float(xt[:, 0].mean()), var_mean=float(xt.var(dim=0).mean()), var_expected=1 - np.exp(-1.0))
+        if not args.quick:
+            # BASELINE.json config 4 at its full size: 10^6 paths, checked against the exact law of the Euler recursion
+            # m <- (I + A h) m, S <- (I + A h) S (I + A h)' + h I and against dLinSDE's S_t = (1 - e^-t) I, E X = e^{At} x0
+            P6 = 1_000_000
+            del XT
+            XT = torch.empty(P6 * d, dtype=torch.float64, device=dev)
+            ms = best_ms(lambda: eng.run("linear", "euler", params, np.arange(n + 1) * (1.0 / n), x0, nx=d, nB=d, npaths=P6, seed=4,
+                                         XT=XT, want_time=True), reps=1)
+            xt = XT.view(P6, d)
+            h = 1.0 / n
+            M = np.eye(d) + A * h
+            m, S = x0.copy(), np.zeros((d, d))
+            for _ in range(n):
+                m = M @ m
+                S = M @ S @ M.T + h * np.eye(d)
+            C = torch.cov(xt.T).cpu().numpy()
+            mean = xt.mean(dim=0).cpu().numpy()
+            se_m = np.sqrt(np.diag(S) / P6)
+            law = sde.dLinSDE(A, G, 1.0, x0=x0)
+            emit("c4_full_size", paths=P6, nsteps=n, ms=ms, path_steps_per_s=P6 * n / ms * 1e3, tflops=fl * P6 * n / ms / 1e9,
+                 frac=fl * P6 * n / ms / 1e9 / fp64,
+                 max_mean_err_in_se=float(np.max(np.abs(mean - m) / se_m)),
+                 max_cov_err_in_se=float(np.max(np.abs(C - S)) / (np.max(np.diag(S)) * np.sqrt(2.0 / P6))),
+                 discrete_vs_dLinSDE_cov=float(np.max(np.abs(S - law["St"]))), mc_vs_dLinSDE_cov=float(np.max(np.abs(C - law["St"]))),
+                 mc_vs_dLinSDE_mean=float(np.max(np.abs(mean - law["EX"]))))
 
 
 if __name__ == "__main__":
