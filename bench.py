@@ -53,6 +53,21 @@ def cpu_leg(paths: int, nsteps: int, threads: int, reps: int = 1):
     return paths * nsteps / best, best
 
 
+def interpreted_proxy(nsteps: int = 2000):
+    """SURVEY §8(d) baseline (i): the numpy oracle's loop, which mirrors R's interpreted loop call for call (closure
+    calls per step, row extraction, per-step mat-vec) on one core — a stand-in for what interpreted R costs per
+    path-step, labelled as a proxy, not as R."""
+    from oracle import sde_oracle as O
+    f, g, _, _ = O.catalogue("cir", [CIR["lam"], CIR["xi"], CIR["gamma"]])
+    t = np.arange(nsteps + 1) * (CIR["T"] / nsteps)
+    B = O.rBM(t, rng=np.random.default_rng(1))
+    t0 = time.perf_counter()
+    O.heun(f, g, t, CIR["x0"], B=B, p=abs)
+    dt = time.perf_counter() - t0
+    return {"value": nsteps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"1 path x {nsteps} steps of the oracle's interpreted (numpy) restatement of heun(), {dt:.2f} s: R-structure proxy"}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -243,7 +258,8 @@ def run_ours(args):
                          "flops_convention": "85 algorithmic FP64 flops per path-step (SURVEY.md §8d)",
                          "hbm_peak_gbs_measured_file": peaks.get("hbm_gbs")},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cpu_paths} of {P} paths x {nsteps} steps, {cpu_s:.1f} s (plain-C oracle, OpenMP)"},
+                             "sample": f"{cpu_paths} of {P} paths x {nsteps} steps, {cpu_s:.1f} s (plain-C oracle, OpenMP)",
+                             "interpreted_proxy": interpreted_proxy()},
             "clocks": sampler.summary(),
             "check": {"paths_counted": n_in, "paths_expected": world * P, "mean": 1.0 + float(stats[1] / stats[0]) if stats[0] else None},
             "device": eng.info["name"], "sm_count": eng.info["sm_count"],
