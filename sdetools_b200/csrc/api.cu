@@ -391,10 +391,14 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         CU(cudaMemcpyAsync(c->out2.p, hc.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         la.center = (const double *)c->out2.p;
-        if (dmma_eligible(la, pr->params + (size_t)nx * nx)) {
-            const size_t dp = ((size_t)nx + 31) / 32 * 32;          // the kernel pads to a multiple of 32 rows
+        const int mode = dmma_mode(la, pr->params + (size_t)nx * nx);
+        const size_t dp = ((size_t)nx + 31) / 32 * 32;              // the tensor kernels pad to a multiple of 32 rows
+        if (mode == 1) {
             CU(c->scratch.reserve(sizeof(double) * (dp * dp + dp)));
             cuerr = launch_linear_dmma(la, (double *)c->scratch.p, c->prop.multiProcessorCount, c->stream);
+        } else if (mode == 2) {
+            CU(c->scratch.reserve(sizeof(double) * (dp * dp + dp * 4 * (((size_t)pr->nB + 3) / 4))));
+            cuerr = launch_linear_dmma_dense(la, (double *)c->scratch.p, c->prop.multiProcessorCount, c->stream);
         } else
             cuerr = launch_linear(la, c->prop.multiProcessorCount, c->stream);
         if (cuerr) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: linear kernel launch: %s", cudaGetErrorString((cudaError_t)cuerr));

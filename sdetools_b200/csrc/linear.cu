@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
     const int d = a.d, nB = a.nB, nsteps = a.nt - 1;
     double *xs = sm, *ys = xs + (size_t)PT * d, *ns = ys + (size_t)PT * d;
     double *dBs = ns + (size_t)PT * d, *zs = dBs + (size_t)PT * nB;
-    double *sh_tab = zs + (((size_t)PT * nB + 1) & ~(size_t)1);      // 16-byte aligned
+    double *sh_tab = sm + (((size_t)3 * PT * d + (size_t)2 * PT * nB + 1) & ~(size_t)1);    // 16-byte aligned from the base
     const int tid = threadIdx.x;
     if (!a.B) icdf_stage(sh_tab, a.icdf, tid, LIN_THREADS);
     __syncthreads();

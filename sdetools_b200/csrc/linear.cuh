@@ -28,5 +28,8 @@ int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream);
 // FP64 tensor-core (DMMA) path: euler, fused generator, nB = d, diagonal G, d a multiple of 32 up to 256
 bool dmma_eligible(const LinearArgs &a, const double *hostG);
 int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream);
+// 0: not eligible, 1: diagonal G, 2: dense G (any nB <= d that fits two tiles in shared memory; scratch dp*dp + dp*4*ceil(nB/4))
+int dmma_mode(const LinearArgs &a, const double *hostG);
+int launch_linear_dmma_dense(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream);
 
 }  // namespace sdegpu

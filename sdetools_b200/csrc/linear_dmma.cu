@@ -30,12 +30,11 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// A (dr x dr, column-major), zero-padded to d x d (d a multiple of 32)
-//   -> fragment order: Apk[((w*KK + kk)*MA + mi)*32 + lane] = A[32w + 8mi + lane/4, 4kk + lane%4]
-__global__ void k_pack_A(const double *__restrict__ A, double *__restrict__ Apk, int d, int dr)
+// M (dr x kc, column-major, leading dimension dr), zero-padded to d rows (a multiple of 32) x 4*KK columns
+//   -> fragment order: Mpk[((w*KK + kk)*MA + mi)*32 + lane] = M[32w + 8mi + lane/4, 4kk + lane%4]
+__global__ void k_pack_A(const double *__restrict__ A, double *__restrict__ Apk, int d, int dr, int KK, int kc)
 {
-    const int KK = d / 4;
-    const size_t n = (size_t)d * d;
+    const size_t n = (size_t)d * 4 * KK;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
         const int lane = (int)(idx & 31);
         size_t t = idx >> 5;
@@ -43,7 +42,7 @@ __global__ void k_pack_A(const double *__restrict__ A, double *__restrict__ Apk,
         const int kk = (int)(t % KK);
         const int w = (int)(t / KK);
         const int row = 32 * w + 8 * mi + (lane >> 2), col = 4 * kk + (lane & 3);
-        Apk[idx] = (row < dr && col < dr) ? A[(size_t)col * dr + row] : 0.0;
+        Apk[idx] = (row < dr && col < kc) ? A[(size_t)col * dr + row] : 0.0;
     }
 }
 
@@ -149,22 +148,185 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs
     }
 }
 
-bool dmma_eligible(const LinearArgs &a, const double *hostG)
+// Dense G (correlated noise; the exact-transition model of laws.linear_exact): the increment term is a second GEMM,
+// G (d x nB) times a tile Z (nB x 64) of scaled normals kept in shared memory next to X, accumulated into the same
+// registers:  acc = (A X) dt + G (sqrt(dt) Z),  X' = X + acc.  Same generator stream as every other linear kernel
+// (one Philox block per path, step and channel pair).  Two tiles in shared memory: d + nB <= ~320 rows.
+template <int NWARPS>
+__global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma_dense(const LinearArgs a, const double *__restrict__ Apk,
+                                                                      const double *__restrict__ Gpk, const int KKG)
 {
-    // any 32 < d <= 256 (rounded up to a multiple of 32 with zero rows); at d <= 32 a one-warp CTA cannot feed the SM
-    if (a.B || a.scheme != SDEGPU_EULER || a.X || a.nB != a.d || a.d <= 32 || a.d > 256) return false;
-    for (int c = 0; c < a.d; ++c)
-        for (int r = 0; r < a.d; ++r)
-            if (r != c && hostG[(size_t)c * a.d + r] != 0.0) return false;
-    return true;
+    constexpr int D = 32 * NWARPS, KK = D / 4;
+    extern __shared__ __align__(16) double sm[];
+    double *sh_tab = sm;
+    double *xs = sm + ICDF_TABLE_DOUBLES;                        // X tile, xs[k*DM_LDX + n]
+    double *zs = xs + D * DM_LDX;                                // Z tile, zs[k*DM_LDX + n], k < 4*KKG
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    icdf_stage(sh_tab, a.icdf, tid, 32 * NWARPS);
+    const int nsteps = a.nt - 1, dr = a.d, nB = a.nB, npairs = 2 * KKG;            // channel pairs incl. zero padding
+    const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
+    const double *Aw = Apk + (size_t)w * KK * DM_MA * 32 + lane;
+    const double *Gw = Gpk + (size_t)w * KKG * DM_MA * 32 + lane;
+    for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const uint64_t p0 = grp * DM_PT;
+        const int np = (int)((a.npaths - p0 < (uint64_t)DM_PT) ? (a.npaths - p0) : DM_PT);
+        __syncthreads();
+        for (int e = tid; e < D * DM_PT; e += 32 * NWARPS) {
+            const int n = e / D, k = e - n * D;
+            xs[k * DM_LDX + n] = (n < np && k < dr) ? (a.x0 ? a.x0[(p0 + n) * dr + k] : a.x0_shared[k]) : 0.0;
+        }
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 ds = __ldg(&a.dtsq[i]);
+            // Z tile: sqrt(dt) times the normals of (channel pair, path); padding channels and paths are zero
+            for (int e = tid; e < npairs * DM_PT; e += 32 * NWARPS) {
+                const int kp = e / DM_PT, n = e - kp * DM_PT;
+                double z0 = 0.0, z1 = 0.0;
+                if (nB == 1) {                                   // a single channel draws from the scalar models' stream
+                    if (kp == 0 && n < np) {
+                        double zq[4];
+                        normal_quad(a.seed, a.path_offset + p0 + n, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+                        const int s4 = i & 3;
+                        z0 = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
+                    }
+                } else if (2 * kp < nB && n < np)
+                    normal_pair(a.seed, a.path_offset + p0 + n, (uint32_t)i, 0x80000000u + (uint32_t)kp, sh_tab, z0, z1);
+                zs[(2 * kp) * DM_LDX + n] = ds.y * z0;
+                zs[(2 * kp + 1) * DM_LDX + n] = (2 * kp + 1 < nB) ? ds.y * z1 : 0.0;
+            }
+            __syncthreads();                                     // X_i and Z_i are in place
+            double acc[DM_MA][DM_NB][2];
+#pragma unroll
+            for (int mi = 0; mi < DM_MA; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            double an[DM_MA];
+#pragma unroll
+            for (int mi = 0; mi < DM_MA; ++mi) an[mi] = __ldg(Aw + mi * 32);
+#pragma unroll 2
+            for (int kk = 0; kk < KK; ++kk) {
+                double ac[DM_MA], b[DM_NB];
+#pragma unroll
+                for (int mi = 0; mi < DM_MA; ++mi) ac[mi] = an[mi];
+                if (kk + 1 < KK) {
+#pragma unroll
+                    for (int mi = 0; mi < DM_MA; ++mi) an[mi] = __ldg(Aw + ((size_t)(kk + 1) * DM_MA + mi) * 32);
+                }
+                const double *xb = xs + (4 * kk + tig) * DM_LDX + gid;
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) b[ni] = xb[8 * ni];
+#pragma unroll
+                for (int mi = 0; mi < DM_MA; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < DM_NB; ++ni) dmma884(acc[mi][ni], ac[mi], b[ni]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < DM_MA; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) { acc[mi][ni][0] *= ds.x; acc[mi][ni][1] *= ds.x; }
+            for (int kk = 0; kk < KKG; ++kk) {
+                double ac[DM_MA], b[DM_NB];
+#pragma unroll
+                for (int mi = 0; mi < DM_MA; ++mi) ac[mi] = __ldg(Gw + ((size_t)kk * DM_MA + mi) * 32);
+                const double *zb = zs + (4 * kk + tig) * DM_LDX + gid;
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) b[ni] = zb[8 * ni];
+#pragma unroll
+                for (int mi = 0; mi < DM_MA; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < DM_NB; ++ni) dmma884(acc[mi][ni], ac[mi], b[ni]);
+            }
+            __syncthreads();                                     // every warp is done reading X_i and Z_i
+#pragma unroll
+            for (int mi = 0; mi < DM_MA; ++mi) {
+                const int r = 32 * w + 8 * mi + gid;
+#pragma unroll
+                for (int ni = 0; ni < DM_NB; ++ni) {
+                    const int c = 8 * ni + 2 * tig;
+                    double2 xo = *reinterpret_cast<double2 *>(xs + r * DM_LDX + c);
+                    xo.x += acc[mi][ni][0];
+                    xo.y += acc[mi][ni][1];
+                    *reinterpret_cast<double2 *>(xs + r * DM_LDX + c) = xo;
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < D * np; e += 32 * NWARPS) {
+            const int n = e / D, k = e - n * D;
+            if (a.XT && k < dr) a.XT[(p0 + n) * dr + k] = xs[k * DM_LDX + n];
+        }
+        if (a.moments) {
+            for (int k = tid; k < dr; k += 32 * NWARPS) {
+                double s[5] = {0, 0, 0, 0, 0};
+                const double cen = a.center[k];
+                for (int n = 0; n < np; ++n) {
+                    const double dd = xs[k * DM_LDX + n] - cen;
+                    if (isfinite(dd)) {
+                        const double d2 = dd * dd;
+                        s[0] += 1.0; s[1] += dd; s[2] += d2; s[3] += d2 * dd; s[4] += d2 * d2;
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < 5; ++m) atomicAdd(&a.moments[k * 5 + m], s[m]);
+            }
+        }
+    }
 }
+
+static size_t dense_smem(int dp, int kkg)
+{
+    return sizeof(double) * ((size_t)ICDF_TABLE_DOUBLES + (size_t)(dp + 4 * kkg) * DM_LDX);
+}
+
+// 0: not eligible, 1: diagonal G (normals in the GEMM epilogue), 2: dense G (second GEMM on a tile of normals)
+int dmma_mode(const LinearArgs &a, const double *hostG)
+{
+    if (a.B || a.scheme != SDEGPU_EULER || a.X || a.d <= 32 || a.d > 256 || a.nB < 1) return 0;
+    bool diag = a.nB == a.d;
+    for (int c = 0; c < a.nB && diag; ++c)
+        for (int r = 0; r < a.d; ++r)
+            if (r != c && hostG[(size_t)c * a.d + r] != 0.0) { diag = false; break; }
+    if (diag) return 1;
+    const int dp = (a.d + 31) / 32 * 32, kkg = (a.nB + 3) / 4;
+    return dense_smem(dp, kkg) <= 226 * 1024 ? 2 : 0;
+}
+
+// scratch: dp*dp + dp*4*kkg doubles (packed A, packed G)
+int launch_linear_dmma_dense(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream)
+{
+    const int dr = a.d, d = (dr + 31) / 32 * 32, kkg = (a.nB + 3) / 4;
+    double *Apk = scratch, *Gpk = scratch + (size_t)d * d;
+    k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d, dr, d / 4, dr);
+    k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.G, Gpk, d, dr, kkg, a.nB);
+    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * dr, stream);
+    const size_t smem = dense_smem(d, kkg);
+    const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
+#define SDEGPU_DMMA_DENSE_CASE(NW)                                                                             \
+    case NW: {                                                                                                 \
+        auto k = k_linear_dmma_dense<NW>;                                                                      \
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
+        int per_sm = 1;                                                                                        \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 32 * NW, smem);                              \
+        const uint64_t cap = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;                                   \
+        const int grid = (int)(ngroups < cap ? ngroups : cap);                                                 \
+        k<<<grid, 32 * NW, smem, stream>>>(a, Apk, Gpk, kkg);                                                  \
+    } break;
+    switch (d / 32) {
+        SDEGPU_DMMA_DENSE_CASE(2) SDEGPU_DMMA_DENSE_CASE(3) SDEGPU_DMMA_DENSE_CASE(4) SDEGPU_DMMA_DENSE_CASE(5)
+        SDEGPU_DMMA_DENSE_CASE(6) SDEGPU_DMMA_DENSE_CASE(7) SDEGPU_DMMA_DENSE_CASE(8)
+    default: return (int)cudaErrorInvalidValue;
+    }
+#undef SDEGPU_DMMA_DENSE_CASE
+    return (int)cudaGetLastError();
+}
+
+bool dmma_eligible(const LinearArgs &a, const double *hostG) { return dmma_mode(a, hostG) == 1; }
 
 // scratch: dp*dp + dp doubles (packed A, diagonal of G), dp = d rounded up to a multiple of 32
 int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream)
 {
     const int dr = a.d, d = (dr + 31) / 32 * 32;
     double *Apk = scratch, *gdiag = scratch + (size_t)d * d;
-    k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d, dr);
+    k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d, dr, d / 4, dr);
     cudaMemsetAsync(gdiag, 0, sizeof(double) * d, stream);
     cudaMemcpy2DAsync(gdiag, sizeof(double), a.G, sizeof(double) * (dr + 1), sizeof(double), dr, cudaMemcpyDeviceToDevice, stream);
     if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * dr, stream);

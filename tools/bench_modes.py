@@ -271,6 +271,14 @@ def main():
             fl = 2.0 * d * d + 4 * d
             emit(f"linear_dmma_d{d}", paths=P, nsteps=n, ms=ms, path_steps_per_s=P * n / ms * 1e3, tflops=fl * P * n / ms / 1e9,
                  frac=fl * P * n / ms / 1e9 / fp64)
+            # dense (lower-triangular) G: the increment term is a second GEMM; 2d^2 + d(d+1) + 2d flops per path-step
+            Gd = np.tril(rng.standard_normal((d, d))) / np.sqrt(d)
+            pd = np.concatenate([A.ravel(order="F"), Gd.ravel(order="F")])
+            ms = best_ms(lambda: eng.run("linear", "euler", pd, np.arange(n + 1) * (1.0 / n), x0, nx=d, nB=d, npaths=P, seed=4,
+                                         XT=XT, want_time=True), reps=2)
+            fld = 4.0 * d * d + 2 * d
+            emit(f"linear_dmma_dense_d{d}", paths=P, nsteps=n, ms=ms, path_steps_per_s=P * n / ms * 1e3,
+                 tflops=fld * P * n / ms / 1e9, frac=fld * P * n / ms / 1e9 / fp64)
             del XT
         torch.cuda.empty_cache()
 
