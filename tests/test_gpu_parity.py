@@ -814,3 +814,30 @@ def test_exact_stepping_at_d128_runs_on_the_tensor_path(sde):
     assert np.max(np.abs(XT.mean(axis=1) - law["EX"]) / se) < 5.0
     C = np.cov(XT)
     assert np.max(np.abs(C - law["St"])) < 5.5 * np.max(np.diag(law["St"])) * np.sqrt(2.0 / P)
+
+
+@pytest.mark.parametrize("nbins", [1, 8192])
+def test_histogram_bin_count_extremes(eng, nbins):
+    """1 bin and the maximum of 8192 bins (32 KB of shared memory next to the 151 KB quantile table), through the
+    register-resident, trajectory and supplied-B kernels, against the oracle's histogram of the terminal states."""
+    from sdetools_b200._lib import SdeGpuError
+    P, nt = 5000, 41
+    t = np.arange(nt) * 0.025
+    lo, hi = 0.0, 3.0
+    for want_x in (False, True):
+        XT = np.empty((1, P), order="F")
+        hc = np.zeros(nbins + 3, np.uint64)
+        X = np.empty((nt, 1, P), order="F") if want_x else None
+        eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=P, projection="abs", seed=2, XT=XT, X=X,
+                hist_counts=hc, hist=(lo, hi, nbins))
+        assert np.array_equal(hc, O.hist_counts(XT[0], lo, hi, nbins)) and int(hc.sum()) == P
+    tb, B = brownian(nt, 1, 300, 4, dt=0.025)
+    XT = np.empty((1, 300), order="F")
+    hc = np.zeros(nbins + 3, np.uint64)
+    eng.run("cir", "heun", [1.0, 1.0, 1.0], tb, [1.0], nx=1, npaths=300, B=np.asfortranarray(B), projection="abs", XT=XT,
+            hist_counts=hc, hist=(lo, hi, nbins))
+    assert np.array_equal(hc, O.hist_counts(XT[0], lo, hi, nbins))
+    with pytest.raises(SdeGpuError):
+        eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=10, seed=2, hist_counts=np.zeros(8196, np.uint64), hist=(lo, hi, 8193))
+    with pytest.raises(SdeGpuError):
+        eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=10, seed=2, hist_counts=np.zeros(7, np.uint64), hist=(1.0, 1.0, 4))
