@@ -841,3 +841,26 @@ def test_histogram_bin_count_extremes(eng, nbins):
         eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=10, seed=2, hist_counts=np.zeros(8196, np.uint64), hist=(lo, hi, 8193))
     with pytest.raises(SdeGpuError):
         eng.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], nx=1, npaths=10, seed=2, hist_counts=np.zeros(7, np.uint64), hist=(1.0, 1.0, 4))
+
+
+def test_killing_and_stopping_on_the_second_component(sde):
+    """nx = 2 (van der Pol): rate and stopping rule read the velocity component; path by path against the numpy
+    restatement of R's loop, and the lane-refill kernel against the trajectory kernel."""
+    t, B = brownian(401, 1, 64, 31)
+    f, g = sde.catalogue.vdp(1.0, 0.5)
+    r = sde.catalogue.kill_quad(0.8, 0.0, component=1)
+    h = sde.catalogue.stop_outside(-1.5, 1.2, component=1)
+    Stau = np.random.default_rng(6).random(64)
+    got = sde.heun(f, g, t, [0.1, -0.2], B, r=r, h=h, Stau=Stau)
+    fo, go, _, _ = O.catalogue("vdp", [1.0, 0.5])
+    ends = set()
+    for p in range(64):
+        ref = O.heun(fo, go, t, [0.1, -0.2], B=B[:, :, p], r=lambda x: 0.8 * (x[1] * x[1]),
+                     h=lambda tt, x: (x[1] + 1.5) * (1.2 - x[1]), Stau=Stau[p])
+        k = ref["times"].size
+        assert got["tau"][p] == ref["tau"]
+        assert np.array_equal(got["X"][:k, :, p], ref["X"]) and np.all(np.isnan(got["X"][k:, :, p]))
+        ends.add(k == t.size)
+    assert ends == {True, False}
+    term = sde.heun(f, g, t, [0.1, -0.2], B, r=r, h=h, Stau=Stau, output="terminal")
+    assert np.array_equal(term["tau"], got["tau"]) and np.array_equal(term["XT"], got["XT"]) and np.array_equal(term["S"], got["S"])
