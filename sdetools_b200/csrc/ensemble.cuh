@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(TrajThreads<M::NX>::value, 1) k_traj(const Run
             const uint64_t e0 = (p * NX + j) * (uint64_t)a.nt;
             row[j] = a.X + e0 + 1;
             d[j] = vec_ok ? (int)((e0 + 1) & 3) : 4;             // 4: element-wise stores only
-            if (valid && d[j] != 1) a.X[e0] = x[j];              // X[1,] <- x0 (:441); with d = 1 it opens the first sector
+            if (valid && (d[j] != 1 || ngroups == 0)) a.X[e0] = x[j];   // X[1,] <- x0 (:441); with d = 1 it opens the first
+                                                                         // sector (if there is one: nt >= 5)
 #pragma unroll
             for (int k = 0; k < 4; ++k) pv[j][k] = x[j];
         }

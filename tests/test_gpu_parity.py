@@ -864,3 +864,59 @@ def test_killing_and_stopping_on_the_second_component(sde):
     assert ends == {True, False}
     term = sde.heun(f, g, t, [0.1, -0.2], B, r=r, h=h, Stau=Stau, output="terminal")
     assert np.array_equal(term["tau"], got["tau"]) and np.array_equal(term["XT"], got["XT"]) and np.array_equal(term["S"], got["S"])
+
+
+def test_fuzz_shapes_supplied_B_bit_identical(eng):
+    """Sixty random shapes — nt from 2, a single path, ragged counts, non-uniform grids, shared or per-path x0, every
+    model, scheme and projection — through the supplied-B STRICT path (sector loads/stores with per-row phases)
+    and the integral kernels, against the C oracle bit for bit."""
+    rng = np.random.default_rng(20261020)
+    models = [c for c in CASES]
+    for it in range(60):
+        model, params, x0, proj = models[int(rng.integers(len(models)))]
+        scheme = ("euler", "heun")[int(rng.integers(2))]
+        nt = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 12, 17, 33, 70]))
+        P = int(rng.choice([1, 2, 3, 31, 32, 33, 64, 90]))
+        nx = len(x0)
+        t = np.concatenate(([0.0], np.cumsum(rng.uniform(0.002, 0.03, nt - 1))))
+        B = np.cumsum(np.concatenate([np.zeros((1, 1, P)), rng.standard_normal((nt - 1, 1, P)) * np.sqrt(np.diff(t))[:, None, None]]), axis=0)
+        per_path = bool(rng.integers(2))
+        x0a = np.abs(np.array(x0)[None, :] + 0.1 * rng.standard_normal((P, nx))) if per_path else np.array(x0, float)
+        Xo, XTo = c_oracle.ensemble(SCH[scheme], O.MODEL_IDS[model], params, nx, 1, O.PROJ_IDS[proj], t,
+                                    np.ascontiguousarray(x0a), B=np.ascontiguousarray(B.transpose(2, 1, 0)))
+        X = np.empty((nt, nx, P), order="F")
+        XT = np.empty((nx, P), order="F")
+        eng.run(model, scheme, params, t, np.ascontiguousarray(x0a), nx=nx, npaths=P, B=np.asfortranarray(B), projection=proj,
+                arith="strict", X=X, XT=XT)
+        assert np.array_equal(X, Xo.transpose(2, 1, 0)), (it, model, scheme, nt, P, per_path)
+        assert np.array_equal(XT, XTo.T), (it, model, scheme, nt, P)
+        # integrals of the first component against the long-double cumsum
+        Xc = np.ascontiguousarray(X[:, 0, :].T)
+        Bc = np.ascontiguousarray(B[:, 0, :].T)
+        out = np.empty((nt, P), order="F")
+        eng.itointegral(np.asfortranarray(X[:, 0, :]), np.asfortranarray(B[:, 0, :]), nt, P, out)
+        assert np.array_equal(out, c_oracle.integral(0, Xc, Bc).T), (it, "ito", nt, P)
+        eng.qv(np.asfortranarray(X[:, 0, :]), nt, P, out)
+        assert np.array_equal(out, c_oracle.integral(3, Xc).T), (it, "qv", nt, P)
+
+
+def test_fuzz_shapes_fused_generator(eng):
+    """Random small shapes through the generator kernels: the trajectory kernel, the register-resident kernel and the
+    oracle's loop fed with the device's normals must agree (1e-12), for nt from 2 and path counts around the warp size."""
+    rng = np.random.default_rng(77)
+    for it in range(40):
+        model, params, x0, proj = CASES[int(rng.integers(len(CASES)))]
+        scheme = ("euler", "heun")[int(rng.integers(2))]
+        nt = int(rng.choice([2, 3, 4, 5, 6, 8, 9, 13, 40]))
+        P = int(rng.choice([1, 5, 31, 33, 100]))
+        nx, seed, off = len(x0), int(rng.integers(1 << 30)), int(rng.integers(1 << 40))
+        t = np.concatenate(([0.0], np.cumsum(rng.uniform(0.002, 0.03, nt - 1))))
+        X = np.empty((nt, nx, P), order="F")
+        XT = np.empty((nx, P), order="F")
+        eng.run(model, scheme, params, t, x0, nx=nx, npaths=P, projection=proj, seed=seed, path_offset=off, X=X)
+        eng.run(model, scheme, params, t, x0, nx=nx, npaths=P, projection=proj, seed=seed, path_offset=off, XT=XT)
+        z = eng.normals(seed, off, P, nt - 1)
+        dB = (np.sqrt(O.r_diff(t))[:, None] * z)[:, None, :]
+        want = O.ensemble(scheme, model, params, t, x0, dB=dB, proj=proj)
+        assert np.allclose(X, want, rtol=1e-12, atol=1e-13), (it, model, scheme, nt, P)
+        assert np.allclose(XT, X[-1], rtol=1e-13, atol=1e-15), (it, model, scheme, nt, P)
