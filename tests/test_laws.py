@@ -323,3 +323,28 @@ def test_edge_cases_of_the_law_and_brownian_entry_points(sde):
     assert np.all(W[0] == -2.0)
     with pytest.raises(SdeGpuError, match="non-decreasing"):
         sde.rvBM_functionals([0.0, 2.0, 1.0], 3, seed=1)
+
+
+@pytest.mark.gpu
+def test_fuzz_shapes_rvbm_and_functionals(sde):
+    """Random small shapes through the Brownian kernels (sector stores with per-column phases): nt from 1, column counts
+    around the warp size, times[0] zero or not — against the oracle's rBM fed with the device's normals, bit for bit,
+    and the functionals against those of the stored matrix."""
+    from oracle import sde_oracle as O
+    eng = sde.default_engine(0)
+    rng = np.random.default_rng(5)
+    for it in range(40):
+        nt = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 33]))
+        n = int(rng.choice([1, 2, 5, 31, 32, 33, 100]))
+        t0 = float(rng.choice([0.0, 0.3]))
+        t = t0 + np.concatenate(([0.0], np.cumsum(rng.uniform(0.01, 0.2, nt - 1))))
+        sigma, B0, u, seed, off = float(rng.uniform(0.5, 2)), float(rng.normal()), float(rng.normal()), int(rng.integers(1 << 30)), int(rng.integers(1 << 36))
+        B = sde.rvBM(t, n, sigma=sigma, B0=B0, u=u, seed=seed, path_offset=off)
+        z = eng.normals(seed, off, n, nt)
+        for c in range(n):
+            assert np.array_equal(B[:, c], O.rBM(t, sigma, B0, u, z=z[:, c])), (it, nt, n, c)
+        lvl = B0 + 0.3
+        F = sde.rvBM_functionals(t, n, sigma=sigma, B0=B0, u=u, level=lvl, seed=seed, path_offset=off)
+        assert np.array_equal(F["max"], B.max(axis=0)) and np.array_equal(F["tmin"], t[B.argmin(axis=0)]), (it, nt, n)
+        hit = B >= lvl
+        assert np.array_equal(F["thit"], np.where(hit.any(axis=0), t[hit.argmax(axis=0)], np.nan), equal_nan=True), (it, nt, n)
