@@ -920,3 +920,40 @@ def test_fuzz_shapes_fused_generator(eng):
         want = O.ensemble(scheme, model, params, t, x0, dB=dB, proj=proj)
         assert np.allclose(X, want, rtol=1e-12, atol=1e-13), (it, model, scheme, nt, P)
         assert np.allclose(XT, X[-1], rtol=1e-13, atol=1e-15), (it, model, scheme, nt, P)
+
+
+def test_fuzz_shapes_killed_functionals_linear(sde, eng):
+    """Small and ragged shapes (nt from 2) through the remaining kernels: lane-refill vs one-path-per-thread killing,
+    fused path integrals vs the integral functions on the stored path, linear kernels with and without trajectory."""
+    rng = np.random.default_rng(99)
+    f, g = sde.catalogue.ou(1.0, 0.0, 1.0)
+    for it in range(25):
+        nt = int(rng.choice([2, 3, 4, 5, 6, 9, 30]))
+        P = int(rng.choice([1, 7, 33, 200]))
+        t = np.concatenate(([0.0], np.cumsum(rng.uniform(0.01, 0.2, nt - 1))))
+        seed = int(rng.integers(1 << 30))
+        kw = dict(r=sde.catalogue.kill_exp(0.8, 1.0), h=sde.catalogue.stop_outside(-0.7, 0.9), seed=seed, npaths=P)
+        a = sde.euler(f, g, t, 0.1, output="path", **kw)
+        b = sde.euler(f, g, t, 0.1, output="terminal", **kw)
+        assert np.array_equal(np.asarray(a["tau"]), np.asarray(b["tau"])) and np.array_equal(np.asarray(a["S"]), np.asarray(b["S"])), (it, nt, P)
+        assert np.array_equal(np.asarray(a["XT"]), np.asarray(b["XT"])), (it, nt, P)
+        # fused integrals, supplied B
+        B = np.cumsum(np.concatenate([np.zeros((1, 1, P)), rng.standard_normal((nt - 1, 1, P)) * np.sqrt(np.diff(t))[:, None, None]]), axis=0)
+        fv, gv = sde.catalogue.vdp(1.0, 0.5)
+        path = sde.heun(fv, gv, t, [0.1, -0.2], B)["X"].reshape(nt, 2, P)
+        I = sde.heun(fv, gv, t, [0.1, -0.2], B, integrals=True)["integrals"]
+        for j in range(2):
+            Xj, Bj = path[:, j, :], B[:, 0, :]
+            assert np.array_equal(np.asarray(I["QV"]).reshape(2, P)[j], np.atleast_2d(sde.QuadraticVariation(Xj).reshape(nt, P))[-1]), (it, nt, P)
+            assert np.array_equal(np.asarray(I["strat"]).reshape(2, P)[j], np.atleast_2d(sde.stochint(Xj, Bj, "c").reshape(nt, P))[-1]), (it, nt, P)
+        # linear kernels: small, warp and generic shapes
+        d, nB = [(2, 2), (3, 1), (7, 4), (20, 20), (40, 3)][int(rng.integers(5))]
+        A = -0.5 * np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
+        G = rng.standard_normal((d, nB))
+        x0 = rng.standard_normal(d)
+        fl, gl = sde.catalogue.linear(A, G)
+        for fn in (sde.euler, sde.heun):
+            X = fn(fl, gl, t, x0, npaths=P, seed=seed)["X"].reshape(nt, d, P)
+            XT = np.asarray(fn(fl, gl, t, x0, npaths=P, seed=seed, output="terminal")["XT"]).reshape(d, P)
+            assert np.array_equal(X[0], np.repeat(x0[:, None], P, axis=1)), (it, d, nB, nt, P)
+            assert np.allclose(X[-1], XT, rtol=1e-10, atol=1e-12), (it, d, nB, nt, P)
