@@ -957,3 +957,27 @@ def test_fuzz_shapes_killed_functionals_linear(sde, eng):
             XT = np.asarray(fn(fl, gl, t, x0, npaths=P, seed=seed, output="terminal")["XT"]).reshape(d, P)
             assert np.array_equal(X[0], np.repeat(x0[:, None], P, axis=1)), (it, d, nB, nt, P)
             assert np.allclose(X[-1], XT, rtol=1e-10, atol=1e-12), (it, d, nB, nt, P)
+
+
+def test_fuzz_shapes_tensor_path(eng):
+    """The DMMA kernels on awkward shapes: d just above 32 and just below 256, one step, path counts around the
+    64-path tile, diagonal and dense G — terminal output against the generic kernel's trajectory."""
+    rng = np.random.default_rng(123)
+    for it in range(14):
+        d = int(rng.choice([33, 63, 65, 127, 129, 255]))
+        dense = bool(rng.integers(2))
+        nB = d if not dense else int(rng.choice([1, 2, 5, min(d, 60)]))
+        nt = int(rng.choice([2, 3, 6]))
+        P = int(rng.choice([1, 63, 64, 65, 130]))
+        R = rng.standard_normal((d, d))
+        A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
+        G = np.diag(rng.uniform(0.5, 1.5, d)) if not dense else rng.standard_normal((d, nB)) / np.sqrt(d)
+        params = np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
+        t = np.concatenate(([0.0], np.cumsum(rng.uniform(0.005, 0.02, nt - 1))))
+        x0 = rng.standard_normal(d)
+        seed = int(rng.integers(1 << 30))
+        XT = np.empty((d, P), order="F")
+        X = np.empty((nt, d, P), order="F")
+        eng.run("linear", "euler", params, t, x0, nx=d, nB=nB, npaths=P, seed=seed, XT=XT)
+        eng.run("linear", "euler", params, t, x0, nx=d, nB=nB, npaths=P, seed=seed, X=X)
+        assert np.allclose(XT, X[-1], rtol=1e-11, atol=1e-12), (it, d, nB, nt, P, dense)
