@@ -981,3 +981,25 @@ def test_fuzz_shapes_tensor_path(eng):
         eng.run("linear", "euler", params, t, x0, nx=d, nB=nB, npaths=P, seed=seed, XT=XT)
         eng.run("linear", "euler", params, t, x0, nx=d, nB=nB, npaths=P, seed=seed, X=X)
         assert np.allclose(XT, X[-1], rtol=1e-11, atol=1e-12), (it, d, nB, nt, P, dense)
+
+
+def test_fuzz_shapes_integral_functions(sde):
+    """stochint (every subset of rules), itointegral, QuadraticVariation, CrossVariation on vectors and matrices with
+    n from 1 and column counts around the warp size, against the long-double oracle bit for bit."""
+    rng = np.random.default_rng(314)
+    for it in range(40):
+        n = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 64, 129]))
+        nc = int(rng.choice([1, 2, 31, 33, 70]))
+        f = rng.standard_normal((n, nc)) * 10.0 ** rng.integers(-3, 4, (n, nc))
+        g = np.cumsum(rng.standard_normal((n, nc)), axis=0)
+        fa, ga = np.ascontiguousarray(f.T), np.ascontiguousarray(g.T)
+        rules = [r for r in "lrc" if rng.integers(2)] or ["c"]
+        got = sde.stochint(f, g, rules)
+        for r in rules:
+            want = c_oracle.integral({"l": 0, "r": 1, "c": 2}[r], fa, ga).T
+            assert np.array_equal(np.asarray(got[r]).reshape(n, nc), want), (it, n, nc, r)
+        assert np.array_equal(sde.itointegral(f, g).reshape(n, nc), c_oracle.integral(0, fa, ga).T), (it, n, nc)
+        assert np.array_equal(sde.QuadraticVariation(g).reshape(n, nc), c_oracle.integral(3, ga).T), (it, n, nc)
+        assert np.array_equal(sde.CrossVariation(f, g).reshape(n, nc), c_oracle.integral(4, fa, ga).T), (it, n, nc)
+        one = sde.stochint(f[:, 0], g[:, 0], "r")
+        assert one.shape == (n,) and np.array_equal(one, O.stochint(f[:, 0], g[:, 0], "r"))
