@@ -56,7 +56,9 @@ typedef enum {
     SDEGPU_MODEL_LOGISTIC = 3,   /* f = x*(1-x) - c*(x*x)      g = sigma*x             params {sigma, c} */
     SDEGPU_MODEL_GBM = 4,        /* f = mu*x                   g = sigma*x             params {mu, sigma} */
     SDEGPU_MODEL_DOUBLEWELL = 5, /* f = x - x*x*x              g = sigma               params {sigma} */
-    SDEGPU_MODEL_LINEAR = 6      /* f = A %*% x                g = G (nx x nB)         params {A col-major, G col-major} */
+    SDEGPU_MODEL_LINEAR = 6,     /* f = A %*% x                g = G (nx x nB)         params {A col-major, G col-major} */
+    SDEGPU_MODEL_DWSQRT = 7,     /* f = x - x*x*x              g = sqrt(1 + x*x)       no params   (vignettes/ItoIntegrals.Rmd:66-69) */
+    SDEGPU_MODEL_LOGLOGISTIC = 8 /* f = (1 - exp(y)) - 0.5*sigma*sigma   g = sigma     params {sigma}  (vignettes/ItosFormula.Rmd:113-116) */
 } sdegpu_model;
 
 typedef enum { SDEGPU_EULER = 0, SDEGPU_HEUN = 1 } sdegpu_scheme;            /* euler :375-470 / heun :240-338 */

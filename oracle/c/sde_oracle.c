@@ -24,7 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { M_OU = 0, M_CIR = 1, M_VDP = 2, M_LOGISTIC = 3, M_GBM = 4, M_DOUBLEWELL = 5, M_LINEAR = 6 };
+enum { M_OU = 0, M_CIR = 1, M_VDP = 2, M_LOGISTIC = 3, M_GBM = 4, M_DOUBLEWELL = 5, M_LINEAR = 6, M_DWSQRT = 7, M_LOGLOGISTIC = 8 };
 enum { P_ID = 0, P_ABS = 1, P_RELU = 2 };
 enum { S_EULER = 0, S_HEUN = 1 };
 
@@ -37,7 +37,9 @@ static void drift(int model, const double *P, int nx, const double *x, double *f
     case M_VDP: f[0] = x[1]; f[1] = x[1] * (P[0] - x[0] * x[0]) - x[0]; break;
     case M_LOGISTIC: f[0] = x[0] * (1.0 - x[0]) - P[1] * (x[0] * x[0]); break;
     case M_GBM: f[0] = P[0] * x[0]; break;
-    case M_DOUBLEWELL: f[0] = x[0] - x[0] * x[0] * x[0]; break;
+    case M_DOUBLEWELL:
+    case M_DWSQRT: f[0] = x[0] - x[0] * x[0] * x[0]; break;
+    case M_LOGLOGISTIC: f[0] = (1.0 - exp(x[0])) - 0.5 * (P[0] * P[0]); break;
     case M_LINEAR: {                                                /* A %*% x, A = P[0..d*d) col-major */
         for (int j = 0; j < nx; ++j) f[j] = P[j] * x[0];
         for (int k = 1; k < nx; ++k)
@@ -55,6 +57,8 @@ static void diffusion(int model, const double *P, int nx, int nB, const double *
     case M_LOGISTIC: g[0] = P[0] * x[0]; break;
     case M_GBM: g[0] = P[1] * x[0]; break;
     case M_DOUBLEWELL: g[0] = P[0]; break;
+    case M_DWSQRT: g[0] = sqrt(1.0 + x[0] * x[0]); break;
+    case M_LOGLOGISTIC: g[0] = P[0]; break;
     case M_LINEAR: memcpy(g, P + (size_t)nx * nx, sizeof(double) * nx * nB); break;
     }
 }

@@ -238,7 +238,7 @@ def heun(f, g, times, x0, B=None, p=lambda x: x, h=None, r=None, S0=1.0, Stau=No
 # model catalogue: the closures the R-side constructors would return, with the
 # operation order fixed as in SURVEY.md App. A / App. C
 # --------------------------------------------------------------------------
-MODEL_IDS = {"ou": 0, "cir": 1, "vdp": 2, "logistic": 3, "gbm": 4, "doublewell": 5, "linear": 6}
+MODEL_IDS = {"ou": 0, "cir": 1, "vdp": 2, "logistic": 3, "gbm": 4, "doublewell": 5, "linear": 6, "dwsqrt": 7, "loglogistic": 8}
 PROJ_IDS = {"identity": 0, "abs": 1, "relu": 2}
 
 
@@ -269,6 +269,11 @@ def catalogue(model: str, params):
     if model == "doublewell":  # SDEtools.Rmd:50-55  x - x^3 written x - x*x*x / sigma
         sig, = P
         return (lambda x: x - x * x * x), (lambda x: sig + 0.0 * x), 1, 1
+    if model == "dwsqrt":      # ItoIntegrals.Rmd:66-69  x - x^3 / sqrt(1 + x^2)
+        return (lambda x: x - x * x * x), (lambda x: np.sqrt(1.0 + x * x)), 1, 1
+    if model == "loglogistic":  # ItosFormula.Rmd:113-116  1 - exp(y) - 0.5*sigma^2 / sigma
+        sig, = P
+        return (lambda x: (1.0 - np.exp(x)) - 0.5 * (sig * sig)), (lambda x: sig + 0.0 * x), 1, 1
     if model == "linear":      # R/sdetools.R:360-368  A %*% x / G
         A, G = params
         A = np.asarray(A, dtype=np.float64)

@@ -6,7 +6,7 @@
 ## oracle the GPU path is tested against.  Signatures below keep every reference argument in place;
 ## new arguments are appended with defaults, so positional calls keep their meaning.
 
-.sdegpu_models <- c(ou = 0L, cir = 1L, vdp = 2L, logistic = 3L, gbm = 4L, doublewell = 5L, linear = 6L)
+.sdegpu_models <- c(ou = 0L, cir = 1L, vdp = 2L, logistic = 3L, gbm = 4L, doublewell = 5L, linear = 6L, dwsqrt = 7L, loglogistic = 8L)
 
 .catalogue <- function(model, params, f, g, nx = 1L, nB = 1L) {
   tag <- function(fn) { attr(fn, "sdegpu_model") <- model; attr(fn, "sdegpu_params") <- as.numeric(params)
@@ -28,6 +28,10 @@ sde.gbm <- function(mu = 0, sigma = 1)
   .catalogue("gbm", c(mu, sigma), function(x) mu * x, function(x) sigma * x)
 sde.doublewell <- function(sigma = 0.5)
   .catalogue("doublewell", sigma, function(x) x - x * x * x, function(x) sigma)
+sde.dwsqrt <- function()                                      # vignettes/ItoIntegrals.Rmd:66-69
+  .catalogue("dwsqrt", numeric(0), function(x) x - x * x * x, function(x) sqrt(1 + x * x))
+sde.loglogistic <- function(sigma = 0.25)                     # vignettes/ItosFormula.Rmd:113-116
+  .catalogue("loglogistic", sigma, function(y) (1 - exp(y)) - 0.5 * (sigma * sigma), function(y) sigma)
 sde.linear <- function(A, G) {
   A <- as.matrix(A); G <- matrix(G, nrow = nrow(A))
   .catalogue("linear", c(as.numeric(A), as.numeric(G)), function(x) A %*% x, function(x) G, nx = nrow(A), nB = ncol(G))

@@ -12,7 +12,7 @@ ABI_VERSION = 3
 DEVICE_PTRS = 1
 ACCUMULATE = 2
 
-MODEL = {"ou": 0, "cir": 1, "vdp": 2, "logistic": 3, "gbm": 4, "doublewell": 5, "linear": 6}
+MODEL = {"ou": 0, "cir": 1, "vdp": 2, "logistic": 3, "gbm": 4, "doublewell": 5, "linear": 6, "dwsqrt": 7, "loglogistic": 8}
 SCHEME = {"euler": 0, "heun": 1}
 PROJ = {"identity": 0, "abs": 1, "relu": 2}
 ARITH = {"strict": 0, "fast": 1}

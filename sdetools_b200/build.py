@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE]
-N_SCALAR_MODELS = 6
+SCALAR_MODELS = (0, 1, 2, 3, 4, 5, 7, 8)        # sdegpu_model ids compiled from ensemble_model.cu (6 = linear has its own files)
 
 
 def _nvcc() -> str:
@@ -32,7 +32,7 @@ def _nvcc() -> str:
 def _units():
     units = [("api.o", "api.cu", []), ("integrals.o", "integrals.cu", []), ("linear.o", "linear.cu", []),
              ("linear_dmma.o", "linear_dmma.cu", []), ("laws.o", "laws.cu", [])]
-    units += [(f"ensemble_model_{m}.o", "ensemble_model.cu", [f"-DSDEGPU_TU_MODEL={m}"]) for m in range(N_SCALAR_MODELS)]
+    units += [(f"ensemble_model_{m}.o", "ensemble_model.cu", [f"-DSDEGPU_TU_MODEL={m}"]) for m in SCALAR_MODELS]
     return [u for u in units if os.path.exists(os.path.join(CSRC, u[1]))]
 
 

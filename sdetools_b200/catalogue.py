@@ -69,6 +69,16 @@ def doublewell(sigma=0.5):
     return _pair("doublewell", [sigma], lambda x: x - x * x * x, lambda x: sigma + 0.0 * x)
 
 
+def dwsqrt():
+    """f = x - x^3 (evaluated x - x*x*x), g = sqrt(1 + x^2): the example of vignettes/ItoIntegrals.Rmd:66-69."""
+    return _pair("dwsqrt", [], lambda x: x - x * x * x, lambda x: np.sqrt(1.0 + x * x))
+
+
+def loglogistic(sigma=0.25):
+    """dY = (1 - exp(Y) - sigma^2/2) dt + sigma dB: Y = log X of stochastic logistic growth (vignettes/ItosFormula.Rmd:113-116)."""
+    return _pair("loglogistic", [sigma], lambda y: (1.0 - np.exp(y)) - 0.5 * (sigma * sigma), lambda y: sigma + 0.0 * y)
+
+
 def linear(A, G):
     """dX = A X dt + G dB with matrix-valued g: nB = ncol(G) channels (R/sdetools.R:360-368)."""
     A = np.atleast_2d(np.asarray(A, dtype=np.float64))

@@ -23,6 +23,8 @@ int launch_model_2(const RunArgs &, const LaunchCfg &, int *);
 int launch_model_3(const RunArgs &, const LaunchCfg &, int *);
 int launch_model_4(const RunArgs &, const LaunchCfg &, int *);
 int launch_model_5(const RunArgs &, const LaunchCfg &, int *);
+int launch_model_7(const RunArgs &, const LaunchCfg &, int *);
+int launch_model_8(const RunArgs &, const LaunchCfg &, int *);
 
 }  // namespace sdegpu
 
@@ -73,8 +75,8 @@ struct sdegpu_ctx {
     int max_grid = 0;
 };
 
-static const int MODEL_NX[6] = {1, 1, 2, 1, 1, 1};
-static const int MODEL_NP[6] = {3, 3, 2, 2, 2, 1};
+static const int MODEL_NX[9] = {1, 1, 2, 1, 1, 1, 0, 1, 1};      // [6] linear: nx is free
+static const int MODEL_NP[9] = {3, 3, 2, 2, 2, 1, 0, 0, 1};
 
 extern "C" {
 
@@ -200,13 +202,14 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
     if (!c || !pr || !out) return fail(SDEGPU_ERR_ARG, "sdegpu_run: NULL argument");
     if (pr->struct_size != sizeof(sdegpu_problem) || out->struct_size != sizeof(sdegpu_output))
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: struct_size mismatch (ABI %d)", SDEGPU_ABI_VERSION);
-    if (pr->model < 0 || pr->model > SDEGPU_MODEL_LINEAR) return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown model %d", pr->model);
+    if (pr->model < 0 || pr->model > SDEGPU_MODEL_LOGLOGISTIC) return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown model %d", pr->model);
     if (pr->scheme != SDEGPU_EULER && pr->scheme != SDEGPU_HEUN) return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown scheme %d", pr->scheme);
     if (pr->projection < 0 || pr->projection > SDEGPU_PROJ_RELU) return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown projection %d", pr->projection);
     if (pr->arith != SDEGPU_ARITH_STRICT && pr->arith != SDEGPU_ARITH_FAST) return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown arith %d", pr->arith);
     // dB <- apply(B,2,diff) collapses for nt = 2 in the reference; nt >= 2 is well defined here
     if (pr->nt < 2) return fail(SDEGPU_ERR_ARG, "sdegpu_run: need at least 2 time points, got %d", pr->nt);
-    if (!pr->times || !pr->x0 || !pr->params) return fail(SDEGPU_ERR_ARG, "sdegpu_run: times/x0/params must not be NULL");
+    if (!pr->times || !pr->x0 || (!pr->params && pr->nparams > 0) || pr->nparams < 0)
+        return fail(SDEGPU_ERR_ARG, "sdegpu_run: times/x0/params must not be NULL");
     if (pr->x0_stride != 0 && pr->x0_stride != pr->nx) return fail(SDEGPU_ERR_ARG, "sdegpu_run: x0_stride must be 0 or nx");
     const bool killed = pr->kill_kind != SDEGPU_KILL_NONE || pr->stop_kind != SDEGPU_STOP_NONE;
     if (pr->kill_kind < 0 || pr->kill_kind > SDEGPU_KILL_QUAD || pr->stop_kind < 0 || pr->stop_kind > SDEGPU_STOP_OUTSIDE)
@@ -359,7 +362,9 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         case 2: cuerr = launch_model_2(a, cfg, &grid_used); break;
         case 3: cuerr = launch_model_3(a, cfg, &grid_used); break;
         case 4: cuerr = launch_model_4(a, cfg, &grid_used); break;
-        default: cuerr = launch_model_5(a, cfg, &grid_used); break;
+        case 5: cuerr = launch_model_5(a, cfg, &grid_used); break;
+        case 7: cuerr = launch_model_7(a, cfg, &grid_used); break;
+        default: cuerr = launch_model_8(a, cfg, &grid_used); break;
         }
         if (cuerr) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: kernel launch: %s", cudaGetErrorString((cudaError_t)cuerr));
         if (grid_used > c->max_grid) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: grid %d exceeds partials capacity", grid_used);

@@ -83,6 +83,20 @@ template <> struct Model<SDEGPU_MODEL_DOUBLEWELL> {    // SDEtools.Rmd:50-55 (x^
     template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *, double *o) { o[0] = P.p[0]; }
 };
 
+template <> struct Model<SDEGPU_MODEL_DWSQRT> {        // ItoIntegrals.Rmd:66-69: f = x - x^3, g = sqrt(1 + x^2)
+    static constexpr int NX = 1, NPARAMS = 0;
+    template <class A> static __device__ __forceinline__ void f(const KParams &, const double *x, double *o)
+    { o[0] = A::sub(x[0], A::mul(A::mul(x[0], x[0]), x[0])); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &, const double *x, double *o)
+    { o[0] = A::strict ? __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(x[0], x[0]))) : sqrt(fma(x[0], x[0], 1.0)); }
+};
+template <> struct Model<SDEGPU_MODEL_LOGLOGISTIC> {   // ItosFormula.Rmd:113-116: Y = log X of logistic growth
+    static constexpr int NX = 1, NPARAMS = 1;
+    template <class A> static __device__ __forceinline__ void f(const KParams &P, const double *x, double *o)
+    { o[0] = A::sub(A::sub(1.0, exp(x[0])), A::mul(0.5, A::mul(P.p[0], P.p[0]))); }
+    template <class A> static __device__ __forceinline__ void g(const KParams &P, const double *, double *o) { o[0] = P.p[0]; }
+};
+
 template <int PROJ> __device__ __forceinline__ double project(double v)
 {
     if (PROJ == SDEGPU_PROJ_ABS) return fabs(v);

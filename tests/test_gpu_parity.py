@@ -67,7 +67,7 @@ def test_c1_ou_euler_supplied_B_bit_identical(sde, lam, xi, sig, x0):
 CASES = [("ou", [1.3, 0.7, 0.9], [2.0], "identity"), ("cir", [1.0, 1.0, 1.0], [1.0], "abs"),
          ("cir", [0.5, 0.2, 1.5], [0.05], "relu"), ("vdp", [1.0, 0.5], [0.1, -0.2], "identity"),
          ("logistic", [0.5, 1.0], [0.3], "identity"), ("gbm", [0.4, 1.0], [1.0], "abs"),
-         ("doublewell", [0.5], [0.2], "identity")]
+         ("doublewell", [0.5], [0.2], "identity"), ("dwsqrt", [], [0.0], "identity")]
 
 
 @pytest.mark.parametrize("scheme", ["euler", "heun"])
@@ -1003,3 +1003,32 @@ def test_fuzz_shapes_integral_functions(sde):
         assert np.array_equal(sde.CrossVariation(f, g).reshape(n, nc), c_oracle.integral(4, fa, ga).T), (it, n, nc)
         one = sde.stochint(f[:, 0], g[:, 0], "r")
         assert one.shape == (n,) and np.array_equal(one, O.stochint(f[:, 0], g[:, 0], "r"))
+
+
+def test_vignette_models_ito_integrals_and_itos_formula(sde):
+    """The two vignette examples with their own models.  ItoIntegrals.Rmd:66-93: for dX = (x - x^3) dt + sqrt(1 + x^2) dB
+    the Euler path equals int f dt + int g dB to machine precision.  ItosFormula.Rmd:36-116: Y = log X of stochastic
+    logistic growth solves dY = (1 - e^Y - sigma^2/2) dt + sigma dB; both Euler paths driven by the same B stay close."""
+    t, B = brownian(1001, 1, 32, 17, dt=0.01)
+    f, g = sde.catalogue.dwsqrt()
+    X = sde.euler(f, g, t, 0.0, B)["X"][:, 0, :]
+    Bm = B[:, 0, :]
+    tt = np.repeat(t[:, None], 32, axis=1)
+    resid = X - sde.itointegral(X - X * X * X, tt) - sde.itointegral(np.sqrt(1.0 + X * X), Bm)
+    assert np.max(np.abs(resid)) < 5e-14 * max(1.0, np.max(np.abs(X)))
+    fo, go, _, _ = O.catalogue("dwsqrt", [])
+    assert np.array_equal(O.euler(fo, go, t, 0.0, B=B[:, :, 3])["X"][:, 0], X[:, 3])            # bit-identical to the R loop restated
+    sigma, x0 = 0.25, 0.01
+    fl, gl = sde.catalogue.logistic(sigma, 0.0)
+    fy, gy = sde.catalogue.loglogistic(sigma)
+    Xl = sde.euler(fl, gl, t, x0, B)["X"][:, 0, :]
+    Y = sde.euler(fy, gy, t, np.log(x0), B)["X"][:, 0, :]
+    assert np.max(np.abs(Y - np.log(Xl))) < 0.05                                                    # O(dt) apart, as in the vignette's plot
+    foy, goy, _, _ = O.catalogue("loglogistic", [sigma])
+    want = O.euler(foy, goy, t, np.log(x0), B=B[:, :, 5])["X"][:, 0]
+    assert np.allclose(Y[:, 5], want, rtol=1e-12, atol=1e-13)                                       # exp(): last-ulp differences only
+    # fused generator and heun run as well; terminal-only kernel agrees with the trajectory kernel
+    for fq, gq, x0q in ((f, g, 0.0), (fy, gy, np.log(x0))):
+        a = sde.heun(fq, gq, t[:101], x0q, npaths=100, seed=3)["X"][-1, 0]
+        b = sde.heun(fq, gq, t[:101], x0q, npaths=100, seed=3, output="terminal")["XT"][0]
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-13)
