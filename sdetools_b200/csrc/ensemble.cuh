@@ -7,6 +7,10 @@
 //   k_traj     : fused generator, full trajectory X written as 32-byte sectors (HBM-write bound)
 //   k_stream   : supplied B read, X written, both as per-thread 32-byte sectors (HBM bound; the
 //                bit-exact STRICT path)
+//   k_functionals   : integrals along the path (QV, Ito, Stratonovich, time) accumulated in the step loop with
+//                     cumsum's 80-bit accumulator, nothing stored
+//   k_killed        : killing rate r / stopping rule h with trajectory (NaN after tau)
+//   k_killed_refill : the same without trajectory; lanes whose path ended take the warp's next path
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
