@@ -182,7 +182,7 @@ SDEGPU_HD double f80_to_double(const F80 &acc)
 // The same accumulator as a pair of doubles: S = h + l with h = RN53(S), so that (double)S — what
 // cumsum stores — is h itself.  S has a 64-bit significand, hence l (at most 11 bits) is exact.
 // S' = RN64(S + x) is formed without integer arithmetic on the significand:
-//   four TwoSums give V = S + x = a + b + c exactly (|b| <= ulp(a)/2, |c| <= ulp(b)/2);
+//   two TwoSums and two FastTwoSums give V = S + x = a + b + c exactly (|b| <= ulp(a)/2, |c| <= ulp(b)/2);
 //   the 64-bit grid q = 2^(e-63) follows from a's exponent (one binade lower when a is a power of
 //   two and the remainder points back towards zero); b is rounded to that grid, ties to even, with
 //   the add-and-subtract constant 1.5 * 2^52 * q, c only ever deciding an exact tie;
@@ -240,8 +240,13 @@ SDEGPU_HD bool f80p_add(double &h, double &l, double x)
     double s1, e1, s2, e2, a, b0, b, c;
     f80p_two_sum(h, x, s1, e1);
     f80p_two_sum(e1, l, s2, e2);
-    f80p_two_sum(s1, s2, a, b0);
-    f80p_two_sum(b0, e2, b, c);
+    // the last two sums are ordered, so the three-operation FastTwoSum is exact for them:
+    //  |s2| <= ulp(s1)/2 + ulp(h)/2 <= |s1| unless h + x cancelled exactly — and then s1 is a non-zero multiple of
+    //  ulp(h)/2 >= |l| = |s2|, or zero (FastTwoSum(0, y) is exact);  b0 is zero or at least one ulp of s2 > 2|e2|.
+    a = s1 + s2;
+    b0 = s2 - (a - s1);
+    b = b0 + e2;
+    c = e2 - (b - b0);
     const uint32_t ah = f80_hi(a), al = f80_lo(a);
     const uint32_t ae = (ah >> 20) & 0x7FFu;
     if (((ah << 1) | al) == 0) {                               // exact cancellation: +0 in round-to-nearest

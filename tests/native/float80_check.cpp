@@ -73,7 +73,7 @@ int main(int argc, char **argv)
         long double cur = 0.0L;                                          // x87 sum of xs so far (for targeted cases)
         for (int i = 0; i < n; ++i) {
             double v = nd(rng);
-            switch (rep % 14) {
+            switch (rep % 15) {
             case 0: break;                                              // N(0,1) increments
             case 1: v = std::ldexp(v, ex(rng)); break;                  // mixed magnitudes
             case 2: v = std::ldexp(v, wide(rng)); break;                // incl. subnormals / huge
@@ -99,6 +99,13 @@ int main(int argc, char **argv)
                 if (k < 3) v += std::ldexp(1.0, e - 65 - 20 - (int)(rng() % 30));   // just above
                 else if (k < 6) v -= std::ldexp(1.0, e - 65 - 20 - (int)(rng() % 30));  // just below
                 if (coin(rng) < 2) v = -v;
+                break;
+            }
+            case 14: {                                                   // cancel the rounded sum itself: h + x = 0 or a few ulps, l survives
+                if (cur == 0.0L || (i % 2) == 0) { v = std::ldexp((double)((rng() >> 11) | 1), ex(rng) / 2 - 52) * ((rng() & 1) ? 1 : -1); break; }
+                const double hcur = (double)cur;
+                int e; std::frexp(hcur, &e);
+                v = -hcur + std::ldexp((double)((int)(rng() % 5) - 2), e - 53 - (int)(rng() % 2));
                 break;
             }
             case 13: {                                                   // sums that cross a power of two downwards / upwards
