@@ -527,6 +527,7 @@ __global__ void __launch_bounds__(FUNC_THREADS) k_functionals(const RunArgs a)
         double x[NX];
         load_x0<NX>(a, p, x);
         CumsumAcc qv[NX], il[NX], ir[NX], it[NX];
+        F80 big[NX][FUNC_PER_COMP];                              // integer fallback states (local memory, rarely touched)
         double out[NX][FUNC_PER_COMP];
 #pragma unroll
         for (int j = 0; j < NX; ++j)
@@ -554,10 +555,10 @@ __global__ void __launch_bounds__(FUNC_THREADS) k_functionals(const RunArgs a)
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
                 const double dx = __dsub_rn(x[j], xo[j]);
-                out[j][0] = qv[j].add(__dmul_rn(dx, dx));
-                out[j][1] = il[j].add(__dmul_rn(xo[j], dB));
-                out[j][2] = ir[j].add(__dmul_rn(x[j], dB));
-                out[j][3] = it[j].add(__dmul_rn(xo[j], dt.x));
+                out[j][0] = qv[j].add(__dmul_rn(dx, dx), &big[j][0]);
+                out[j][1] = il[j].add(__dmul_rn(xo[j], dB), &big[j][1]);
+                out[j][2] = ir[j].add(__dmul_rn(x[j], dB), &big[j][2]);
+                out[j][3] = it[j].add(__dmul_rn(xo[j], dt.x), &big[j][3]);
             }
         }
 #pragma unroll

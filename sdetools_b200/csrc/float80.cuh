@@ -297,14 +297,16 @@ static __device__ __noinline__ double f80_slow_add(F80 *big, bool first, double 
     return f80_to_double(*big);
 }
 
+// The integer state lives in a separate object (`big`, one per accumulator, its address is taken): kept inside this
+// struct it dragged h, l and the flag into local memory with it — a load and a store per element (ncu: half of all
+// stalls were long-scoreboard waits on those).
 struct CumsumAcc {
     double h = 0.0, l = 0.0;
     bool slow = false;
-    F80 big;
-    __device__ __forceinline__ double add(double x)
+    __device__ __forceinline__ double add(double x, F80 *big)
     {
         if (!slow && f80p_add(h, l, x)) return h;
-        const double out = f80_slow_add(&big, !slow, h, l, x);
+        const double out = f80_slow_add(big, !slow, h, l, x);
         slow = true;
         return out;
     }

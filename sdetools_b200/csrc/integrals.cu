@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(INT_THREADS, MODE == 1 ? 3 : SDEGPU_INT_MIN_BL
         const uint64_t base = col * q.n;
         const double *pa = q.a + base, *pb = q.b + base;
         CumsumAcc accl, accr;
+        F80 bigl, bigr;                                          // integer fallback state (local memory, rarely touched)
         if (q.l) q.l[base] = 0.0;                                // c(0, ...)
         if (MODE == 0 && q.r) q.r[base] = 0.0;
         if (MODE == 0 && q.c) q.c[base] = 0.0;
@@ -62,11 +63,11 @@ __global__ void __launch_bounds__(INT_THREADS, MODE == 1 ? 3 : SDEGPU_INT_MIN_BL
         auto element = [&](double a1, double b1) {               // consumes (a0,b0)->(a1,b1), produces out[s+1]
             if (MODE == 0) {
                 const double dg = __dsub_rn(b1, b0);
-                ol = need_l ? accl.add(__dmul_rn(a0, dg)) : 0.0;
-                orr = need_r ? accr.add(__dmul_rn(a1, dg)) : 0.0;
+                ol = need_l ? accl.add(__dmul_rn(a0, dg), &bigl) : 0.0;
+                orr = need_r ? accr.add(__dmul_rn(a1, dg), &bigr) : 0.0;
                 oc = __dmul_rn(0.5, __dadd_rn(ol, orr));
             } else {
-                ol = accl.add(__dmul_rn(__dsub_rn(a1, a0), __dsub_rn(b1, b0)));
+                ol = accl.add(__dmul_rn(__dsub_rn(a1, a0), __dsub_rn(b1, b0)), &bigl);
             }
             a0 = a1; b0 = b1;
         };
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(BM_THREADS) k_rvbm(const BMArgs q, const int v
         if (col >= q.ncols) continue;
         double *row = q.B + col * (uint64_t)q.nt;
         CumsumAcc acc;
+        F80 big;
         double zq[4] = {0.0, 0.0, 0.0, 0.0};
         auto element = [&](int i) -> double {                    // B[i] of this column
             if ((i & 3) == 0) normal_quad(q.seed, q.path_offset + col, (uint32_t)(i >> 2), 0u, sh_tab, zq);
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(BM_THREADS) k_rvbm(const BMArgs q, const int v
             const double z = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
             // rnorm(mean=u*dt, sd=sigma*sqrt(dt)) = mean + sd*Z
             const double dB = __dadd_rn(__dmul_rn(q.u, d.x), __dmul_rn(__dmul_rn(q.sigma, d.y), z));
-            return __dadd_rn(q.B0, acc.add(dB));
+            return __dadd_rn(q.B0, acc.add(dB, &big));
         };
         int head = vec_ok ? (int)((4 - ((col * (uint64_t)q.nt) & 3)) & 3) : q.nt;   // elements before the first sector boundary
         if (head > q.nt) head = q.nt;
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_bm_functionals(const BMFuncArgs
     const uint64_t stride = (uint64_t)gridDim.x * INT_THREADS;
     for (uint64_t col = (uint64_t)blockIdx.x * INT_THREADS + threadIdx.x; col < q.bm.ncols; col += stride) {
         CumsumAcc acc;
+        F80 big;
         double zq[4] = {0.0, 0.0, 0.0, 0.0};
         double vmax = 0.0, vmin = 0.0;
         int imax = 0, imin = 0, ihit = -1;
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_bm_functionals(const BMFuncArgs
             const int s4 = i & 3;
             const double z = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
             const double dB = __dadd_rn(__dmul_rn(q.bm.u, d.x), __dmul_rn(__dmul_rn(q.bm.sigma, d.y), z));
-            const double b = __dadd_rn(q.bm.B0, acc.add(dB));
+            const double b = __dadd_rn(q.bm.B0, acc.add(dB, &big));
             if (i == 0 || b > vmax) { vmax = b; imax = i; }      // which.max / which.min: first occurrence
             if (i == 0 || b < vmin) { vmin = b; imin = i; }
             if (ihit < 0 && (up ? b >= q.level : b <= q.level)) ihit = i;
