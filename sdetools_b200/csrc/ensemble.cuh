@@ -86,7 +86,12 @@ __device__ __forceinline__ void accumulate_terminal(const RunArgs &a, const doub
             }
         }
     }
-    if (a.hist) atomicAdd(&sh_hist[hist_bin(x[a.hist_comp < NX ? a.hist_comp : 0], a)], 1u);
+    if (a.hist) {
+        double xh = x[0];                                        // selected without indexing x[] by a run-time value:
+#pragma unroll                                                   // that would force the state array into local memory
+        for (int j = 1; j < NX; ++j) xh = a.hist_comp == j ? x[j] : xh;
+        atomicAdd(&sh_hist[hist_bin(xh, a)], 1u);
+    }
 }
 
 // Deterministic block reduction: shuffle tree per warp, then warps in index order.
@@ -575,6 +580,16 @@ __global__ void __launch_bounds__(FUNC_THREADS) k_functionals(const RunArgs a)
     flush_block_stats<NX, FUNC_THREADS>(a, acc, sh_hist);
 }
 
+// component `comp` of the state without indexing the register array by a run-time value
+template <int NX>
+__device__ __forceinline__ double pick_component(const double (&x)[NX], int comp)
+{
+    double v = x[0];
+#pragma unroll
+    for (int j = 1; j < NX; ++j) v = comp == j ? x[j] : v;
+    return v;
+}
+
 // ---- mortality and stopping (R/sdetools.R:397-416,455-469; vignettes/Killing.Rmd:152-190) ----------
 // Per step, in the reference's order: the new state is tested against h (stop: S is not updated and
 // reads 0); otherwise S <- S * exp(-r(X_i) * dt_i) with the OLD state, and the path is killed when
@@ -586,7 +601,7 @@ constexpr int KILLED_THREADS = 256;
 template <int NX>
 __device__ __forceinline__ double kill_rate(const RunArgs &a, const double (&x)[NX])
 {
-    const double v = x[a.kill_comp < NX ? a.kill_comp : 0];
+    const double v = pick_component<NX>(x, a.kill_comp);
     if (a.kill_kind == SDEGPU_KILL_CONST) return a.kill_a;
     if (a.kill_kind == SDEGPU_KILL_EXP) return __dmul_rn(a.kill_a, exp(__dmul_rn(a.kill_b, v)));
     if (a.kill_kind == SDEGPU_KILL_QUAD) { const double t = __dsub_rn(v, a.kill_b); return __dmul_rn(a.kill_a, __dmul_rn(t, t)); }
@@ -596,7 +611,7 @@ __device__ __forceinline__ double kill_rate(const RunArgs &a, const double (&x)[
 template <int NX>
 __device__ __forceinline__ double stop_value(const RunArgs &a, const double (&x)[NX])
 {
-    const double v = x[a.stop_comp < NX ? a.stop_comp : 0];
+    const double v = pick_component<NX>(x, a.stop_comp);
     if (a.stop_kind == SDEGPU_STOP_BELOW) return __dsub_rn(v, a.stop_lo);
     if (a.stop_kind == SDEGPU_STOP_ABOVE) return __dsub_rn(a.stop_hi, v);
     if (a.stop_kind == SDEGPU_STOP_OUTSIDE) return __dmul_rn(__dsub_rn(v, a.stop_lo), __dsub_rn(a.stop_hi, v));
