@@ -508,7 +508,10 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const RunArgs a, cons
 // each sum in cumsum's 80-bit accumulator (float80.cuh) and each term formed with the same individually
 // rounded operations k_integral uses, so with a supplied B they are bit-identical to running the
 // integral kernels on the stored trajectory.  Without B, dB_i is the generator's increment sqrt(dt_i) Z_i.
-constexpr int FUNC_THREADS = 128;
+#ifndef SDEGPU_FUNC_THREADS
+#define SDEGPU_FUNC_THREADS 128
+#endif
+constexpr int FUNC_THREADS = SDEGPU_FUNC_THREADS;
 constexpr int FUNC_PER_COMP = 4;
 
 template <class M, int SCHEME, int PROJ, class A>
