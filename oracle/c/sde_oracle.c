@@ -138,8 +138,10 @@ static double bits_to_normal(uint32_t lo, uint32_t hi)
     return (lo & 0x800u) ? -a : a;
 }
 
-/* one Brownian channel: four normals per block from 32-bit words; draws beyond 2^-12 in the tail take 21 more
- * mantissa bits from the extension block (channel | 0x40000000) so the tail keeps 52-bit resolution */
+/* one Brownian channel, "stream v2" (sdetools_b200/csrc/philox.cuh): four normals per block from 32-bit words.
+ * w -> odd integer s = (w|1) - 2^31, sign(z) = sign(s), v = |s|, u = v 2^-31; draws beyond 2^-12 in the tail
+ * (v < 2^19) refine their cell with the top 22 bits of the extension block's word (channel | 0x40000000):
+ * u = ((v-1) 2^21 + e22 + 1) 2^-52, so the tail keeps 52-bit resolution */
 static void normal_quad(uint64_t seed, uint64_t path, uint32_t block, uint32_t channel, double z[4])
 {
     uint32_t c[4] = { (uint32_t)path, (uint32_t)(path >> 32), block, channel };
@@ -147,14 +149,16 @@ static void normal_quad(uint64_t seed, uint64_t path, uint32_t block, uint32_t c
     int have_ext = 0;
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     for (int s = 0; s < 4; ++s) {
-        uint64_t m = (uint64_t)(c[s] & 0x7FFFFFFFu) << 21;
-        if ((c[s] & 0x7FFFFFFFu) < (1u << 19)) {
+        const int64_t si = (int64_t)(c[s] | 1u) - ((int64_t)1 << 31);
+        const uint64_t v = (uint64_t)(si < 0 ? -si : si);
+        uint64_t m = v << 21;
+        if (v < (1u << 19)) {
             if (!have_ext) { philox4x32_10(e, (uint32_t)seed, (uint32_t)(seed >> 32)); have_ext = 1; }
-            m |= e[s] >> 11;
+            m = ((v - 1) << 21) + (e[s] >> 10) + 1;
         }
-        double u = m ? (double)m * 0x1p-52 : 0x1p-52;
+        double u = (double)m * 0x1p-52;
         double a = -as241_qnorm(0.5 * u);
-        z[s] = (c[s] & 0x80000000u) ? -a : a;
+        z[s] = si < 0 ? -a : a;
     }
 }
 

@@ -9,10 +9,10 @@ generator exactly so the device stream can be checked draw by draw:
 
   key      = (seed & 0xffffffff, seed >> 32)
   counter  = (path & 0xffffffff, path >> 32, block, channel)      one block = FOUR steps
-  r0..r3   = philox4x32_10(counter, key);  step 4*block+s uses word r_s:
-    sign = bit 31, m31 = low 31 bits, m = m31 << 21
-    if m31 < 2^19: m |= e_s >> 11 with e = philox4x32_10((path, block, channel | 0x40000000), key)
-    u    = m * 2^-52  (u = 2^-52 if m == 0);   z = (-1)^sign * -qnorm(u/2)
+  r0..r3   = philox4x32_10(counter, key);  step 4*block+s uses word w = r_s ("stream v2"):
+    s = (w | 1) - 2^31 (odd, never 0), v = |s|, m = v << 21
+    if v < 2^19: m = ((v-1) << 21) + (e_s >> 10) + 1 with e = philox4x32_10((path, block, channel | 0x40000000), key)
+    u    = m * 2^-52;   z = sign(s) * -qnorm(u/2)
   dB[i,k]  = sqrt(dt[i]) * z[i]   for channel k
 (The linear model's matrix-valued g uses one block per (path, step, channel pair) with 52-bit uniforms;
 only the C oracle restates that variant.)
@@ -59,10 +59,12 @@ def normals(paths, nsteps, channel, seed):
     z = np.empty((4 * nblk, paths.shape[0]))
     for s_ in range(4):
         w = np.broadcast_to(r[s_], (nblk, paths.shape[0]))
-        m31 = w & np.uint64(0x7FFFFFFF)
-        m = m31 << np.uint64(21)
-        m = np.where(m31 < np.uint64(1 << 19), m | (np.broadcast_to(e[s_], m.shape) >> np.uint64(11)), m)
-        u = np.where(m == 0, 2.0 ** -52, m.astype(np.float64) * 2.0 ** -52)
+        si = (w | np.uint64(1)).astype(np.int64) - np.int64(1 << 31)
+        v = np.abs(si).astype(np.uint64)
+        m = v << np.uint64(21)
+        ext = ((v - np.uint64(1)) << np.uint64(21)) + (np.broadcast_to(e[s_], m.shape) >> np.uint64(10)) + np.uint64(1)
+        m = np.where(v < np.uint64(1 << 19), ext, m)
+        u = m.astype(np.float64) * 2.0 ** -52
         a = -ndtri(0.5 * u)
-        z[s_::4] = np.where((w >> np.uint64(31)) != 0, -a, a)
+        z[s_::4] = np.where(si < 0, -a, a)
     return z[:nsteps]

@@ -11,6 +11,7 @@ SO_PATH = os.path.join(HERE, "libsdegpu.so")
 ABI_VERSION = 3
 DEVICE_PTRS = 1
 ACCUMULATE = 2
+EXACT_GRID = 4
 
 MODEL = {"ou": 0, "cir": 1, "vdp": 2, "logistic": 3, "gbm": 4, "doublewell": 5, "linear": 6, "dwsqrt": 7, "loglogistic": 8}
 SCHEME = {"euler": 0, "heun": 1}

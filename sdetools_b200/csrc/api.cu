@@ -10,6 +10,7 @@
 
 // the half-normal quantile table of the fused generator lives in this translation unit
 #define ICDF_TABLE_DEFINE __device__ const unsigned long long g_icdf_table
+#define ICDF32_TABLE_DEFINE __device__ const unsigned long long g_icdf32_table
 #include "../../include/sdegpu.h"
 #include "ensemble.cuh"
 #include "integrals.cuh"
@@ -71,7 +72,7 @@ struct sdegpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill, coef;
-    const double *icdf = nullptr;
+    const double *icdf = nullptr, *icdf32 = nullptr;
     int max_grid = 0;
 };
 
@@ -109,6 +110,7 @@ int sdegpu_create(int device, sdegpu_ctx **out)
     c->max_grid = c->prop.multiProcessorCount * 32;
     if (e == cudaSuccess) e = c->partials.reserve(sizeof(double) * (size_t)c->max_grid * 5 * MAX_NX);
     if (e == cudaSuccess) e = cudaGetSymbolAddress((void **)&c->icdf, g_icdf_table);
+    if (e == cudaSuccess) e = cudaGetSymbolAddress((void **)&c->icdf32, g_icdf32_table);
     if (e != cudaSuccess) {
         delete c;
         return fail(SDEGPU_ERR_CUDA, "sdegpu_create: %s", cudaGetErrorString(e));
@@ -303,14 +305,23 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         for (int i = 0; i < pr->nparams; ++i) a.P.p[i] = pr->params[i];
         a.dtsq = dtsq;
         a.icdf = c->icdf;
+        a.icdf32 = c->icdf32;
+        bool uniform = false;
         if (!pr->B && !out->X && !killed && !out->path_integrals) {   // k_terminal: folded step coefficients (FAST only)
-            std::vector<double> hc((size_t)(nt - 1) * FAST_NCOEF);
-            bool folded = true;
-            for (int i = 0; i + 1 < nt && folded; ++i) {
-                const double dt = pr->times[i + 1] - pr->times[i];
-                folded = fast_step_coefficients(pr->model, pr->params, dt, sqrt(dt), &hc[(size_t)i * FAST_NCOEF]);
-            }
-            if (folded) {
+            // A grid whose increments agree to the rounding of its own time stamps (seq(0, T, by = h) gives
+            // t_i = i*h rounded, so diff(times) scatters by ~ulp(T)) is integrated as the uniform grid it
+            // stands for, dt = (t_n - t_0)/n: one coefficient row as a kernel parameter instead of a table.
+            const double tmax = fmax(fabs(pr->times[0]), fabs(pr->times[nt - 1]));
+            const double dtbar = (pr->times[nt - 1] - pr->times[0]) / (double)(nt - 1), tol = 4.0 * 2.220446049250313e-16 * tmax;
+            uniform = !(pr->flags & SDEGPU_EXACT_GRID) && dtbar > 0.0;
+            for (int i = 0; i + 1 < nt && uniform; ++i) uniform = fabs((pr->times[i + 1] - pr->times[i]) - dtbar) <= tol;
+            if (uniform) fast_step_coefficients(pr->model, pr->params, dtbar, sqrt(dtbar), a.ucoef);
+            else {
+                std::vector<double> hc((size_t)(nt - 1) * FAST_NCOEF);
+                for (int i = 0; i + 1 < nt; ++i) {
+                    const double dt = pr->times[i + 1] - pr->times[i];
+                    fast_step_coefficients(pr->model, pr->params, dt, sqrt(dt), &hc[(size_t)i * FAST_NCOEF]);
+                }
                 CU(c->coef.reserve(sizeof(double) * hc.size()));
                 CU(cudaMemcpyAsync(c->coef.p, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
@@ -352,7 +363,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
             else { CU(c->out2.reserve(bytesF)); a.func = (double *)c->out2.p; }
         }
         LaunchCfg cfg;
-        cfg.killed = killed; cfg.want_func = out->path_integrals != nullptr;
+        cfg.killed = killed; cfg.want_func = out->path_integrals != nullptr; cfg.uniform = uniform;
         cfg.scheme = pr->scheme; cfg.proj = pr->projection; cfg.arith = pr->B ? pr->arith : SDEGPU_ARITH_FAST;
         cfg.src_b = pr->B != nullptr; cfg.want_x = out->X != nullptr;
         cfg.grid = 0; cfg.sm_count = c->prop.multiProcessorCount; cfg.stream = c->stream;

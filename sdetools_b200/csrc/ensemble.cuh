@@ -36,8 +36,10 @@ constexpr int TERMINAL_THREADS = SDEGPU_TERMINAL_THREADS;
 struct RunArgs {
     KParams P;
     const double2 *dtsq;            // [nt-1] {dt_i, sqrt(dt_i)},  dt_i = times[i+1]-times[i]  (:446)
-    const double *icdf;             // device, half-normal quantile table (philox.cuh)
-    const double *coef;             // [nt-1][FAST_NCOEF] folded step coefficients (models.cuh FastStep) or nullptr
+    const double *icdf;             // device, half-normal quantile table, generic form (philox.cuh)
+    const double *icdf32;           // device, quantile table of the fast evaluation (register-resident kernels)
+    const double *coef;             // [nt-1][FAST_NCOEF] folded step coefficients (models.cuh FastStep), non-uniform grids
+    double ucoef[FAST_NCOEF];       // the one coefficient row of a uniform grid (constant-bank operands)
     const double *x0;               // per-path x0 (device) or nullptr
     double x0s[MAX_NX];             // shared x0
     const double *B;                // device, B[p*nt+i]  (nB = 1)
@@ -131,17 +133,44 @@ __device__ __forceinline__ void load_x0(const RunArgs &a, uint64_t p, double (&x
 }
 
 // ---- register-resident, fused-generator kernel ------------------------------
-template <class M, int SCHEME, int PROJ>
-__global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) k_terminal(const RunArgs a)
+// One thread per path, grid-stride.  Per four steps: one Philox block (generated one iteration ahead, so its integer
+// rounds issue under the dependent FP64 chain), four quantile evaluations, four steps.  UNIFORM: the grid's
+// increments agree to rounding (sdegpu_run decides), so the step's coefficient row is a kernel parameter and its
+// noise factor is folded into the staged quantile table; otherwise rows stream from global memory (L1-resident).
+#ifndef SDEGPU_TERMINAL_REPL
+#define SDEGPU_TERMINAL_REPL 8
+#endif
+constexpr int TERMINAL_REPL = SDEGPU_TERMINAL_REPL;
+
+struct CoefRow {                                                // a step's row loaded as three 128-bit words
+    double v[FAST_NCOEF];
+    __device__ __forceinline__ double operator[](int k) const { return v[k]; }
+    __device__ __forceinline__ void load(const double *p)
+    {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p + 2)),
+                      c = __ldg(reinterpret_cast<const double2 *>(p + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+    }
+};
+struct CoefUniform {                                            // reads the kernel parameter: constant-bank operands
+    const double *c;
+    __device__ __forceinline__ double operator[](int k) const { return c[k]; }
+};
+
+template <class M, int SCHEME, int PROJ, bool UNIFORM>
+__global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) k_terminal(const __grid_constant__ RunArgs a)
 {
     constexpr int NX = M::NX;
     using FS = FastStep<M, SCHEME, PROJ>;
-    extern __shared__ __align__(16) double sh_tab[];             // [quantile table, hot layout][histogram]
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + ICDF_HOT_TABLE_DOUBLES);
-    icdf_stage_hot(sh_tab, a.icdf, threadIdx.x, TERMINAL_THREADS);
+    using TL = Icdf32Layout<TERMINAL_REPL>;
+    extern __shared__ __align__(16) double sh_tab[];             // [quantile table, replicated][histogram]
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + TL::DOUBLES);
+    icdf32_stage<TERMINAL_REPL>(sh_tab, a.icdf32, UNIFORM ? a.ucoef[0] : 1.0, threadIdx.x, TERMINAL_THREADS);
     if (a.hist)
         for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TERMINAL_THREADS) sh_hist[i] = 0u;
     __syncthreads();
+    NormalGen<TERMINAL_REPL> gen;
+    gen.init(sh_tab, a.icdf, UNIFORM ? a.ucoef[0] : 1.0);
     double acc[NX][5];
 #pragma unroll
     for (int j = 0; j < NX; ++j)
@@ -151,6 +180,7 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
     const int nsteps = a.nt - 1;
     constexpr int NP = SDEGPU_TERMINAL_NP;                       // independent paths advanced together by one thread (ILP)
     const uint64_t stride = (uint64_t)gridDim.x * TERMINAL_THREADS;
+    const CoefUniform cu{a.ucoef};
     for (uint64_t pb = (uint64_t)blockIdx.x * TERMINAL_THREADS + threadIdx.x; pb < a.npaths; pb += stride * NP) {
         double x[NP][NX];
         uint64_t pq[NP];
@@ -160,25 +190,40 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
             pq[q] = pb + (uint64_t)q * stride;
             const uint64_t pl = pq[q] < a.npaths ? pq[q] : pb;   // a missing partner recomputes path pb and is discarded
             load_x0<NX>(a, pl, x[q]);
-            // Software-pipelined: the Philox block of steps i+4..i+7 is generated while steps i..i+3
-            // integrate, so the integer rounds issue in the shadow of the dependent FP64 chain.
             philox_block(a.seed, a.path_offset + pl, 0u, 0u, r[q][0], r[q][1], r[q][2], r[q][3]);
         }
         int i = 0;
         for (; i + 3 < nsteps; i += 4) {
-            double2 dts[4];
+            CoefRow row[4];
+            if (!UNIFORM) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dts[k] = FS::uses_coef ? make_double2(0.0, 0.0) : __ldg(&a.dtsq[i + k]);
+                for (int k = 0; k < 4; ++k) row[k].load(a.coef + (size_t)(i + k) * FAST_NCOEF);
+            }
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const uint64_t gp = a.path_offset + (pq[q] < a.npaths ? pq[q] : pb);
                 uint32_t n[4];
+#ifdef SDEGPU_EXP_NOPHILOX                                       // decomposition experiment: a one-IMAD word source
+#pragma unroll
+                for (int k = 0; k < 4; ++k) n[k] = r[q][k] * 1664525u + 1013904223u + (uint32_t)gp;
+#else
                 philox_block(a.seed, gp, (uint32_t)(i >> 2) + 1u, 0u, n[0], n[1], n[2], n[3]);
+#endif
                 double z[4];
-                normals_from_block<true>(a.seed, gp, (uint32_t)(i >> 2), 0u, r[q], sh_tab, z);
+#ifdef SDEGPU_EXP_NOICDF                                         // decomposition experiment: a uniform instead of a normal
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[k] = (__hiloint2double(0x43300000, (int)r[q][k]) - 4503601774854144.0) * 4.6566128730773926e-10;
+#else
+                gen.quad(a.seed, gp, (uint32_t)(i >> 2), 0u, r[q], z);
+#endif
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    FS::apply(a.P, x[q], dts[k], a.coef + (size_t)(i + k) * FAST_NCOEF, z[k]);
+#ifdef SDEGPU_EXP_NOSTEP                                         // decomposition experiment: the step is one DADD
+                    x[q][0] += z[k];
+#else
+                    if (UNIFORM) FS::apply(a.P, x[q], cu, z[k]);
+                    else FS::apply(a.P, x[q], row[k], row[k][0] * z[k]);
+#endif
                     r[q][k] = n[k];
                 }
             }
@@ -188,10 +233,17 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
             for (int q = 0; q < NP; ++q) {
                 const uint64_t gp = a.path_offset + (pq[q] < a.npaths ? pq[q] : pb);
                 double z[4];
-                normals_from_block<true>(a.seed, gp, (uint32_t)(i >> 2), 0u, r[q], sh_tab, z);
+                gen.quad(a.seed, gp, (uint32_t)(i >> 2), 0u, r[q], z);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    if (i + k < nsteps) FS::apply(a.P, x[q], __ldg(&a.dtsq[i + k]), a.coef + (size_t)(i + k) * FAST_NCOEF, z[k]);
+                    if (i + k < nsteps) {
+                        if (UNIFORM) FS::apply(a.P, x[q], cu, z[k]);
+                        else {
+                            CoefRow row;
+                            row.load(a.coef + (size_t)(i + k) * FAST_NCOEF);
+                            FS::apply(a.P, x[q], row, row[0] * z[k]);
+                        }
+                    }
             }
         }
 #pragma unroll
@@ -230,6 +282,10 @@ constexpr int TRAJ_CHUNK = 1024;    // steps of the {dt, sqrt dt} table staged i
 #ifndef SDEGPU_TRAJ_THREADS_NX1
 #define SDEGPU_TRAJ_THREADS_NX1 768
 #endif
+#ifndef SDEGPU_TRAJ_REPL
+#define SDEGPU_TRAJ_REPL 8
+#endif
+constexpr int TRAJ_REPL = SDEGPU_TRAJ_REPL;
 template <int NX> struct TrajThreads { static constexpr int value = NX == 1 ? SDEGPU_TRAJ_THREADS_NX1 : SDEGPU_TRAJ_THREADS; };
 
 __device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d)
@@ -241,11 +297,13 @@ template <class M, int SCHEME, int PROJ>
 __global__ void __launch_bounds__(TrajThreads<M::NX>::value, 1) k_traj(const RunArgs a, const int vec_ok, const int Q)
 {
     constexpr int NX = M::NX, TRAJ_THREADS = TrajThreads<NX>::value;
-    extern __shared__ __align__(16) double sh_tab[];             // [quantile table][histogram]
-    // [quantile table, hot layout][step table chunk: TRAJ_CHUNK x {dt, sqrt dt}][histogram]
-    double2 *sh_dt = reinterpret_cast<double2 *>(sh_tab + ICDF_HOT_TABLE_DOUBLES);
+    extern __shared__ __align__(16) double sh_tab[];
+    // [quantile table, replicated][step table chunk: TRAJ_CHUNK x {dt, sqrt dt}][histogram]
+    double2 *sh_dt = reinterpret_cast<double2 *>(sh_tab + Icdf32Layout<TRAJ_REPL>::DOUBLES);
     unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_dt + TRAJ_CHUNK);
-    icdf_stage_hot(sh_tab, a.icdf, threadIdx.x, TRAJ_THREADS);
+    icdf32_stage<TRAJ_REPL>(sh_tab, a.icdf32, 1.0, threadIdx.x, TRAJ_THREADS);
+    NormalGen<TRAJ_REPL> gen;
+    gen.init(sh_tab, a.icdf, 1.0);
     if (a.hist)
         for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TRAJ_THREADS) sh_hist[i] = 0u;
     __syncthreads();
@@ -291,7 +349,11 @@ __global__ void __launch_bounds__(TrajThreads<M::NX>::value, 1) k_traj(const Run
 #pragma unroll
             for (int k = 0; k < 4; ++k) dts[k] = sh_dt[4 * (m & (TRAJ_CHUNK / 4 - 1)) + k];
             double z[4];                                         // one Philox block per group of four steps
-            normal_quad<true>(a.seed, gp, (uint32_t)m, 0u, sh_tab, z);
+            {
+                uint32_t r[4];
+                philox_block(a.seed, gp, (uint32_t)m, 0u, r[0], r[1], r[2], r[3]);
+                gen.quad(a.seed, gp, (uint32_t)m, 0u, r, z);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dts[k].x, dts[k].y * z[k]);
@@ -327,7 +389,11 @@ __global__ void __launch_bounds__(TrajThreads<M::NX>::value, 1) k_traj(const Run
         }
         if (4 * ngroups < nsteps) {                               // up to three trailing steps, element-wise
             double z[4];
-            normal_quad<true>(a.seed, gp, (uint32_t)ngroups, 0u, sh_tab, z);
+            {
+                uint32_t r[4];
+                philox_block(a.seed, gp, (uint32_t)ngroups, 0u, r[0], r[1], r[2], r[3]);
+                gen.quad(a.seed, gp, (uint32_t)ngroups, 0u, r, z);
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int i = 4 * ngroups + k;
@@ -800,6 +866,7 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed_refill(const RunArgs 
 struct LaunchCfg {
     int scheme, proj, arith;
     bool src_b, want_x, killed, want_func;
+    bool uniform;        // the time grid is uniform to rounding: one coefficient row as a kernel parameter
     int grid;            // 0: choose from occupancy
     int sm_count;
     cudaStream_t stream;

@@ -19,6 +19,7 @@ static int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, uint
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (per_sm < 1) per_sm = 1;
     if (max_per_sm > 0 && per_sm > max_per_sm) per_sm = max_per_sm;
+    if (per_sm > 32) per_sm = 32;                  // the context's block-partials buffer holds 32 blocks per SM
     uint64_t g = (uint64_t)per_sm * sm_count;
     if (g > work_blocks) g = work_blocks;
     return (int)(g < 1 ? 1 : g);
@@ -27,10 +28,10 @@ static int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, uint
 template <int SCHEME, int PROJ>
 static int launch_terminal(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
-    auto kernel = k_terminal<M, SCHEME, PROJ>;
-    const size_t smem = ICDF_HOT_TABLE_BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    auto kernel = c.uniform ? k_terminal<M, SCHEME, PROJ, true> : k_terminal<M, SCHEME, PROJ, false>;
+    const size_t smem = Icdf32Layout<TERMINAL_REPL>::BYTES + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + TERMINAL_THREADS - 1) / TERMINAL_THREADS;
-    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TERMINAL_THREADS, smem, c.sm_count, work);
+    const int grid = c.grid > 0 ? min(c.grid, 32 * c.sm_count) : occupancy_grid(kernel, TERMINAL_THREADS, smem, c.sm_count, work);
     kernel<<<grid, TERMINAL_THREADS, smem, c.stream>>>(a);
     *grid_used = grid;
     return (int)cudaGetLastError();
@@ -40,10 +41,10 @@ template <int SCHEME, int PROJ>
 static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
     auto kernel = k_traj<M, SCHEME, PROJ>;
-    const size_t smem = ICDF_HOT_TABLE_BYTES + sizeof(double2) * TRAJ_CHUNK + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
+    const size_t smem = Icdf32Layout<TRAJ_REPL>::BYTES + sizeof(double2) * TRAJ_CHUNK + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     constexpr int TRAJ_THREADS = TrajThreads<M::NX>::value;
     const uint64_t work = (a.npaths + TRAJ_THREADS - 1) / TRAJ_THREADS;
-    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, TRAJ_THREADS, smem, c.sm_count, work);
+    const int grid = c.grid > 0 ? min(c.grid, 32 * c.sm_count) : occupancy_grid(kernel, TRAJ_THREADS, smem, c.sm_count, work);
     const int vec_ok = (reinterpret_cast<uintptr_t>(a.X) & 31) == 0;
     const unsigned long long span = (unsigned long long)M::NX * (unsigned long long)a.nt;
     const int Q = (span % 4 == 0) ? 1 : ((span % 2 == 0) ? 2 : 4);   // lanes take every Q-th path: uniform sector phase
@@ -58,7 +59,7 @@ static int launch_stream(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     auto kernel = k_stream<M, SCHEME, PROJ, A>;
     const size_t smem = a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0;
     const uint64_t work = (a.npaths + STREAM_THREADS - 1) / STREAM_THREADS;
-    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, STREAM_THREADS, smem, c.sm_count, work, SDEGPU_STREAM_BLOCKS_PER_SM);
+    const int grid = c.grid > 0 ? min(c.grid, 32 * c.sm_count) : occupancy_grid(kernel, STREAM_THREADS, smem, c.sm_count, work, SDEGPU_STREAM_BLOCKS_PER_SM);
     const int vec_in = (reinterpret_cast<uintptr_t>(a.B) & 31) == 0;
     const int vec_out = a.X && (reinterpret_cast<uintptr_t>(a.X) & 31) == 0;
     kernel<<<grid, STREAM_THREADS, smem, c.stream>>>(a, vec_in, vec_out);
@@ -72,7 +73,7 @@ static int launch_killed(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     auto kernel = a.X ? k_killed<M, SCHEME, PROJ> : k_killed_refill<M, SCHEME, PROJ>;   // no trajectory: lanes refill
     const size_t smem = (a.B ? 0 : ICDF_TABLE_BYTES) + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + KILLED_THREADS - 1) / KILLED_THREADS;
-    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, KILLED_THREADS, smem, c.sm_count, work);
+    const int grid = c.grid > 0 ? min(c.grid, 32 * c.sm_count) : occupancy_grid(kernel, KILLED_THREADS, smem, c.sm_count, work);
     kernel<<<grid, KILLED_THREADS, smem, c.stream>>>(a);
     *grid_used = grid;
     return (int)cudaGetLastError();
@@ -84,7 +85,7 @@ static int launch_functionals(const RunArgs &a, const LaunchCfg &c, int *grid_us
     auto kernel = k_functionals<M, SCHEME, PROJ, A>;
     const size_t smem = (a.B ? 0 : ICDF_TABLE_BYTES) + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + FUNC_THREADS - 1) / FUNC_THREADS;
-    const int grid = c.grid > 0 ? c.grid : occupancy_grid(kernel, FUNC_THREADS, smem, c.sm_count, work);
+    const int grid = c.grid > 0 ? min(c.grid, 32 * c.sm_count) : occupancy_grid(kernel, FUNC_THREADS, smem, c.sm_count, work);
     kernel<<<grid, FUNC_THREADS, smem, c.stream>>>(a);
     *grid_used = grid;
     return (int)cudaGetLastError();

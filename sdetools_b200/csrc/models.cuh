@@ -137,58 +137,78 @@ __device__ __forceinline__ void sde_step(const KParams &P, double (&x)[M::NX], d
     }
 }
 
-// ---- FAST-arithmetic step kernels with per-step coefficients folded on the host ------------------
-// For the register-resident fused-generator kernel the step is regrouped algebraically (allowed in FAST
-// mode, never in STRICT): everything that depends only on (params, dt_i) is precomputed once per run
-// into a 6-double row per step, so e.g. heun/CIR drops from 31 to 18 FP64 instructions:
-//   Y  = p( s w + (A x + Bc) ),  s = sqrt|x|, w = C z
-//   X' = p( hw (s + sY) + (A2 x + Bc - H Y) ),  sY = sqrt|Y|, hw = C2 z
-// with A = 1-lambda dt, Bc = lambda xi dt, C = gamma sqrt(dt), C2 = C/2, A2 = 1-lambda dt/2, H = lambda dt/2.
+// ---- FAST-arithmetic steps of the fused-generator kernels, per-step constants folded on the host ------------
+// Everything that depends only on (params, dt_i) is precomputed once per run into a row of FAST_NCOEF doubles
+// per step; row[0] is the factor that turns the standard normal into the noise term the step consumes.  On a
+// uniform grid there is ONE row: it travels as a kernel parameter (constant-bank operands, no loads) and row[0]
+// is folded into the staged quantile table, so the generator hands over row[0]*z directly.
+//   generic   row = {sqrt(dt), dt}                          dB = row[0] z, sde_step<Fast>
+//   OU        row = {sigma sqrt(dt), A, Bc, A2, H}          A = 1 - lambda dt, Bc = lambda xi dt, A2 = 1 - H, H = lambda dt/2
+//             Y  = p( w + (A x + Bc) ),                     w = row[0] z
+//             X' = p( w + (A2 x + Bc - H Y) )               (g constant: 0.5 (g + g) = g)
+//   CIR       row = {gamma sqrt(dt)/2, A, Bc, A2, H}
+//             Y  = p( s2 w + (A x + Bc) ),                  s2 = sqrt(4|x|) = 2 sqrt|x|, w = row[0] z
+//             X' = p( w (s2/2 + sY) + (A2 x + Bc - H Y) ),  sY = sqrt|Y|          — 16 FP64 per Heun step
+// (allowed in FAST mode, never in STRICT).
 constexpr int FAST_NCOEF = 6;
 
+// sqrt(k |x|) for finite x, k = 1 or 4, without the special cases of the IEEE routine: a = k|x| + 2^-1000 keeps the
+// MUFU.RSQ64H seed y finite at x = 0 (one FP64 instruction, no integer clamp), then one second-order step
+// sqrt(a) = t + t e / 2, t = a y, e = 1 - t y  (seed error e ~ 2^-22: relative error 3 e^2 / 8 ~ 2e-14), or the
+// third-order step of Fast::sqrt_ when ORDER = 3.
+#ifndef SDEGPU_FASTSQRT_ORDER
+#define SDEGPU_FASTSQRT_ORDER 2
+#endif
+template <int K> __device__ __forceinline__ double fast_sqrt_abs(double x)
+{
+    const double tiny = 9.3326361850321888e-302;                 // 2^-1000
+    const double a = K == 1 ? fabs(x) + tiny : fma((double)K, fabs(x), tiny);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double t = a * y;
+    const double e = fma(-t, y, 1.0);
+    if (SDEGPU_FASTSQRT_ORDER == 2) return fma(t * e, 0.5, t);
+    const double p = fma(0.375, e, 0.5);
+    return fma(t, p * e, t);
+}
+
 template <class M, int SCHEME, int PROJ> struct FastStep {
-    static constexpr bool uses_coef = false;
-    static __device__ __forceinline__ void apply(const KParams &P, double (&x)[M::NX], double2 d, const double *, double z)
-    { sde_step<M, SCHEME, PROJ, Fast>(P, x, d.x, d.y * z); }
+    template <class C> static __device__ __forceinline__ void apply(const KParams &P, double (&x)[M::NX], const C &c, double w)
+    { sde_step<M, SCHEME, PROJ, Fast>(P, x, c[1], w); }
 };
 
 template <int SCHEME, int PROJ> struct FastStep<Model<SDEGPU_MODEL_CIR>, SCHEME, PROJ> {
-    static constexpr bool uses_coef = true;
-    static __device__ __forceinline__ void apply(const KParams &, double (&x)[1], double2, const double *c, double z)
+    template <class C> static __device__ __forceinline__ void apply(const KParams &, double (&x)[1], const C &c, double w)
     {
-        const double2 ab = __ldg(reinterpret_cast<const double2 *>(c)), cc = __ldg(reinterpret_cast<const double2 *>(c + 2));
-        const double s = Fast::sqrt_(fabs(x[0])), w = cc.x * z;
-        const double Y = project<PROJ>(fma(s, w, fma(ab.x, x[0], ab.y)));
+        const double s2 = fast_sqrt_abs<4>(x[0]);
+        const double Y = project<PROJ>(fma(s2, w, fma(c[1], x[0], c[2])));
         if (SCHEME == SDEGPU_EULER) { x[0] = Y; return; }
-        const double2 ah = __ldg(reinterpret_cast<const double2 *>(c + 4));
-        const double sY = Fast::sqrt_(fabs(Y)), hw = cc.y * z;
-        x[0] = project<PROJ>(fma(hw, s + sY, fma(-ah.y, Y, fma(ah.x, x[0], ab.y))));
+        const double sY = fast_sqrt_abs<1>(Y);
+        const double q = fma(0.5, s2, sY);
+        x[0] = project<PROJ>(fma(w, q, fma(-c[4], Y, fma(c[3], x[0], c[2]))));
     }
 };
 
 template <int SCHEME, int PROJ> struct FastStep<Model<SDEGPU_MODEL_OU>, SCHEME, PROJ> {
-    static constexpr bool uses_coef = true;
-    static __device__ __forceinline__ void apply(const KParams &, double (&x)[1], double2, const double *c, double z)
+    template <class C> static __device__ __forceinline__ void apply(const KParams &, double (&x)[1], const C &c, double w)
     {
-        const double2 ab = __ldg(reinterpret_cast<const double2 *>(c)), cc = __ldg(reinterpret_cast<const double2 *>(c + 2));
-        const double w = cc.x * z;                                // sigma sqrt(dt) z
-        const double Y = project<PROJ>(w + fma(ab.x, x[0], ab.y));
+        const double Y = project<PROJ>(w + fma(c[1], x[0], c[2]));
         if (SCHEME == SDEGPU_EULER) { x[0] = Y; return; }
-        const double2 ah = __ldg(reinterpret_cast<const double2 *>(c + 4));
-        x[0] = project<PROJ>(w + fma(-ah.y, Y, fma(ah.x, x[0], ab.y)));      // g constant: 0.5*(g+g) = g
+        x[0] = project<PROJ>(w + fma(-c[4], Y, fma(c[3], x[0], c[2])));
     }
 };
 
-// host side: the coefficient row of one step (returns false when the model has no folded form)
-inline bool fast_step_coefficients(int model, const double *p, double dt, double sq, double *c)
+// host side: the coefficient row of one step
+inline void fast_step_coefficients(int model, const double *p, double dt, double sq, double *c)
 {
+    for (int k = 0; k < FAST_NCOEF; ++k) c[k] = 0.0;
     if (model == SDEGPU_MODEL_CIR || model == SDEGPU_MODEL_OU) {
         const double lam = p[0], xi = p[1], vol = p[2];
-        c[0] = 1.0 - lam * dt; c[1] = lam * xi * dt; c[2] = vol * sq; c[3] = 0.5 * vol * sq;
-        c[4] = 1.0 - 0.5 * lam * dt; c[5] = 0.5 * lam * dt;
-        return true;
+        c[0] = model == SDEGPU_MODEL_CIR ? 0.5 * vol * sq : vol * sq;
+        c[1] = 1.0 - lam * dt; c[2] = lam * xi * dt; c[3] = 1.0 - 0.5 * lam * dt; c[4] = 0.5 * lam * dt;
+    } else {
+        c[0] = sq; c[1] = dt;
     }
-    return false;
 }
 
 }  // namespace sdegpu

@@ -7,23 +7,32 @@
 //   key     = (seed lo, seed hi)
 //   r0..r3  = Philox4x32-10(counter, key)   (Salmon et al. SC'11; KATs in SURVEY.md App. F)
 //
-//   One Brownian channel (every catalogue model with a vector-valued g):
-//     counter = (path lo, path hi, block, channel), one block = FOUR consecutive steps, step 4*block+s uses r_s:
-//       sign = bit 31, m = low 31 bits, u = m * 2^-31                               (P(octave k) = 2^-(k+1) exactly)
-//       if m < 2^19 (probability 2^-12: the draw lies beyond 2^-12 in the tail) the 21 low mantissa bits of u
-//       are filled from word s of the extension block, counter (path, block, channel | 0x40000000): tail draws
-//       keep full 52-bit resolution down to u = 2^-52 (|z| up to 8.2) while the bulk spends 32 bits per normal.
+//   One Brownian channel (every catalogue model with a vector-valued g) — "stream v2":
+//     counter = (path lo, path hi, block, channel), one block = FOUR consecutive steps, step 4*block+s uses word w = r_s:
+//       s = (w | 1) - 2^31   an odd integer in (-2^31, 2^31): symmetric, never zero;  sign(z) = sign(s), v = |s|
+//       u = v * 2^-31        (31-bit resolution, P(v < 2^k) = 2^(k-31) exactly)
+//       if v < 2^19 (probability 2^-12: the draw lies beyond 2^-12 in the tail) the cell is refined with the top 22
+//       bits e of word s of the extension block, counter (path, block, channel | 0x40000000):
+//       u = ((v-1) 2^21 + e + 1) 2^-52, so tail draws keep 52-bit resolution down to u = 2^-52 (|z| up to 8.2)
+//       while the bulk spends 32 bits per normal.
 //   Matrix-valued g (linear model, nB channels):
 //     counter = (path lo, path hi, step, 0x80000000 + pair), channel 2*pair uses (r0,r1), 2*pair+1 uses (r2,r3):
 //       52-bit u from the top 52 bits of hi:lo, sign = bit 11 of lo.
-//   z = sign * a(u), a(u) = -qnorm(u/2) (half-normal quantile): a table of cubics on 52 octaves x 32 mantissa
-//   sub-intervals indexed straight from the exponent/mantissa bits of u (tools/gen_icdf_table.py, |error| < 8e-10:
+//   z = sign * a(u), a(u) = -qnorm(u/2) (half-normal quantile), evaluated from piecewise cubics (|error| < 8e-10:
 //   a Kolmogorov distance ~3e-10 from the normal law, three orders below the 1/sqrt(N) resolution of a 10^13-draw
-//   ensemble), staged in shared memory: 2 DADD + 3 DFMA + 2 LDS.128, no transcendental, no conversion, no branch.
+//   ensemble) in one of two ways that approximate the same function:
+//     generic  52 octaves x 32 mantissa sub-intervals of u, indexed from the exponent/mantissa bits of u, local
+//              coordinate r (icdf_table.inc, 52 KB in shared memory): any u in [2^-52, 1).
+//     fast     the register-resident kernels: s is formed from w in ONE exact FP64 subtraction ({w|1, 0x43300000} as a
+//              double is 2^52 + (w|1)), its high word indexes 12 octaves x 32 sub-intervals of v directly and the cubic
+//              runs in the raw variable |s| (icdf32_table.inc, 12 KB, replicated REPL-fold in shared memory so that the
+//              lanes of a quarter-warp hit different bank quads): LOP3 + DADD + LOP3 + LEA + 2 LDS.128 + 3 DFMA + LOP3
+//              per normal, no branch; the 2^-12 tail leaves through an out-of-line call that uses the generic tables.
 #pragma once
 #include <stdint.h>
 
 #include "icdf_table.inc"
+#include "icdf32_table.inc"
 
 namespace sdegpu {
 
@@ -127,11 +136,19 @@ __device__ __forceinline__ double icdf_normal(uint32_t lo, uint32_t hi, const do
     return icdf_eval<HOT>(0x3FF00000u | (hi >> 12), (hi << 20) | (lo >> 12), (lo << 20) & 0x80000000u, sh_tab);
 }
 
-// one standard normal from a 32-bit word plus the (usually zero) 21 extension bits
+// one standard normal of stream v2 from a 32-bit word and the word of the extension block (used only when the
+// draw is in the tail), generic evaluation: u's 52 mantissa bits are v << 21, or (v-1) << 21 | e22, + 1 in the tail
 template <bool HOT = false>
-__device__ __forceinline__ double icdf_normal32(uint32_t w, uint32_t ext21, const double *sh_tab)
+__device__ __forceinline__ double icdf_normal32(uint32_t w, uint32_t extw, const double *sh_tab)
 {
-    return icdf_eval<HOT>(0x3FF00000u | ((w >> 11) & 0x000FFFFFu), (w << 21) | ext21, w & 0x80000000u, sh_tab);
+    const int32_t si = (int32_t)((w | 1u) ^ 0x80000000u);         // (w|1) - 2^31
+    const uint32_t v = (uint32_t)(si < 0 ? -si : si);
+    uint32_t hi = v >> 11, lo = v << 21;
+    if (v < (1u << 19)) {
+        const uint64_t m = (((uint64_t)(v - 1u)) << 21) + (uint64_t)(extw >> 10) + 1ull;
+        hi = (uint32_t)(m >> 32); lo = (uint32_t)m;
+    }
+    return icdf_eval<HOT>(0x3FF00000u | hi, lo, si < 0 ? 0x80000000u : 0u, sh_tab);
 }
 
 // The 128 random bits of (path, block, channel).
@@ -159,23 +176,26 @@ static __device__ __noinline__ uint4 philox_extension(uint32_t seed_lo, uint32_t
     return make_uint4(c0, c1, c2, c3);
 }
 
-// Four standard normals (steps 4*block .. 4*block+3 of one channel) from the words of a Philox block.
-// The tail extension is evaluated once per block and taken by ~1 block in 1000.
+// is any of the four words a tail draw?  v < 2^19  <=>  (w|1) - (2^31 - 2^19) < 2^20 as unsigned
+__device__ __forceinline__ bool philox_block_has_tail(const uint32_t (&r)[4])
+{
+    const uint32_t off = 0x80000000u - (1u << 19);
+    const uint32_t d0 = (r[0] | 1u) - off, d1 = (r[1] | 1u) - off, d2 = (r[2] | 1u) - off, d3 = (r[3] | 1u) - off;
+    return min(min(d0, d1), min(d2, d3)) < (1u << 20);
+}
+
+// Four standard normals (steps 4*block .. 4*block+3 of one channel) from the words of a Philox block, generic
+// evaluation.  The tail extension is generated once per block and taken by ~1 block in 1000.
 template <bool HOT = false>
 __device__ __forceinline__ void normals_from_block(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
                                                    const uint32_t (&r)[4], const double *sh_tab, double (&z)[4])
 {
-    uint32_t ext[4] = {0u, 0u, 0u, 0u};
-    const uint32_t m0 = r[0] & 0x7FFFFFFFu, m1 = r[1] & 0x7FFFFFFFu, m2 = r[2] & 0x7FFFFFFFu, m3 = r[3] & 0x7FFFFFFFu;
-    if (min(min(m0, m1), min(m2, m3)) < (1u << 19)) {
-        const uint4 e = philox_extension(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel);
-        ext[0] = m0 < (1u << 19) ? e.x >> 11 : 0u;
-        ext[1] = m1 < (1u << 19) ? e.y >> 11 : 0u;
-        ext[2] = m2 < (1u << 19) ? e.z >> 11 : 0u;
-        ext[3] = m3 < (1u << 19) ? e.w >> 11 : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) z[k] = icdf_normal32<HOT>(r[k], ext[k], sh_tab);
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    if (philox_block_has_tail(r)) e = philox_extension(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel);
+    z[0] = icdf_normal32<HOT>(r[0], e.x, sh_tab);
+    z[1] = icdf_normal32<HOT>(r[1], e.y, sh_tab);
+    z[2] = icdf_normal32<HOT>(r[2], e.z, sh_tab);
+    z[3] = icdf_normal32<HOT>(r[3], e.w, sh_tab);
 }
 
 template <bool HOT = false>
@@ -197,5 +217,102 @@ __device__ __forceinline__ void normal_pair(const PhiloxKey &key, uint64_t path,
     z0 = icdf_normal<HOT>(c0, c1, sh_tab);
     z1 = icdf_normal<HOT>(c2, c3, sh_tab);
 }
+
+// ---- fast evaluation of stream v2 (register-resident kernels) ------------------------------------------------
+// Shared-memory layout: plane A {c0,c1} then plane B {c2,c3}, each ICDF32_NSEG segments x REPL replicas of 16 bytes;
+// lane L reads replica L % REPL, so with REPL = 8 the eight lanes a 128-bit load serves per wavefront sit in eight
+// different bank quads whatever segments they want.  `scale` multiplies every coefficient while staging: a kernel
+// whose grid is uniform folds sqrt(dt) (times the model's noise constant) into the table and gets dB straight
+// out of the Horner chain.
+constexpr int ICDF32_DOUBLES = 4 * ICDF32_NSEG;
+template <int REPL> struct Icdf32Layout {
+    static_assert(REPL == 1 || REPL == 2 || REPL == 4 || REPL == 8 || REPL == 16, "REPL must be a power of two");
+    static constexpr int LOG = REPL == 1 ? 0 : REPL == 2 ? 1 : REPL == 4 ? 2 : REPL == 8 ? 3 : 4;
+    static constexpr int PLANE_BYTES = ICDF32_NSEG * REPL * 16;
+    static constexpr int BYTES = 2 * PLANE_BYTES;
+    static constexpr int DOUBLES = BYTES / 8;
+};
+
+template <int REPL>
+__device__ __forceinline__ void icdf32_stage(double *sh_tab, const double *__restrict__ g32, double scale, int tid, int nthreads)
+{
+    const double2 *src = reinterpret_cast<const double2 *>(g32);
+    double2 *dst = reinterpret_cast<double2 *>(sh_tab);
+    constexpr int PLANE = ICDF32_NSEG * REPL;
+    for (int i = tid; i < 2 * PLANE; i += nthreads) {
+        const int plane = i / PLANE, seg = (i - plane * PLANE) / REPL;
+        const double2 c = __ldg(src + plane * ICDF32_NSEG + seg);
+        dst[i] = make_double2(c.x * scale, c.y * scale);
+    }
+}
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// The tail of the fast path, out of line on purpose (one block in ~1000): all four normals of the block through
+// the generic tables in global memory, scaled like the staged table.  zout is a scratch array of the caller.
+static __device__ __noinline__ void icdf32_tail_quad(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+                                                     uint32_t block, uint32_t channel, uint32_t w0, uint32_t w1, uint32_t w2,
+                                                     uint32_t w3, const double *g52, double scale, double *zout)
+{
+    const uint4 e = philox_extension(seed_lo, seed_hi, path_lo, path_hi, block, channel);
+    zout[0] = scale * icdf_normal32<false>(w0, e.x, g52);
+    zout[1] = scale * icdf_normal32<false>(w1, e.y, g52);
+    zout[2] = scale * icdf_normal32<false>(w2, e.z, g52);
+    zout[3] = scale * icdf_normal32<false>(w3, e.w, g52);
+}
+
+template <int REPL> struct NormalGen {
+    using L = Icdf32Layout<REPL>;
+    uint32_t base;            // shared-space byte address of plane A with the lane's replica and the exponent bias folded in
+    const double *g52;        // generic 52-octave table in global memory (tail draws only)
+    double scale;
+
+    __device__ __forceinline__ void init(const double *sh_tab, const double *g52_, double scale_)
+    {
+        const uint32_t b = smem_addr_u32(sh_tab) + ((threadIdx.x & (REPL - 1)) << 4) - (((1023u + ICDF32_OCT0) << 5) << (4 + L::LOG));
+        asm volatile("mov.u32 %0, %1;" : "=r"(base) : "r"(b));   // opaque: kept in a register, not recomputed in the hot loop
+        g52 = g52_;
+        scale = scale_;
+    }
+
+    // scale * z for steps 4*block .. 4*block+3 of (path, channel) from the words of its Philox block
+    __device__ __forceinline__ void quad(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
+                                         const uint32_t (&r)[4], double (&z)[4]) const
+    {
+        double s[4];
+        uint32_t xm[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s[k] = __hiloint2double(0x43300000, (int)(r[k] | 1u)) - 4503601774854144.0;   // 2^52 + (w|1) - (2^52 + 2^31), exact
+            xm[k] = (uint32_t)__double2hiint(s[k]) & 0x7FFF8000u;                         // (exponent, 5 mantissa bits) of |s|
+        }
+        if (min(min(xm[0], xm[1]), min(xm[2], xm[3])) < 0x41200000u) {                    // some |s| < 2^19: a tail draw
+            double zt[4];                                        // its address is taken: kept apart from z, which stays in registers
+            icdf32_tail_quad(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, r[0], r[1], r[2], r[3],
+                             g52, scale, zt);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z[k] = zt[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t addr = base + (xm[k] >> (11 - L::LOG));
+                const double2 c01 = lds_f64x2(addr), c23 = lds_f64x2(addr + L::PLANE_BYTES);
+                const double v = fabs(s[k]);
+                double a = fma(c23.y, v, c23.x);
+                a = fma(a, v, c01.y);
+                a = fma(a, v, c01.x);
+                // sign(s) onto scale*a(|s|) with one LOP3 (an XOR, so a negative scale keeps its meaning)
+                z[k] = __hiloint2double(__double2hiint(a) ^ (__double2hiint(s[k]) & (int)0x80000000u), __double2loint(a));
+            }
+        }
+    }
+};
 
 }  // namespace sdegpu

@@ -63,7 +63,7 @@ class Engine:
     def run(self, model, scheme, params, times, x0, *, nx, nB=1, npaths, B=None, projection="identity",
             arith=None, seed=0, path_offset=0, X=None, XT=None, power_sums=None, center=None,
             hist_counts=None, hist=None, accumulate=False, want_time=False, kill=None, stop=None, S0=1.0,
-            Stau=None, tau=None, S_tau=None, path_integrals=None):
+            Stau=None, tau=None, S_tau=None, path_integrals=None, exact_grid=False):
         """Thin, allocation-free call of sdegpu_run.  B / per-path x0 / outputs are either all numpy
         (host pointers) or all torch CUDA tensors (device pointers: work is only enqueued, on torch's current stream).
         Layouts are the reference's: B[(p*nB+k)*nt+i], X[(p*nx+j)*nt+i], XT[p*nx+j]."""
@@ -100,7 +100,7 @@ class Engine:
         pr.npaths, pr.path_offset, pr.seed = int(npaths), int(path_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
         if on_dev:
             self._follow_torch_stream()
-        pr.flags = (_lib.DEVICE_PTRS if on_dev else 0) | (_lib.ACCUMULATE if accumulate else 0)
+        pr.flags = (_lib.DEVICE_PTRS if on_dev else 0) | (_lib.ACCUMULATE if accumulate else 0) | (_lib.EXACT_GRID if exact_grid else 0)
         if kill is not None:                 # catalogue.KillRate
             pr.kill_kind, pr.kill_comp, pr.kill_a, pr.kill_b = _lib.KILL[kill.sdegpu_kill], kill.component, kill.a, kill.b
         if stop is not None:                 # catalogue.StopRule

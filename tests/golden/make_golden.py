@@ -93,10 +93,43 @@ def oracle_vectors():
     return out
 
 
+def write_hex(path, a):
+    """C99 hexadecimal doubles, one per line, column-major, after a line with the dimensions: what
+    make_reference_fixtures.R reads with as.numeric() and writes back with sprintf("%a")."""
+    a = np.asarray(a, dtype=np.float64)
+    with open(path, "w") as fh:
+        fh.write(" ".join(str(d) for d in (a.shape if a.ndim else (1,))) + "\n")
+        fh.write("\n".join(float(v).hex() for v in a.ravel(order="F")) + "\n")
+
+
+def read_hex(path):
+    with open(path) as fh:
+        dims = [int(d) for d in fh.readline().split()]
+        vals = [float("nan") if tok in ("NA", "NaN") else (float("inf") if tok == "Inf" else (float("-inf") if tok == "-Inf" else float.fromhex(tok)))
+                for tok in fh.read().split()]
+    return np.array(vals).reshape(dims, order="F")
+
+
+def reference_inputs(vec):
+    """Inputs of tests/golden/make_reference_fixtures.R (run where R exists; see that file)."""
+    d = os.path.join(HERE, "reference_R_inputs")
+    os.makedirs(d, exist_ok=True)
+    for k in ("times", "B", "lin_A", "lin_G", "lin_x0", "lin_B", "int_f", "int_g"):
+        write_hex(os.path.join(d, k + ".txt"), vec[k])
+    rng = np.random.default_rng(20261021)                  # its own stream: oracle_vectors.npz does not move
+    P = vec["B"].shape[2]
+    write_hex(os.path.join(d, "Stau.txt"), rng.uniform(0.5, 0.95, P))
+    tb = np.concatenate(([0.25], 0.25 + np.cumsum(rng.uniform(0.01, 0.05, 30))))   # times[1] > 0: first increment spans [0, t1]
+    write_hex(os.path.join(d, "rbm_times.txt"), tb)
+    write_hex(os.path.join(d, "rbm_z.txt"), rng.standard_normal((tb.size, 3)))
+
+
 def main():
     with open(os.path.join(HERE, "reference_known_answers.json"), "w") as fh:
         json.dump(known_answers(), fh, indent=1)
-    np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **oracle_vectors())
+    vec = oracle_vectors()
+    np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **vec)
+    reference_inputs(vec)
     print("wrote", os.listdir(HERE))
 
 

@@ -147,6 +147,35 @@ def test_icdf_table_matches_qnorm():
     assert np.all(a > -1e-9)          # next to u = 1 the true value (~1e-16) is below the table's error
 
 
+def test_icdf32_table_matches_qnorm():
+    """The fast quantile table of stream v2 (csrc/icdf32_table.inc), evaluated here exactly as NormalGen::quad does —
+    s = (w|1) - 2^31 in FP64, segment from the high word of s, cubic in the raw |s| — against -qnorm(u/2), u = |s| 2^-31."""
+    from scipy.special import ndtri
+    txt = open(os.path.join(ROOT, "sdetools_b200", "csrc", "icdf32_table.inc")).read()
+    nseg = int(re.search(r"#define ICDF32_NSEG (\d+)", txt).group(1))
+    oct0 = int(re.search(r"#define ICDF32_OCT0 (\d+)", txt).group(1))
+    body = txt[txt.index("] = {") + 5:txt.index("};")]
+    words = np.array([int(v.strip().rstrip("ul"), 16) for v in body.split(",") if v.strip()], dtype=np.uint64)
+    planes = words.view(np.float64).reshape(2, nseg, 2)
+    c0, c1, c2, c3 = planes[0, :, 0], planes[0, :, 1], planes[1, :, 0], planes[1, :, 1]
+    rng = np.random.default_rng(1)
+    w = np.concatenate([rng.integers(0, 2 ** 32, 400000), [0, 1, 2 ** 32 - 1, 2 ** 31 + 2 ** 19, 2 ** 31 - 2 ** 19 - 2,
+                                                            2 ** 31 + 2 ** 19 + 1, 2 ** 31 - 2 ** 19 - 1]]).astype(np.uint64)
+    magic = ((np.uint64(0x43300000) << np.uint64(32)) | (w | np.uint64(1))).view(np.float64)
+    s = magic - 4503601774854144.0                                # exact: an odd integer in (-2^31, 2^31)
+    assert np.array_equal(s, (w | np.uint64(1)).astype(np.float64) - 2.0 ** 31)
+    sh = (s.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    xm = sh & 0x7FFF8000
+    fast = xm >= 0x41200000                                       # |s| >= 2^19: the fast path's domain
+    assert 0.9995 < fast.mean() < 1.0
+    t = (xm[fast] >> 15) - ((1023 + oct0) << 5)
+    assert t.min() >= 0 and t.max() < nseg
+    v = np.abs(s[fast])
+    a = ((c3[t] * v + c2[t]) * v + c1[t]) * v + c0[t]
+    want = -ndtri(0.5 * v * 2.0 ** -31)
+    assert np.max(np.abs(a - want)) < 1e-9
+
+
 def test_r_shim_compiles_against_mock_r_headers():
     """R is not installed: the .Call shim (r/src/sdegpu_shim.c) is type-checked against a mock of R's C API."""
     r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "mock_r"),
