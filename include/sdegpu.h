@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDEGPU_ABI_VERSION 3
+#define SDEGPU_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SDEGPU_API __attribute__((visibility("default")))
@@ -147,6 +147,10 @@ typedef struct {
                                  k=0 QuadraticVariation(X_j) (R/sdetools.R:134-137), k=1 itointegral(X_j,B) (:155-158),
                                  k=2 stochint(X_j,B,"c") (:105-113), k=3 itointegral(X_j,times); 80-bit cumsum each.
                                  With a supplied B bit-identical to those functions run on the stored path. */
+    /* --- ABI 4: the survival path of a mortality run, the `S` of list(times, X, S, tau) (R/sdetools.R:443-444,456,468; heun :336) --- */
+    double *S;                /* nt*npaths, S[p*nt + i]: S[0] = S0, S_{i+1} = S_i exp(-r(X_i) dt_i) up to tau; after an h-stop the
+                                 entry at tau reads 0 (the reference's S <- numeric(nt) is never written there); NaN after tau.
+                                 For one path S[0 .. k-1] with times[k-1] = tau is exactly the reference's S[1:(i+1)]. */
 } sdegpu_output;
 
 typedef struct {

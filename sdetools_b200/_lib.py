@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libsdegpu.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DEVICE_PTRS = 1
 ACCUMULATE = 2
 EXACT_GRID = 4
@@ -38,7 +38,8 @@ class Output(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("hist_component", C.c_int32), ("X", C.c_void_p), ("XT", C.c_void_p),
                 ("power_sums", C.c_void_p), ("center", C.c_void_p), ("hist_counts", C.c_void_p),
                 ("hist_lo", C.c_double), ("hist_hi", C.c_double), ("hist_nbins", C.c_int32), ("reserved", C.c_int32),
-                ("elapsed_ms", C.c_void_p), ("tau", C.c_void_p), ("S_tau", C.c_void_p), ("path_integrals", C.c_void_p)]
+                ("elapsed_ms", C.c_void_p), ("tau", C.c_void_p), ("S_tau", C.c_void_p), ("path_integrals", C.c_void_p),
+                ("S", C.c_void_p)]
 
 
 class DevInfo(C.Structure):

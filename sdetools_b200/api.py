@@ -88,12 +88,13 @@ def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, outpu
     killed = h is not None or r is not None
     tau = np.empty(npaths) if killed else None
     S_tau = np.empty(npaths) if r is not None else None
+    S_path = np.empty((nt, npaths), order="F") if (r is not None and want_path) else None
     Stau_arr = None
     if killed and Stau is not None:              # one threshold per path (the reference: one runif(1) per call)
         Stau_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(Stau, dtype=np.float64), (npaths,)))
     eng.run(model, scheme, params, times, x0c, nx=nx, nB=nB, npaths=npaths, B=Bdev, projection=proj, arith=arith,
             seed=seed, path_offset=path_offset, X=X, XT=XT, power_sums=ps, center=center, hist_counts=hc, hist=hist,
-            kill=r, stop=h, S0=S0, Stau=Stau_arr, tau=tau, S_tau=S_tau, path_integrals=PI)
+            kill=r, stop=h, S0=S0, Stau=Stau_arr, tau=tau, S_tau=S_tau, path_integrals=PI, S_path=S_path)
     res = {"times": times}
     if PI is not None:                     # terminal entries of the reference's integral functions on each path
         res["integrals"] = {k: (PI[i] if ensemble else PI[i, :, 0]) for i, k in enumerate(("QV", "ito", "strat", "time"))}
@@ -103,7 +104,15 @@ def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, outpu
         res["tau"] = tau if ensemble else float(tau[0])
         if S_tau is not None:
             res["S"] = S_tau if ensemble else float(S_tau[0])
-    if want_path:
+        if S_path is not None:
+            res["S_path"] = S_path         # nt x npaths: every path's S vector, NaN after its tau
+    if want_path and killed and r is not None and not ensemble:
+        # one path with mortality: exactly the reference's list(times[1:(i+1)], X[1:(i+1),], S[1:(i+1)], tau)  (:466-468)
+        k = int(np.searchsorted(times, tau[0], side="left")) + 1
+        res["times"] = times[:k]
+        res["X"] = X[:k, 0, 0] if nx == 1 else X[:k, :, 0]
+        res["S"] = S_path[:k, 0]
+    elif want_path:
         res["X"] = X if ensemble else X[:, :, 0]
     if XT is not None:
         res["XT"] = XT if ensemble else XT[:, 0]

@@ -222,7 +222,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: killing/stopping is not available for the linear model");
     if (out->path_integrals && (killed || out->X || pr->model == SDEGPU_MODEL_LINEAR))
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: path_integrals needs a catalogue model without kill/stop rule and X = NULL");
-    if ((out->tau || out->S_tau) && !killed) return fail(SDEGPU_ERR_ARG, "sdegpu_run: tau/S_tau outputs need a kill or stop rule");
+    if ((out->tau || out->S_tau || out->S) && !killed) return fail(SDEGPU_ERR_ARG, "sdegpu_run: tau/S_tau/S outputs need a kill or stop rule");
     if (!pr->B && pr->arith == SDEGPU_ARITH_STRICT && !killed)
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: STRICT arithmetic is defined for a supplied B; fused-generator runs are FAST");
     for (int i = 0; i + 1 < pr->nt; ++i)
@@ -345,9 +345,9 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
             CU(c->times.reserve(sizeof(double) * nt));
             CU(cudaMemcpyAsync(c->times.p, pr->times, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
             a.times = (const double *)c->times.p;
-            if (dev) { a.Stau = pr->Stau; a.tau = out->tau; a.S_tau = out->S_tau; }
+            if (dev) { a.Stau = pr->Stau; a.tau = out->tau; a.S_tau = out->S_tau; a.Spath = out->S; }
             else {
-                CU(c->kill.reserve(sizeof(double) * 3 * pr->npaths));
+                CU(c->kill.reserve(sizeof(double) * (3 + (out->S ? (size_t)nt : 0)) * pr->npaths));
                 double *kb = (double *)c->kill.p;
                 if (pr->Stau) {
                     CU(cudaMemcpyAsync(kb, pr->Stau, sizeof(double) * pr->npaths, cudaMemcpyHostToDevice, c->stream));
@@ -355,6 +355,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
                 }
                 if (out->tau) a.tau = kb + pr->npaths;
                 if (out->S_tau) a.S_tau = kb + 2 * pr->npaths;
+                if (out->S) a.Spath = kb + 3 * pr->npaths;
             }
         }
         const size_t bytesF = sizeof(double) * 4 * (size_t)nx * pr->npaths;
@@ -430,6 +431,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         if (out->hist_counts) CU(cudaMemcpyAsync(out->hist_counts, dh, sizeof(unsigned long long) * nh, cudaMemcpyDeviceToHost, c->stream));
         if (out->tau) CU(cudaMemcpyAsync(out->tau, (double *)c->kill.p + pr->npaths, sizeof(double) * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
         if (out->S_tau) CU(cudaMemcpyAsync(out->S_tau, (double *)c->kill.p + 2 * pr->npaths, sizeof(double) * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
+        if (out->S) CU(cudaMemcpyAsync(out->S, (double *)c->kill.p + 3 * pr->npaths, sizeof(double) * pr->npaths * nt, cudaMemcpyDeviceToHost, c->stream));
     }
     if (!dev || out->elapsed_ms) {
         CU(cudaStreamSynchronize(c->stream));

@@ -58,6 +58,7 @@ struct RunArgs {
     const double *Stau;             // per-path thresholds or nullptr (drawn from Philox)
     const double *times;            // device copy of the time grid (tau = times[i+1])
     double *tau, *S_tau;
+    double *Spath;                  // device, survival path S[p*nt+i] (k_killed) or nullptr
     double *func;                   // device, path integrals func[(p*nx+j)*4 + {QV, ito, strat, time}] (k_functionals)
 };
 
@@ -722,6 +723,8 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
         }
         const double *brow = a.B ? a.B + p * (uint64_t)a.nt : nullptr;
         double S = a.S0, Sout = a.S0, zq[4] = {0.0, 0.0, 0.0, 0.0};
+        double *srow = a.Spath ? a.Spath + p * (uint64_t)a.nt : nullptr;
+        if (srow) srow[0] = a.S0;                                // S[1] <- S0  (:444)
         int last = nsteps;                                       // index of the last valid row of X
         for (int i = 0; i < nsteps; ++i) {
             const double2 dt = __ldg(&a.dtsq[i]);
@@ -741,20 +744,24 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
             }
             if (a.stop_kind != SDEGPU_STOP_NONE && !(stop_value<NX>(a, x) > 0.0)) {      // h(...) <= 0  (:455)
                 last = i + 1; Sout = 0.0;
+                if (srow) srow[i + 1] = 0.0;                     // S <- numeric(nt) is not written at the stop (:443,:455)
                 break;
             }
             if (a.kill_kind != SDEGPU_KILL_NONE) {
                 S = __dmul_rn(S, exp(__dmul_rn(-kill_rate<NX>(a, xo), dt.x)));           // :456, old state
                 Sout = S;
+                if (srow) srow[i + 1] = S;
                 if (S < Stau) { last = i + 1; break; }                                    // :457
-            }
+            } else if (srow) srow[i + 1] = S;
         }
+        const double nan = __longlong_as_double(0x7FF8000000000000ll);
         if (a.X) {                                               // rows after the break stay NA in the reference (:439)
-            const double nan = __longlong_as_double(0x7FF8000000000000ll);
             for (int i = last + 1; i <= nsteps; ++i)
 #pragma unroll
                 for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt + i] = nan;
         }
+        if (srow)                                                // the reference returns S[1:(i+1)]: nothing after tau
+            for (int i = last + 1; i <= nsteps; ++i) srow[i] = nan;
         if (a.tau) a.tau[p] = a.times[last];                     // tau <- times[i+1]  (:467)
         if (a.S_tau) a.S_tau[p] = Sout;
         if (a.XT) {

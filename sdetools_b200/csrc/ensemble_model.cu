@@ -70,7 +70,7 @@ static int launch_stream(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 template <int SCHEME, int PROJ>
 static int launch_killed(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
-    auto kernel = a.X ? k_killed<M, SCHEME, PROJ> : k_killed_refill<M, SCHEME, PROJ>;   // no trajectory: lanes refill
+    auto kernel = a.X || a.Spath ? k_killed<M, SCHEME, PROJ> : k_killed_refill<M, SCHEME, PROJ>;   // no trajectory: lanes refill
     const size_t smem = (a.B ? 0 : ICDF_TABLE_BYTES) + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + KILLED_THREADS - 1) / KILLED_THREADS;
     const int grid = c.grid > 0 ? min(c.grid, 32 * c.sm_count) : occupancy_grid(kernel, KILLED_THREADS, smem, c.sm_count, work);

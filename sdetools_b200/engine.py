@@ -63,11 +63,11 @@ class Engine:
     def run(self, model, scheme, params, times, x0, *, nx, nB=1, npaths, B=None, projection="identity",
             arith=None, seed=0, path_offset=0, X=None, XT=None, power_sums=None, center=None,
             hist_counts=None, hist=None, accumulate=False, want_time=False, kill=None, stop=None, S0=1.0,
-            Stau=None, tau=None, S_tau=None, path_integrals=None, exact_grid=False):
+            Stau=None, tau=None, S_tau=None, path_integrals=None, exact_grid=False, S_path=None):
         """Thin, allocation-free call of sdegpu_run.  B / per-path x0 / outputs are either all numpy
         (host pointers) or all torch CUDA tensors (device pointers: work is only enqueued, on torch's current stream).
         Layouts are the reference's: B[(p*nB+k)*nt+i], X[(p*nx+j)*nt+i], XT[p*nx+j]."""
-        bufs = [b for b in (B, X, XT, power_sums, hist_counts, Stau, tau, S_tau, path_integrals) if b is not None]
+        bufs = [b for b in (B, X, XT, power_sums, hist_counts, Stau, tau, S_tau, path_integrals, S_path) if b is not None]
         on_dev = any(_is_torch(b) for b in bufs)
         if on_dev and not all(_is_torch(b) and b.is_cuda for b in bufs):
             raise TypeError("mixing host and device buffers in one call is not supported")
@@ -110,7 +110,7 @@ class Engine:
         out = Output()
         out.struct_size = C.sizeof(Output)
         out.X, out.XT, out.power_sums, out.hist_counts = _ptr(X), _ptr(XT), _ptr(power_sums), _ptr(hist_counts)
-        out.tau, out.S_tau, out.path_integrals = _ptr(tau), _ptr(S_tau), _ptr(path_integrals)
+        out.tau, out.S_tau, out.path_integrals, out.S = _ptr(tau), _ptr(S_tau), _ptr(path_integrals), _ptr(S_path)
         center_keep = None
         if center is not None:
             center_keep = np.ascontiguousarray(np.ravel(center), dtype=np.float64)

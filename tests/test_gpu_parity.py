@@ -495,8 +495,39 @@ def test_killing_matches_reference_loop(sde):
         assert np.all(np.isnan(got["X"][k:, 0, p]))
         assert got["S"][p] == pytest.approx(ref["S"][-1], rel=1e-13)
         assert got["XT"][0, p] == np.atleast_1d(ref["X"]).ravel()[-1]
+        # the survival path: the reference's S[1:(i+1)] (:443-444,456,468), NaN after tau
+        assert np.allclose(got["S_path"][:k, p], ref["S"], rtol=1e-13, atol=0) and got["S_path"][0, p] == 1.0
+        assert np.all(np.isnan(got["S_path"][k:, p]))
         n_killed += ref["tau"] < t[-1]
     assert 20 < n_killed < 96                                 # both outcomes are exercised
+    # one path: the reference's own return shape list(times[1:(i+1)], X[1:(i+1),], S[1:(i+1)], tau)  (:466-468)
+    p = int(np.argmin(got["tau"]))
+    one = sde.euler(f, g, t, 0.0, B[:, :, p], r=r, Stau=float(Stau[p]))
+    ref = O.euler(fo, go, t, 0.0, B=B[:, :, p], r=ro, Stau=Stau[p])
+    assert one["tau"] == ref["tau"] and np.array_equal(one["times"], ref["times"])
+    assert np.array_equal(one["X"], np.atleast_1d(ref["X"]).ravel()) and np.allclose(one["S"], ref["S"], rtol=1e-13, atol=0)
+
+
+def test_survival_path_with_stopping_reads_zero_at_the_stop(sde):
+    """h and r together (R/sdetools.R:455-457): a path stopped by h keeps S = 0 at tau (the reference's S <- numeric(nt)
+    is never written there), a killed one its last survival; both NaN afterwards."""
+    t, B = brownian(401, 1, 80, 23)
+    f, g = sde.catalogue.ou(1.0, 0.0, 1.0)
+    r, h = sde.catalogue.kill_exp(0.5, 2.0), sde.catalogue.stop_outside(-0.4, 0.9)
+    Stau = np.random.default_rng(4).random(80)
+    for scheme in ("euler", "heun"):
+        got = getattr(sde, scheme)(f, g, t, 0.1, B, r=r, h=h, Stau=Stau)
+        fo, go, _, _ = O.catalogue("ou", [1.0, 0.0, 1.0])
+        nstop = 0
+        for p in range(80):
+            ref = getattr(O, scheme)(fo, go, t, 0.1, B=B[:, :, p], r=lambda x: 0.5 * np.exp(2.0 * x[0]),
+                                     h=lambda tt, x: (x[0] + 0.4) * (0.9 - x[0]), Stau=Stau[p])
+            k = ref["times"].size
+            assert got["tau"][p] == ref["tau"]
+            assert np.allclose(got["S_path"][:k, p], ref["S"], rtol=1e-13, atol=0)
+            assert np.all(np.isnan(got["S_path"][k:, p]))
+            nstop += ref["S"][-1] == 0.0
+        assert 5 < nstop < 80
 
 
 def test_stopping_rule_matches_reference_loop(sde):
