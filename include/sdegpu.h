@@ -89,7 +89,7 @@ typedef enum {
 enum {
     SDEGPU_DEVICE_PTRS = 1u,  /* B, per-path x0 and every output buffer are device pointers */
     SDEGPU_ACCUMULATE = 2u,   /* add into power_sums / hist_counts instead of overwriting */
-    SDEGPU_EXACT_GRID = 4u    /* fused-generator runs without trajectory treat a grid whose increments agree to the
+    SDEGPU_EXACT_GRID = 4u    /* fused-generator runs (no B, no kill/stop rule) treat a grid whose increments agree to the
                                  rounding of its time stamps (|dt_i - mean dt| <= 4 eps max|t|, e.g. seq(0, T, by = h)) as
                                  the uniform grid dt = (t_n - t_0)/n; this flag keeps every dt_i = times[i+1]-times[i] */
 };

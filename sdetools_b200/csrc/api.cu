@@ -307,7 +307,7 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         a.icdf = c->icdf;
         a.icdf32 = c->icdf32;
         bool uniform = false;
-        if (!pr->B && !out->X && !killed && !out->path_integrals) {   // k_terminal: folded step coefficients (FAST only)
+        if (!pr->B && !killed && !out->path_integrals) {   // k_terminal, k_traj: folded step coefficients (FAST only)
             // A grid whose increments agree to the rounding of its own time stamps (seq(0, T, by = h) gives
             // t_i = i*h rounded, so diff(times) scatters by ~ulp(T)) is integrated as the uniform grid it
             // stands for, dt = (t_n - t_0)/n: one coefficient row as a kernel parameter instead of a table.

@@ -126,6 +126,34 @@ __device__ __forceinline__ void flush_block_stats(const RunArgs &a, double (&acc
             if (sh_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)sh_hist[i]);
 }
 
+// the same for a block size known only at run time: `scratch` holds (warps) x (5*NX) doubles of shared memory
+template <int NX>
+__device__ __forceinline__ void flush_block_stats_dyn(const RunArgs &a, double (&acc)[NX][5], unsigned int *sh_hist, double *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();                                             // the scratch area may alias rings that are still being read
+    if (a.partials) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                double v = acc[j][m];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) scratch[warp * (NX * 5) + j * 5 + m] = v;
+            }
+    }
+    __syncthreads();
+    if (a.partials && threadIdx.x < NX * 5) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += scratch[w * (NX * 5) + threadIdx.x];
+        a.partials[(size_t)blockIdx.x * (NX * 5) + threadIdx.x] = v;
+    }
+    if (a.hist)
+        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += blockDim.x)
+            if (sh_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)sh_hist[i]);
+}
+
 template <int NX>
 __device__ __forceinline__ void load_x0(const RunArgs &a, uint64_t p, double (&x)[NX])
 {
@@ -262,157 +290,236 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 }
 
 // ---- full-trajectory kernel, fused generator (HBM-write bound) ----------------
-// X[(p*nx+j)*nt + i] is time-fastest per path (the reference's column-major nt x nx matrix), so the
-// 32 paths of a warp write 32 rows that are nt*8 bytes apart and nothing coalesces across lanes.
-// Partial-sector stores make L2 fetch the rest of the sector from HBM (measured: 0.43 B read per B
-// written with 16-byte stores), so each thread keeps four consecutive time points of its own row in
-// registers and writes them as ONE aligned 32-byte sector (sm_100 256-bit store, STG.E.256).  Rows
-// start at arbitrary element offsets (nt is usually odd), so the sector grid is shifted per row by
-// d = (row start + 1) mod 4: the sector that completes in a 4-step group is made of the last d values
-// of the previous group and the first 4-d of this one.  Paths are dealt to lanes with stride Q
-// (Q*nx*nt = 0 mod 4) so that d is warp-uniform and the four-way switch does not diverge.  Only the
-// first/last partial sector of a row is written element by element.
-constexpr int TRAJ_CHUNK = 1024;    // steps of the {dt, sqrt dt} table staged in shared memory at a time (16 KB)
-// Threads per CTA (one CTA per SM), tuned on the device.  Two components (C3, 16 B per step): 128: 2.85, 192: 3.5,
-// 256: 4.6, 320: 4.35, 384: 4.3, 512: 4.15 TB/s — fewer rows in flight suit the memory system.  One component writes
-// half the bytes per generated normal, so there the generator is the cost and more warps win: OU/euler 256: 3.3e11,
-// 512: 4.3e11, 768: 4.3e11 path-steps/s; CIR/heun 1.9e11, 2.7e11, 2.9e11.
-#ifndef SDEGPU_TRAJ_THREADS
-#define SDEGPU_TRAJ_THREADS 256
-#endif
-#ifndef SDEGPU_TRAJ_THREADS_NX1
-#define SDEGPU_TRAJ_THREADS_NX1 768
+// X[(p*nx+j)*nt + i] is time-fastest per path (the reference's column-major nt x nx matrix, R/sdetools.R:439-441,464),
+// so the 32 paths of a warp own 32*nx rows that are nt*8 bytes apart and nothing coalesces across lanes while the
+// paths advance.  Round 1 wrote one 32-byte sector per lane per four steps straight from registers (4.6 TB/s).  The
+// store microbenchmark (profiles/r1_tma_store_microbench.txt) says what the memory system prefers: few rows in flight
+// per SM (256 rather than 512) and bursts of >= 128 bytes per row — 5.1-5.3 TB/s.  So: TMA-staged.
+//   tile      per warp and component, a ring of 2*CH chunks; a chunk is 32 rows (one per lane) x 16 time points
+//             (128 bytes per row, 4 KB), laid out as the 3-D TMA box {16 doubles, 32 rows, CH chunks} with the
+//             128-byte hardware swizzle, so a lane's 16-byte store lands in bank quad (k ^ lane%8).
+//   body      16 steps (four Philox blocks) advance in registers, then every component's 16 values go to its tile
+//             as 128-bit shared stores; after CH bodies ONE elected lane issues one `cp.async.bulk.tensor.3d` per
+//             component (SASS UTMASTG): CH*128 bytes per row, 32 rows.  The other half of the ring is being read
+//             by the previous store meanwhile (cp.async.bulk.wait_group.read 0 before it is overwritten).
+//   alignment rows start at arbitrary element offsets (nt is usually odd) but TMA wants 16-byte and the memory system
+//             32-byte (sector) alignment: rows are split into S = lcm(4/gcd(nt,4), nx) classes by (row mod S); within
+//             a class all rows start at the same offset mod 4, so one tensor map per class, based at the class's
+//             first sector boundary h in 1..4 elements into the row, covers every row of the class with a stride of
+//             S*nt*8 bytes.  Lanes take every (S/nx)-th path so that a warp's rows of one component are consecutive
+//             rows of one class.  The h head elements, and the < 16+3 elements behind the last whole chunk, are written
+//             element by element (two partial sectors per row).
+// The step is the folded FAST step of k_terminal (same coefficient rows, same generator), so X[nt,] of a trajectory run
+// equals XT of a terminal run bit for bit.
+#ifndef SDEGPU_TRAJ_CH
+#define SDEGPU_TRAJ_CH 2
 #endif
 #ifndef SDEGPU_TRAJ_REPL
 #define SDEGPU_TRAJ_REPL 8
 #endif
-constexpr int TRAJ_REPL = SDEGPU_TRAJ_REPL;
-template <int NX> struct TrajThreads { static constexpr int value = NX == 1 ? SDEGPU_TRAJ_THREADS_NX1 : SDEGPU_TRAJ_THREADS; };
+#ifndef SDEGPU_TRAJ_MAX_THREADS
+#define SDEGPU_TRAJ_MAX_THREADS 256
+#endif
+constexpr int TRAJ_REPL = SDEGPU_TRAJ_REPL, TRAJ_CH = SDEGPU_TRAJ_CH, TRAJ_MAX_THREADS = SDEGPU_TRAJ_MAX_THREADS;
+constexpr int TRAJ_NSLOT = 2 * TRAJ_CH;                          // chunk slots in a component's ring
+constexpr int TRAJ_MAX_CLASSES = 4;                              // lcm(4, nx) for nx <= 2
+
+struct __align__(64) TrajMaps {
+    unsigned char m[TRAJ_MAX_CLASSES][128];                      // CUtensorMap, one per row class
+};
+struct TrajGeom {
+    int sp;                                                      // lanes take every sp-th path; classes = sp*nx
+    int nchunks;                                                 // whole 16-point chunks every class has behind its head
+    int head[TRAJ_MAX_CLASSES];                                  // elements in front of the class's first sector boundary, 1..4
+};
 
 __device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d)
 {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
-
-template <class M, int SCHEME, int PROJ>
-__global__ void __launch_bounds__(TrajThreads<M::NX>::value, 1) k_traj(const RunArgs a, const int vec_ok, const int Q)
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double v0, double v1)
 {
-    constexpr int NX = M::NX, TRAJ_THREADS = TrajThreads<NX>::value;
-    extern __shared__ __align__(16) double sh_tab[];
-    // [quantile table, replicated][step table chunk: TRAJ_CHUNK x {dt, sqrt dt}][histogram]
-    double2 *sh_dt = reinterpret_cast<double2 *>(sh_tab + Icdf32Layout<TRAJ_REPL>::DOUBLES);
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_dt + TRAJ_CHUNK);
-    icdf32_stage<TRAJ_REPL>(sh_tab, a.icdf32, 1.0, threadIdx.x, TRAJ_THREADS);
-    NormalGen<TRAJ_REPL> gen;
-    gen.init(sh_tab, a.icdf, 1.0);
-    if (a.hist)
-        for (int i = threadIdx.x; i < a.hist_nbins + 3; i += TRAJ_THREADS) sh_hist[i] = 0u;
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
+}
+// swizzled byte offset of time slot s (0..15) of the lane's row inside a chunk; l7 = (lane & 7) << 4
+__device__ __forceinline__ uint32_t traj_slot(uint32_t lane_row, uint32_t l7, int s)
+{
+    return lane_row + ((((uint32_t)s >> 1) << 4) ^ l7) + (((uint32_t)s & 1u) << 3);
+}
+
+// The 16 values of body m (times 16m+1 .. 16m+16) of one component into the ring: slot u + D of chunk m, or slot
+// 16 + u + D of chunk m-1 when u + D < 0 (D = 1 - head in 0,-1,-2,-3); in body 0 those are head elements of the row.
+template <int D>
+__device__ __forceinline__ void traj_put(const double (&v)[16], uint32_t cur, uint32_t prev, uint32_t lane_row, uint32_t l7,
+                                         bool first, bool valid, double *grow)
+{
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int vs = u + D;                                    // slot in chunk m; negative: slot 16 + vs of chunk m-1
+        const bool even = (vs & 1) == 0, pair = even && u + 1 < 16;
+        if (!even && u != 0) continue;                           // second half of the pair stored at u - 1
+        if (vs < 0) {
+            if (first) {
+                if (valid) {
+                    grow[1 + u] = v[u];
+                    if (pair) grow[2 + u] = v[u + 1];
+                }
+            } else if (pair) sts_f64x2(prev + traj_slot(lane_row, l7, 16 + vs), v[u], v[u + 1]);
+            else sts_f64(prev + traj_slot(lane_row, l7, 16 + vs), v[u]);
+        } else if (pair) sts_f64x2(cur + traj_slot(lane_row, l7, vs), v[u], v[u + 1]);
+        else sts_f64(cur + traj_slot(lane_row, l7, vs), v[u]);
+    }
+}
+
+template <class M, int SCHEME, int PROJ, bool UNIFORM>
+__global__ void __launch_bounds__(TRAJ_MAX_THREADS, 1)
+k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps, const __grid_constant__ TrajGeom geo)
+{
+    constexpr int NX = M::NX, CH = TRAJ_CH, NSLOT = TRAJ_NSLOT;
+    constexpr uint32_t CHUNK = 4096u, RING = NSLOT * CHUNK;
+    using FS = FastStep<M, SCHEME, PROJ>;
+    using TL = Icdf32Layout<TRAJ_REPL>;
+    extern __shared__ __align__(1024) unsigned char sh_raw[];    // [rings: warps x NX x NSLOT chunks][quantile table][histogram][scratch]
+    const int nthreads = blockDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+    double *sh_tab = reinterpret_cast<double *>(sh_raw + (size_t)nwarps * NX * RING);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + TL::DOUBLES);
+    const int nhist = a.hist ? ((a.hist_nbins + 3 + 3) & ~3) : 0;
+    icdf32_stage<TRAJ_REPL>(sh_tab, a.icdf32, UNIFORM ? a.ucoef[0] : 1.0, threadIdx.x, nthreads);
+    for (int i = threadIdx.x; i < nhist; i += nthreads) sh_hist[i] = 0u;
     __syncthreads();
+    NormalGen<TRAJ_REPL> gen;
+    gen.init(sh_tab, a.icdf, UNIFORM ? a.ucoef[0] : 1.0);
     double acc[NX][5];
 #pragma unroll
     for (int j = 0; j < NX; ++j)
 #pragma unroll
         for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
 
-    const int nsteps = a.nt - 1, ngroups = nsteps >> 2;
-    const uint64_t stride = (uint64_t)gridDim.x * TRAJ_THREADS;
-    const uint64_t W = 32u * (unsigned)Q;                        // paths per lane-interleaved group of Q warps
-    const uint64_t Tmax = (a.npaths + W - 1) / W * W, nrounds = (Tmax + stride - 1) / stride;
-    for (uint64_t round = 0; round < nrounds; ++round) {         // every thread of the CTA runs every round: the step
-        const uint64_t T = round * stride + (uint64_t)blockIdx.x * TRAJ_THREADS + threadIdx.x;    // table is staged
-        const uint64_t within = T % W, p = (T - within) + (within >> 5) + (uint64_t)Q * (within & 31);        // cooperatively
+    const int nt = a.nt, nsteps = nt - 1, sp = geo.sp, nbody = geo.nchunks;
+    const uint32_t ring0 = smem_addr_u32(sh_raw) + (uint32_t)warp * NX * RING;
+    const uint32_t lane_row = (uint32_t)lane << 7, l7 = ((uint32_t)lane & 7u) << 4;
+    const CoefUniform cu{a.ucoef};
+    const uint64_t ntasks = (a.npaths + 31) >> 5;                // task T: paths {32*sp*(T/sp) + T%sp + sp*L, L = 0..31}
+    for (uint64_t T = (uint64_t)blockIdx.x * nwarps + warp; T < (ntasks + sp - 1) / sp * sp; T += (uint64_t)gridDim.x * nwarps) {
+        const uint64_t grp = T / (unsigned)sp;
+        const int w = (int)(T - grp * (unsigned)sp);
+        const uint64_t pbase = grp * 32u * (unsigned)sp + (unsigned)w;
+        if (pbase >= a.npaths) continue;
+        const uint64_t p = pbase + (uint64_t)sp * lane;
         const bool valid = p < a.npaths;
-        double x[NX], v[NX][4], pv[NX][4];
-        double *row[NX];                                         // &X[row start + 1]: stream position 0
-        int d[NX];
-        load_x0<NX>(a, valid ? p : 0, x);
+        const uint64_t pl = valid ? p : pbase, gp = a.path_offset + pl;
+        double x[NX];
+        load_x0<NX>(a, pl, x);
+        double *grow[NX];
+        int hd[NX];
 #pragma unroll
         for (int j = 0; j < NX; ++j) {
-            const uint64_t e0 = (p * NX + j) * (uint64_t)a.nt;
-            row[j] = a.X + e0 + 1;
-            d[j] = vec_ok ? (int)((e0 + 1) & 3) : 4;             // 4: element-wise stores only
-            if (valid && (d[j] != 1 || ngroups == 0)) a.X[e0] = x[j];   // X[1,] <- x0 (:441); with d = 1 it opens the first
-                                                                         // sector (if there is one: nt >= 5)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) pv[j][k] = x[j];
+            grow[j] = a.X + (pl * NX + j) * (uint64_t)nt;
+            hd[j] = geo.head[w * NX + j];
+            if (valid) grow[j][0] = x[j];                        // X[1,] <- x0 (:441)
         }
-        const uint64_t gp = a.path_offset + p;
-        for (int m = 0; m < ngroups; ++m) {
-            // {dt_i, sqrt dt_i} through shared memory, TRAJ_CHUNK steps at a time: global loads of the table queue
-            // behind this SM's scattered sector stores in the LSU (measured: 29 % long-scoreboard stalls)
-            if ((m & (TRAJ_CHUNK / 4 - 1)) == 0) {
-                __syncthreads();
-                for (int i = threadIdx.x; i < TRAJ_CHUNK && 4 * m + i < nsteps; i += TRAJ_THREADS) sh_dt[i] = __ldg(&a.dtsq[4 * m + i]);
-                __syncthreads();
+        uint32_t r[4][4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) philox_block(a.seed, gp, (uint32_t)b, 0u, r[b][0], r[b][1], r[b][2], r[b][3]);
+        int issued = 0;
+        uint32_t cur = 0u, prev = (NSLOT - 1) * CHUNK;           // ring offsets of chunks m and m-1
+        for (int m = 0; m < nbody; ++m) {
+            double v[NX][16], z[16];
+            gen.template multi<4>(a.seed, gp, (uint32_t)(4 * m), 0u, r, z);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {                        // words of the next body: integer work under the FP64 chain
+                philox_block(a.seed, gp, (uint32_t)(4 * (m + 1) + b), 0u, r[b][0], r[b][1], r[b][2], r[b][3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (UNIFORM) FS::apply(a.P, x, cu, z[4 * b + k]);
+                    else {
+                        CoefRow row;
+                        row.load(a.coef + (size_t)(16 * m + 4 * b + k) * FAST_NCOEF);
+                        FS::apply(a.P, x, row, row[0] * z[4 * b + k]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) v[j][4 * b + k] = x[j];
+                }
             }
-            if (!valid) continue;
-            double2 dts[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dts[k] = sh_dt[4 * (m & (TRAJ_CHUNK / 4 - 1)) + k];
-            double z[4];                                         // one Philox block per group of four steps
-            {
-                uint32_t r[4];
-                philox_block(a.seed, gp, (uint32_t)m, 0u, r[0], r[1], r[2], r[3]);
-                gen.quad(a.seed, gp, (uint32_t)m, 0u, r, z);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dts[k].x, dts[k].y * z[k]);
-#pragma unroll
-                for (int j = 0; j < NX; ++j) v[j][k] = x[j];
+            if (m % CH == 0) {                                   // entering the ring half the store before last read from
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
             }
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
-                double *g = row[j] + 4 * (int64_t)m;             // stream position 4m
-                if (d[j] == 4 || (m == 0 && d[j] >= 2)) {        // no vector store possible: the sector starts before the row
-                    const int n = d[j] == 4 ? 4 : 4 - d[j];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k < n) g[k] = v[j][k];
-                } else if (d[j] == 0) st_sector(g, v[j][0], v[j][1], v[j][2], v[j][3]);
-                else if (d[j] == 1) st_sector(g - 1, pv[j][3], v[j][0], v[j][1], v[j][2]);
-                else if (d[j] == 2) st_sector(g - 2, pv[j][2], pv[j][3], v[j][0], v[j][1]);
-                else st_sector(g - 3, pv[j][1], pv[j][2], pv[j][3], v[j][0]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) pv[j][k] = v[j][k];
-            }
-        }
-        if (!valid) continue;
-        // values of the last group that opened a sector the row does not complete in a full group
-        if (ngroups > 0) {
-#pragma unroll
-            for (int j = 0; j < NX; ++j)
-                if (d[j] >= 1 && d[j] <= 3) {
-#pragma unroll
-                    for (int k = 1; k < 4; ++k)
-                        if (k >= 4 - d[j]) row[j][4 * (int64_t)(ngroups - 1) + k] = pv[j][k];
+                const uint32_t rj = ring0 + (uint32_t)j * RING;
+                switch (hd[j]) {                                 // warp-uniform
+                case 1: traj_put<0>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
+                case 2: traj_put<-1>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
+                case 3: traj_put<-2>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
+                default: traj_put<-3>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
                 }
+            }
+            if (m > 0 && m % CH == 0) {                          // chunks m-CH .. m-1 are complete for every component
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j)
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                     ::"l"(&maps.m[w * NX + j]), "r"(0), "r"((int)(grp * 32u)), "r"(m - CH),
+                                       "r"(ring0 + (uint32_t)j * RING + (uint32_t)((m - CH) % NSLOT) * CHUNK) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                issued = m;
+            }
+            prev = cur;
+            cur = cur + CHUNK == RING ? 0u : cur + CHUNK;
         }
-        if (4 * ngroups < nsteps) {                               // up to three trailing steps, element-wise
+        // the steps behind the last whole body (< 16 + 3 of them): slots of chunk nbody-1 still go to the ring, the
+        // rest of the row is written element by element
+        for (int i = 16 * nbody; i < nsteps; i += 4) {
             double z[4];
-            {
-                uint32_t r[4];
-                philox_block(a.seed, gp, (uint32_t)ngroups, 0u, r[0], r[1], r[2], r[3]);
-                gen.quad(a.seed, gp, (uint32_t)ngroups, 0u, r, z);
-            }
+            if (i != 16 * nbody) philox_block(a.seed, gp, (uint32_t)(i >> 2), 0u, r[0][0], r[0][1], r[0][2], r[0][3]);
+            gen.quad(a.seed, gp, (uint32_t)(i >> 2), 0u, r[0], z);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int i = 4 * ngroups + k;
-                if (i < nsteps) {
-                    const double2 dt = __ldg(&a.dtsq[i]);
-                    sde_step<M, SCHEME, PROJ, Fast>(a.P, x, dt.x, dt.y * z[k]);
+            for (int k = 0; k < 4; ++k)
+                if (i + k < nsteps) {
+                    if (UNIFORM) FS::apply(a.P, x, cu, z[k]);
+                    else {
+                        CoefRow row;
+                        row.load(a.coef + (size_t)(i + k) * FAST_NCOEF);
+                        FS::apply(a.P, x, row, row[0] * z[k]);
+                    }
+                    const int t = i + k + 1;
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) row[j][i] = x[j];
+                    for (int j = 0; j < NX; ++j) {
+                        const int s = t - hd[j];
+                        if (s >= 0 && s < 16 * nbody) sts_f64(ring0 + (uint32_t)j * RING + prev + traj_slot(lane_row, l7, s & 15), x[j]);
+                        else if (valid) grow[j][t] = x[j];
+                    }
                 }
+        }
+        if (issued < nbody) {                                    // the last 1..CH chunks (the box is clipped at nbody chunks)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                 ::"l"(&maps.m[w * NX + j]), "r"(0), "r"((int)(grp * 32u)), "r"(issued),
+                                   "r"(ring0 + (uint32_t)j * RING + (uint32_t)(issued % NSLOT) * CHUNK) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
-        if (a.XT) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (valid) {
+            if (a.XT) {
 #pragma unroll
-            for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+                for (int j = 0; j < NX; ++j) a.XT[p * NX + j] = x[j];
+            }
+            accumulate_terminal<NX>(a, x, acc, sh_hist);
         }
-        accumulate_terminal<NX>(a, x, acc, sh_hist);
     }
-    flush_block_stats<NX, TRAJ_THREADS>(a, acc, sh_hist);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    flush_block_stats_dyn<NX>(a, acc, sh_hist, reinterpret_cast<double *>(sh_hist + nhist));
 }
 
 // ---- supplied-B kernel: Brownian paths in, trajectory and/or terminal state out ----------------

@@ -198,6 +198,32 @@ template <int SCHEME, int PROJ> struct FastStep<Model<SDEGPU_MODEL_OU>, SCHEME, 
     }
 };
 
+// van der Pol: the recurrence's critical cycle is what a kernel with few warps per SM waits for, so the step is grouped for
+// depth, not for operation count.  row = {sigma sqrt(dt), dt, 1 + mu dt, mu, dt/2}, w = row[0] z.
+//   Euler   X0' = x0 + dt x1                                     (depth 1)
+//           X1' = x1 (1 + mu dt - dt x0^2) + (w - dt x0)          (depth 3 from x0, 1 from x1)
+//   Heun    the predictor as written in the reference, then the trapezoid with g constant (0.5 (g + g) dB = w)
+template <int SCHEME, int PROJ> struct FastStep<Model<SDEGPU_MODEL_VDP>, SCHEME, PROJ> {
+    template <class C> static __device__ __forceinline__ void apply(const KParams &, double (&x)[2], const C &c, double w)
+    {
+        if (SCHEME == SDEGPU_EULER) {
+            const double t = c[1] * x[0];
+            const double a = fma(-t, x[0], c[2]);
+            const double b = fma(-c[1], x[0], w);
+            const double n0 = fma(x[1], c[1], x[0]);
+            x[1] = project<PROJ>(fma(x[1], a, b));
+            x[0] = project<PROJ>(n0);
+            return;
+        }
+        const double xw = x[1] + w;
+        const double u = fma(x[1], fma(-x[0], x[0], c[3]), -x[0]);
+        const double Y0 = project<PROJ>(fma(x[1], c[1], x[0])), Y1 = project<PROJ>(fma(u, c[1], xw));
+        const double uY = fma(Y1, fma(-Y0, Y0, c[3]), -Y0);
+        x[0] = project<PROJ>(fma(c[4], x[1] + Y1, x[0]));
+        x[1] = project<PROJ>(fma(c[4], u + uY, xw));
+    }
+};
+
 // host side: the coefficient row of one step
 inline void fast_step_coefficients(int model, const double *p, double dt, double sq, double *c)
 {
@@ -206,6 +232,8 @@ inline void fast_step_coefficients(int model, const double *p, double dt, double
         const double lam = p[0], xi = p[1], vol = p[2];
         c[0] = model == SDEGPU_MODEL_CIR ? 0.5 * vol * sq : vol * sq;
         c[1] = 1.0 - lam * dt; c[2] = lam * xi * dt; c[3] = 1.0 - 0.5 * lam * dt; c[4] = 0.5 * lam * dt;
+    } else if (model == SDEGPU_MODEL_VDP) {
+        c[0] = p[1] * sq; c[1] = dt; c[2] = 1.0 + p[0] * dt; c[3] = p[0]; c[4] = 0.5 * dt;
     } else {
         c[0] = sq; c[1] = dt;
     }

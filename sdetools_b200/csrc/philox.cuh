@@ -282,18 +282,36 @@ template <int REPL> struct NormalGen {
         scale = scale_;
     }
 
+    // (exponent, 5 mantissa bits) of |s| for the exact integer-valued double s = (w|1) - 2^31
+    static __device__ __forceinline__ double word_to_s(uint32_t w) { return __hiloint2double(0x43300000, (int)(w | 1u)) - 4503601774854144.0; }
+    static __device__ __forceinline__ uint32_t seg_bits(double s) { return (uint32_t)__double2hiint(s) & 0x7FFF8000u; }
+
+    // does the block hold a tail draw (some |s| < 2^19, 1 block in ~1000)?
+    static __device__ __forceinline__ bool has_tail(const uint32_t (&r)[4])
+    {
+        const uint32_t x0 = seg_bits(word_to_s(r[0])), x1 = seg_bits(word_to_s(r[1])), x2 = seg_bits(word_to_s(r[2])), x3 = seg_bits(word_to_s(r[3]));
+        return min(min(x0, x1), min(x2, x3)) < 0x41200000u;
+    }
+
+    // scale * z of one bulk word (|s| >= 2^19): two 128-bit shared loads, three FMAs, the sign by LOP3
+    __device__ __forceinline__ double bulk(uint32_t w) const
+    {
+        const double s = word_to_s(w);
+        const uint32_t addr = base + (seg_bits(s) >> (11 - L::LOG));
+        const double2 c01 = lds_f64x2(addr), c23 = lds_f64x2(addr + L::PLANE_BYTES);
+        const double v = fabs(s);
+        double a = fma(c23.y, v, c23.x);
+        a = fma(a, v, c01.y);
+        a = fma(a, v, c01.x);
+        // sign(s) onto scale*a(|s|) with one LOP3 (an XOR, so a negative scale keeps its meaning)
+        return __hiloint2double(__double2hiint(a) ^ (__double2hiint(s) & (int)0x80000000u), __double2loint(a));
+    }
+
     // scale * z for steps 4*block .. 4*block+3 of (path, channel) from the words of its Philox block
     __device__ __forceinline__ void quad(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
                                          const uint32_t (&r)[4], double (&z)[4]) const
     {
-        double s[4];
-        uint32_t xm[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            s[k] = __hiloint2double(0x43300000, (int)(r[k] | 1u)) - 4503601774854144.0;   // 2^52 + (w|1) - (2^52 + 2^31), exact
-            xm[k] = (uint32_t)__double2hiint(s[k]) & 0x7FFF8000u;                         // (exponent, 5 mantissa bits) of |s|
-        }
-        if (min(min(xm[0], xm[1]), min(xm[2], xm[3])) < 0x41200000u) {                    // some |s| < 2^19: a tail draw
+        if (has_tail(r)) {
             double zt[4];                                        // its address is taken: kept apart from z, which stays in registers
             icdf32_tail_quad(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, r[0], r[1], r[2], r[3],
                              g52, scale, zt);
@@ -301,16 +319,32 @@ template <int REPL> struct NormalGen {
             for (int k = 0; k < 4; ++k) z[k] = zt[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t addr = base + (xm[k] >> (11 - L::LOG));
-                const double2 c01 = lds_f64x2(addr), c23 = lds_f64x2(addr + L::PLANE_BYTES);
-                const double v = fabs(s[k]);
-                double a = fma(c23.y, v, c23.x);
-                a = fma(a, v, c01.y);
-                a = fma(a, v, c01.x);
-                // sign(s) onto scale*a(|s|) with one LOP3 (an XOR, so a negative scale keeps its meaning)
-                z[k] = __hiloint2double(__double2hiint(a) ^ (__double2hiint(s[k]) & (int)0x80000000u), __double2loint(a));
+            for (int k = 0; k < 4; ++k) z[k] = bulk(r[k]);
+        }
+    }
+
+    // the same for NB consecutive blocks with ONE branch: the bulk case is a single basic block of 4*NB independent
+    // evaluations that the scheduler can interleave (kernels that run few warps per SM need the ILP)
+    template <int NB>
+    __device__ __forceinline__ void multi(const PhiloxKey &key, uint64_t path, uint32_t block0, uint32_t channel,
+                                          const uint32_t (&r)[NB][4], double (&z)[4 * NB]) const
+    {
+        bool tail = false;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) tail |= has_tail(r[b]);
+        if (tail) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                double zq[4];
+                quad(key, path, block0 + (uint32_t)b, channel, r[b], zq);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[4 * b + k] = zq[k];
             }
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[4 * b + k] = bulk(r[b][k]);
         }
     }
 };

@@ -938,11 +938,12 @@ def test_fuzz_shapes_fused_generator(eng):
     """Random small shapes through the generator kernels: the trajectory kernel, the register-resident kernel and the
     oracle's loop fed with the device's normals must agree (1e-12), for nt from 2 and path counts around the warp size."""
     rng = np.random.default_rng(77)
-    for it in range(40):
+    for it in range(80):
         model, params, x0, proj = CASES[int(rng.integers(len(CASES)))]
         scheme = ("euler", "heun")[int(rng.integers(2))]
-        nt = int(rng.choice([2, 3, 4, 5, 6, 8, 9, 13, 40]))
-        P = int(rng.choice([1, 5, 31, 33, 100]))
+        # nt around the trajectory kernel's 16-point chunks, its two-chunk stores and its four-slot ring
+        nt = int(rng.choice([2, 3, 4, 5, 6, 8, 9, 13, 17, 18, 19, 20, 21, 33, 36, 40, 53, 70, 85, 99, 100, 101, 102, 131]))
+        P = int(rng.choice([1, 5, 31, 33, 64, 65, 100, 129, 257]))
         nx, seed, off = len(x0), int(rng.integers(1 << 30)), int(rng.integers(1 << 40))
         t = np.concatenate(([0.0], np.cumsum(rng.uniform(0.002, 0.03, nt - 1))))
         X = np.empty((nt, nx, P), order="F")
@@ -952,8 +953,14 @@ def test_fuzz_shapes_fused_generator(eng):
         z = eng.normals(seed, off, P, nt - 1)
         dB = (np.sqrt(O.r_diff(t))[:, None] * z)[:, None, :]
         want = O.ensemble(scheme, model, params, t, x0, dB=dB, proj=proj)
-        assert np.allclose(X, want, rtol=1e-12, atol=1e-13), (it, model, scheme, nt, P)
-        assert np.allclose(XT, X[-1], rtol=1e-10, atol=1e-12), (it, model, scheme, nt, P)   # folded step: FAST tolerance
+        # a path that a projection held at (or rounding put within 1e-6 of) zero has no 1e-12 bar under sqrt noise: the
+        # next increment g(x) dB = gamma sqrt(x) dB turns a last-bit difference at x ~ 0 into sqrt(1e-16) ~ 1e-8
+        calm = np.abs(want).min(axis=(0, 1)) > 1e-6 if model == "cir" else np.ones(P, bool)
+        # CIR takes the folded step with the second-order square root (models.cuh FastStep, 2e-14 per step): FAST bar 1e-10
+        rtol = 1e-10 if model == "cir" else 1e-12
+        assert np.allclose(X[..., calm], want[..., calm], rtol=rtol, atol=1e-13), (it, model, scheme, nt, P)
+        assert np.allclose(X, want, rtol=1e-6, atol=1e-6), (it, model, scheme, nt, P)
+        assert np.array_equal(XT, X[-1]), (it, model, scheme, nt, P)   # both kernels take the folded FAST step
 
 
 def test_fuzz_shapes_killed_functionals_linear(sde, eng):

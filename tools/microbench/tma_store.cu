@@ -71,14 +71,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_fill(double* X, size_t n4) {
 }
 
 // 3-D box: [16 doubles][32 rows][NCH chunks] -> NCH*128 bytes per row in one TMA store
-template <int NCH>
-__global__ void __launch_bounds__(256, 1) k_tma3(const __grid_constant__ Maps maps, int Q, int nq, int nt) {
+template <int NCH, int NW = 8>
+__global__ void __launch_bounds__(NW * 32, 1) k_tma3(const __grid_constant__ Maps maps, int Q, int nq, int nt) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int TILE = NCH * 32 * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* tile = smem + warp * TILE;
     const int wpc = (nq + 31) / 32, nwarps = Q * wpc;
-    for (int gw = blockIdx.x * 8 + warp; gw < nwarps; gw += gridDim.x * 8) {
+    for (int gw = blockIdx.x * NW + warp; gw < nwarps; gw += gridDim.x * NW) {
         const int cls = gw / wpc, q0 = (gw - cls * wpc) * 32;
         const int head = maps.head[cls];
         double x = 1.0 + lane;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, 1) k_tma3(const __grid_constant__ Maps ma
 }
 
 // reference: per-lane 256-bit sector stores, 4 doubles per lane per store
-template <int HINT>
+template <int HINT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_stg(double* X, int Q, int nq, int nt, const int* heads) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = (nq + 31) / 32, nwarps = Q * wpc;
@@ -198,13 +198,18 @@ int main(int argc, char** argv) {
         CK(cudaGetLastError());
         printf("%-44s %8.3f ms  %8.1f GB/s\n", name, best, bytes / best / 1e6);
     };
-    timeit("per-lane STG.256 sectors", [&] { k_stg<0><<<sm, THREADS>>>(X, Q, nq, nt, dheads); });
-    timeit("per-lane STG.256 sectors .cs", [&] { k_stg<1><<<sm, THREADS>>>(X, Q, nq, nt, dheads); });
-    timeit("per-lane STG.256 sectors evict_last", [&] { k_stg<2><<<sm, THREADS>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors, 16 warps", [&] { k_stg<0, 512><<<sm, 512>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors, 12 warps", [&] { k_stg<0, 384><<<sm, 384>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors, 8 warps", [&] { k_stg<0, 256><<<sm, 256>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors, 6 warps", [&] { k_stg<0, 192><<<sm, 192>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors, 4 warps", [&] { k_stg<0, 128><<<sm, 128>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors, 2 warps", [&] { k_stg<0, 64><<<sm, 64>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors .cs, 8 warps", [&] { k_stg<1, 256><<<sm, 256>>>(X, Q, nq, nt, dheads); });
+    timeit("per-lane STG.256 sectors evict_last, 8 warps", [&] { k_stg<2, 256><<<sm, 256>>>(X, Q, nq, nt, dheads); });
     timeit("coalesced fill (write ceiling)", [&] { k_fill<<<sm * 4, THREADS>>>(X, (size_t)rows * nt / 4); });
     timeit("cudaMemsetAsync", [&] { CK(cudaMemsetAsync(X, 0, (size_t)rows * nt * 8)); });
     // 3-D boxes: NCH x 128 bytes per row per TMA store
-    auto run3 = [&](auto kern, int nch, const char* name) {
+    auto run3 = [&](auto kern, int nch, const char* name, int nw = 8) {
         Maps maps;
         for (int c = 0; c < Q; ++c) {
             const int phi = (int)(((long long)c * nt) % 4), head = (4 - phi) % 4;
@@ -216,14 +221,22 @@ int main(int argc, char** argv) {
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { printf("encode3 failed %d\n", (int)r); exit(1); }
         }
-        const int smem = 8 * nch * 4096;
+        const int smem = nw * nch * 4096;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        timeit(name, [&] { kern<<<sm, 256, smem>>>(maps, Q, nq, nt); });
+        timeit(name, [&] { kern<<<sm, nw * 32, smem>>>(maps, Q, nq, nt); });
     };
     run3(k_tma3<1>, 1, "tma 3-D box 128 B/row, 8 warps");
     run3(k_tma3<2>, 2, "tma 3-D box 256 B/row, 8 warps");
     run3(k_tma3<4>, 4, "tma 3-D box 512 B/row, 8 warps");
     run3(k_tma3<6>, 6, "tma 3-D box 768 B/row, 8 warps");
+    run3(k_tma3<1, 16>, 1, "tma 3-D box 128 B/row, 16 warps", 16);
+    run3(k_tma3<2, 16>, 2, "tma 3-D box 256 B/row, 16 warps", 16);
+    run3(k_tma3<1, 4>, 1, "tma 3-D box 128 B/row, 4 warps", 4);
+    run3(k_tma3<2, 4>, 2, "tma 3-D box 256 B/row, 4 warps", 4);
+    run3(k_tma3<4, 4>, 4, "tma 3-D box 512 B/row, 4 warps", 4);
+    run3(k_tma3<12, 4>, 12, "tma 3-D box 1536 B/row, 4 warps", 4);
+    run3(k_tma3<2, 2>, 2, "tma 3-D box 256 B/row, 2 warps", 2);
+    run3(k_tma3<8, 2>, 8, "tma 3-D box 1024 B/row, 2 warps", 2);
     CK(cudaDeviceSynchronize());
     return 0;
 }
