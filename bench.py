@@ -31,6 +31,15 @@ FLOPS_PER_PATH_STEP = 85.0
 CIR = dict(lam=1.0, xi=1.0, gamma=1.0, x0=1.0, T=1.0, seed=0x5DE70015, hist=(0.0, 8.0, 256))
 
 
+def load_profile(name):
+    """A committed profile summary under profiles/ (what the `executed` block of the roofline cites), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -118,7 +127,7 @@ def run_reference(args):
         cpu_leg(sample_paths, args.nsteps, cores)
     wall = time.perf_counter() - t0
     value = args.steps * sample_paths * args.nsteps / wall
-    sample = f"{sample_paths} of {args.paths} paths x {args.nsteps} steps per step (CIR heun, fused Philox+Box-Muller, terminal state)"
+    sample = f"{sample_paths} of {args.paths} paths x {args.nsteps} steps per step (CIR heun, fused Philox + table-inversion normals, terminal state); value is a rate over this sample"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -228,7 +237,16 @@ def run_ours(args):
         value = world * args.steps * P * nsteps / (total_ms * 1e-3)
         k_ms = float(np.mean(kernel_ms))
         fp64_peak = eng.measure_fp64_peak()
-        achieved = FLOPS_PER_PATH_STEP * P * nsteps / (k_ms * 1e-3) / 1e12
+        rate_k = P * nsteps / (k_ms * 1e-3)                       # path-steps/s of the kernel alone
+        sass, ncu = load_profile("r2_sass_k_terminal.json"), load_profile("r2_ncu_k_terminal.json")
+        sass = sass if isinstance(sass, dict) else {}
+        ncu = ncu[0] if isinstance(ncu, list) and ncu else {}
+        n64, nins = sass.get("fp64_per_path_step"), sass.get("instructions_per_path_step")
+        # FP64 pipe: one warp instruction holds a sub-partition's 16 FP64 lanes for 2 cycles, so the DFMA stream that
+        # measures `peak` (2 flops per slot) is also the pipe's slot rate; `achieved` = executed FP64-pipe slots x 2
+        achieved = 2.0 * n64 * rate_k / 1e12 if n64 else None
+        issue_peak = eng.info["sm_count"] * 4 * eng.info["clock_khz"] * 1e3          # warp instructions/s, 4 schedulers per SM
+        issue_achieved = nins * rate_k / 32.0 if nins else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -247,15 +265,27 @@ def run_ours(args):
                     "api": "sdetools_b200.heun(f, g, times, x0, p=abs, npaths=..., hist=..., moments=True) with host buffers"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None,
-                         "executed": {"fp64_pipe_busy": 0.477, "issue_slots_busy": 0.673, "instructions_per_path_step": 71.3,
-                                      "source": "ncu --set full, profiles/r1_ncu_k_terminal_cir_heun.txt: the kernel is issue-bound; "
-                                                "`frac` credits the survey's algorithmic flop count, not executed FP64 instructions"},
-                         "traffic": 607232, "traffic_source": "ncu --set full dram__bytes_read+write per launch "
-                                                              "(profiles/r1_ncu_k_terminal_cir_heun.txt): tables only, no path data",
+                         "frac": achieved / fp64_peak if fp64_peak and achieved else None,
+                         "definition": "FP64-pipe utilisation: FP64 instructions in the kernel's SASS step loop (DFMA/DADD/DMUL/DSETP, "
+                                       "tools/sass_count.py -> profiles/r2_sass_k_terminal.json) x live path-steps/s x 2, over the DFMA-stream "
+                                       "peak measured in this run; not the survey's 85-flop convention (VERDICT r1 weak #2)",
+                         "executed": {"fp64_instructions_per_path_step": n64, "instructions_per_path_step": nins,
+                                      "fp64_flops_per_path_step": sass.get("fp64_flops_per_path_step"),
+                                      "fp64_tflops_true": sass.get("fp64_flops_per_path_step", 0) * rate_k / 1e12 if sass else None,
+                                      "issue_slots": {"achieved_warp_inst_per_s": issue_achieved, "peak_warp_inst_per_s": issue_peak,
+                                                      "frac": issue_achieved / issue_peak if issue_achieved else None,
+                                                      "note": "the binding bound: 4 schedulers x 1 instruction per cycle per SM"},
+                                      "ncu": {"fp64_pipe_busy_pct": ncu.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                                              "issue_active_pct": ncu.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                              "warps_active_pct": ncu.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                                              "stalls_pct": ncu.get("stalls_pct"),
+                                              "source": "profiles/r2_ncu_k_terminal.json (ncu --set full, tools/prof_terminal.py)"}},
+                         "traffic": (ncu.get("dram__bytes_read.sum_bytes") or 0) + (ncu.get("dram__bytes_write.sum_bytes") or 0) or None,
+                         "traffic_source": "ncu --set full dram__bytes_read+write per launch: tables only, no path data",
                          "kernel": "k_terminal<cir,heun,abs>", "kernel_ms": k_ms,
                          "peak_source": "sdegpu_measure_fp64_peak: DFMA stream measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                         "flops_convention": "85 algorithmic FP64 flops per path-step (SURVEY.md §8d)",
+                         "survey_convention": {"flops_per_path_step": FLOPS_PER_PATH_STEP, "tflops": FLOPS_PER_PATH_STEP * rate_k / 1e12,
+                                               "note": "SURVEY 8(d) Box-Muller-priced count, kept for comparison with round 1 only"},
                          "hbm_peak_gbs_measured_file": peaks.get("hbm_gbs")},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cpu_paths} of {P} paths x {nsteps} steps, {cpu_s:.1f} s (plain-C oracle, OpenMP)",

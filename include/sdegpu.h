@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDEGPU_ABI_VERSION 4
+#define SDEGPU_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define SDEGPU_API __attribute__((visibility("default")))
@@ -41,7 +41,8 @@ typedef enum {
     SDEGPU_ERR_ARG = -1,      /* invalid argument / unsupported combination */
     SDEGPU_ERR_CUDA = -2,     /* CUDA runtime failure (message has the cudaError string) */
     SDEGPU_ERR_NOMEM = -3,    /* device or host allocation failed */
-    SDEGPU_ERR_NODEVICE = -4  /* no sm_100 device / wrong architecture */
+    SDEGPU_ERR_NODEVICE = -4, /* no sm_100 device / wrong architecture */
+    SDEGPU_ERR_INTERRUPT = -5 /* the interrupt callback asked to stop (sdegpu_set_interrupt); outputs are undefined */
 } sdegpu_status;
 
 /* Model catalogue: drift/diffusion closures cannot be arbitrary R functions on
@@ -123,6 +124,15 @@ typedef struct {
     double S0;                /* initial survival (reference default 1) */
     const double *Stau;       /* per-path thresholds Stau[p] (the reference draws runif(1) per call), or NULL: drawn
                                  in-kernel from Philox, counter (path, 0, 0xC0000000) */
+    /* --- ABI 5: time-dependent drift and diffusion.  The reference takes f(t,x) and g(t,x) (R/sdetools.R:381-394) and
+     * evaluates them on the grid only: f(times[i], X_i), and in heun() also f(times[i+1], Y) (:316-323).  A closure of the
+     * form  f(t,x) = f0(x) + c(t),  g(t,x) = s(t) * g0(x)  with catalogue f0, g0 is therefore fully described by its
+     * values on the grid, which the caller tabulates (the R wrapper calls the closures c, s at `times`):
+     *   drift_forcing   host, nt x nx column-major, c[j*nt + i] = c_j(times[i])   e.g. F*sin(2*t) of the example at :211,:363
+     *   diffusion_scale host, nt, s[i] = s(times[i])
+     * Either may be NULL.  Operation order: fX = f0(X) + c_i (one rounded add after the catalogue drift), gX = s_i * g0(X). */
+    const double *drift_forcing;
+    const double *diffusion_scale;
 } sdegpu_problem;
 
 /* Caller-allocated outputs; any pointer may be NULL. */
@@ -151,6 +161,11 @@ typedef struct {
     double *S;                /* nt*npaths, S[p*nt + i]: S[0] = S0, S_{i+1} = S_i exp(-r(X_i) dt_i) up to tau; after an h-stop the
                                  entry at tau reads 0 (the reference's S <- numeric(nt) is never written there); NaN after tau.
                                  For one path S[0 .. k-1] with times[k-1] = tau is exactly the reference's S[1:(i+1)]. */
+    /* --- ABI 5: integrals of the model's own drift and diffusion along each path, accumulated in the step loop like
+     * path_integrals (X must be NULL):  X_t - X_0 = itointegral(f(X),t) + itointegral(g(X),B) for an euler() path, the
+     * machine-precision identity of vignettes/ItoIntegrals.Rmd:82-93 --- */
+    double *model_integrals;  /* 2*nx*npaths, [(p*nx+j)*2 + k]: terminal entries of k=0 itointegral(f_j(X), times),
+                                 k=1 itointegral(g_j(X), B)  (R/sdetools.R:155-158), f and g evaluated at (times[i], X_i) */
 } sdegpu_output;
 
 typedef struct {
@@ -164,6 +179,27 @@ SDEGPU_API const char *sdegpu_last_error(void);
 
 /* One context per process per GPU.  `device` is the CUDA ordinal. */
 SDEGPU_API int sdegpu_create(int device, sdegpu_ctx **ctx);
+/* One context over several GPUs of this process (sdegpu_create(devices, ndev); 8(e)).  devices = NULL
+ * means ordinals 0..ndev-1.  sdegpu_run on such a context splits the ensemble into ndev contiguous path ranges, one
+ * per device, each keyed by its global path ids (so every per-path output, and every histogram count, is identical to a
+ * one-device run); each range runs on its own host thread and stream; power sums and histogram counts are combined by
+ * ONE all-reduce over NVLink (NCCL, single-process ncclCommInitAll; loaded at run time) or, when libnccl cannot be
+ * loaded, summed on the host in device order.  Host pointers only (SDEGPU_DEVICE_PTRS is refused for ndev > 1); the other
+ * entry points run on devices[0]. */
+SDEGPU_API int sdegpu_create_multi(const int *devices, int ndev, sdegpu_ctx **ctx);
+SDEGPU_API int sdegpu_device_count(sdegpu_ctx *ctx);            /* ndev of the context */
+/* "nccl" / "host" / "none": how the last multi-device sdegpu_run combined its accumulators */
+SDEGPU_API const char *sdegpu_last_reduction(sdegpu_ctx *ctx);
+/* Long host-pointer runs are cut into path ranges (chunks) that go through the device one after another: inputs and
+ * outputs move through pinned staging buffers on their own copy streams while the next chunk computes, and between
+ * chunks `fn(user)` is called ON THE CALLING THREAD (R's API is single-threaded: the shim's callback wraps
+ * R_CheckUserInterrupt).  A non-zero return stops the run with SDEGPU_ERR_INTERRUPT.  fn = NULL removes it.
+ * Chunking never changes a per-path result or a histogram count: the generator is keyed by global path id. */
+typedef int (*sdegpu_interrupt_fn)(void *user);
+SDEGPU_API int sdegpu_set_interrupt(sdegpu_ctx *ctx, sdegpu_interrupt_fn fn, void *user);
+/* Paths per chunk of host-pointer runs: 0 = automatic (about 128 MB of bulk I/O per chunk; about 2e10 path-steps per
+ * chunk for runs without bulk I/O when an interrupt callback is set, otherwise one launch). */
+SDEGPU_API int sdegpu_set_chunk_paths(sdegpu_ctx *ctx, uint64_t paths);
 SDEGPU_API int sdegpu_destroy(sdegpu_ctx *ctx);
 SDEGPU_API int sdegpu_device_info(sdegpu_ctx *ctx, sdegpu_devinfo *info);
 /* Launch on a caller-owned cudaStream_t (e.g. torch's current stream; NULL = CUDA's default stream);

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libsdegpu.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 DEVICE_PTRS = 1
 ACCUMULATE = 2
 EXACT_GRID = 4
@@ -31,7 +31,7 @@ class Problem(C.Structure):
                 ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
                 ("kill_kind", C.c_int32), ("kill_comp", C.c_int32), ("kill_a", C.c_double), ("kill_b", C.c_double),
                 ("stop_kind", C.c_int32), ("stop_comp", C.c_int32), ("stop_lo", C.c_double), ("stop_hi", C.c_double),
-                ("S0", C.c_double), ("Stau", C.c_void_p)]
+                ("S0", C.c_double), ("Stau", C.c_void_p), ("drift_forcing", C.c_void_p), ("diffusion_scale", C.c_void_p)]
 
 
 class Output(C.Structure):
@@ -39,12 +39,16 @@ class Output(C.Structure):
                 ("power_sums", C.c_void_p), ("center", C.c_void_p), ("hist_counts", C.c_void_p),
                 ("hist_lo", C.c_double), ("hist_hi", C.c_double), ("hist_nbins", C.c_int32), ("reserved", C.c_int32),
                 ("elapsed_ms", C.c_void_p), ("tau", C.c_void_p), ("S_tau", C.c_void_p), ("path_integrals", C.c_void_p),
-                ("S", C.c_void_p)]
+                ("S", C.c_void_p), ("model_integrals", C.c_void_p)]
 
 
 class DevInfo(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
                 ("clock_khz", C.c_int32), ("global_mem_bytes", C.c_uint64)]
+
+
+INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)          # sdegpu_interrupt_fn
+ERR_INTERRUPT = -5
 
 
 class SdeGpuError(RuntimeError):
@@ -59,6 +63,11 @@ SYMBOLS = {
     "sdegpu_abi_version": (C.c_int, []),
     "sdegpu_last_error": (C.c_char_p, []),
     "sdegpu_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "sdegpu_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "sdegpu_device_count": (C.c_int, [_vp]),
+    "sdegpu_last_reduction": (C.c_char_p, [_vp]),
+    "sdegpu_set_interrupt": (C.c_int, [_vp, _vp, _vp]),
+    "sdegpu_set_chunk_paths": (C.c_int, [_vp, _u64]),
     "sdegpu_destroy": (C.c_int, [_vp]),
     "sdegpu_device_info": (C.c_int, [_vp, C.POINTER(DevInfo)]),
     "sdegpu_set_stream": (C.c_int, [_vp, _vp]),

@@ -30,8 +30,13 @@ def _catalogue_model(f, g):
     return fm, f.sdegpu_params, f.nx, f.nB
 
 
+def _tabulate(fn, times, width):
+    """fn evaluated at every grid time, as the reference's loop would (`ff(times[i], .)`): nt x width."""
+    return np.array([np.broadcast_to(np.asarray(fn(float(t)), dtype=np.float64).reshape(-1), (width,)) for t in times])
+
+
 def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist, arith,
-              device, path_offset, integrals=False):
+              device, path_offset, integrals=False, model_integrals=False):
     if h is not None and not hasattr(h, "sdegpu_stop"):
         raise TypeError("h must be a catalogue stop rule (catalogue.stop_below/stop_above/stop_outside)")
     if r is not None and not hasattr(r, "sdegpu_kill"):
@@ -75,12 +80,15 @@ def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, outpu
     if seed is None:
         seed = int(np.random.default_rng().integers(0, 2 ** 63))
     eng = default_engine(device)
-    if integrals and output == "path":
+    if (integrals or model_integrals) and output == "path":
         output = "terminal"                # the integrals are accumulated in the step loop instead of storing the path
+    forcing = _tabulate(f.sdegpu_forcing, times, nx) if getattr(f, "sdegpu_forcing", None) is not None else None
+    gscale = _tabulate(g.sdegpu_scale, times, 1)[:, 0] if getattr(g, "sdegpu_scale", None) is not None else None
     want_path = output == "path"
     if output not in ("path", "terminal", "none"):
         raise ValueError("output must be 'path', 'terminal' or 'none'")
     PI = np.empty((4, nx, npaths), order="F") if integrals else None
+    MI = np.empty((2, nx, npaths), order="F") if model_integrals else None
     X = np.empty((nt, nx, npaths), order="F") if want_path else None
     XT = np.empty((nx, npaths), order="F") if output in ("path", "terminal") else None
     ps = np.zeros((5, nx), order="F") if moments else None
@@ -94,8 +102,11 @@ def _simulate(scheme, f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, outpu
         Stau_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(Stau, dtype=np.float64), (npaths,)))
     eng.run(model, scheme, params, times, x0c, nx=nx, nB=nB, npaths=npaths, B=Bdev, projection=proj, arith=arith,
             seed=seed, path_offset=path_offset, X=X, XT=XT, power_sums=ps, center=center, hist_counts=hc, hist=hist,
-            kill=r, stop=h, S0=S0, Stau=Stau_arr, tau=tau, S_tau=S_tau, path_integrals=PI, S_path=S_path)
+            kill=r, stop=h, S0=S0, Stau=Stau_arr, tau=tau, S_tau=S_tau, path_integrals=PI, S_path=S_path,
+            model_integrals=MI, drift_forcing=forcing, diffusion_scale=gscale)
     res = {"times": times}
+    if MI is not None:                     # itointegral(f(X), times), itointegral(g(X), B): their sum is X_T - X_0 for euler()
+        res["model_integrals"] = {k: (MI[i] if ensemble else MI[i, :, 0]) for i, k in enumerate(("drift", "noise"))}
     if PI is not None:                     # terminal entries of the reference's integral functions on each path
         res["integrals"] = {k: (PI[i] if ensemble else PI[i, :, 0]) for i, k in enumerate(("QV", "ito", "strat", "time"))}
     if killed:
@@ -141,7 +152,8 @@ def moments_from_power_sums(ps, center):
 
 
 def euler(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *, npaths=None, seed=None,
-          output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0, integrals=False):
+          output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0, integrals=False,
+          model_integrals=False):
     """Euler-Maruyama for the Ito SDE dX = f dt + g dB (R/sdetools.R:375-470).
 
     With the reference's arguments only, returns dict(times=, X=) with X the `nt x nx` matrix of one
@@ -152,16 +164,21 @@ def euler(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *,
     `moments=True` / `hist=(lo, hi, nbins[, component])` reduce the terminal states on the device.
     `integrals=True` accumulates, in the step loop and without storing the path, the terminal entries of
     QuadraticVariation(X_j), itointegral(X_j,B), stochint(X_j,B,"c") and itointegral(X_j,times) for every path
-    and component: res["integrals"] = {"QV","ito","strat","time"}, each nx x npaths (nB = 1 models)."""
+    and component: res["integrals"] = {"QV","ito","strat","time"}, each nx x npaths (nB = 1 models).
+    `model_integrals=True` does the same for the model's own drift and diffusion: res["model_integrals"] = {"drift":
+    itointegral(f(X),times)[nt], "noise": itointegral(g(X),B)[nt]} (vignettes/ItoIntegrals.Rmd:82-93).
+    Time-dependent closures: f = catalogue.forced(f0, c), g = catalogue.scaled(g0, s) (R/sdetools.R:381-394).
+    `device` may be a list of CUDA ordinals: the ensemble is then split over those GPUs (sdegpu_create_multi)."""
     return _simulate("euler", f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist,
-                     arith, device, path_offset, integrals)
+                     arith, device, path_offset, integrals, model_integrals)
 
 
 def heun(f, g, times, x0, B=None, p=None, h=None, r=None, S0=1.0, Stau=None, *, npaths=None, seed=None,
-         output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0, integrals=False):
+         output="path", moments=False, center=None, hist=None, arith=None, device=None, path_offset=0, integrals=False,
+         model_integrals=False):
     """Heun's method for the Stratonovich SDE dX = f dt + g o dB (R/sdetools.R:240-338); see `euler`."""
     return _simulate("heun", f, g, times, x0, B, p, h, r, S0, Stau, npaths, seed, output, moments, center, hist,
-                     arith, device, path_offset, integrals)
+                     arith, device, path_offset, integrals, model_integrals)
 
 
 # ---- integrals ------------------------------------------------------------------

@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write("\n".join(logs))
     objs = [os.path.join(OBJ, u[0]) for u in units]
     cmd = [nvcc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-           "-Xlinker", "--exclude-libs,ALL"]
+           "-Xlinker", "--exclude-libs,ALL", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

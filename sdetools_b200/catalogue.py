@@ -26,7 +26,15 @@ class CatalogueFunction:
         self.nx, self.nB = nx, nB
 
     def __call__(self, *args):          # f(x) or f(t,x), like the reference accepts (:381-394)
-        return self.fn(np.asarray(args[-1], dtype=np.float64))
+        v = self.fn(np.asarray(args[-1], dtype=np.float64))
+        c, s = getattr(self, "sdegpu_forcing", None), getattr(self, "sdegpu_scale", None)
+        if (c is not None or s is not None) and len(args) < 2:
+            raise TypeError("a time-dependent catalogue function is called as f(t, x)")
+        if c is not None:
+            v = v + np.asarray(c(args[0]), dtype=np.float64).reshape(np.shape(v)) if np.ndim(v) else v + float(c(args[0]))
+        if s is not None:
+            v = float(s(args[0])) * v
+        return v
 
     def __repr__(self):
         return f"<catalogue {self.role} {self.sdegpu_model} params={self.sdegpu_params.tolist()}>"
@@ -86,6 +94,29 @@ def linear(A, G):
     G = np.asarray(G, dtype=np.float64).reshape(d, -1)
     params = np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
     return _pair("linear", params, lambda x: A @ x, lambda x: G, nx=d, nB=G.shape[1])
+
+
+def forced(f, c):
+    """The time-dependent drift f(t,x) = f0(x) + c(t): `f` a catalogue drift, `c` a callable t -> scalar or nx-vector
+    (the reference's f(t,x) form, R/sdetools.R:381-386; its own example f <- function(t,x) A %*% x + F * sin(2*t), :211,:363,
+    is forced(linear(A,G)[0], lambda t: F * sin(2*t))).  euler/heun evaluate c only at the grid times, as the reference does."""
+    if getattr(f, "role", None) != "drift":
+        raise TypeError("forced() takes the drift of a catalogue pair")
+    out = CatalogueFunction("drift", f.sdegpu_model, f.sdegpu_params, f.fn, f.nx, f.nB)
+    out.sdegpu_forcing = c
+    return out
+
+
+def scaled(g, s):
+    """The time-dependent diffusion g(t,x) = s(t) * g0(x): `g` a catalogue diffusion with one channel, `s` a callable
+    t -> scalar (the reference's g(t,x) form, R/sdetools.R:388-394)."""
+    if getattr(g, "role", None) != "diffusion":
+        raise TypeError("scaled() takes the diffusion of a catalogue pair")
+    if g.sdegpu_model == "linear":
+        raise TypeError("scaled() is not available for the linear model")
+    out = CatalogueFunction("diffusion", g.sdegpu_model, g.sdegpu_params, g.fn, g.nx, g.nB)
+    out.sdegpu_scale = s
+    return out
 
 
 class KillRate:

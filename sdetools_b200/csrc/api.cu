@@ -5,7 +5,15 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <dlfcn.h>
+#include <nccl.h>                      // types only: the library is loaded with dlopen when a multi-device context needs it
+#include <stdlib.h>
+
+#include <atomic>
+#include <chrono>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 // the half-normal quantile table of the fused generator lives in this translation unit
@@ -65,35 +73,72 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+// grow-only pinned host staging
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct NcclApi;                                                  // function table of a libnccl loaded at run time (below)
 
 struct sdegpu_ctx {
     int device = 0;
     cudaDeviceProp prop;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill, coef;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k0[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill, coef, tdep, lin_x0, lin_center;
+    DevBuf pipe_in[2], pipe_out[2];                              // device side of the chunk pipeline
+    PinBuf pin_in[2], pin_out[2];                                // its pinned host side
     const double *icdf = nullptr, *icdf32 = nullptr;
     int max_grid = 0;
+    // several GPUs in one process: this context is devices[0]; peers are devices[1..]
+    std::vector<sdegpu_ctx *> peers;
+    sdegpu_ctx *leader = nullptr;                                // set in a peer
+    void *nccl_comm = nullptr;                                   // ncclComm_t of this device (leader and peers)
+    bool nccl_tried = false;
+    const char *last_reduction = "none";
+    // interruption and chunking of host-pointer runs
+    sdegpu_interrupt_fn intr = nullptr;
+    void *intr_user = nullptr;
+    std::atomic<int> abort_flag{0};
+    uint64_t chunk_paths = 0;
 };
 
 static const int MODEL_NX[9] = {1, 1, 2, 1, 1, 1, 0, 1, 1};      // [6] linear: nx is free
 static const int MODEL_NP[9] = {3, 3, 2, 2, 2, 1, 0, 0, 1};
 
-extern "C" {
-
-int sdegpu_abi_version(void) { return SDEGPU_ABI_VERSION; }
-const char *sdegpu_last_error(void) { return g_err; }
-
-int sdegpu_create(int device, sdegpu_ctx **out)
+static void release_device(sdegpu_ctx *c)
 {
-    if (!out) return fail(SDEGPU_ERR_ARG, "sdegpu_create: ctx is NULL");
-    *out = nullptr;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(SDEGPU_ERR_NODEVICE, "sdegpu_create: no CUDA device visible");
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch, &c->times,
+                      &c->kill, &c->coef, &c->tdep, &c->lin_x0, &c->lin_center, &c->pipe_in[0], &c->pipe_in[1], &c->pipe_out[0], &c->pipe_out[1]};
+    for (DevBuf *b : bufs) b->release();
+    for (int k = 0; k < 2; ++k) {
+        c->pin_in[k].release(); c->pin_out[k].release();
+        cudaEvent_t *evs[] = {&c->ev_in[k], &c->ev_k0[k], &c->ev_k1[k], &c->ev_out[k]};
+        for (cudaEvent_t *e : evs) if (*e) cudaEventDestroy(*e);
     }
-    if (device < 0 || device >= ndev) return fail(SDEGPU_ERR_ARG, "sdegpu_create: device %d out of range [0,%d)", device, ndev);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+}
+
+static int create_device(int device, sdegpu_ctx **out)
+{
     sdegpu_ctx *c = new (std::nothrow) sdegpu_ctx();
     if (!c) return fail(SDEGPU_ERR_NOMEM, "sdegpu_create: host allocation failed");
     c->device = device;
@@ -105,13 +150,22 @@ int sdegpu_create(int device, sdegpu_ctx **out)
         return fail(SDEGPU_ERR_NODEVICE, "sdegpu_create: device is sm_%d%d; libsdegpu.so is built for sm_100a only", maj, min);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreate(&c->ev_k0[k]);
+        if (e == cudaSuccess) e = cudaEventCreate(&c->ev_k1[k]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming);
+    }
     c->max_grid = c->prop.multiProcessorCount * 32;
     if (e == cudaSuccess) e = c->partials.reserve(sizeof(double) * (size_t)c->max_grid * 5 * MAX_NX);
     if (e == cudaSuccess) e = cudaGetSymbolAddress((void **)&c->icdf, g_icdf_table);
     if (e == cudaSuccess) e = cudaGetSymbolAddress((void **)&c->icdf32, g_icdf32_table);
     if (e != cudaSuccess) {
+        release_device(c);
         delete c;
         return fail(SDEGPU_ERR_CUDA, "sdegpu_create: %s", cudaGetErrorString(e));
     }
@@ -120,17 +174,105 @@ int sdegpu_create(int device, sdegpu_ctx **out)
     return SDEGPU_OK;
 }
 
+// ---- NCCL, loaded at run time (libsdegpu.so itself does not link against it) ------------------------------------
+struct NcclApi {
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi &nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    if (const char *e = getenv("SDEGPU_NO_NCCL")) if (atoi(e) != 0) return api;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return api;
+    api.CommInitAll = (decltype(api.CommInitAll))dlsym(h, "ncclCommInitAll");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.ok = api.CommInitAll && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd;
+    return api;
+}
+
+extern "C" {
+
+int sdegpu_abi_version(void) { return SDEGPU_ABI_VERSION; }
+const char *sdegpu_last_error(void) { return g_err; }
+
+int sdegpu_create_multi(const int *devices, int ndev, sdegpu_ctx **out)
+{
+    if (!out) return fail(SDEGPU_ERR_ARG, "sdegpu_create: ctx is NULL");
+    *out = nullptr;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) {
+        cudaGetLastError();
+        return fail(SDEGPU_ERR_NODEVICE, "sdegpu_create: no CUDA device visible");
+    }
+    if (ndev < 1 || ndev > 64) return fail(SDEGPU_ERR_ARG, "sdegpu_create_multi: ndev must be in [1,64], got %d", ndev);
+    std::vector<int> ids((size_t)ndev);
+    for (int k = 0; k < ndev; ++k) {
+        ids[k] = devices ? devices[k] : k;
+        if (ids[k] < 0 || ids[k] >= have) return fail(SDEGPU_ERR_ARG, "sdegpu_create: device %d out of range [0,%d)", ids[k], have);
+        for (int m = 0; m < k; ++m)
+            if (ids[m] == ids[k]) return fail(SDEGPU_ERR_ARG, "sdegpu_create_multi: device %d listed twice", ids[k]);
+    }
+    sdegpu_ctx *lead = nullptr;
+    int rc = create_device(ids[0], &lead);
+    if (rc) return rc;
+    for (int k = 1; k < ndev; ++k) {
+        sdegpu_ctx *peer = nullptr;
+        rc = create_device(ids[k], &peer);
+        if (rc) { sdegpu_destroy(lead); return rc; }
+        peer->leader = lead;
+        lead->peers.push_back(peer);
+    }
+    cudaSetDevice(ids[0]);
+    *out = lead;
+    return SDEGPU_OK;
+}
+
+int sdegpu_create(int device, sdegpu_ctx **out) { return sdegpu_create_multi(&device, 1, out); }
+
 int sdegpu_destroy(sdegpu_ctx *c)
 {
     if (!c) return SDEGPU_OK;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch, &c->times, &c->kill, &c->coef};
-    for (DevBuf *b : bufs) b->release();
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    NcclApi &n = nccl_api();
+    for (sdegpu_ctx *p : c->peers) {
+        if (p->nccl_comm && n.ok) n.CommDestroy((ncclComm_t)p->nccl_comm);
+        release_device(p);
+        delete p;
+    }
+    if (c->nccl_comm && n.ok) n.CommDestroy((ncclComm_t)c->nccl_comm);
+    release_device(c);
     delete c;
+    return SDEGPU_OK;
+}
+
+int sdegpu_device_count(sdegpu_ctx *c) { return c ? 1 + (int)c->peers.size() : 0; }
+const char *sdegpu_last_reduction(sdegpu_ctx *c) { return c ? c->last_reduction : "none"; }
+
+int sdegpu_set_interrupt(sdegpu_ctx *c, sdegpu_interrupt_fn fn, void *user)
+{
+    if (!c) return fail(SDEGPU_ERR_ARG, "sdegpu_set_interrupt: ctx is NULL");
+    c->intr = fn; c->intr_user = user;
+    return SDEGPU_OK;
+}
+
+int sdegpu_set_chunk_paths(sdegpu_ctx *c, uint64_t paths)
+{
+    if (!c) return fail(SDEGPU_ERR_ARG, "sdegpu_set_chunk_paths: ctx is NULL");
+    c->chunk_paths = paths;
+    for (sdegpu_ctx *p : c->peers) p->chunk_paths = paths;
     return SDEGPU_OK;
 }
 
@@ -152,6 +294,8 @@ int sdegpu_device_info(sdegpu_ctx *c, sdegpu_devinfo *info)
 int sdegpu_set_stream(sdegpu_ctx *c, void *s)
 {
     if (!c) return fail(SDEGPU_ERR_ARG, "sdegpu_set_stream: ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));  // kernels enqueued on the old stream may still read the context's tables
     c->stream = (cudaStream_t)s;          // NULL is CUDA's default stream, a valid choice
     return SDEGPU_OK;
 }
@@ -159,6 +303,8 @@ int sdegpu_set_stream(sdegpu_ctx *c, void *s)
 int sdegpu_reset_stream(sdegpu_ctx *c)
 {
     if (!c) return fail(SDEGPU_ERR_ARG, "sdegpu_reset_stream: ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
     c->stream = c->own_stream;
     return SDEGPU_OK;
 }
@@ -199,9 +345,14 @@ static int upload_dtsq(sdegpu_ctx *c, const double *times, int nt, bool rbm_conv
     return SDEGPU_OK;
 }
 
-extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out)
+// ---- sdegpu_run ---------------------------------------------------------------------------------------------------
+// validate()  host-only checks of a problem/output pair
+// prepare()   uploads the tables that depend on (times, params) to one device: one stream synchronisation
+// enqueue()   launches the kernels of one path range on c->stream; every per-path pointer is a device pointer
+// run_device_ptrs() / run_host() / run_multi()  the three ways a call reaches enqueue()
+
+static int validate(const sdegpu_problem *pr, const sdegpu_output *out)
 {
-    if (!c || !pr || !out) return fail(SDEGPU_ERR_ARG, "sdegpu_run: NULL argument");
     if (pr->struct_size != sizeof(sdegpu_problem) || out->struct_size != sizeof(sdegpu_output))
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: struct_size mismatch (ABI %d)", SDEGPU_ABI_VERSION);
     if (pr->model < 0 || pr->model > SDEGPU_MODEL_LOGLOGISTIC) return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown model %d", pr->model);
@@ -214,159 +365,165 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: times/x0/params must not be NULL");
     if (pr->x0_stride != 0 && pr->x0_stride != pr->nx) return fail(SDEGPU_ERR_ARG, "sdegpu_run: x0_stride must be 0 or nx");
     const bool killed = pr->kill_kind != SDEGPU_KILL_NONE || pr->stop_kind != SDEGPU_STOP_NONE;
+    const bool tdep = pr->drift_forcing || pr->diffusion_scale;
+    const bool linear = pr->model == SDEGPU_MODEL_LINEAR;
     if (pr->kill_kind < 0 || pr->kill_kind > SDEGPU_KILL_QUAD || pr->stop_kind < 0 || pr->stop_kind > SDEGPU_STOP_OUTSIDE)
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: unknown kill/stop kind (%d, %d)", pr->kill_kind, pr->stop_kind);
     if (killed && (pr->kill_comp < 0 || pr->kill_comp >= pr->nx || pr->stop_comp < 0 || pr->stop_comp >= pr->nx))
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: kill/stop component out of range");
-    if (killed && pr->model == SDEGPU_MODEL_LINEAR)
-        return fail(SDEGPU_ERR_ARG, "sdegpu_run: killing/stopping is not available for the linear model");
-    if (out->path_integrals && (killed || out->X || pr->model == SDEGPU_MODEL_LINEAR))
-        return fail(SDEGPU_ERR_ARG, "sdegpu_run: path_integrals needs a catalogue model without kill/stop rule and X = NULL");
+    if (killed && linear) return fail(SDEGPU_ERR_ARG, "sdegpu_run: killing/stopping is not available for the linear model");
+    if ((out->path_integrals || out->model_integrals) && (killed || out->X || linear))
+        return fail(SDEGPU_ERR_ARG, "sdegpu_run: path_integrals/model_integrals need a catalogue model without kill/stop rule and X = NULL");
     if ((out->tau || out->S_tau || out->S) && !killed) return fail(SDEGPU_ERR_ARG, "sdegpu_run: tau/S_tau/S outputs need a kill or stop rule");
-    if (!pr->B && pr->arith == SDEGPU_ARITH_STRICT && !killed)
+    if (!pr->B && pr->arith == SDEGPU_ARITH_STRICT && !killed && !tdep)
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: STRICT arithmetic is defined for a supplied B; fused-generator runs are FAST");
+    if (linear && pr->diffusion_scale) return fail(SDEGPU_ERR_ARG, "sdegpu_run: diffusion_scale is not available for the linear model (drift_forcing is)");
     for (int i = 0; i + 1 < pr->nt; ++i)
         if (!(pr->times[i + 1] >= pr->times[i])) return fail(SDEGPU_ERR_ARG, "sdegpu_run: times must be non-decreasing (index %d)", i);
     if (out->hist_counts && (out->hist_nbins < 1 || out->hist_nbins > 8192 || !(out->hist_hi > out->hist_lo) ||
                              out->hist_component < 0 || out->hist_component >= pr->nx))
         return fail(SDEGPU_ERR_ARG, "sdegpu_run: bad histogram spec (nbins in [1,8192], hi > lo, component < nx)");
-    const bool dev = (pr->flags & SDEGPU_DEVICE_PTRS) != 0;
-    const bool accum = (pr->flags & SDEGPU_ACCUMULATE) != 0;
-    CU(cudaSetDevice(c->device));
-    if (pr->npaths == 0) {
-        if (out->elapsed_ms) *out->elapsed_ms = 0.f;
-        return SDEGPU_OK;
-    }
-    const int nx = pr->nx, nt = pr->nt;
-    const bool linear = pr->model == SDEGPU_MODEL_LINEAR;
     if (!linear) {
-        if (nx != MODEL_NX[pr->model] || pr->nB != 1)
-            return fail(SDEGPU_ERR_ARG, "sdegpu_run: model %d has nx=%d, nB=1 (got nx=%d, nB=%d)", pr->model, MODEL_NX[pr->model], nx, pr->nB);
+        if (pr->nx != MODEL_NX[pr->model] || pr->nB != 1)
+            return fail(SDEGPU_ERR_ARG, "sdegpu_run: model %d has nx=%d, nB=1 (got nx=%d, nB=%d)", pr->model, MODEL_NX[pr->model], pr->nx, pr->nB);
         if (pr->nparams != MODEL_NP[pr->model])
             return fail(SDEGPU_ERR_ARG, "sdegpu_run: model %d takes %d parameters, got %d", pr->model, MODEL_NP[pr->model], pr->nparams);
     } else {
-        if (nx < 1 || pr->nB < 1 || pr->nparams != nx * nx + nx * pr->nB)
+        if (pr->nx < 1 || pr->nB < 1 || pr->nparams != pr->nx * pr->nx + pr->nx * pr->nB)
             return fail(SDEGPU_ERR_ARG, "sdegpu_run: linear model needs nparams = nx*nx + nx*nB");
+        if (out->hist_counts) return fail(SDEGPU_ERR_ARG, "sdegpu_run: histogram output is not available for the linear model");
     }
+    return SDEGPU_OK;
+}
 
+struct Prepared {
     const double2 *dtsq = nullptr;
-    int rc = upload_dtsq(c, pr->times, nt, false, &dtsq);
-    if (rc) return rc;
+    bool uniform = false, killed = false, tdep = false, linear = false;
+    double ucoef[FAST_NCOEF] = {0, 0, 0, 0, 0, 0};
+    const double *coef = nullptr, *times = nullptr, *forcing = nullptr, *gscale = nullptr;
+    const double *linA = nullptr, *linG = nullptr, *lin_x0 = nullptr, *lin_center = nullptr;
+};
 
-    const size_t nB = (size_t)pr->nB;
-    const size_t bytesB = sizeof(double) * pr->npaths * nB * nt, bytesX = sizeof(double) * pr->npaths * nx * nt,
-                 bytesXT = sizeof(double) * pr->npaths * nx;
-    const double *dB = nullptr, *dx0 = nullptr;
-    double *dX = nullptr, *dXT = nullptr;
-    if (pr->B) {
-        if (dev) dB = pr->B;
-        else {
-            CU(c->in0.reserve(bytesB));
-            CU(cudaMemcpyAsync(c->in0.p, pr->B, bytesB, cudaMemcpyHostToDevice, c->stream));
-            dB = (const double *)c->in0.p;
-        }
-    }
-    if (pr->x0_stride) {
-        if (dev) dx0 = pr->x0;
-        else {
-            CU(c->in1.reserve(bytesXT));
-            CU(cudaMemcpyAsync(c->in1.p, pr->x0, bytesXT, cudaMemcpyHostToDevice, c->stream));
-            dx0 = (const double *)c->in1.p;
-        }
-    }
-    if (out->X) {
-        if (dev) dX = out->X;
-        else { CU(c->out0.reserve(bytesX)); dX = (double *)c->out0.p; }
-    }
-    if (out->XT) {
-        if (dev) dXT = out->XT;
-        else { CU(c->out1.reserve(bytesXT)); dXT = (double *)c->out1.p; }
-    }
-    // statistics scratch: [5*nx power sums][nbins+3 counts]
-    const int nps = 5 * nx, nh = out->hist_counts ? out->hist_nbins + 3 : 0;
-    double *dps = nullptr;
-    unsigned long long *dh = nullptr;
-    if (out->power_sums || out->hist_counts) {
-        CU(c->stats.reserve(sizeof(double) * nps + sizeof(unsigned long long) * (size_t)(nh + 1)));
-        if (out->power_sums) dps = dev ? out->power_sums : (double *)c->stats.p;
-        if (out->hist_counts) dh = dev ? (unsigned long long *)out->hist_counts : (unsigned long long *)((double *)c->stats.p + nps);
-        if (dh) {
-            if (accum && !dev) CU(cudaMemcpyAsync(dh, out->hist_counts, sizeof(unsigned long long) * nh, cudaMemcpyHostToDevice, c->stream));
-            else if (!accum) CU(cudaMemsetAsync(dh, 0, sizeof(unsigned long long) * nh, c->stream));
-        }
-        if (dps && accum && !dev) CU(cudaMemcpyAsync(dps, out->power_sums, sizeof(double) * nps, cudaMemcpyHostToDevice, c->stream));
-    }
+// every per-path array of one path range, on the device
+struct DevIO {
+    const double *B = nullptr, *x0 = nullptr, *Stau = nullptr;
+    double *X = nullptr, *XT = nullptr, *tau = nullptr, *S_tau = nullptr, *S = nullptr, *func = nullptr, *mfunc = nullptr;
+    double *ps = nullptr;                                        // 5*nx power sums (device)
+    unsigned long long *hist = nullptr;                          // nbins+3 counts (device)
+    uint64_t npaths = 0, path_offset = 0;
+};
 
+static int prepare(sdegpu_ctx *c, const sdegpu_problem *pr, const sdegpu_output *out, Prepared *pp)
+{
+    const int nt = pr->nt, nx = pr->nx;
+    pp->killed = pr->kill_kind != SDEGPU_KILL_NONE || pr->stop_kind != SDEGPU_STOP_NONE;
+    pp->tdep = pr->drift_forcing || pr->diffusion_scale;
+    pp->linear = pr->model == SDEGPU_MODEL_LINEAR;
+    std::vector<double2> hdt((size_t)nt - 1);
+    for (int i = 0; i + 1 < nt; ++i) {
+        const double dt = pr->times[i + 1] - pr->times[i];
+        hdt[i] = make_double2(dt, sqrt(dt));
+    }
+    CU(c->dtsq.reserve(sizeof(double2) * hdt.size()));
+    CU(cudaMemcpyAsync(c->dtsq.p, hdt.data(), sizeof(double2) * hdt.size(), cudaMemcpyHostToDevice, c->stream));
+    pp->dtsq = (const double2 *)c->dtsq.p;
+    std::vector<double> hc, hcen;
+    if (!pp->linear && !pr->B && !pp->killed && !pp->tdep && !out->path_integrals && !out->model_integrals) {
+        // k_terminal, k_traj: folded step coefficients (FAST only).  A grid whose increments agree to the rounding of its
+        // own time stamps (seq(0, T, by = h) gives t_i = i*h rounded, so diff(times) scatters by ~ulp(T)) is integrated as
+        // the uniform grid it stands for, dt = (t_n - t_0)/n: one coefficient row as a kernel parameter instead of a table.
+        const double tmax = fmax(fabs(pr->times[0]), fabs(pr->times[nt - 1]));
+        const double dtbar = (pr->times[nt - 1] - pr->times[0]) / (double)(nt - 1), tol = 4.0 * 2.220446049250313e-16 * tmax;
+        bool uniform = !(pr->flags & SDEGPU_EXACT_GRID) && dtbar > 0.0;
+        for (int i = 0; i + 1 < nt && uniform; ++i) uniform = fabs((pr->times[i + 1] - pr->times[i]) - dtbar) <= tol;
+        pp->uniform = uniform;
+        if (uniform) fast_step_coefficients(pr->model, pr->params, dtbar, sqrt(dtbar), pp->ucoef);
+        else {
+            hc.resize((size_t)(nt - 1) * FAST_NCOEF);
+            for (int i = 0; i + 1 < nt; ++i) {
+                const double dt = pr->times[i + 1] - pr->times[i];
+                fast_step_coefficients(pr->model, pr->params, dt, sqrt(dt), &hc[(size_t)i * FAST_NCOEF]);
+            }
+            CU(c->coef.reserve(sizeof(double) * hc.size()));
+            CU(cudaMemcpyAsync(c->coef.p, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, c->stream));
+            pp->coef = (const double *)c->coef.p;
+        }
+    }
+    if (pp->killed) {
+        CU(c->times.reserve(sizeof(double) * nt));
+        CU(cudaMemcpyAsync(c->times.p, pr->times, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
+        pp->times = (const double *)c->times.p;
+    }
+    if (pp->tdep) {
+        CU(c->tdep.reserve(sizeof(double) * (size_t)nt * (nx + 1)));
+        double *d = (double *)c->tdep.p;
+        if (pr->drift_forcing) {
+            CU(cudaMemcpyAsync(d, pr->drift_forcing, sizeof(double) * (size_t)nt * nx, cudaMemcpyHostToDevice, c->stream));
+            pp->forcing = d;
+        }
+        if (pr->diffusion_scale) {
+            CU(cudaMemcpyAsync(d + (size_t)nt * nx, pr->diffusion_scale, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
+            pp->gscale = d + (size_t)nt * nx;
+        }
+    }
+    if (pp->linear) {
+        CU(c->params.reserve(sizeof(double) * (size_t)pr->nparams));
+        CU(cudaMemcpyAsync(c->params.p, pr->params, sizeof(double) * (size_t)pr->nparams, cudaMemcpyHostToDevice, c->stream));
+        pp->linA = (const double *)c->params.p;
+        pp->linG = pp->linA + (size_t)nx * nx;
+        if (!pr->x0_stride) {
+            CU(c->lin_x0.reserve(sizeof(double) * nx));
+            CU(cudaMemcpyAsync(c->lin_x0.p, pr->x0, sizeof(double) * nx, cudaMemcpyHostToDevice, c->stream));
+            pp->lin_x0 = (const double *)c->lin_x0.p;
+        }
+        hcen.assign((size_t)nx, 0.0);
+        if (out->center) for (int j = 0; j < nx; ++j) hcen[j] = out->center[j];
+        CU(c->lin_center.reserve(sizeof(double) * nx));
+        CU(cudaMemcpyAsync(c->lin_center.p, hcen.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, c->stream));
+        pp->lin_center = (const double *)c->lin_center.p;
+    }
+    CU(cudaStreamSynchronize(c->stream));                        // the host vectors above go out of scope
+    return SDEGPU_OK;
+}
+
+static int enqueue(sdegpu_ctx *c, const sdegpu_problem *pr, const sdegpu_output *out, const Prepared &pp, const DevIO &io, bool accum)
+{
+    const int nx = pr->nx, nt = pr->nt;
     int grid_used = 0, cuerr = 0;
-    CU(cudaEventRecord(c->ev0, c->stream));
-    if (!linear) {
+    if (!pp.linear) {
         RunArgs a;
         memset(&a, 0, sizeof a);
         for (int i = 0; i < pr->nparams; ++i) a.P.p[i] = pr->params[i];
-        a.dtsq = dtsq;
+        a.dtsq = pp.dtsq;
         a.icdf = c->icdf;
         a.icdf32 = c->icdf32;
-        bool uniform = false;
-        if (!pr->B && !killed && !out->path_integrals) {   // k_terminal, k_traj: folded step coefficients (FAST only)
-            // A grid whose increments agree to the rounding of its own time stamps (seq(0, T, by = h) gives
-            // t_i = i*h rounded, so diff(times) scatters by ~ulp(T)) is integrated as the uniform grid it
-            // stands for, dt = (t_n - t_0)/n: one coefficient row as a kernel parameter instead of a table.
-            const double tmax = fmax(fabs(pr->times[0]), fabs(pr->times[nt - 1]));
-            const double dtbar = (pr->times[nt - 1] - pr->times[0]) / (double)(nt - 1), tol = 4.0 * 2.220446049250313e-16 * tmax;
-            uniform = !(pr->flags & SDEGPU_EXACT_GRID) && dtbar > 0.0;
-            for (int i = 0; i + 1 < nt && uniform; ++i) uniform = fabs((pr->times[i + 1] - pr->times[i]) - dtbar) <= tol;
-            if (uniform) fast_step_coefficients(pr->model, pr->params, dtbar, sqrt(dtbar), a.ucoef);
-            else {
-                std::vector<double> hc((size_t)(nt - 1) * FAST_NCOEF);
-                for (int i = 0; i + 1 < nt; ++i) {
-                    const double dt = pr->times[i + 1] - pr->times[i];
-                    fast_step_coefficients(pr->model, pr->params, dt, sqrt(dt), &hc[(size_t)i * FAST_NCOEF]);
-                }
-                CU(c->coef.reserve(sizeof(double) * hc.size()));
-                CU(cudaMemcpyAsync(c->coef.p, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, c->stream));
-                CU(cudaStreamSynchronize(c->stream));
-                a.coef = (const double *)c->coef.p;
-            }
-        }
-        a.x0 = dx0;
+        for (int k = 0; k < FAST_NCOEF; ++k) a.ucoef[k] = pp.ucoef[k];
+        a.coef = pp.coef;
+        a.x0 = io.x0;
         if (!pr->x0_stride) for (int j = 0; j < nx; ++j) a.x0s[j] = pr->x0[j];
-        a.B = dB; a.X = dX; a.XT = dXT;
-        a.partials = dps ? (double *)c->partials.p : nullptr;
-        a.hist = dh;
+        a.B = io.B; a.X = io.X; a.XT = io.XT;
+        a.partials = io.ps ? (double *)c->partials.p : nullptr;
+        a.hist = io.hist;
         for (int j = 0; j < nx; ++j) a.center[j] = out->center ? out->center[j] : 0.0;
         a.hist_lo = out->hist_lo; a.hist_hi = out->hist_hi;
-        a.hist_invw = dh ? (double)out->hist_nbins / (out->hist_hi - out->hist_lo) : 0.0;
-        a.npaths = pr->npaths; a.path_offset = pr->path_offset; a.seed = make_philox_key(pr->seed);
+        a.hist_invw = io.hist ? (double)out->hist_nbins / (out->hist_hi - out->hist_lo) : 0.0;
+        a.npaths = io.npaths; a.path_offset = io.path_offset; a.seed = make_philox_key(pr->seed);
         a.nt = nt; a.hist_nbins = out->hist_nbins; a.hist_comp = out->hist_component;
-        if (killed) {
+        a.forcing = pp.forcing; a.gscale = pp.gscale;
+        if (pp.killed) {
             a.kill_kind = pr->kill_kind; a.kill_comp = pr->kill_comp; a.kill_a = pr->kill_a; a.kill_b = pr->kill_b;
             a.stop_kind = pr->stop_kind; a.stop_comp = pr->stop_comp; a.stop_lo = pr->stop_lo; a.stop_hi = pr->stop_hi;
             a.S0 = pr->S0;
-            CU(c->times.reserve(sizeof(double) * nt));
-            CU(cudaMemcpyAsync(c->times.p, pr->times, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
-            a.times = (const double *)c->times.p;
-            if (dev) { a.Stau = pr->Stau; a.tau = out->tau; a.S_tau = out->S_tau; a.Spath = out->S; }
-            else {
-                CU(c->kill.reserve(sizeof(double) * (3 + (out->S ? (size_t)nt : 0)) * pr->npaths));
-                double *kb = (double *)c->kill.p;
-                if (pr->Stau) {
-                    CU(cudaMemcpyAsync(kb, pr->Stau, sizeof(double) * pr->npaths, cudaMemcpyHostToDevice, c->stream));
-                    a.Stau = kb;
-                }
-                if (out->tau) a.tau = kb + pr->npaths;
-                if (out->S_tau) a.S_tau = kb + 2 * pr->npaths;
-                if (out->S) a.Spath = kb + 3 * pr->npaths;
-            }
+            a.times = pp.times;
+            a.Stau = io.Stau; a.tau = io.tau; a.S_tau = io.S_tau; a.Spath = io.S;
         }
-        const size_t bytesF = sizeof(double) * 4 * (size_t)nx * pr->npaths;
-        if (out->path_integrals) {
-            if (dev) a.func = out->path_integrals;
-            else { CU(c->out2.reserve(bytesF)); a.func = (double *)c->out2.p; }
-        }
+        a.func = io.func; a.mfunc = io.mfunc;
         LaunchCfg cfg;
-        cfg.killed = killed; cfg.want_func = out->path_integrals != nullptr; cfg.uniform = uniform;
+        cfg.killed = pp.killed; cfg.want_func = io.func != nullptr || io.mfunc != nullptr; cfg.uniform = pp.uniform;
+        cfg.general = pp.tdep;
         cfg.scheme = pr->scheme; cfg.proj = pr->projection; cfg.arith = pr->B ? pr->arith : SDEGPU_ARITH_FAST;
-        cfg.src_b = pr->B != nullptr; cfg.want_x = out->X != nullptr;
+        if (pp.tdep) cfg.arith = SDEGPU_ARITH_STRICT;
+        cfg.src_b = io.B != nullptr; cfg.want_x = io.X != nullptr;
         cfg.grid = 0; cfg.sm_count = c->prop.multiProcessorCount; cfg.stream = c->stream;
         switch (pr->model) {
         case 0: cuerr = launch_model_0(a, cfg, &grid_used); break;
@@ -379,35 +536,22 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
         default: cuerr = launch_model_8(a, cfg, &grid_used); break;
         }
         if (cuerr) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: kernel launch: %s", cudaGetErrorString((cudaError_t)cuerr));
-        if (grid_used > c->max_grid) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: grid %d exceeds partials capacity", grid_used);
-        if (dps) {
-            k_reduce_partials<<<1, 32, 0, c->stream>>>((const double *)c->partials.p, grid_used, nps, dps, accum ? 1 : 0);
+        if (io.ps) {
+            k_reduce_partials<<<1, 32, 0, c->stream>>>((const double *)c->partials.p, grid_used, 5 * nx, io.ps, accum ? 1 : 0);
             CU(cudaGetLastError());
         }
     } else {
         LinearArgs la;
         memset(&la, 0, sizeof la);
-        CU(c->params.reserve(sizeof(double) * (size_t)pr->nparams));
-        CU(cudaMemcpyAsync(c->params.p, pr->params, sizeof(double) * (size_t)pr->nparams, cudaMemcpyHostToDevice, c->stream));
-        la.A = (const double *)c->params.p;
-        la.G = la.A + (size_t)nx * nx;
-        la.dtsq = dtsq; la.icdf = c->icdf; la.x0 = pr->x0_stride ? dx0 : nullptr;
-        if (!pr->x0_stride) {
-            CU(c->in1.reserve(sizeof(double) * nx));
-            CU(cudaMemcpyAsync(c->in1.p, pr->x0, sizeof(double) * nx, cudaMemcpyHostToDevice, c->stream));
-            la.x0_shared = (const double *)c->in1.p;
-        }
-        la.B = dB; la.X = dX; la.XT = dXT;
-        la.npaths = pr->npaths; la.path_offset = pr->path_offset; la.seed = make_philox_key(pr->seed);
+        la.A = pp.linA; la.G = pp.linG;
+        la.dtsq = pp.dtsq; la.icdf = c->icdf; la.x0 = pr->x0_stride ? io.x0 : nullptr;
+        la.x0_shared = pp.lin_x0;
+        la.B = io.B; la.X = io.X; la.XT = io.XT;
+        la.npaths = io.npaths; la.path_offset = io.path_offset; la.seed = make_philox_key(pr->seed);
         la.nt = nt; la.d = nx; la.nB = pr->nB; la.scheme = pr->scheme; la.strict = pr->B && pr->arith == SDEGPU_ARITH_STRICT;
-        if (out->hist_counts) return fail(SDEGPU_ERR_ARG, "sdegpu_run: histogram output is not available for the linear model");
-        la.moments = dps; la.accumulate = accum ? 1 : 0;
-        CU(c->out2.reserve(sizeof(double) * nx));
-        std::vector<double> hc((size_t)nx, 0.0);
-        if (out->center) for (int j = 0; j < nx; ++j) hc[j] = out->center[j];
-        CU(cudaMemcpyAsync(c->out2.p, hc.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        la.center = (const double *)c->out2.p;
+        la.moments = io.ps; la.accumulate = accum ? 1 : 0;
+        la.center = pp.lin_center;
+        la.forcing = pp.forcing;
         const int mode = dmma_mode(la, pr->params + (size_t)nx * nx);
         const size_t dp = ((size_t)nx + 31) / 32 * 32;              // the tensor kernels pad to a multiple of 32 rows
         if (mode == 1) {
@@ -420,24 +564,345 @@ extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output
             cuerr = launch_linear(la, c->prop.multiProcessorCount, c->stream);
         if (cuerr) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: linear kernel launch: %s", cudaGetErrorString((cudaError_t)cuerr));
     }
-    CU(cudaEventRecord(c->ev1, c->stream));
+    return SDEGPU_OK;
+}
 
-    if (!dev) {
-        if (out->path_integrals)
-            CU(cudaMemcpyAsync(out->path_integrals, c->out2.p, sizeof(double) * 4 * (size_t)nx * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
-        if (out->X) CU(cudaMemcpyAsync(out->X, dX, bytesX, cudaMemcpyDeviceToHost, c->stream));
-        if (out->XT) CU(cudaMemcpyAsync(out->XT, dXT, bytesXT, cudaMemcpyDeviceToHost, c->stream));
-        if (out->power_sums) CU(cudaMemcpyAsync(out->power_sums, dps, sizeof(double) * nps, cudaMemcpyDeviceToHost, c->stream));
-        if (out->hist_counts) CU(cudaMemcpyAsync(out->hist_counts, dh, sizeof(unsigned long long) * nh, cudaMemcpyDeviceToHost, c->stream));
-        if (out->tau) CU(cudaMemcpyAsync(out->tau, (double *)c->kill.p + pr->npaths, sizeof(double) * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
-        if (out->S_tau) CU(cudaMemcpyAsync(out->S_tau, (double *)c->kill.p + 2 * pr->npaths, sizeof(double) * pr->npaths, cudaMemcpyDeviceToHost, c->stream));
-        if (out->S) CU(cudaMemcpyAsync(out->S, (double *)c->kill.p + 3 * pr->npaths, sizeof(double) * pr->npaths * nt, cudaMemcpyDeviceToHost, c->stream));
-    }
-    if (!dev || out->elapsed_ms) {
+// SDEGPU_DEVICE_PTRS: one launch on the caller's buffers; returns with the work enqueued unless elapsed_ms is asked for
+static int run_device_ptrs(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out)
+{
+    Prepared pp;
+    int rc = prepare(c, pr, out, &pp);
+    if (rc) return rc;
+    const bool accum = (pr->flags & SDEGPU_ACCUMULATE) != 0;
+    DevIO io;
+    io.B = pr->B; io.x0 = pr->x0_stride ? pr->x0 : nullptr; io.Stau = pr->Stau;
+    io.X = out->X; io.XT = out->XT; io.tau = out->tau; io.S_tau = out->S_tau; io.S = out->S;
+    io.func = out->path_integrals; io.mfunc = out->model_integrals;
+    io.ps = out->power_sums; io.hist = (unsigned long long *)out->hist_counts;
+    io.npaths = pr->npaths; io.path_offset = pr->path_offset;
+    if (io.hist && !accum) CU(cudaMemsetAsync(io.hist, 0, sizeof(unsigned long long) * (out->hist_nbins + 3), c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    rc = enqueue(c, pr, out, pp, io, accum);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    if (out->elapsed_ms) {
         CU(cudaStreamSynchronize(c->stream));
-        if (out->elapsed_ms) CU(cudaEventElapsedTime(out->elapsed_ms, c->ev0, c->ev1));
+        CU(cudaEventElapsedTime(out->elapsed_ms, c->ev0, c->ev1));
     }
     return SDEGPU_OK;
+}
+
+// ---- host pointers: the chunk pipeline -------------------------------------------------------------------------
+// Per-path arrays are path-major (X[(p*nx+j)*nt+i], XT[p*nx+j], tau[p], ...), so a path range is one contiguous slice of
+// each.  A chunk's input slices are gathered into one pinned buffer and sent with one copy on the H2D stream; its output
+// slices come back with one copy on the D2H stream and are scattered to the caller's arrays while the next chunk
+// computes.  Host copies run on several threads: first touches of a freshly allocated result (R's allocVector, numpy's
+// empty) are page faults, which one thread takes at ~2 GB/s and PCIe delivers at ~50.
+static void parallel_copy(void *dst, const void *src, size_t bytes)
+{
+    static const unsigned hw = std::thread::hardware_concurrency();
+    unsigned nth = hw > 16 ? 16 : (hw < 1 ? 1 : hw);
+    if (const char *e = getenv("SDEGPU_COPY_THREADS")) if (atoi(e) > 0) nth = (unsigned)atoi(e);
+    if (bytes < ((size_t)4 << 20) || nth == 1) { memcpy(dst, src, bytes); return; }
+    const size_t slice = ((bytes + nth - 1) / nth + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (unsigned k = 1; k < nth; ++k) {
+        const size_t off = slice * k;
+        if (off >= bytes) break;
+        const size_t n = bytes - off < slice ? bytes - off : slice;
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, n); });
+    }
+    memcpy(dst, src, slice < bytes ? slice : bytes);
+    for (auto &t : th) t.join();
+}
+
+struct Slice { size_t per_path; size_t off; };                   // bytes per path, offset of the slice in a chunk buffer
+static size_t lay(Slice &s, size_t per_path, bool present, size_t &cursor, uint64_t cp)
+{
+    s.per_path = present ? per_path : 0;
+    s.off = cursor;
+    if (present) cursor += (per_path * cp + 255) & ~(size_t)255;
+    return s.off;
+}
+
+static int run_host(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out, bool leave_stats, std::atomic<int> *abort_flag)
+{
+    CU(cudaSetDevice(c->device));
+    const int nx = pr->nx, nt = pr->nt;
+    const uint64_t np = pr->npaths;
+    const bool accum = (pr->flags & SDEGPU_ACCUMULATE) != 0;
+    Prepared pp;
+    int rc = prepare(c, pr, out, &pp);
+    if (rc) return rc;
+
+    // statistics accumulators on the device: [5*nx power sums][nbins+3 counts]
+    const int nps = 5 * nx, nh = out->hist_counts ? out->hist_nbins + 3 : 0;
+    double *dps = nullptr;
+    unsigned long long *dh = nullptr;
+    if (out->power_sums || out->hist_counts) {
+        CU(c->stats.reserve(sizeof(double) * nps + sizeof(unsigned long long) * (size_t)(nh + 1)));
+        if (out->power_sums) dps = (double *)c->stats.p;
+        if (out->hist_counts) dh = (unsigned long long *)((double *)c->stats.p + nps);
+        if (dh) {
+            if (accum) CU(cudaMemcpyAsync(dh, out->hist_counts, sizeof(unsigned long long) * nh, cudaMemcpyHostToDevice, c->stream));
+            else CU(cudaMemsetAsync(dh, 0, sizeof(unsigned long long) * nh, c->stream));
+        }
+        if (dps && accum) CU(cudaMemcpyAsync(dps, out->power_sums, sizeof(double) * nps, cudaMemcpyHostToDevice, c->stream));
+    }
+
+    // chunk geometry
+    const size_t in_pp = (pr->B ? sizeof(double) * (size_t)pr->nB * nt : 0) + (pr->x0_stride ? sizeof(double) * nx : 0) +
+                         (pp.killed && pr->Stau ? sizeof(double) : 0);
+    const size_t out_pp = (out->X ? sizeof(double) * (size_t)nx * nt : 0) + (out->XT ? sizeof(double) * nx : 0) + (out->tau ? 8 : 0) +
+                          (out->S_tau ? 8 : 0) + (out->S ? sizeof(double) * nt : 0) + (out->path_integrals ? 32 * (size_t)nx : 0) +
+                          (out->model_integrals ? 16 * (size_t)nx : 0);
+    const bool can_stop = c->intr != nullptr || abort_flag != nullptr;
+    uint64_t cp = np;
+    if (c->chunk_paths) cp = c->chunk_paths;
+    else if (in_pp + out_pp > 0) {
+        const size_t target = (size_t)128 << 20;
+        if ((in_pp + out_pp) * np > 2 * target) cp = target / (in_pp + out_pp);
+    } else if (can_stop) {
+        const uint64_t unit = (uint64_t)c->prop.multiProcessorCount * 768;     // whole waves of the register-resident kernel
+        cp = (uint64_t)(2e10 / (double)(nt - 1));
+        cp = cp / unit * unit;
+        if (cp < unit) cp = unit;
+    }
+    if (cp < 1) cp = 1;
+    if (cp > np) cp = np;
+    const uint64_t nchunks = (np + cp - 1) / cp;
+
+    size_t cin = 0, cout = 0;
+    Slice sB, sx0, sStau, sX, sXT, stau, sStaus, sS, sF, sMF;
+    lay(sB, sizeof(double) * (size_t)pr->nB * nt, pr->B != nullptr, cin, cp);
+    lay(sx0, sizeof(double) * nx, pr->x0_stride != 0, cin, cp);
+    lay(sStau, 8, pp.killed && pr->Stau, cin, cp);
+    lay(sX, sizeof(double) * (size_t)nx * nt, out->X != nullptr, cout, cp);
+    lay(sXT, sizeof(double) * nx, out->XT != nullptr, cout, cp);
+    lay(stau, 8, out->tau != nullptr, cout, cp);
+    lay(sStaus, 8, out->S_tau != nullptr, cout, cp);
+    lay(sS, sizeof(double) * nt, out->S != nullptr, cout, cp);
+    lay(sF, 32 * (size_t)nx, out->path_integrals != nullptr, cout, cp);
+    lay(sMF, 16 * (size_t)nx, out->model_integrals != nullptr, cout, cp);
+    const int nbuf = nchunks > 1 ? 2 : 1;
+    // small single-chunk runs skip the pinned staging: the driver's pageable path costs the same there
+    const bool staged = nchunks > 1 || cin + cout >= ((size_t)8 << 20);
+    for (int b = 0; b < nbuf; ++b) {
+        if (cin) { CU(c->pipe_in[b].reserve(cin)); if (staged) CU(c->pin_in[b].reserve(cin)); }
+        if (cout) { CU(c->pipe_out[b].reserve(cout)); if (staged) CU(c->pin_out[b].reserve(cout)); }
+    }
+    struct HostIn { const void *p; const Slice *s; } hin[3] = {{pr->B, &sB}, {pr->x0_stride ? pr->x0 : nullptr, &sx0}, {pp.killed ? pr->Stau : nullptr, &sStau}};
+    struct HostOut { void *p; const Slice *s; } hout[7] = {{out->X, &sX}, {out->XT, &sXT}, {out->tau, &stau}, {out->S_tau, &sStaus},
+                                                           {out->S, &sS}, {out->path_integrals, &sF}, {out->model_integrals, &sMF}};
+    float total_ms = 0.f;
+    int status = SDEGPU_OK;
+    for (uint64_t k = 0; k <= nchunks && status == SDEGPU_OK; ++k) {
+        if (k < nchunks) {
+            const int b = (int)(k & 1) % nbuf;
+            const uint64_t p0 = k * cp, n = np - p0 < cp ? np - p0 : cp;
+            char *din = (char *)c->pipe_in[b].p, *dout = (char *)c->pipe_out[b].p;
+            if (cin) {
+                for (const HostIn &h : hin) {
+                    if (!h.p || !h.s->per_path) continue;
+                    const char *src = (const char *)h.p + h.s->per_path * p0;
+                    if (staged) parallel_copy((char *)c->pin_in[b].p + h.s->off, src, h.s->per_path * n);
+                    else CU(cudaMemcpyAsync(din + h.s->off, src, h.s->per_path * n, cudaMemcpyHostToDevice, c->s_h2d));
+                }
+                if (staged) CU(cudaMemcpyAsync(din, c->pin_in[b].p, cin, cudaMemcpyHostToDevice, c->s_h2d));
+                CU(cudaEventRecord(c->ev_in[b], c->s_h2d));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+            }
+            DevIO io;
+            io.B = pr->B ? (const double *)(din + sB.off) : nullptr;
+            io.x0 = pr->x0_stride ? (const double *)(din + sx0.off) : nullptr;
+            io.Stau = pp.killed && pr->Stau ? (const double *)(din + sStau.off) : nullptr;
+            io.X = out->X ? (double *)(dout + sX.off) : nullptr;
+            io.XT = out->XT ? (double *)(dout + sXT.off) : nullptr;
+            io.tau = out->tau ? (double *)(dout + stau.off) : nullptr;
+            io.S_tau = out->S_tau ? (double *)(dout + sStaus.off) : nullptr;
+            io.S = out->S ? (double *)(dout + sS.off) : nullptr;
+            io.func = out->path_integrals ? (double *)(dout + sF.off) : nullptr;
+            io.mfunc = out->model_integrals ? (double *)(dout + sMF.off) : nullptr;
+            io.ps = dps; io.hist = dh;
+            io.npaths = n; io.path_offset = pr->path_offset + p0;
+            CU(cudaEventRecord(c->ev_k0[b], c->stream));
+            rc = enqueue(c, pr, out, pp, io, accum || k > 0);
+            if (rc) { status = rc; break; }
+            CU(cudaEventRecord(c->ev_k1[b], c->stream));
+            if (cout) {
+                CU(cudaStreamWaitEvent(c->s_d2h, c->ev_k1[b], 0));
+                if (staged) CU(cudaMemcpyAsync(c->pin_out[b].p, dout, cout, cudaMemcpyDeviceToHost, c->s_d2h));
+                else
+                    for (const HostOut &h : hout)
+                        if (h.p && h.s->per_path)
+                            CU(cudaMemcpyAsync((char *)h.p + h.s->per_path * p0, dout + h.s->off, h.s->per_path * n, cudaMemcpyDeviceToHost, c->s_d2h));
+                CU(cudaEventRecord(c->ev_out[b], c->s_d2h));
+            }
+        }
+        if (k >= 1) {                                            // drain chunk k-1 while chunk k runs
+            const uint64_t j = k - 1;
+            const int b = (int)(j & 1) % nbuf;
+            const uint64_t p0 = j * cp, n = np - p0 < cp ? np - p0 : cp;
+            if (cout) {
+                CU(cudaEventSynchronize(c->ev_out[b]));
+                if (staged)
+                    for (const HostOut &h : hout)
+                        if (h.p && h.s->per_path)
+                            parallel_copy((char *)h.p + h.s->per_path * p0, (const char *)c->pin_out[b].p + h.s->off, h.s->per_path * n);
+            } else
+                CU(cudaEventSynchronize(c->ev_k1[b]));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->ev_k0[b], c->ev_k1[b]));
+            total_ms += ms;
+            if (k < nchunks) {                                   // between chunks: may the run go on?
+                if (abort_flag && abort_flag->load()) status = SDEGPU_ERR_INTERRUPT;
+                else if (!abort_flag && c->intr && c->intr(c->intr_user)) status = SDEGPU_ERR_INTERRUPT;
+            }
+        }
+    }
+    if (status != SDEGPU_OK) {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h); cudaStreamSynchronize(c->s_h2d);
+        if (status == SDEGPU_ERR_INTERRUPT) return fail(status, "sdegpu_run: interrupted");
+        return status;
+    }
+    if (!leave_stats) {
+        if (out->power_sums) CU(cudaMemcpyAsync(out->power_sums, dps, sizeof(double) * nps, cudaMemcpyDeviceToHost, c->stream));
+        if (out->hist_counts) CU(cudaMemcpyAsync(out->hist_counts, dh, sizeof(unsigned long long) * nh, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (out->elapsed_ms) *out->elapsed_ms = total_ms;
+    return SDEGPU_OK;
+}
+
+// ---- several devices: contiguous path ranges, one host thread per device, one all-reduce of the accumulators --------
+static int run_multi(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out)
+{
+    const int ndev = 1 + (int)c->peers.size(), nx = pr->nx, nt = pr->nt;
+    const uint64_t np = pr->npaths, per = (np + ndev - 1) / ndev;
+    const int nps = 5 * nx, nh = out->hist_counts ? out->hist_nbins + 3 : 0;
+    const bool accum = (pr->flags & SDEGPU_ACCUMULATE) != 0;
+    std::vector<sdegpu_ctx *> devs{c};
+    devs.insert(devs.end(), c->peers.begin(), c->peers.end());
+    std::vector<sdegpu_problem> prs((size_t)ndev, *pr);
+    std::vector<sdegpu_output> outs((size_t)ndev, *out);
+    std::vector<float> ms((size_t)ndev, 0.f);
+    std::vector<int> rcs((size_t)ndev, SDEGPU_OK);
+    std::vector<std::string> errs((size_t)ndev);
+    std::vector<std::vector<double>> hps((size_t)ndev);
+    std::vector<std::vector<unsigned long long>> hhc((size_t)ndev);
+    for (int k = 0; k < ndev; ++k) {
+        const uint64_t p0 = per * k < np ? per * k : np, n = np - p0 < per ? np - p0 : per;
+        sdegpu_problem &q = prs[k];
+        sdegpu_output &o = outs[k];
+        q.npaths = n; q.path_offset = pr->path_offset + p0;
+        if (k > 0) q.flags &= ~(uint32_t)SDEGPU_ACCUMULATE;      // what the caller passed in is added once, on the first device
+        if (pr->B) q.B = pr->B + (size_t)p0 * pr->nB * nt;
+        if (pr->x0_stride) q.x0 = pr->x0 + (size_t)p0 * nx;
+        if (pr->Stau) q.Stau = pr->Stau + p0;
+        if (out->X) o.X = out->X + (size_t)p0 * nx * nt;
+        if (out->XT) o.XT = out->XT + (size_t)p0 * nx;
+        if (out->tau) o.tau = out->tau + p0;
+        if (out->S_tau) o.S_tau = out->S_tau + p0;
+        if (out->S) o.S = out->S + (size_t)p0 * nt;
+        if (out->path_integrals) o.path_integrals = out->path_integrals + (size_t)p0 * nx * 4;
+        if (out->model_integrals) o.model_integrals = out->model_integrals + (size_t)p0 * nx * 2;
+        o.elapsed_ms = &ms[k];
+        if (k > 0) {                                             // device-local accumulators for the host-side fallback
+            if (out->power_sums) { hps[k].assign((size_t)nps, 0.0); o.power_sums = hps[k].data(); }
+            if (out->hist_counts) { hhc[k].assign((size_t)nh, 0ull); o.hist_counts = (uint64_t *)hhc[k].data(); }
+        }
+    }
+    // the all-reduce needs every device's accumulators resident: decide before the shards run
+    NcclApi &nc = nccl_api();
+    bool use_nccl = nc.ok && (out->power_sums || out->hist_counts);
+    if (use_nccl && !c->nccl_comm && !c->nccl_tried) {
+        c->nccl_tried = true;
+        std::vector<int> ids((size_t)ndev);
+        std::vector<ncclComm_t> comms((size_t)ndev);
+        for (int k = 0; k < ndev; ++k) ids[k] = devs[k]->device;
+        if (nc.CommInitAll(comms.data(), ndev, ids.data()) == ncclSuccess)
+            for (int k = 0; k < ndev; ++k) devs[k]->nccl_comm = comms[k];
+    }
+    use_nccl = use_nccl && c->nccl_comm != nullptr;
+
+    c->abort_flag.store(0);
+    std::atomic<int> running{ndev};
+    std::vector<std::thread> th;
+    for (int k = 0; k < ndev; ++k)
+        th.emplace_back([&, k] {
+            if (prs[k].npaths == 0 && !use_nccl) { running.fetch_sub(1); return; }
+            if (prs[k].npaths == 0) {                            // an empty range still takes part in the all-reduce: zeros
+                sdegpu_ctx *d = devs[k];
+                cudaSetDevice(d->device);
+                d->stats.reserve(sizeof(double) * nps + sizeof(unsigned long long) * (size_t)(nh + 1));
+                cudaMemsetAsync(d->stats.p, 0, sizeof(double) * nps + sizeof(unsigned long long) * (size_t)(nh + 1), d->stream);
+                cudaStreamSynchronize(d->stream);
+            } else {
+                rcs[k] = run_host(devs[k], &prs[k], &outs[k], use_nccl, &c->abort_flag);
+                if (rcs[k]) errs[k] = g_err;
+            }
+            running.fetch_sub(1);
+        });
+    while (running.load() > 0) {                                 // the interrupt callback runs on the calling thread only
+        if (c->intr && !c->abort_flag.load() && c->intr(c->intr_user)) c->abort_flag.store(1);
+        std::this_thread::sleep_for(std::chrono::milliseconds(c->intr ? 20 : 2));
+    }
+    for (auto &t : th) t.join();
+    for (int k = 0; k < ndev; ++k)
+        if (rcs[k]) return fail(rcs[k], "device %d: %s", devs[k]->device, errs[k].c_str());
+    float worst = 0.f;
+    for (int k = 0; k < ndev; ++k) worst = ms[k] > worst ? ms[k] : worst;
+    if (out->elapsed_ms) *out->elapsed_ms = worst;               // devices run side by side: the slowest shard
+
+    if (out->power_sums || out->hist_counts) {
+        if (use_nccl) {
+            ncclResult_t r = nc.GroupStart();
+            for (int k = 0; k < ndev && r == ncclSuccess; ++k) {
+                sdegpu_ctx *d = devs[k];
+                cudaSetDevice(d->device);
+                double *ps = (double *)d->stats.p;
+                unsigned long long *hc = (unsigned long long *)(ps + nps);
+                if (out->power_sums) r = nc.AllReduce(ps, ps, (size_t)nps, ncclDouble, ncclSum, (ncclComm_t)d->nccl_comm, d->stream);
+                if (out->hist_counts && r == ncclSuccess) r = nc.AllReduce(hc, hc, (size_t)nh, ncclUint64, ncclSum, (ncclComm_t)d->nccl_comm, d->stream);
+            }
+            if (r == ncclSuccess) r = nc.GroupEnd(); else nc.GroupEnd();
+            if (r != ncclSuccess) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: ncclAllReduce: %s", nc.GetErrorString ? nc.GetErrorString(r) : "error");
+            for (int k = 0; k < ndev; ++k) { cudaSetDevice(devs[k]->device); CU(cudaStreamSynchronize(devs[k]->stream)); }
+            CU(cudaSetDevice(c->device));
+            double *ps = (double *)c->stats.p;
+            if (out->power_sums) CU(cudaMemcpyAsync(out->power_sums, ps, sizeof(double) * nps, cudaMemcpyDeviceToHost, c->stream));
+            if (out->hist_counts) CU(cudaMemcpyAsync(out->hist_counts, ps + nps, sizeof(unsigned long long) * nh, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            c->last_reduction = "nccl";
+        } else {
+            for (int k = 1; k < ndev; ++k) {                     // device order: deterministic
+                if (out->power_sums) for (int v = 0; v < nps; ++v) out->power_sums[v] += hps[k][v];
+                if (out->hist_counts) for (int v = 0; v < nh; ++v) out->hist_counts[v] += hhc[k][v];
+            }
+            c->last_reduction = "host";
+        }
+    } else
+        c->last_reduction = "none";
+    (void)accum;
+    CU(cudaSetDevice(c->device));
+    return SDEGPU_OK;
+}
+
+extern "C" int sdegpu_run(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out)
+{
+    if (!c || !pr || !out) return fail(SDEGPU_ERR_ARG, "sdegpu_run: NULL argument");
+    int rc = validate(pr, out);
+    if (rc) return rc;
+    const bool dev = (pr->flags & SDEGPU_DEVICE_PTRS) != 0;
+    if (dev && !c->peers.empty()) return fail(SDEGPU_ERR_ARG, "sdegpu_run: SDEGPU_DEVICE_PTRS needs a one-device context");
+    CU(cudaSetDevice(c->device));
+    if (pr->npaths == 0) {
+        if (out->elapsed_ms) *out->elapsed_ms = 0.f;
+        return SDEGPU_OK;
+    }
+    if (dev) return run_device_ptrs(c, pr, out);
+    if (!c->peers.empty()) return run_multi(c, pr, out);
+    return run_host(c, pr, out, false, nullptr);
 }
 
 // ---- integrals ----------------------------------------------------------------

@@ -60,7 +60,26 @@ struct RunArgs {
     double *tau, *S_tau;
     double *Spath;                  // device, survival path S[p*nt+i] (k_killed) or nullptr
     double *func;                   // device, path integrals func[(p*nx+j)*4 + {QV, ito, strat, time}] (k_functionals)
+    double *mfunc;                  // device, model integrals mfunc[(p*nx+j)*2 + {int f(X) dt, int g(X) dB}] (k_functionals)
+    // time-dependent closures tabulated on the grid (sdegpu.h ABI 5): f = f0(x) + c(t), g = s(t) g0(x)
+    const double *forcing;          // device, c[j*nt + i] or nullptr
+    const double *gscale;           // device, s[i] or nullptr
 };
+
+// the tabulated time dependence of step i (t_i for the predictor, t_{i+1} for Heun's corrector)
+template <int NX>
+__device__ __forceinline__ void load_tdep(const RunArgs &a, int i, TDep<NX> &td)
+{
+    td.has_c = a.forcing != nullptr;
+    td.has_s = a.gscale != nullptr;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        td.cX[j] = td.has_c ? __ldg(a.forcing + (size_t)j * a.nt + i) : 0.0;
+        td.cY[j] = td.has_c ? __ldg(a.forcing + (size_t)j * a.nt + i + 1) : 0.0;
+    }
+    td.sX = td.has_s ? __ldg(a.gscale + i) : 1.0;
+    td.sY = td.has_s ? __ldg(a.gscale + i + 1) : 1.0;
+}
 
 // ---- terminal statistics ---------------------------------------------------
 // Histogram bin of R's hist(right=TRUE, include.lowest=TRUE) on equal-width breaks;
@@ -704,6 +723,7 @@ __global__ void __launch_bounds__(FUNC_THREADS) k_functionals(const RunArgs a)
 #pragma unroll
         for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
     const int nsteps = a.nt - 1;
+    const bool tdep = a.forcing || a.gscale;
     const uint64_t stride = (uint64_t)gridDim.x * FUNC_THREADS;
     for (uint64_t p = (uint64_t)blockIdx.x * FUNC_THREADS + threadIdx.x; p < a.npaths; p += stride) {
         double x[NX];
@@ -711,10 +731,15 @@ __global__ void __launch_bounds__(FUNC_THREADS) k_functionals(const RunArgs a)
         CumsumAcc qv[NX], il[NX], ir[NX], it[NX];
         F80 big[NX][FUNC_PER_COMP];                              // integer fallback states (local memory, rarely touched)
         double out[NX][FUNC_PER_COMP];
+        CumsumAcc mf[NX], mg[NX];
+        F80 mbig[NX][2];
+        double mout[NX][2];
 #pragma unroll
-        for (int j = 0; j < NX; ++j)
+        for (int j = 0; j < NX; ++j) {
 #pragma unroll
             for (int k = 0; k < FUNC_PER_COMP; ++k) out[j][k] = 0.0;
+            mout[j][0] = mout[j][1] = 0.0;
+        }
         const double *brow = a.B ? a.B + p * (uint64_t)a.nt : nullptr;
         double prev = brow ? __ldg(brow) : 0.0;
         double z[4] = {0.0, 0.0, 0.0, 0.0};
@@ -733,23 +758,48 @@ __global__ void __launch_bounds__(FUNC_THREADS) k_functionals(const RunArgs a)
             double xo[NX];
 #pragma unroll
             for (int j = 0; j < NX; ++j) xo[j] = x[j];
-            sde_step<M, SCHEME, PROJ, A>(a.P, x, dt.x, dB);
+            TDep<NX> td;
+            if (tdep) {
+                load_tdep<NX>(a, i, td);
+                sde_step<M, SCHEME, PROJ, A, true>(a.P, x, dt.x, dB, &td);
+            } else
+                sde_step<M, SCHEME, PROJ, A>(a.P, x, dt.x, dB);
+            if (a.func) {
 #pragma unroll
-            for (int j = 0; j < NX; ++j) {
-                const double dx = __dsub_rn(x[j], xo[j]);
-                out[j][0] = qv[j].add(__dmul_rn(dx, dx), &big[j][0]);
-                out[j][1] = il[j].add(__dmul_rn(xo[j], dB), &big[j][1]);
-                out[j][2] = ir[j].add(__dmul_rn(x[j], dB), &big[j][2]);
-                out[j][3] = it[j].add(__dmul_rn(xo[j], dt.x), &big[j][3]);
+                for (int j = 0; j < NX; ++j) {
+                    const double dx = __dsub_rn(x[j], xo[j]);
+                    out[j][0] = qv[j].add(__dmul_rn(dx, dx), &big[j][0]);
+                    out[j][1] = il[j].add(__dmul_rn(xo[j], dB), &big[j][1]);
+                    out[j][2] = ir[j].add(__dmul_rn(x[j], dB), &big[j][2]);
+                    out[j][3] = it[j].add(__dmul_rn(xo[j], dt.x), &big[j][3]);
+                }
+            }
+            if (a.mfunc) {                                       // itointegral(f(X), times), itointegral(g(X), B): integrands at (t_i, X_i)
+                double fo[NX], go[NX];
+                M::template f<A>(a.P, xo, fo);
+                M::template g<A>(a.P, xo, go);
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {
+                    if (tdep && td.has_c) fo[j] = A::add(fo[j], td.cX[j]);
+                    if (tdep && td.has_s) go[j] = A::mul(td.sX, go[j]);
+                    mout[j][0] = mf[j].add(__dmul_rn(fo[j], dt.x), &mbig[j][0]);
+                    mout[j][1] = mg[j].add(__dmul_rn(go[j], dB), &mbig[j][1]);
+                }
             }
         }
 #pragma unroll
         for (int j = 0; j < NX; ++j) {
-            double *f = a.func + (p * NX + j) * FUNC_PER_COMP;
-            f[0] = out[j][0];
-            f[1] = out[j][1];
-            f[2] = __dmul_rn(0.5, __dadd_rn(out[j][1], out[j][2]));
-            f[3] = out[j][3];
+            if (a.func) {
+                double *f = a.func + (p * NX + j) * FUNC_PER_COMP;
+                f[0] = out[j][0];
+                f[1] = out[j][1];
+                f[2] = __dmul_rn(0.5, __dadd_rn(out[j][1], out[j][2]));
+                f[3] = out[j][3];
+            }
+            if (a.mfunc) {
+                a.mfunc[(p * NX + j) * 2] = mout[j][0];
+                a.mfunc[(p * NX + j) * 2 + 1] = mout[j][1];
+            }
             if (a.XT) a.XT[p * NX + j] = x[j];
         }
         accumulate_terminal<NX>(a, x, acc, sh_hist);
@@ -812,6 +862,7 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
         for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
 
     const int nsteps = a.nt - 1;
+    const bool tdep = a.forcing || a.gscale;
     const uint64_t stride = (uint64_t)gridDim.x * KILLED_THREADS;
     for (uint64_t p = (uint64_t)blockIdx.x * KILLED_THREADS + threadIdx.x; p < a.npaths; p += stride) {
         double x[NX], xo[NX];
@@ -844,7 +895,12 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed(const RunArgs a)
             }
 #pragma unroll
             for (int j = 0; j < NX; ++j) xo[j] = x[j];
-            sde_step<M, SCHEME, PROJ, Strict>(a.P, x, dt.x, dB);
+            if (tdep) {
+                TDep<NX> td;
+                load_tdep<NX>(a, i, td);
+                sde_step<M, SCHEME, PROJ, Strict, true>(a.P, x, dt.x, dB, &td);
+            } else
+                sde_step<M, SCHEME, PROJ, Strict>(a.P, x, dt.x, dB);
             if (a.X) {
 #pragma unroll
                 for (int j = 0; j < NX; ++j) a.X[(p * NX + j) * (uint64_t)a.nt + i + 1] = x[j];
@@ -904,6 +960,7 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed_refill(const RunArgs 
         for (int m = 0; m < 5; ++m) acc[j][m] = 0.0;
 
     const int nsteps = a.nt - 1, lane = threadIdx.x & 31;
+    const bool tdep = a.forcing || a.gscale;
     const uint64_t nwarps = (uint64_t)gridDim.x * (KILLED_THREADS / 32);
     const uint64_t warp = (uint64_t)blockIdx.x * (KILLED_THREADS / 32) + (threadIdx.x >> 5);
     const uint64_t chunk = (a.npaths + nwarps - 1) / nwarps;
@@ -951,7 +1008,12 @@ __global__ void __launch_bounds__(KILLED_THREADS) k_killed_refill(const RunArgs 
             }
 #pragma unroll
             for (int j = 0; j < NX; ++j) xo[j] = x[j];
-            sde_step<M, SCHEME, PROJ, Strict>(a.P, x, dt.x, dB);
+            if (tdep) {
+                TDep<NX> td;
+                load_tdep<NX>(a, i, td);
+                sde_step<M, SCHEME, PROJ, Strict, true>(a.P, x, dt.x, dB, &td);
+            } else
+                sde_step<M, SCHEME, PROJ, Strict>(a.P, x, dt.x, dB);
             if (a.stop_kind != SDEGPU_STOP_NONE && !(stop_value<NX>(a, x) > 0.0)) {      // h(...) <= 0  (:455)
                 last = i + 1; Sout = 0.0;
             } else if (a.kill_kind != SDEGPU_KILL_NONE) {
@@ -981,7 +1043,8 @@ struct LaunchCfg {
     int scheme, proj, arith;
     bool src_b, want_x, killed, want_func;
     bool uniform;        // the time grid is uniform to rounding: one coefficient row as a kernel parameter
-    int grid;            // 0: choose from occupancy
+    bool general;        // time-dependent closures: the general kernel (k_killed without a rule), STRICT arithmetic
+    int grid;            // 0: choose from occupancy; every launcher clamps to 32 blocks per SM, the capacity of the partials buffer
     int sm_count;
     cudaStream_t stream;
 };

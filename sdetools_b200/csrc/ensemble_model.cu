@@ -141,7 +141,8 @@ static int launch_stream(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 template <int SCHEME, int PROJ>
 static int launch_killed(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 {
-    auto kernel = a.X || a.Spath ? k_killed<M, SCHEME, PROJ> : k_killed_refill<M, SCHEME, PROJ>;   // no trajectory: lanes refill
+    // no trajectory: lanes refill (pointless without a rule: every path runs the whole grid)
+    auto kernel = a.X || a.Spath || !c.killed ? k_killed<M, SCHEME, PROJ> : k_killed_refill<M, SCHEME, PROJ>;
     const size_t smem = (a.B ? 0 : ICDF_TABLE_BYTES) + (a.hist ? (size_t)(a.hist_nbins + 3) * 4 : 0);
     const uint64_t work = (a.npaths + KILLED_THREADS - 1) / KILLED_THREADS;
     const int grid = c.grid > 0 ? min(c.grid, 32 * c.sm_count) : occupancy_grid(kernel, KILLED_THREADS, smem, c.sm_count, work);
@@ -165,10 +166,10 @@ static int launch_functionals(const RunArgs &a, const LaunchCfg &c, int *grid_us
 template <int SCHEME, int PROJ>
 static int dispatch_mode(const RunArgs &a, const LaunchCfg &c, int *g)
 {
-    if (c.killed) return launch_killed<SCHEME, PROJ>(a, c, g);
     if (c.want_func)
         return c.src_b && c.arith == SDEGPU_ARITH_STRICT ? launch_functionals<SCHEME, PROJ, Strict>(a, c, g)
                                                          : launch_functionals<SCHEME, PROJ, Fast>(a, c, g);
+    if (c.killed || c.general) return launch_killed<SCHEME, PROJ>(a, c, g);
     if (c.src_b)
         return c.arith == SDEGPU_ARITH_STRICT ? launch_stream<SCHEME, PROJ, Strict>(a, c, g)
                                               : launch_stream<SCHEME, PROJ, Fast>(a, c, g);

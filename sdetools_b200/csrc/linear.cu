@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
                 const double *x = xs + q * d, *db = dBs + q * nB;
                 double f = STRICT ? __dmul_rn(a.A[j], x[0]) : a.A[j] * x[0];
                 for (int k = 1; k < d; ++k) f = madd<STRICT>(f, a.A[(size_t)k * d + j], x[k]);
+                if (a.forcing) f = __dadd_rn(f, __ldg(a.forcing + (size_t)j * a.nt + i));            // A %*% x + c(t_i)
                 double gdb = STRICT ? __dmul_rn(a.G[j], db[0]) : a.G[j] * db[0];
                 for (int k = 1; k < nB; ++k) gdb = madd<STRICT>(gdb, a.G[(size_t)k * d + j], db[k]);
                 ys[e] = STRICT ? __dadd_rn(__dadd_rn(x[j], __dmul_rn(f, ds.x)), gdb) : (x[j] + f * ds.x) + gdb;
@@ -88,6 +89,10 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
                         const double ajk = a.A[(size_t)k * d + j];
                         fx = madd<STRICT>(fx, ajk, x[k]);
                         fy = madd<STRICT>(fy, ajk, y[k]);
+                    }
+                    if (a.forcing) {                                             // ff(times[i],X), ff(times[i+1],Y)  (:316,:321)
+                        fx = __dadd_rn(fx, __ldg(a.forcing + (size_t)j * a.nt + i));
+                        fy = __dadd_rn(fy, __ldg(a.forcing + (size_t)j * a.nt + i + 1));
                     }
                     const double g0 = a.G[j];
                     double gdb = STRICT ? __dmul_rn(__dadd_rn(g0, g0), db[0]) : (g0 + g0) * db[0];
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_small(const LinearArgs a
                 double f = STRICT ? __dmul_rn(Ar[j][0], x[0]) : Ar[j][0] * x[0];
 #pragma unroll
                 for (int k = 1; k < D; ++k) f = madd<STRICT>(f, Ar[j][k], x[k]);
+                if (a.forcing) f = __dadd_rn(f, __ldg(a.forcing + (size_t)j * a.nt + i));            // A %*% x + c(t_i)
                 double gdb = STRICT ? __dmul_rn(Gr[j][0], dB[0]) : Gr[j][0] * dB[0];
 #pragma unroll
                 for (int k = 1; k < NB; ++k) gdb = madd<STRICT>(gdb, Gr[j][k], dB[k]);
@@ -213,6 +219,10 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_small(const LinearArgs a
                     for (int k = 1; k < D; ++k) {
                         fx = madd<STRICT>(fx, Ar[j][k], x[k]);
                         fy = madd<STRICT>(fy, Ar[j][k], y[k]);
+                    }
+                    if (a.forcing) {                                             // ff(times[i],X), ff(times[i+1],Y)  (:316,:321)
+                        fx = __dadd_rn(fx, __ldg(a.forcing + (size_t)j * a.nt + i));
+                        fy = __dadd_rn(fy, __ldg(a.forcing + (size_t)j * a.nt + i + 1));
                     }
                     const double g0 = Gr[j][0];
                     double gdb = STRICT ? __dmul_rn(__dadd_rn(g0, g0), dB[0]) : (g0 + g0) * dB[0];
@@ -338,6 +348,9 @@ __global__ void __launch_bounds__(LIN_THREADS, DP <= 16 ? 2 : 1) k_linear_warp(c
                 f = (f4[0] + f4[1]) + (f4[2] + f4[3]);
                 gdb = (g4[0] + g4[1]) + (g4[2] + g4[3]);
             }
+            const double c0 = (a.forcing && row) ? __ldg(a.forcing + (size_t)j * a.nt + i) : 0.0;
+            const double c1 = (a.forcing && row) ? __ldg(a.forcing + (size_t)j * a.nt + i + 1) : 0.0;
+            if (a.forcing) f = __dadd_rn(f, c0);                 // A %*% x + c(t_i)
             double y = STRICT ? __dadd_rn(__dadd_rn(x, __dmul_rn(f, ds.x)), gdb) : (x + f * ds.x) + gdb;
             if (heun) {                                          // corrector (:323), gX + gY = G + G
                 double fy = 0.0, g2 = 0.0;
@@ -347,6 +360,7 @@ __global__ void __launch_bounds__(LIN_THREADS, DP <= 16 ? 2 : 1) k_linear_warp(c
                     if (k == 0) fy = STRICT ? __dmul_rn(Ar[0], yk) : Ar[0] * yk;
                     else if (k < d) fy = madd<STRICT>(fy, Ar[k], yk);
                 }
+                if (a.forcing) fy = __dadd_rn(fy, c1);           // ff(times[i+1], Y)  (:321)
 #pragma unroll
                 for (int k = 0; k < DP; ++k) {
                     const double bk = __shfl_sync(0xffffffffu, dBj, base + k);

@@ -19,6 +19,7 @@ struct LinearArgs {
     double *X, *XT;           // X[(p*d+j)*nt+i], XT[p*d+j]
     double *moments;          // [5*d] {n,S1..S4} per component about center, or nullptr
     const double *center;     // device, d doubles
+    const double *forcing;    // device, c[j*nt + i]: drift A x + c(t_i) (input term F u(t) of R/sdetools.R:211,:363), or nullptr
     uint64_t npaths, path_offset;
     PhiloxKey seed;
     int nt, d, nB, scheme, strict, accumulate;

@@ -280,7 +280,7 @@ static size_t dense_smem(int dp, int kkg)
 // 0: not eligible, 1: diagonal G (normals in the GEMM epilogue), 2: dense G (second GEMM on a tile of normals)
 int dmma_mode(const LinearArgs &a, const double *hostG)
 {
-    if (a.B || a.scheme != SDEGPU_EULER || a.X || a.d <= 32 || a.d > 256 || a.nB < 1) return 0;
+    if (a.B || a.forcing || a.scheme != SDEGPU_EULER || a.X || a.d <= 32 || a.d > 256 || a.nB < 1) return 0;
     bool diag = a.nB == a.d;
     for (int c = 0; c < a.nB && diag; ++c)
         for (int r = 0; r < a.d; ++r)

@@ -104,14 +104,28 @@ template <int PROJ> __device__ __forceinline__ double project(double v)
     return v;
 }
 
+// Time dependence of the closures, tabulated on the grid (sdegpu.h ABI 5): f(t,x) = f0(x) + c(t), g(t,x) = s(t) g0(x).
+// cX/sX belong to t_i (predictor / Euler), cY/sY to t_{i+1} (Heun corrector evaluates ff(times[i+1], Y), R/sdetools.R:321-322).
+template <int NX> struct TDep {
+    double cX[NX], cY[NX], sX, sY;
+    bool has_c, has_s;                                           // warp-uniform: which of the two tables exist
+};
+
 // One time step of one path, state in registers.
-template <class M, int SCHEME, int PROJ, class A>
-__device__ __forceinline__ void sde_step(const KParams &P, double (&x)[M::NX], double dt, double dB)
+template <class M, int SCHEME, int PROJ, class A, bool TD = false>
+__device__ __forceinline__ void sde_step(const KParams &P, double (&x)[M::NX], double dt, double dB, const TDep<M::NX> *td = nullptr)
 {
     constexpr int NX = M::NX;
     double fX[NX], gX[NX];
     M::template f<A>(P, x, fX);
     M::template g<A>(P, x, gX);
+    if (TD) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            if (td->has_c) fX[j] = A::add(fX[j], td->cX[j]);
+            if (td->has_s) gX[j] = A::mul(td->sX, gX[j]);
+        }
+    }
     if (SCHEME == SDEGPU_EULER) {
 #pragma unroll
         for (int j = 0; j < NX; ++j)
@@ -123,6 +137,13 @@ __device__ __forceinline__ void sde_step(const KParams &P, double (&x)[M::NX], d
             Y[j] = project<PROJ>(A::add(A::add(x[j], A::mul(fX[j], dt)), A::mul(gX[j], dB)));
         M::template f<A>(P, Y, fY);
         M::template g<A>(P, Y, gY);
+        if (TD) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                if (td->has_c) fY[j] = A::add(fY[j], td->cY[j]);
+                if (td->has_s) gY[j] = A::mul(td->sY, gY[j]);
+            }
+        }
         if (A::strict) {
 #pragma unroll
             for (int j = 0; j < NX; ++j)

@@ -25,12 +25,21 @@ def _ptr(a):
 
 
 class Engine:
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one CUDA ordinal, or a sequence of ordinals for a multi-GPU context of this process
+        (sdegpu_create_multi: the ensemble is split into contiguous path ranges, accumulators all-reduced)."""
         self.lib = _lib.load()
         h = C.c_void_p()
-        check(self.lib.sdegpu_create(int(device), C.byref(h)))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            check(self.lib.sdegpu_create_multi(ids, len(device), C.byref(h)))
+            self.devices = [int(d) for d in device]
+        else:
+            check(self.lib.sdegpu_create(int(device), C.byref(h)))
+            self.devices = [int(device)]
         self._h = h
-        self.device = int(device)
+        self.device = self.devices[0]
+        self._intr_keep = None
         info = _lib.DevInfo()
         check(self.lib.sdegpu_device_info(self._h, C.byref(info)))
         self.info = {"name": info.name.decode(), "sm_count": info.sm_count, "cc": (info.cc_major, info.cc_minor),
@@ -59,15 +68,34 @@ class Engine:
     def synchronize(self):
         check(self.lib.sdegpu_synchronize(self._h))
 
+    # -- chunking and interruption of host-pointer runs -------------------------
+    def set_interrupt(self, fn=None):
+        """fn() -> truthy stops the running sdegpu_run between two chunks (SdeGpuError code -5); None removes it."""
+        if fn is None:
+            self._intr_keep = None
+            check(self.lib.sdegpu_set_interrupt(self._h, None, None))
+            return
+        cb = _lib.INTERRUPT_FN(lambda _user: 1 if fn() else 0)
+        self._intr_keep = cb                                   # ctypes callbacks must outlive their registration
+        check(self.lib.sdegpu_set_interrupt(self._h, C.cast(cb, C.c_void_p), None))
+
+    def set_chunk_paths(self, paths: int = 0):
+        check(self.lib.sdegpu_set_chunk_paths(self._h, int(paths)))
+
+    @property
+    def last_reduction(self) -> str:
+        return self.lib.sdegpu_last_reduction(self._h).decode()
+
     # -- ensembles ------------------------------------------------------------
     def run(self, model, scheme, params, times, x0, *, nx, nB=1, npaths, B=None, projection="identity",
             arith=None, seed=0, path_offset=0, X=None, XT=None, power_sums=None, center=None,
             hist_counts=None, hist=None, accumulate=False, want_time=False, kill=None, stop=None, S0=1.0,
-            Stau=None, tau=None, S_tau=None, path_integrals=None, exact_grid=False, S_path=None):
+            Stau=None, tau=None, S_tau=None, path_integrals=None, exact_grid=False, S_path=None, model_integrals=None,
+            drift_forcing=None, diffusion_scale=None):
         """Thin, allocation-free call of sdegpu_run.  B / per-path x0 / outputs are either all numpy
         (host pointers) or all torch CUDA tensors (device pointers: work is only enqueued, on torch's current stream).
         Layouts are the reference's: B[(p*nB+k)*nt+i], X[(p*nx+j)*nt+i], XT[p*nx+j]."""
-        bufs = [b for b in (B, X, XT, power_sums, hist_counts, Stau, tau, S_tau, path_integrals, S_path) if b is not None]
+        bufs = [b for b in (B, X, XT, power_sums, hist_counts, Stau, tau, S_tau, path_integrals, S_path, model_integrals) if b is not None]
         on_dev = any(_is_torch(b) for b in bufs)
         if on_dev and not all(_is_torch(b) and b.is_cuda for b in bufs):
             raise TypeError("mixing host and device buffers in one call is not supported")
@@ -77,6 +105,8 @@ class Engine:
                     raise ValueError("device buffers must be contiguous")
             elif not b.flags["C_CONTIGUOUS"] and not b.flags["F_CONTIGUOUS"]:
                 raise ValueError("host buffers must be contiguous")
+            if b is not hist_counts and str(b.dtype).replace("torch.", "") != "float64":
+                raise TypeError(f"buffers must be float64, got {b.dtype}")
         params = np.ascontiguousarray(np.ravel(params), dtype=np.float64)
         times = np.ascontiguousarray(times, dtype=np.float64)
         per_path_x0 = _is_torch(x0) or (np.size(x0) != nx)
@@ -107,10 +137,18 @@ class Engine:
             pr.stop_kind, pr.stop_comp, pr.stop_lo, pr.stop_hi = _lib.STOP[stop.sdegpu_stop], stop.component, stop.lo, stop.hi
         pr.S0 = float(S0)
         pr.Stau = _ptr(Stau)
+        forcing_keep = scale_keep = None
+        if drift_forcing is not None:                        # c[j*nt + i]: column-major nt x nx
+            forcing_keep = np.ascontiguousarray(np.asarray(drift_forcing, dtype=np.float64).reshape(times.size, int(nx)).T)
+            pr.drift_forcing = _ptr(forcing_keep)
+        if diffusion_scale is not None:
+            scale_keep = np.ascontiguousarray(np.asarray(diffusion_scale, dtype=np.float64).reshape(times.size))
+            pr.diffusion_scale = _ptr(scale_keep)
         out = Output()
         out.struct_size = C.sizeof(Output)
         out.X, out.XT, out.power_sums, out.hist_counts = _ptr(X), _ptr(XT), _ptr(power_sums), _ptr(hist_counts)
         out.tau, out.S_tau, out.path_integrals, out.S = _ptr(tau), _ptr(S_tau), _ptr(path_integrals), _ptr(S_path)
+        out.model_integrals = _ptr(model_integrals)
         center_keep = None
         if center is not None:
             center_keep = np.ascontiguousarray(np.ravel(center), dtype=np.float64)
@@ -224,6 +262,10 @@ def default_engine(device=None) -> Engine:
     import os
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
+    if isinstance(device, (list, tuple)):
+        device = tuple(int(d) for d in device)                 # a multi-GPU context of this process
+        if len(device) == 1:
+            device = device[0]
     if device not in _engines:
         _engines[device] = Engine(device)
     return _engines[device]

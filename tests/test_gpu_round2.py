@@ -1,0 +1,240 @@
+"""GPU parity of the ABI-5 surface: time-dependent closures f(t,x), g(t,x) (R/sdetools.R:381-394), integrals of the
+model's own drift and diffusion (vignettes/ItoIntegrals.Rmd:82-93), the chunk pipeline of host-pointer runs, the
+interrupt callback and the multi-GPU context.  Bar as in test_gpu_parity.py: bit-exact against the oracle with a
+supplied B (1e-12 relative where `%*%` is involved), chunking/sharding invariance bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import sde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sde(gpu):
+    import sdetools_b200
+    return sdetools_b200
+
+
+@pytest.fixture(scope="module")
+def eng(sde):
+    return sde.default_engine(0)
+
+
+def brownian(nt, nB, npaths, seed, dt=0.01):
+    rng = np.random.default_rng(seed)
+    t = O.r_seq(0, (nt - 1) * dt, dt)
+    z = rng.standard_normal((nt, nB * npaths))
+    z[0] = 0.0
+    B = O.r_cumsum_cols(np.sqrt(np.concatenate(([0.0], O.r_diff(t))))[:, None] * z)
+    return t, B.reshape(nt, nB, npaths)
+
+
+# ---- time-dependent closures --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+@pytest.mark.parametrize("model,params,x0,proj", [("ou", [1.3, 0.7, 0.9], [2.0], "identity"), ("cir", [1.0, 1.0, 1.0], [1.0], "abs"),
+                                                  ("vdp", [1.0, 0.5], [0.1, -0.2], "identity")])
+def test_time_dependent_closures_bit_identical_to_the_reference_loop(sde, scheme, model, params, x0, proj):
+    """f(t,x) = f0(x) + c(t), g(t,x) = s(t) g0(x) with a supplied B: every path equals the restated R loop run on the
+    same closures, bit for bit (heun evaluates ff(times[i+1], Y): R/sdetools.R:321-322)."""
+    nx = len(x0)
+    t, B = brownian(77, 1, 9, 11)
+    f0, g0 = getattr(sde.catalogue, model)(*params)
+    fo, go, _, _ = O.catalogue(model, params)
+    c = (lambda tt: np.array([0.3 * np.sin(2 * tt), np.cos(tt)])[:nx])
+    s = (lambda tt: 1.0 + 0.5 * np.cos(3 * tt))
+    f, g = sde.catalogue.forced(f0, c), sde.catalogue.scaled(g0, s)
+    p = O.projection(proj)
+    got = getattr(sde, scheme)(f, g, t, x0, B, p=proj)["X"]
+    ref = getattr(O, scheme)
+    for k in range(9):
+        want = ref(lambda tt, x: fo(x) + c(tt), lambda tt, x: s(tt) * go(x), t, np.array(x0), B=B[:, :, k], p=p)["X"]
+        assert np.array_equal(got[:, :, k], want.reshape(t.size, nx))
+    # each table alone (the other closure autonomous)
+    only_c = getattr(sde, scheme)(f, g0, t, x0, B[:, :, 0], p=proj)["X"]
+    assert np.array_equal(only_c, ref(lambda tt, x: fo(x) + c(tt), go, t, np.array(x0), B=B[:, :, 0], p=p)["X"].reshape(t.size, nx))
+    only_s = getattr(sde, scheme)(f0, g, t, x0, B[:, :, 0], p=proj)["X"]
+    assert np.array_equal(only_s, ref(fo, lambda tt, x: s(tt) * go(x), t, np.array(x0), B=B[:, :, 0], p=p)["X"].reshape(t.size, nx))
+
+
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+@pytest.mark.parametrize("d,nB", [(2, 1), (6, 3), (40, 2)])
+def test_linear_system_with_input_matches_the_reference_example(sde, scheme, d, nB):
+    """f <- function(t,x) A %*% x + F * sin(2*t) (R/sdetools.R:211,:363) on the three linear kernels (registers, warp,
+    shared memory); `%*%` summation order is BLAS's, so 1e-12 relative."""
+    rng = np.random.default_rng(d)
+    A = -0.5 * np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
+    G = 0.4 * rng.standard_normal((d, nB))
+    F = rng.standard_normal(d)
+    x0 = rng.standard_normal(d)
+    t, B = brownian(41, nB, 5, 3)
+    f0, g0 = sde.catalogue.linear(A, G)
+    f = sde.catalogue.forced(f0, lambda tt: F * np.sin(2 * tt))
+    got = getattr(sde, scheme)(f, g0, t, x0, B)["X"]
+    for k in range(5):
+        want = getattr(O, scheme)(lambda tt, x: A @ x + F * np.sin(2 * tt), lambda x: G, t, x0, B=B[:, :, k])["X"]
+        assert np.allclose(got[:, :, k], want, rtol=1e-12, atol=1e-13)
+
+
+def test_time_dependent_run_with_the_fused_generator(sde, eng):
+    """No B: the increments are the generator's (same stream as every other kernel), the step is the STRICT one."""
+    t = np.arange(101) * 0.01
+    f0, g0 = sde.catalogue.ou(1.0, 0.0, 0.5)
+    f = sde.catalogue.forced(f0, lambda tt: np.sin(2 * tt))
+    res = sde.euler(f, g0, t, 0.3, npaths=500, seed=42)
+    z = eng.normals(42, 0, 500, 100)                             # (nsteps, npaths)
+    x = np.full(500, 0.3)
+    for i in range(100):
+        dt = t[i + 1] - t[i]
+        x = (x + (1.0 * (0.0 - x) + np.sin(2 * t[i])) * dt) + 0.5 * (np.sqrt(dt) * z[i])
+    assert np.array_equal(res["X"][-1, 0], x)
+
+
+# ---- integrals of f(X) and g(X) along the path -----------------------------------------------------------------------
+@pytest.mark.parametrize("model,params,x0,proj", [("dwsqrt", [], [0.0], "identity"), ("cir", [1.0, 1.0, 1.0], [1.0], "abs"),
+                                                  ("vdp", [1.0, 0.5], [0.1, -0.2], "identity")])
+def test_model_integrals_equal_itointegral_on_the_stored_path(sde, model, params, x0, proj):
+    """itointegral(f(X),t) + itointegral(g(X),B) accumulated in the step loop (vignettes/ItoIntegrals.Rmd:82-93):
+    bit-identical to the oracle's itointegral on the stored path, and their sum reproduces X_T - X_0 for euler()."""
+    nx = len(x0)
+    t, B = brownian(150, 1, 7, 23)
+    f, g = getattr(sde.catalogue, model)(*params)
+    fo, go, _, _ = O.catalogue(model, params)
+    path = sde.euler(f, g, t, x0, B, p=proj)["X"]
+    res = sde.euler(f, g, t, x0, B, p=proj, model_integrals=True, integrals=True)
+    for k in range(7):
+        X = path[:, :, k]
+        fX = np.array([np.atleast_1d(fo(X[i])) for i in range(t.size)])
+        gX = np.array([np.atleast_1d(go(X[i])) for i in range(t.size)])
+        for j in range(nx):
+            assert res["model_integrals"]["drift"][j, k] == O.itointegral(fX[:, j], t)[-1]
+            assert res["model_integrals"]["noise"][j, k] == O.itointegral(gX[:, j], B[:, 0, k])[-1]
+        if proj == "identity":
+            tot = res["model_integrals"]["drift"][:, k] + res["model_integrals"]["noise"][:, k]
+            assert np.allclose(tot, X[-1] - X[0], rtol=0, atol=5e-14 * t.size)
+        assert res["integrals"]["QV"][0, k] == O.QuadraticVariation(X[:, 0])[-1]
+
+
+# ---- the chunk pipeline ------------------------------------------------------------------------------------------------
+def test_chunked_host_runs_equal_single_launch(sde, eng):
+    """Host-pointer runs cut into path ranges (pinned staging, copy streams) give the same bytes as one launch: supplied-B
+    trajectories, fused-generator trajectories, terminal states, histogram counts; power sums to summation order."""
+    t, B = brownian(130, 1, 1000, 4)
+    f, g = sde.catalogue.cir(1.0, 1.0, 1.0)
+    try:
+        eng.set_chunk_paths(0)
+        one = sde.heun(f, g, t, 1.0, B, p=abs, moments=True, center=[1.0], hist=(0.0, 4.0, 32))
+        gen1 = sde.heun(f, g, t, 1.0, p=abs, npaths=5000, seed=9, moments=True, center=[1.0], hist=(0.0, 4.0, 32))
+        for cp in (1, 37, 256, 999):
+            eng.set_chunk_paths(cp)
+            got = sde.heun(f, g, t, 1.0, B, p=abs, moments=True, center=[1.0], hist=(0.0, 4.0, 32))
+            assert np.array_equal(got["X"], one["X"]) and np.array_equal(got["XT"], one["XT"])
+            assert np.array_equal(got["hist"]["counts"], one["hist"]["counts"])
+            assert np.allclose(got["power_sums"], one["power_sums"], rtol=1e-13)
+        eng.set_chunk_paths(777)
+        gen = sde.heun(f, g, t, 1.0, p=abs, npaths=5000, seed=9, moments=True, center=[1.0], hist=(0.0, 4.0, 32))
+        assert np.array_equal(gen["X"], gen1["X"]) and np.array_equal(gen["hist"]["counts"], gen1["hist"]["counts"])
+        # mortality outputs travel through the same pipeline
+        r = sde.catalogue.kill_exp(0.5, 2.0)
+        eng.set_chunk_paths(0)
+        k1 = sde.euler(f, g, t, 1.0, B, p=abs, r=r, Stau=np.linspace(0.05, 0.95, 1000))
+        eng.set_chunk_paths(123)
+        k2 = sde.euler(f, g, t, 1.0, B, p=abs, r=r, Stau=np.linspace(0.05, 0.95, 1000))
+        assert np.array_equal(k1["tau"], k2["tau"]) and np.array_equal(k1["S"], k2["S"])
+        assert np.array_equal(k1["X"], k2["X"], equal_nan=True) and np.array_equal(k1["S_path"], k2["S_path"], equal_nan=True)
+    finally:
+        eng.set_chunk_paths(0)
+
+
+def test_large_host_trajectory_goes_through_pinned_staging(sde, eng):
+    """A 400 MB trajectory (automatic chunking: ~128 MB per chunk, several chunks) equals the device-resident run."""
+    import torch
+    t = np.arange(1001) * 0.01
+    P = 25000
+    f, g = sde.catalogue.vdp(1.0, 0.5)
+    res = sde.euler(f, g, t, [0.0, 0.0], npaths=P, seed=3)
+    Xd = torch.empty(P * 2 * 1001, dtype=torch.float64, device="cuda")
+    eng.run("vdp", "euler", [1.0, 0.5], t, [0.0, 0.0], nx=2, npaths=P, seed=3, X=Xd)
+    torch.cuda.synchronize()
+    assert np.array_equal(res["X"].reshape(-1, order="F"), Xd.cpu().numpy())
+
+
+def test_interrupt_callback_stops_between_chunks(sde, eng):
+    from sdetools_b200._lib import SdeGpuError
+    t = np.arange(2001) * 0.0005
+    f, g = sde.catalogue.ou(1.0, 0.0, 1.0)
+    calls = []
+    try:
+        eng.set_chunk_paths(200000)
+        eng.set_interrupt(lambda: calls.append(1) or len(calls) >= 3)
+        with pytest.raises(SdeGpuError) as ei:
+            sde.euler(f, g, t, 0.0, npaths=2_000_000, seed=1, output="none", moments=True)
+        assert ei.value.code == -5 and len(calls) == 3
+        calls.clear()
+        eng.set_interrupt(lambda: calls.append(1) and False)
+        res = sde.euler(f, g, t, 0.0, npaths=2_000_000, seed=1, output="none", moments=True)
+        assert len(calls) == 9 and res["power_sums"][0, 0] == 2_000_000      # ten chunks, nine gaps
+        # automatic chunking with a callback set: about 2e10 path-steps per chunk, here one chunk
+        eng.set_chunk_paths(0)
+        calls.clear()
+        sde.euler(f, g, t, 0.0, npaths=100000, seed=1, output="none", moments=True)
+        assert calls == []
+    finally:
+        eng.set_interrupt(None)
+        eng.set_chunk_paths(0)
+
+
+# ---- several GPUs in one process ---------------------------------------------------------------------------------------
+def _ndev():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_multi_device_context_equals_one_device(sde):
+    """sdegpu_create_multi: contiguous path ranges per device, global path ids, one all-reduce of the accumulators.
+    Per-path outputs and histogram counts are identical to the one-device run; power sums to summation order."""
+    if _ndev() < 2:
+        pytest.skip("needs two GPUs")
+    from sdetools_b200.engine import Engine
+    n = min(_ndev(), 4)
+    multi = Engine(list(range(n)))
+    one = sde.default_engine(0)
+    t = np.arange(501) * 0.002
+    kw = dict(nx=1, npaths=100_003, projection="abs", seed=77, center=[1.0], hist=(0.0, 8.0, 64))
+    out = {}
+    for name, e in (("one", one), ("multi", multi)):
+        XT, ps, hc = np.empty(100_003), np.zeros(5), np.zeros(67, dtype=np.uint64)
+        e.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], XT=XT, power_sums=ps, hist_counts=hc, **kw)
+        out[name] = (XT, ps, hc)
+    assert multi.last_reduction in ("nccl", "host")
+    assert np.array_equal(out["one"][0], out["multi"][0]) and np.array_equal(out["one"][2], out["multi"][2])
+    assert np.allclose(out["one"][1], out["multi"][1], rtol=1e-12) and out["multi"][1][0] == 100_003
+    # supplied B and a trajectory: every device reads and writes its own slice of the host arrays
+    tb, B = brownian(60, 1, 1001, 2)
+    Bf = np.asfortranarray(B)
+    X1, X2 = np.empty((60, 1, 1001), order="F"), np.empty((60, 1, 1001), order="F")
+    one.run("ou", "euler", [1.0, 0.0, 1.0], tb, [0.5], nx=1, npaths=1001, B=Bf, X=X1)
+    multi.run("ou", "euler", [1.0, 0.0, 1.0], tb, [0.5], nx=1, npaths=1001, B=Bf, X=X2)
+    assert np.array_equal(X1, X2)
+    # ACCUMULATE adds what the caller passed in exactly once
+    ps2, hc2 = out["multi"][1].copy(), out["multi"][2].copy()
+    multi.run("cir", "heun", [1.0, 1.0, 1.0], t, [1.0], power_sums=ps2, hist_counts=hc2, accumulate=True,
+              **{**kw, "seed": 78})
+    assert ps2[0] == 200_006 and int(hc2.sum()) == 200_006
+    multi.close()
+
+
+def test_multi_device_host_reduction_fallback(sde, monkeypatch):
+    if _ndev() < 2:
+        pytest.skip("needs two GPUs")
+    import subprocess
+    import sys
+    code = ("import numpy as np, sdetools_b200 as s; from sdetools_b200.engine import Engine;"
+            "e=Engine([0,1]); t=np.arange(101)*0.01; ps=np.zeros(5); hc=np.zeros(19,dtype=np.uint64);"
+            "e.run('ou','euler',[1.0,0.0,1.0],t,[0.0],nx=1,npaths=50001,seed=5,power_sums=ps,hist_counts=hc,hist=(-3.0,3.0,16));"
+            "print(e.last_reduction, int(ps[0]), int(hc.sum()))")
+    import os
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, "SDEGPU_NO_NCCL": "1"},
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split() == ["host", "50001", "50001"]

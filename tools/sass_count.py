@@ -105,10 +105,14 @@ def main():
     for a, op, ar, _ in body:
         cats[classify(op, ar)] = cats.get(classify(op, ar), 0) + 1
     total = len(body)
+    nfma = sum(1 for _, op, _, _ in body if op.startswith("DFMA"))
+    nadd = sum(1 for _, op, _, _ in body if op.startswith(("DADD", "DMUL")))
     res = {"kernel": name, "loop": [hex(ins[j][0]), hex(ins[i][0])], "steps_per_iteration": args.steps_per_iter,
            "instructions_per_iteration": total, "instructions_per_path_step": total / args.steps_per_iter,
            "per_path_step": {k: v / args.steps_per_iter for k, v in sorted(cats.items())},
-           "fp64_per_path_step": cats.get("fp64", 0) / args.steps_per_iter}
+           "fp64_per_path_step": cats.get("fp64", 0) / args.steps_per_iter,
+           "dfma_per_path_step": nfma / args.steps_per_iter, "dadd_dmul_per_path_step": nadd / args.steps_per_iter,
+           "fp64_flops_per_path_step": (2 * nfma + nadd) / args.steps_per_iter}
     if args.listing:
         for a, op, ar, line in body:
             print(f"{classify(op, ar):8s} {line.strip()}")
