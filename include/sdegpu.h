@@ -266,6 +266,20 @@ SDEGPU_API int sdegpu_law_eval(sdegpu_ctx *ctx, int32_t law, int32_t what, const
                 int32_t stratonovich, const double *x0, int64_t x0_stride, const double *x, uint64_t n, double *out,
                 uint32_t flags);
 
+/* Linear-SDE laws at the dimension the device integrates.  The reference's lyap() solves the
+ * d^2 x d^2 Kronecker system (O(d^6), R/sdetools.R:593-600) and cannot validate a d = 256 run; these are O(d^3) and
+ * GEMM-shaped, with the matrix products on the GPU.  All matrices are HOST pointers, column-major (R's layout).
+ *   sdegpu_lyap     lyap(A, Q): X with A X + X t(A) + Q = 0, d x d.  d <= 40: the reference's Kronecker system itself;
+ *                   larger: bilinear transform + doubling, which needs the spectrum of A strictly on one side of the
+ *                   imaginary axis (SDEGPU_ERR_ARG otherwise, like the reference's solve() error for a singular system).
+ *   sdegpu_dlinsde  dLinSDE(A, G, t, x0, u, S0) (:508-572).  G is d x nB.  S0 NULL = 0*A.  x0 NULL: eAt (d x d) and St are
+ *                   written (list(eAt, St), :536-538); else EX (d) and St.  u NULL / u_cols = 1 (zero-order hold, :545-553)
+ *                   / u_cols = 2 (first-order hold from u[,1] to u[,2], :559-571).  St follows the reference: Sinf from the
+ *                   Lyapunov equation when it has a solution, Van Loan's block exponential otherwise (:520-534). */
+SDEGPU_API int sdegpu_lyap(sdegpu_ctx *ctx, const double *A, const double *Q, int32_t d, double *X);
+SDEGPU_API int sdegpu_dlinsde(sdegpu_ctx *ctx, const double *A, const double *G, int32_t d, int32_t nB, double t, const double *x0,
+                   const double *u, int32_t u_cols, const double *S0, double *eAt, double *EX, double *St);
+
 /* Generator introspection (tests / known-answer vectors). */
 SDEGPU_API int sdegpu_philox4x32_10(sdegpu_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* z[i*npaths + p] = standard normal handed to step i, channel `channel`, of path path_offset+p (host ptr). */

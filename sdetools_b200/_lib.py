@@ -83,6 +83,8 @@ SYMBOLS = {
                                         _vp, _vp, _vp, _vp, _vp, _u32]),
     "sdegpu_rlaw": (C.c_int, [_vp, _i32, _dp, C.c_double, _i32, _vp, C.c_int64, _u64, _i32, _u64, _u64, _vp, _vp, _u32]),
     "sdegpu_law_eval": (C.c_int, [_vp, _i32, _i32, _dp, C.c_double, _i32, _vp, C.c_int64, _vp, _u64, _vp, _u32]),
+    "sdegpu_lyap": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "sdegpu_dlinsde": (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.c_double, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "sdegpu_philox4x32_10": (C.c_int, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "sdegpu_normals": (C.c_int, [_vp, _u64, _u64, _u64, _u32, _i32, _vp]),
     "sdegpu_measure_fp64_peak": (C.c_int, [_vp, _dp]),

@@ -24,6 +24,7 @@
 #include "integrals.cuh"
 #include "laws.cuh"
 #include "linear.cuh"
+#include "linlaws.cuh"
 
 namespace sdegpu {
 int launch_model_0(const RunArgs &, const LaunchCfg &, int *);
@@ -1149,6 +1150,38 @@ int sdegpu_rlaw(sdegpu_ctx *c, int32_t law, const double params[3], double t, in
         if (path) CU(cudaMemcpyAsync(path, q.path, path_bytes, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     }
+    return SDEGPU_OK;
+}
+
+}  // extern "C"
+
+// ---- linear-SDE laws --------------------------------------------------------------
+extern "C" {
+
+int sdegpu_lyap(sdegpu_ctx *c, const double *A, const double *Q, int32_t d, double *X)
+{
+    if (!c || !A || !Q || !X) return fail(SDEGPU_ERR_ARG, "sdegpu_lyap: NULL argument");
+    if (d < 1 || d > 8192) return fail(SDEGPU_ERR_ARG, "sdegpu_lyap: d must be in [1, 8192]");
+    CU(cudaSetDevice(c->device));
+    const char *why = "";
+    const int rc = linlaws_lyap(c->stream, A, Q, d, X, &why);
+    if (rc) return fail(rc, "sdegpu_lyap: %s", why);
+    return SDEGPU_OK;
+}
+
+int sdegpu_dlinsde(sdegpu_ctx *c, const double *A, const double *G, int32_t d, int32_t nB, double t, const double *x0, const double *u,
+                   int32_t u_cols, const double *S0, double *eAt, double *EX, double *St)
+{
+    if (!c || !A || !G || !St) return fail(SDEGPU_ERR_ARG, "sdegpu_dlinsde: NULL argument");
+    if (d < 1 || d > 2048 || nB < 1) return fail(SDEGPU_ERR_ARG, "sdegpu_dlinsde: d must be in [1, 2048] and nB >= 1");
+    if (!isfinite(t)) return fail(SDEGPU_ERR_ARG, "sdegpu_dlinsde: t must be finite");
+    if (x0 && !EX) return fail(SDEGPU_ERR_ARG, "sdegpu_dlinsde: EX is NULL although x0 is given");
+    if (u && (u_cols != 1 && u_cols != 2)) return fail(SDEGPU_ERR_ARG, "sdegpu_dlinsde: u_cols must be 1 (constant) or 2 (affine in time)");
+    if (u && u_cols == 2 && t == 0.0) return fail(SDEGPU_ERR_ARG, "sdegpu_dlinsde: first-order hold needs t != 0");
+    CU(cudaSetDevice(c->device));
+    const char *why = "";
+    const int rc = linlaws_dlinsde(c->stream, A, G, d, nB, t, x0, u, u ? u_cols : 0, S0, eAt, EX, St, &why);
+    if (rc) return fail(rc, "sdegpu_dlinsde: %s", why);
     return SDEGPU_OK;
 }
 

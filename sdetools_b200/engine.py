@@ -230,6 +230,32 @@ class Engine:
         check(self.lib.sdegpu_law_eval(self._h, {"ou": 0, "cir": 1}[law], {"d": 0, "p": 1}[what], p, float(t),
                                        int(bool(stratonovich)), _ptr(x0), stride, _ptr(x), n, _ptr(out), self._flags(x0, x, out)))
 
+    # -- linear-SDE laws ----------------------------------------------------------
+    def lyap(self, A, Q):
+        """sdegpu_lyap: X with A X + X A' + Q = 0 (column-major host matrices)."""
+        A = np.asfortranarray(A, dtype=np.float64)
+        Q = np.asfortranarray(Q, dtype=np.float64)
+        X = np.empty_like(A, order="F")
+        check(self.lib.sdegpu_lyap(self._h, _ptr(A), _ptr(Q), A.shape[0], _ptr(X)))
+        return X
+
+    def dlinsde(self, A, G, t, x0=None, u=None, S0=None):
+        """sdegpu_dlinsde: (eAt | EX, St) of dX = (A X + u) dt + G dB over time t."""
+        A = np.asfortranarray(A, dtype=np.float64)
+        d = A.shape[0]
+        G = np.asfortranarray(np.asarray(G, dtype=np.float64).reshape(d, -1))
+        x0k = None if x0 is None else np.ascontiguousarray(np.ravel(x0), dtype=np.float64)
+        uk, ucols = None, 0
+        if u is not None:
+            uk = np.asfortranarray(np.asarray(u, dtype=np.float64).reshape(d, -1))
+            ucols = uk.shape[1]
+        S0k = None if S0 is None else np.asfortranarray(S0, dtype=np.float64)
+        St = np.empty((d, d), order="F")
+        first = np.empty(d) if x0 is not None else np.empty((d, d), order="F")
+        check(self.lib.sdegpu_dlinsde(self._h, _ptr(A), _ptr(G), d, G.shape[1], float(t), _ptr(x0k), _ptr(uk), ucols, _ptr(S0k),
+                                      None if x0 is not None else _ptr(first), _ptr(first) if x0 is not None else None, _ptr(St)))
+        return first, St
+
     # -- introspection ------------------------------------------------------------
     def philox4x32_10(self, ctr, key):
         a = (C.c_uint32 * 4)(*ctr)

@@ -1,23 +1,22 @@
 """Transition laws of linear SDEs at the dimension the device integrates.
 
 Host-side mirror of `dLinSDE` (R/sdetools.R:508-572) and `lyap` (:593-600) with the same arguments and
-return values, but O(d^3): the reference solves the Lyapunov equation through the d^2 x d^2 Kronecker
-system (O(d^6), unusable at the d = 256 the DMMA kernel runs), here it is Bartels-Stewart (LAPACK via
-scipy) and, where the Lyapunov equation is singular, Van Loan's block matrix exponential — the same
-fallback the reference takes (:525-534), reached by the same condition (lambda_i + lambda_j = 0).
+return values, over `sdegpu_lyap` / `sdegpu_dlinsde` of libsdegpu.so (csrc/linlaws.cu): O(d^3) and GEMM-shaped
+(Pade scaling-and-squaring, bilinear transform + doubling), where the reference solves the d^2 x d^2 Kronecker
+system (O(d^6), unusable at the d = 256 the DMMA kernel runs).  Where the Lyapunov equation has no solution the
+library takes Van Loan's block matrix exponential — the reference's own fallback (:525-534).
 
 `linear_exact` turns the law into a catalogue model whose *Euler* step is the exact transition
 X_{k+1} = e^{A dt} X_k + chol(S_dt) Z (vignettes/NoisyOscillator.Rmd:70-80), so euler() on a uniform grid
 samples the linear SDE without discretisation error on the kernels that already exist.
-
-This is host logic of the product (numpy/scipy), not part of the test oracle.
 """
 from __future__ import annotations
 
 import numpy as np
-from scipy import linalg
 
 from . import catalogue as _cat
+from ._lib import SdeGpuError
+from .engine import default_engine
 
 
 def _as_matrix(A):
@@ -27,62 +26,33 @@ def _as_matrix(A):
     return A
 
 
-def _lyapunov_is_singular(A) -> bool:
-    """kron(I,A)+kron(A,I) is singular iff lambda_i + lambda_j = 0 for some pair of eigenvalues."""
-    lam = linalg.eigvals(A)
-    s = np.abs(lam[:, None] + lam[None, :])
-    scale = max(1.0, float(np.max(np.abs(lam))))
-    return bool(np.min(s) <= 1e-12 * scale)
-
-
-def lyap(A, Q):
+def lyap(A, Q, *, device=None):
     """Solve A X + X A' + Q = 0 (R/sdetools.R:593-600).  Raises LinAlgError where the reference's
     `solve` fails: when the equation is singular."""
     A, Q = _as_matrix(A), _as_matrix(Q)
-    if _lyapunov_is_singular(A):
-        raise np.linalg.LinAlgError("Lyapunov equation is singular (lambda_i + lambda_j = 0)")
-    return linalg.solve_continuous_lyapunov(A, -Q)
+    if A.shape != Q.shape:
+        raise ValueError("A and Q must have the same dimensions")
+    try:
+        return default_engine(device).lyap(A, Q)
+    except SdeGpuError as e:
+        if e.code == -1:
+            raise np.linalg.LinAlgError(str(e)) from None
+        raise
 
 
-def _van_loan(A, GG, S0, t):
-    """S_t = e^{At} S0 e^{A't} + int_0^t e^{As} GG' e^{A's} ds from one 2d x 2d matrix exponential."""
-    d = A.shape[0]
-    M = np.zeros((2 * d, 2 * d))
-    M[:d, :d], M[:d, d:], M[d:, d:] = -A, GG, A.T
-    E = linalg.expm(M * t)
-    eAt = E[d:, d:].T
-    return eAt @ E[:d, d:] + eAt @ S0 @ eAt.T
-
-
-def dLinSDE(A, G, t, x0=None, u=None, S0=None):
+def dLinSDE(A, G, t, x0=None, u=None, S0=None, *, device=None):
     """Transition law of dX = (A X + u) dt + G dB over time t (R/sdetools.R:508-572).
     Returns {"eAt", "St"} or, with x0, {"EX", "St"}; u of length nx is held constant (zero-order hold,
     :545-553), u with two columns is interpolated linearly from u[:,0] to u[:,1] (first-order hold, :559-571)."""
     A = _as_matrix(A)
     d = A.shape[0]
-    G = np.asarray(G, dtype=np.float64).reshape(d, -1)
-    GG = G @ G.T
-    S0 = np.zeros((d, d)) if S0 is None else _as_matrix(S0)
-    eAt = linalg.expm(A * t)
-    if _lyapunov_is_singular(A):
-        St = _van_loan(A, GG, S0, t)
-    else:
-        Sinf = linalg.solve_continuous_lyapunov(A, -GG)
-        St = Sinf - eAt @ (Sinf - S0) @ eAt.T
+    if x0 is not None and np.size(x0) != d:
+        raise ValueError("x0 must have one entry per row of A")
+    if u is not None and np.size(u) not in (d, 2 * d):
+        raise ValueError("u must have length nx or be nx x 2")
+    first, St = default_engine(device).dlinsde(A, G, t, x0, u, None if S0 is None else _as_matrix(S0))
     St = 0.5 * (St + St.T)
-    if x0 is None:
-        return {"eAt": eAt, "St": St}
-    x0 = np.atleast_1d(np.asarray(x0, dtype=np.float64))
-    if u is None:
-        return {"EX": eAt @ x0, "St": St}
-    u = np.asarray(u, dtype=np.float64)
-    O, I = np.zeros((d, d)), np.eye(d)
-    if u.size == d:
-        AA = np.block([[A, I], [O, O]])
-        return {"EX": (linalg.expm(AA * t) @ np.concatenate([x0, u.ravel()]))[:d], "St": St}
-    u = u.reshape(d, 2)
-    AAA = np.block([[O, O, O], [I, O, O], [O, I, A]])
-    return {"EX": (linalg.expm(AAA * t) @ np.concatenate([(u[:, 1] - u[:, 0]) / t, u[:, 0], x0]))[-d:], "St": St}
+    return {"eAt": first, "St": St} if x0 is None else {"EX": first, "St": St}
 
 
 def linear_exact(A, G, dt):

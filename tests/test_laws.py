@@ -28,9 +28,11 @@ def test_oracle_rCIR_follows_pCIR(lam, xi, gam, t, x0, strat):
     assert ks.pvalue > 1e-3, ks
 
 
-# ---- CPU: host-side dLinSDE / lyap of the product (O(d^3)) against the oracle's restatement of the reference ----
-def test_product_dLinSDE_reproduces_reference_known_answers_and_oracle():
-    from sdetools_b200 import laws as P                      # host logic: importable without the GPU library
+# ---- dLinSDE / lyap of the product (sdegpu_dlinsde / sdegpu_lyap, O(d^3)) against the oracle's restatement of the reference;
+# ---- the host logic of the same source runs without a GPU in tests/test_linlaws_host.py ----
+@pytest.mark.gpu
+def test_product_dLinSDE_reproduces_reference_known_answers_and_oracle(gpu):
+    from sdetools_b200 import laws as P
     tol = 1.5e-8
     sol = P.dLinSDE(-1, 1, 1, S0=0.5)                        # tests/testthat/test_solvers.R:20-36
     assert sol["eAt"].item() == pytest.approx(np.exp(-1), rel=tol) and sol["St"].item() == pytest.approx(0.5, rel=tol)
@@ -58,17 +60,22 @@ def test_product_dLinSDE_reproduces_reference_known_answers_and_oracle():
         assert np.allclose(P.lyap(Ar, Gr @ Gr.T), laws.lyap(Ar, Gr @ Gr.T), rtol=1e-10, atol=1e-12)
 
 
-def test_product_dLinSDE_at_d256_matches_closed_form():
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [256, 600])
+def test_product_dLinSDE_at_d256_matches_closed_form(gpu, d):
     """C4's matrix: A + A' = -I and A normal, so S_t = sigma^2 (1 - e^{-t}) I — out of reach of the
-    reference's 65536 x 65536 Kronecker solve."""
+    reference's 65536 x 65536 Kronecker solve.  The matrix products run on the device (k_dgemm)."""
     from sdetools_b200 import laws as P
-    d = 256
     R = np.random.default_rng(256).standard_normal((d, d))
     A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
     sol = P.dLinSDE(A, np.eye(d), 1.0)
     assert np.allclose(sol["St"], (1 - np.exp(-1.0)) * np.eye(d), atol=1e-10)
     assert np.allclose(sol["eAt"] @ sol["eAt"].T, np.exp(-1.0) * np.eye(d), atol=1e-10)
     assert np.allclose(P.lyap(A, np.eye(d)), np.eye(d), atol=1e-10)
+    x0, u = np.ones(d), np.linspace(-1, 1, d)
+    from scipy import linalg
+    AA = np.block([[A, np.eye(d)], [np.zeros((d, 2 * d))]])
+    assert np.allclose(P.dLinSDE(A, np.eye(d), 0.5, x0=x0, u=u)["EX"], (linalg.expm(0.5 * AA) @ np.concatenate([x0, u]))[:d], rtol=1e-9, atol=1e-11)
 
 
 # ---- GPU -----------------------------------------------------------------------------------------
