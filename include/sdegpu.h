@@ -197,8 +197,9 @@ SDEGPU_API const char *sdegpu_last_reduction(sdegpu_ctx *ctx);
  * Chunking never changes a per-path result or a histogram count: the generator is keyed by global path id. */
 typedef int (*sdegpu_interrupt_fn)(void *user);
 SDEGPU_API int sdegpu_set_interrupt(sdegpu_ctx *ctx, sdegpu_interrupt_fn fn, void *user);
-/* Paths per chunk of host-pointer runs: 0 = automatic (about 128 MB of bulk I/O per chunk; about 2e10 path-steps per
- * chunk for runs without bulk I/O when an interrupt callback is set, otherwise one launch). */
+/* Paths per chunk of host-pointer runs: 0 = automatic (runs with more than 512 MB of per-path I/O: a quarter of the run
+ * per chunk, between 256 MB and 4 GB; runs without bulk I/O: about 2e10 path-steps per chunk when an interrupt callback
+ * is set, otherwise one launch). */
 SDEGPU_API int sdegpu_set_chunk_paths(sdegpu_ctx *ctx, uint64_t paths);
 SDEGPU_API int sdegpu_destroy(sdegpu_ctx *ctx);
 SDEGPU_API int sdegpu_device_info(sdegpu_ctx *ctx, sdegpu_devinfo *info);

@@ -98,6 +98,8 @@ struct sdegpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k0[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pin_in[2] = {nullptr, nullptr}, ev_pin_out[2] = {nullptr, nullptr};      // a pinned piece has left / arrived
+    unsigned pin_in_turn = 0, pin_out_turn = 0;
     DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill, coef, tdep, lin_x0, lin_center;
     DevBuf pipe_in[2], pipe_out[2];                              // device side of the chunk pipeline
     PinBuf pin_in[2], pin_out[2];                                // its pinned host side
@@ -128,7 +130,7 @@ static void release_device(sdegpu_ctx *c)
     for (DevBuf *b : bufs) b->release();
     for (int k = 0; k < 2; ++k) {
         c->pin_in[k].release(); c->pin_out[k].release();
-        cudaEvent_t *evs[] = {&c->ev_in[k], &c->ev_k0[k], &c->ev_k1[k], &c->ev_out[k]};
+        cudaEvent_t *evs[] = {&c->ev_in[k], &c->ev_k0[k], &c->ev_k1[k], &c->ev_out[k], &c->ev_pin_in[k], &c->ev_pin_out[k]};
         for (cudaEvent_t *e : evs) if (*e) cudaEventDestroy(*e);
     }
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -160,6 +162,8 @@ static int create_device(int device, sdegpu_ctx **out)
         if (e == cudaSuccess) e = cudaEventCreate(&c->ev_k0[k]);
         if (e == cudaSuccess) e = cudaEventCreate(&c->ev_k1[k]);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pin_in[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pin_out[k], cudaEventDisableTiming);
     }
     c->max_grid = c->prop.multiProcessorCount * 32;
     if (e == cudaSuccess) e = c->partials.reserve(sizeof(double) * (size_t)c->max_grid * 5 * MAX_NX);
@@ -595,16 +599,25 @@ static int run_device_ptrs(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_outpu
 
 // ---- host pointers: the chunk pipeline -------------------------------------------------------------------------
 // Per-path arrays are path-major (X[(p*nx+j)*nt+i], XT[p*nx+j], tau[p], ...), so a path range is one contiguous slice of
-// each.  A chunk's input slices are gathered into one pinned buffer and sent with one copy on the H2D stream; its output
-// slices come back with one copy on the D2H stream and are scattered to the caller's arrays while the next chunk
-// computes.  Host copies run on several threads: first touches of a freshly allocated result (R's allocVector, numpy's
-// empty) are page faults, which one thread takes at ~2 GB/s and PCIe delivers at ~50.
+// each.  Two granularities:
+//   chunk  what one kernel launch integrates.  Kernels with one thread (or lane) per path need tens of thousands of paths
+//          to fill the machine, so chunks are large: a quarter of the run, between 256 MB and 4 GB of per-path I/O, two sets
+//          of device buffers (chunk k computes while chunk k-1 drains and chunk k+1 arrives).
+//   piece  what one PCIe copy moves: 64 MB through two pinned buffers per direction on the copy streams.  Host copies
+//          between the caller's arrays and the pinned pieces run on several threads: first touches of a freshly allocated
+//          result (R's allocVector, numpy's empty) are page faults, which one thread takes at ~2 GB/s and PCIe delivers
+//          at ~50; measured on the B200 box: 14 GB/s with one copy thread (= the driver's pageable path), 35 GB/s with 16.
+static const size_t PIECE_BYTES = (size_t)64 << 20;
+static const size_t STAGE_MIN_BYTES = (size_t)32 << 20;          // smaller slices take the driver's pageable path (C1: 8 MB each way)
+
 static void parallel_copy(void *dst, const void *src, size_t bytes)
 {
     static const unsigned hw = std::thread::hardware_concurrency();
     unsigned nth = hw > 16 ? 16 : (hw < 1 ? 1 : hw);
     if (const char *e = getenv("SDEGPU_COPY_THREADS")) if (atoi(e) > 0) nth = (unsigned)atoi(e);
-    if (bytes < ((size_t)4 << 20) || nth == 1) { memcpy(dst, src, bytes); return; }
+    const unsigned by_size = (unsigned)(bytes >> 22);            // a thread per 4 MB
+    if (nth > by_size) nth = by_size;
+    if (nth <= 1) { memcpy(dst, src, bytes); return; }
     const size_t slice = ((bytes + nth - 1) / nth + 4095) & ~(size_t)4095;
     std::vector<std::thread> th;
     for (unsigned k = 1; k < nth; ++k) {
@@ -615,6 +628,55 @@ static void parallel_copy(void *dst, const void *src, size_t bytes)
     }
     memcpy(dst, src, slice < bytes ? slice : bytes);
     for (auto &t : th) t.join();
+}
+
+// host -> device on the H2D stream.  Large slices go piece by piece through the pinned pair; small ones directly.
+static int send_slice(sdegpu_ctx *c, char *dev, const char *host, size_t bytes)
+{
+    if (bytes < STAGE_MIN_BYTES) {
+        CU(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->s_h2d));
+        return SDEGPU_OK;
+    }
+    for (int b = 0; b < 2; ++b) CU(c->pin_in[b].reserve(PIECE_BYTES));
+    for (size_t off = 0; off < bytes; off += PIECE_BYTES) {
+        const size_t n = bytes - off < PIECE_BYTES ? bytes - off : PIECE_BYTES;
+        const int b = (int)(c->pin_in_turn++ & 1);
+        CU(cudaEventSynchronize(c->ev_pin_in[b]));              // the copy that last read this pinned buffer has finished
+        parallel_copy(c->pin_in[b].p, host + off, n);
+        CU(cudaMemcpyAsync(dev + off, c->pin_in[b].p, n, cudaMemcpyHostToDevice, c->s_h2d));
+        CU(cudaEventRecord(c->ev_pin_in[b], c->s_h2d));
+    }
+    return SDEGPU_OK;
+}
+
+// device -> host on the D2H stream (which already waits for the producing kernel); returns when the slice is in `host`
+static int fetch_slice(sdegpu_ctx *c, char *host, const char *dev, size_t bytes)
+{
+    if (bytes < STAGE_MIN_BYTES) {
+        CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+        CU(cudaStreamSynchronize(c->s_d2h));
+        return SDEGPU_OK;
+    }
+    for (int b = 0; b < 2; ++b) CU(c->pin_out[b].reserve(PIECE_BYTES));
+    const size_t npieces = (bytes + PIECE_BYTES - 1) / PIECE_BYTES;
+    const unsigned turn0 = c->pin_out_turn;
+    auto issue = [&](size_t j) -> cudaError_t {
+        const size_t off = j * PIECE_BYTES, n = bytes - off < PIECE_BYTES ? bytes - off : PIECE_BYTES;
+        const int b = (int)((turn0 + j) & 1);
+        cudaError_t e = cudaMemcpyAsync(c->pin_out[b].p, dev + off, n, cudaMemcpyDeviceToHost, c->s_d2h);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_pin_out[b], c->s_d2h);
+        return e;
+    };
+    CU(issue(0));
+    for (size_t j = 0; j < npieces; ++j) {
+        if (j + 1 < npieces) CU(issue(j + 1));                   // the other pinned buffer was emptied in the previous turn
+        const size_t off = j * PIECE_BYTES, n = bytes - off < PIECE_BYTES ? bytes - off : PIECE_BYTES;
+        const int b = (int)((turn0 + j) & 1);
+        CU(cudaEventSynchronize(c->ev_pin_out[b]));
+        parallel_copy(host + off, c->pin_out[b].p, n);
+    }
+    c->pin_out_turn = turn0 + (unsigned)npieces;
+    return SDEGPU_OK;
 }
 
 struct Slice { size_t per_path; size_t off; };                   // bytes per path, offset of the slice in a chunk buffer
@@ -661,8 +723,13 @@ static int run_host(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out,
     uint64_t cp = np;
     if (c->chunk_paths) cp = c->chunk_paths;
     else if (in_pp + out_pp > 0) {
-        const size_t target = (size_t)128 << 20;
-        if ((in_pp + out_pp) * np > 2 * target) cp = target / (in_pp + out_pp);
+        const double total = (double)(in_pp + out_pp) * (double)np;
+        if (total > (double)((size_t)512 << 20)) {
+            double target = total / 4.0;                         // four chunks overlap compute and both copy directions
+            const double lo = (double)((size_t)256 << 20), hi = (double)((size_t)4 << 30);
+            target = target < lo ? lo : (target > hi ? hi : target);
+            cp = (uint64_t)(target / (double)(in_pp + out_pp));
+        }
     } else if (can_stop) {
         const uint64_t unit = (uint64_t)c->prop.multiProcessorCount * 768;     // whole waves of the register-resident kernel
         cp = (uint64_t)(2e10 / (double)(nt - 1));
@@ -686,11 +753,9 @@ static int run_host(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out,
     lay(sF, 32 * (size_t)nx, out->path_integrals != nullptr, cout, cp);
     lay(sMF, 16 * (size_t)nx, out->model_integrals != nullptr, cout, cp);
     const int nbuf = nchunks > 1 ? 2 : 1;
-    // small single-chunk runs skip the pinned staging: the driver's pageable path costs the same there
-    const bool staged = nchunks > 1 || cin + cout >= ((size_t)8 << 20);
     for (int b = 0; b < nbuf; ++b) {
-        if (cin) { CU(c->pipe_in[b].reserve(cin)); if (staged) CU(c->pin_in[b].reserve(cin)); }
-        if (cout) { CU(c->pipe_out[b].reserve(cout)); if (staged) CU(c->pin_out[b].reserve(cout)); }
+        if (cin) CU(c->pipe_in[b].reserve(cin));
+        if (cout) CU(c->pipe_out[b].reserve(cout));
     }
     struct HostIn { const void *p; const Slice *s; } hin[3] = {{pr->B, &sB}, {pr->x0_stride ? pr->x0 : nullptr, &sx0}, {pp.killed ? pr->Stau : nullptr, &sStau}};
     struct HostOut { void *p; const Slice *s; } hout[7] = {{out->X, &sX}, {out->XT, &sXT}, {out->tau, &stau}, {out->S_tau, &sStaus},
@@ -703,13 +768,11 @@ static int run_host(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out,
             const uint64_t p0 = k * cp, n = np - p0 < cp ? np - p0 : cp;
             char *din = (char *)c->pipe_in[b].p, *dout = (char *)c->pipe_out[b].p;
             if (cin) {
-                for (const HostIn &h : hin) {
-                    if (!h.p || !h.s->per_path) continue;
-                    const char *src = (const char *)h.p + h.s->per_path * p0;
-                    if (staged) parallel_copy((char *)c->pin_in[b].p + h.s->off, src, h.s->per_path * n);
-                    else CU(cudaMemcpyAsync(din + h.s->off, src, h.s->per_path * n, cudaMemcpyHostToDevice, c->s_h2d));
-                }
-                if (staged) CU(cudaMemcpyAsync(din, c->pin_in[b].p, cin, cudaMemcpyHostToDevice, c->s_h2d));
+                for (const HostIn &h : hin)
+                    if (h.p && h.s->per_path) {
+                        rc = send_slice(c, din + h.s->off, (const char *)h.p + h.s->per_path * p0, h.s->per_path * n);
+                        if (rc) return rc;
+                    }
                 CU(cudaEventRecord(c->ev_in[b], c->s_h2d));
                 CU(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
             }
@@ -730,26 +793,19 @@ static int run_host(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out,
             rc = enqueue(c, pr, out, pp, io, accum || k > 0);
             if (rc) { status = rc; break; }
             CU(cudaEventRecord(c->ev_k1[b], c->stream));
-            if (cout) {
-                CU(cudaStreamWaitEvent(c->s_d2h, c->ev_k1[b], 0));
-                if (staged) CU(cudaMemcpyAsync(c->pin_out[b].p, dout, cout, cudaMemcpyDeviceToHost, c->s_d2h));
-                else
-                    for (const HostOut &h : hout)
-                        if (h.p && h.s->per_path)
-                            CU(cudaMemcpyAsync((char *)h.p + h.s->per_path * p0, dout + h.s->off, h.s->per_path * n, cudaMemcpyDeviceToHost, c->s_d2h));
-                CU(cudaEventRecord(c->ev_out[b], c->s_d2h));
-            }
         }
-        if (k >= 1) {                                            // drain chunk k-1 while chunk k runs
+        if (k >= 1) {                                            // drain chunk k-1 while chunk k computes
             const uint64_t j = k - 1;
             const int b = (int)(j & 1) % nbuf;
             const uint64_t p0 = j * cp, n = np - p0 < cp ? np - p0 : cp;
+            const char *dout = (const char *)c->pipe_out[b].p;
             if (cout) {
-                CU(cudaEventSynchronize(c->ev_out[b]));
-                if (staged)
-                    for (const HostOut &h : hout)
-                        if (h.p && h.s->per_path)
-                            parallel_copy((char *)h.p + h.s->per_path * p0, (const char *)c->pin_out[b].p + h.s->off, h.s->per_path * n);
+                CU(cudaStreamWaitEvent(c->s_d2h, c->ev_k1[b], 0));
+                for (const HostOut &h : hout)
+                    if (h.p && h.s->per_path) {
+                        rc = fetch_slice(c, (char *)h.p + h.s->per_path * p0, dout + h.s->off, h.s->per_path * n);
+                        if (rc) return rc;
+                    }
             } else
                 CU(cudaEventSynchronize(c->ev_k1[b]));
             float ms = 0.f;
@@ -771,6 +827,7 @@ static int run_host(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out,
         if (out->hist_counts) CU(cudaMemcpyAsync(out->hist_counts, dh, sizeof(unsigned long long) * nh, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->s_h2d));
     if (out->elapsed_ms) *out->elapsed_ms = total_ms;
     return SDEGPU_OK;
 }

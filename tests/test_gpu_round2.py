@@ -147,10 +147,10 @@ def test_chunked_host_runs_equal_single_launch(sde, eng):
 
 
 def test_large_host_trajectory_goes_through_pinned_staging(sde, eng):
-    """A 400 MB trajectory (automatic chunking: ~128 MB per chunk, several chunks) equals the device-resident run."""
+    """A 640 MB trajectory (automatic chunking: three chunks of 256 MB, 64 MB pinned pieces) equals the device-resident run."""
     import torch
     t = np.arange(1001) * 0.01
-    P = 25000
+    P = 40000
     f, g = sde.catalogue.vdp(1.0, 0.5)
     res = sde.euler(f, g, t, [0.0, 0.0], npaths=P, seed=3)
     Xd = torch.empty(P * 2 * 1001, dtype=torch.float64, device="cuda")
