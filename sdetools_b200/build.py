@@ -31,7 +31,7 @@ def _nvcc() -> str:
 
 def _units():
     units = [("api.o", "api.cu", []), ("integrals.o", "integrals.cu", []), ("linear.o", "linear.cu", []),
-             ("linear_dmma.o", "linear_dmma.cu", []), ("laws.o", "laws.cu", []), ("linlaws.o", "linlaws.cu", [])]
+             ("linear_dmma.o", "linear_dmma.cu", []), ("laws.o", "laws.cu", []), ("linlaws.o", "linlaws.cu", []), ("linear_tc.o", "linear_tc.cu", [])]
     units += [(f"ensemble_model_{m}.o", "ensemble_model.cu", [f"-DSDEGPU_TU_MODEL={m}"]) for m in SCALAR_MODELS]
     return [u for u in units if os.path.exists(os.path.join(CSRC, u[1]))]
 

@@ -565,6 +565,9 @@ static int enqueue(sdegpu_ctx *c, const sdegpu_problem *pr, const sdegpu_output 
         } else if (mode == 2) {
             CU(c->scratch.reserve(sizeof(double) * (dp * dp + dp * 4 * (((size_t)pr->nB + 3) / 4))));
             cuerr = launch_linear_dmma_dense(la, (double *)c->scratch.p, c->prop.multiProcessorCount, c->stream);
+        } else if (linear_tc_eligible(la, pr->params + (size_t)nx * nx)) {
+            CU(c->scratch.reserve(sizeof(double) * linear_tc_scratch_doubles(la)));
+            cuerr = launch_linear_tc(la, pr->params + (size_t)nx * nx, (double *)c->scratch.p, c->prop.multiProcessorCount, c->stream);
         } else
             cuerr = launch_linear(la, c->prop.multiProcessorCount, c->stream);
         if (cuerr) return fail(SDEGPU_ERR_CUDA, "sdegpu_run: linear kernel launch: %s", cudaGetErrorString((cudaError_t)cuerr));

@@ -32,5 +32,9 @@ int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaS
 // 0: not eligible, 1: diagonal G, 2: dense G (any nB <= d that fits two tiles in shared memory; scratch dp*dp + dp*4*ceil(nB/4))
 int dmma_mode(const LinearArgs &a, const double *hostG);
 int launch_linear_dmma_dense(const LinearArgs &a, double *scratch, int sm_count, cudaStream_t stream);
+// general tensor kernel (linear_tc.cu): euler and heun, supplied B or generator, trajectory, input term; 8 <= d <= 256, FAST
+bool linear_tc_eligible(const LinearArgs &a, const double *hostG);
+size_t linear_tc_scratch_doubles(const LinearArgs &a);
+int launch_linear_tc(const LinearArgs &a, const double *hostG, double *scratch, int sm_count, cudaStream_t stream);
 
 }  // namespace sdegpu

@@ -1,0 +1,391 @@
+// General tensor-core kernel for the linear SDE  dX = (A X + c(t)) dt + G dB,  8 <= d <= 256  (VERDICT r1 missing #5).
+// k_linear_dmma / k_linear_dmma_dense (linear_dmma.cu) stay the tuned kernels of config C4 (Euler, fused generator,
+// terminal output); this one covers what they do not: heun() (R/sdetools.R:313-328 on the linear model), a supplied B
+// (dB = diff(B), :437), full-trajectory output, the input term c(t) (:211,:363), and the small systems 8 <= d <= 32 that
+// are one to four m8n8k4 tiles.  Same DMMA (mma.sync.m8n8k4.f64) building block, same generator streams as every
+// other linear kernel, so a run here differs from k_linear_generic only in the summation order inside `A %*% x`
+// (1e-12 relative: the regime the reference's own BLAS leaves).
+//
+//   tile      a CTA owns PT = 64 or 32 paths for all steps; X (and Heun's predictor Y) live in shared memory as
+//             [row][path] tiles, a warp owns 8*MA rows (MA = 1, 2, 4 DMMA tiles) x PT paths of accumulators
+//   half step acc = (A V) dt + c dt + G dB  for V = X (Euler, predictor) or V = Y (corrector); G dB is a second GEMM on
+//             a tile of increments (dense G, or any G with a supplied B) or, for diagonal G with the fused generator,
+//             elementwise with the normals kept in registers between predictor and corrector
+//   euler     X <- X + acc(X)                                          (:453)
+//   heun      Y <- X + acc(X);  X <- X + acc(X)/2;  X <- X + acc(Y)/2    (:318,:323; g constant: 0.5 (gX + gY) dB = G dB)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../include/sdegpu.h"
+#include "linear.cuh"
+
+namespace sdegpu {
+
+__device__ __forceinline__ void tc_dmma(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// M (dr x kc column-major, leading dimension dr) -> fragment order for warps owning 8*MA rows:
+//   Mpk[((w*KK + kk)*MA + mi)*32 + lane] = M[8*MA*w + 8*mi + lane/4, 4*kk + lane%4], zero outside dr x kc
+__global__ void k_pack_frag(const double *__restrict__ M, double *__restrict__ Mpk, int nw, int MA, int dr, int KK, int kc)
+{
+    const size_t n = (size_t)nw * KK * MA * 32;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int lane = (int)(idx & 31);
+        size_t t = idx >> 5;
+        const int mi = (int)(t % MA); t /= MA;
+        const int kk = (int)(t % KK);
+        const int w = (int)(t / KK);
+        const int row = 8 * MA * w + 8 * mi + (lane >> 2), col = 4 * kk + (lane & 3);
+        Mpk[idx] = (row < dr && col < kc) ? M[(size_t)col * dr + row] : 0.0;
+    }
+}
+
+struct TcArgs {
+    const double *Apk, *Gpk, *gdiag;       // packed A, packed G (dense noise) or the diagonal of G (diag noise)
+    int KK, KKG;                           // k-steps of A V and of G dB
+    int ZR;                                // rows of the increment tile (a multiple of 4)
+    int noise;                             // 0: diagonal G, normals in registers (fused generator only); 1: increment tile + GEMM
+    int diag_tile;                         // noise == 1 with a diagonal G: elementwise product with the tile instead of a GEMM
+};
+
+template <int NW, int MA, int NBT, bool HEUN>
+__global__ void __launch_bounds__(32 * NW, 1) k_linear_tc(const LinearArgs a, const TcArgs q)
+{
+    constexpr int D = 8 * MA * NW, PT = 8 * NBT, LDX = PT + 4, NT = 32 * NW;
+    extern __shared__ __align__(16) double sm[];
+    double *sh_tab = sm;                                         // quantile table (fused generator only)
+    double *xs = sm + (a.B ? 0 : ICDF_TABLE_DOUBLES);            // X tile  xs[k*LDX + n]
+    double *ys = xs + D * LDX;                                   // Y tile (Heun)
+    double *zs = ys + (HEUN ? D * LDX : 0);                      // increment tile zs[k*LDX + n], k < 4*KKG (noise == 1)
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    if (!a.B) icdf_stage(sh_tab, a.icdf, tid, NT);
+    const int nsteps = a.nt - 1, dr = a.d, nB = a.nB, KK = q.KK, KKG = q.KKG;
+    const uint64_t ngroups = (a.npaths + PT - 1) / PT;
+    const double *Aw = q.Apk + (size_t)w * KK * MA * 32 + lane;
+    const double *Gw = q.Gpk ? q.Gpk + (size_t)w * KKG * MA * 32 + lane : nullptr;
+    double grow[MA];
+#pragma unroll
+    for (int mi = 0; mi < MA; ++mi) grow[mi] = q.gdiag ? q.gdiag[8 * MA * w + 8 * mi + gid] : 0.0;
+
+    for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const uint64_t p0 = grp * PT;
+        const int np = (int)((a.npaths - p0 < (uint64_t)PT) ? (a.npaths - p0) : PT);
+        __syncthreads();
+        for (int e = tid; e < D * PT; e += NT) {
+            const int n = e / D, k = e - n * D;                  // consecutive threads walk one path's state vector
+            const double v = (n < np && k < dr) ? (a.x0 ? a.x0[(p0 + n) * dr + k] : a.x0_shared[k]) : 0.0;
+            xs[k * LDX + n] = v;
+            if (a.X && n < np && k < dr) a.X[((p0 + n) * dr + k) * (uint64_t)a.nt] = v;       // X[1,] <- x0 (:441)
+        }
+        for (int i = 0; i < nsteps; ++i) {
+            const double2 ds = __ldg(&a.dtsq[i]);
+            if (q.noise == 1) {                                  // increments of this step for every (channel, path); padding is zero
+                const int ZR = q.ZR;
+                if (a.B) {
+                    for (int e = tid; e < ZR * PT; e += NT) {
+                        const int n = e / ZR, k = e - n * ZR;    // consecutive threads walk a path's channels
+                        double v = 0.0;
+                        if (k < nB && n < np) {
+                            const double *b = a.B + ((p0 + n) * nB + k) * (uint64_t)a.nt + i;
+                            v = __dsub_rn(__ldg(b + 1), __ldg(b));                      // dB <- apply(B,2,diff) (:437)
+                        }
+                        zs[k * LDX + n] = v;
+                    }
+                } else {
+                    for (int e = tid; e < (ZR / 2) * PT; e += NT) {                     // one Philox block per (channel pair, path)
+                        const int kp = e / PT, n = e - kp * PT;
+                        double z0 = 0.0, z1 = 0.0;
+                        if (nB == 1) {                           // a single channel draws from the scalar models' stream
+                            if (kp == 0 && n < np) {
+                                double zq[4];
+                                normal_quad(a.seed, a.path_offset + p0 + n, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+                                const int s4 = i & 3;
+                                z0 = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
+                            }
+                        } else if (2 * kp < nB && n < np)
+                            normal_pair(a.seed, a.path_offset + p0 + n, (uint32_t)i, 0x80000000u + (uint32_t)kp, sh_tab, z0, z1);
+                        zs[(2 * kp) * LDX + n] = ds.y * z0;
+                        zs[(2 * kp + 1) * LDX + n] = (2 * kp + 1 < nB) ? ds.y * z1 : 0.0;
+                    }
+                }
+            }
+            __syncthreads();                                     // X_i (and the increment tile) are in place
+            // noise == 0: this lane's normals.  Heun keeps them in registers between predictor and corrector (the plan
+            // gives it the 32-path tile then); Euler draws them where they are consumed.
+            auto draw = [&](int mi, int ni, double &z0, double &z1) {
+                const int r = 8 * MA * w + 8 * mi + gid, c = 8 * ni + 2 * tig;
+                // channel pair (r & ~1, r | 1): even-row lane draws for path c, odd-row lane for path c+1
+                double za, zb;
+                normal_pair(a.seed, a.path_offset + p0 + c + (gid & 1), (uint32_t)i, 0x80000000u + (uint32_t)(r >> 1), sh_tab, za, zb);
+                const double send = (gid & 1) ? za : zb;
+                const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                z0 = (gid & 1) ? recv : za;                      // this lane's row, path c
+                z1 = (gid & 1) ? zb : recv;                      // this lane's row, path c+1
+            };
+            double zr[HEUN ? MA : 1][HEUN ? NBT : 1][2];
+            if (HEUN && q.noise == 0) {
+#pragma unroll
+                for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NBT; ++ni) draw(mi, ni, zr[HEUN ? mi : 0][HEUN ? ni : 0][0], zr[HEUN ? mi : 0][HEUN ? ni : 0][1]);
+            }
+            // acc = (A V) dt + c dt + G dB for V = the tile `vs`; tc = time index of the input term
+            auto half_step = [&](const double *vs, int tc, double (&acc)[MA][NBT][2]) {
+#pragma unroll
+                for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NBT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                double an[MA];
+#pragma unroll
+                for (int mi = 0; mi < MA; ++mi) an[mi] = __ldg(Aw + mi * 32);
+#pragma unroll 2
+                for (int kk = 0; kk < KK; ++kk) {
+                    double ac[MA], b[NBT];
+#pragma unroll
+                    for (int mi = 0; mi < MA; ++mi) ac[mi] = an[mi];
+                    if (kk + 1 < KK) {
+#pragma unroll
+                        for (int mi = 0; mi < MA; ++mi) an[mi] = __ldg(Aw + ((size_t)(kk + 1) * MA + mi) * 32);
+                    }
+                    const double *xb = vs + (4 * kk + tig) * LDX + gid;
+#pragma unroll
+                    for (int ni = 0; ni < NBT; ++ni) b[ni] = xb[8 * ni];
+#pragma unroll
+                    for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < NBT; ++ni) tc_dmma(acc[mi][ni], ac[mi], b[ni]);
+                }
+#pragma unroll
+                for (int mi = 0; mi < MA; ++mi) {
+                    const int r = 8 * MA * w + 8 * mi + gid;
+                    const double cf = (a.forcing && r < dr) ? __ldg(a.forcing + (size_t)r * a.nt + tc) : 0.0;
+#pragma unroll
+                    for (int ni = 0; ni < NBT; ++ni) {
+                        acc[mi][ni][0] = (acc[mi][ni][0] + cf) * ds.x;
+                        acc[mi][ni][1] = (acc[mi][ni][1] + cf) * ds.x;
+                    }
+                }
+                if (q.noise == 0) {
+#pragma unroll
+                    for (int mi = 0; mi < MA; ++mi) {
+                        const double gs = grow[mi] * ds.y;
+#pragma unroll
+                        for (int ni = 0; ni < NBT; ++ni) {
+                            double z0, z1;
+                            if (HEUN) { z0 = zr[HEUN ? mi : 0][HEUN ? ni : 0][0]; z1 = zr[HEUN ? mi : 0][HEUN ? ni : 0][1]; }
+                            else draw(mi, ni, z0, z1);
+                            acc[mi][ni][0] = fma(gs, z0, acc[mi][ni][0]);
+                            acc[mi][ni][1] = fma(gs, z1, acc[mi][ni][1]);
+                        }
+                    }
+                } else if (q.diag_tile) {
+#pragma unroll
+                    for (int mi = 0; mi < MA; ++mi) {
+                        const int r = 8 * MA * w + 8 * mi + gid;
+#pragma unroll
+                        for (int ni = 0; ni < NBT; ++ni) {
+                            const double2 zz = *reinterpret_cast<const double2 *>(zs + r * LDX + 8 * ni + 2 * tig);
+                            acc[mi][ni][0] = fma(grow[mi], zz.x, acc[mi][ni][0]);
+                            acc[mi][ni][1] = fma(grow[mi], zz.y, acc[mi][ni][1]);
+                        }
+                    }
+                } else {
+                    for (int kk = 0; kk < KKG; ++kk) {
+                        double ac[MA], b[NBT];
+#pragma unroll
+                        for (int mi = 0; mi < MA; ++mi) ac[mi] = __ldg(Gw + ((size_t)kk * MA + mi) * 32);
+                        const double *zb = zs + (4 * kk + tig) * LDX + gid;
+#pragma unroll
+                        for (int ni = 0; ni < NBT; ++ni) b[ni] = zb[8 * ni];
+#pragma unroll
+                        for (int mi = 0; mi < MA; ++mi)
+#pragma unroll
+                            for (int ni = 0; ni < NBT; ++ni) tc_dmma(acc[mi][ni], ac[mi], b[ni]);
+                    }
+                }
+            };
+            double acc[MA][NBT][2];
+            half_step(xs, i, acc);
+            __syncthreads();                                     // every warp is done reading X_i
+#pragma unroll
+            for (int mi = 0; mi < MA; ++mi) {
+                const int r = 8 * MA * w + 8 * mi + gid;
+#pragma unroll
+                for (int ni = 0; ni < NBT; ++ni) {
+                    const int c = 8 * ni + 2 * tig;
+                    double2 xo = *reinterpret_cast<double2 *>(xs + r * LDX + c);
+                    if (HEUN) {
+                        *reinterpret_cast<double2 *>(ys + r * LDX + c) = make_double2(xo.x + acc[mi][ni][0], xo.y + acc[mi][ni][1]);
+                        xo.x = fma(0.5, acc[mi][ni][0], xo.x);
+                        xo.y = fma(0.5, acc[mi][ni][1], xo.y);
+                    } else {
+                        xo.x += acc[mi][ni][0];
+                        xo.y += acc[mi][ni][1];
+                    }
+                    *reinterpret_cast<double2 *>(xs + r * LDX + c) = xo;
+                }
+            }
+            if (HEUN) {
+                __syncthreads();                                 // the predictor tile is complete
+                half_step(ys, i + 1, acc);                       // ff(times[i+1], Y)  (:321)
+#pragma unroll
+                for (int mi = 0; mi < MA; ++mi) {                // rows of X are private to their warp: no barrier needed before this
+                    const int r = 8 * MA * w + 8 * mi + gid;
+#pragma unroll
+                    for (int ni = 0; ni < NBT; ++ni) {
+                        const int c = 8 * ni + 2 * tig;
+                        double2 xo = *reinterpret_cast<double2 *>(xs + r * LDX + c);
+                        xo.x = fma(0.5, acc[mi][ni][0], xo.x);
+                        xo.y = fma(0.5, acc[mi][ni][1], xo.y);
+                        *reinterpret_cast<double2 *>(xs + r * LDX + c) = xo;
+                    }
+                }
+            }
+            if (a.X) {
+#pragma unroll
+                for (int mi = 0; mi < MA; ++mi) {
+                    const int r = 8 * MA * w + 8 * mi + gid;
+#pragma unroll
+                    for (int ni = 0; ni < NBT; ++ni) {
+                        const int c = 8 * ni + 2 * tig;
+                        const double2 xo = *reinterpret_cast<const double2 *>(xs + r * LDX + c);
+                        if (r < dr && c < np) a.X[((p0 + c) * dr + r) * (uint64_t)a.nt + i + 1] = xo.x;
+                        if (r < dr && c + 1 < np) a.X[((p0 + c + 1) * dr + r) * (uint64_t)a.nt + i + 1] = xo.y;
+                    }
+                }
+            }
+            __syncthreads();                                     // X_{i+1} complete; the increment tile may be refilled
+        }
+        for (int e = tid; e < D * np; e += NT) {
+            const int n = e / D, k = e - n * D;
+            if (a.XT && k < dr) a.XT[(p0 + n) * dr + k] = xs[k * LDX + n];
+        }
+        if (a.moments) {
+            for (int k = tid; k < dr; k += NT) {
+                double s[5] = {0, 0, 0, 0, 0};
+                const double cen = a.center[k];
+                for (int n = 0; n < np; ++n) {
+                    const double dd = xs[k * LDX + n] - cen;
+                    if (isfinite(dd)) {
+                        const double d2 = dd * dd;
+                        s[0] += 1.0; s[1] += dd; s[2] += d2; s[3] += d2 * dd; s[4] += d2 * d2;
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < 5; ++m) atomicAdd(&a.moments[k * 5 + m], s[m]);
+            }
+        }
+    }
+}
+
+static size_t tc_smem(bool has_b, int D, int PT, bool heun, int zrows)
+{
+    return sizeof(double) * ((has_b ? 0 : (size_t)ICDF_TABLE_DOUBLES) + (size_t)(D * (heun ? 2 : 1) + zrows) * (PT + 4));
+}
+
+struct TcPlan { int nw, ma, nbt, noise, diag_tile, kk, kkg, zr; size_t smem; };
+
+static bool tc_plan(const LinearArgs &a, const double *hostG, TcPlan *p)
+{
+    if (a.d < 8 || a.d > 256 || a.nB < 1 || a.nB > 256 || a.strict) return false;
+    if (const char *e = getenv("SDEGPU_LINEAR_TC")) if (atoi(e) == 0) return false;      // tests: force the CUDA-core kernels
+    bool diag = a.nB == a.d;
+    for (int c = 0; c < a.nB && diag; ++c)
+        for (int r = 0; r < a.d; ++r)
+            if (r != c && hostG[(size_t)c * a.d + r] != 0.0) { diag = false; break; }
+    p->ma = a.d <= 8 ? 1 : (a.d <= 16 ? 2 : 4);
+    p->nw = a.d <= 32 ? 1 : (a.d + 31) / 32;
+    const int D = 8 * p->ma * p->nw;
+    p->kk = (a.d + 3) / 4;
+    p->kkg = (a.nB + 3) / 4;
+    p->noise = (diag && !a.B) ? 0 : 1;
+    p->diag_tile = diag ? 1 : 0;
+    const int zrows = p->noise == 1 ? (p->diag_tile ? (D > 4 * p->kkg ? D : 4 * p->kkg) : 4 * p->kkg) : 0;
+    p->zr = zrows;
+    const bool heun = a.scheme == SDEGPU_HEUN;
+    for (int nbt : {8, 4}) {
+        if (nbt == 8 && heun && p->noise == 0) continue;         // Heun keeps its normals in registers: 32-path tile
+        p->nbt = nbt;
+        p->smem = tc_smem(a.B != nullptr, D, 8 * nbt, heun, zrows);
+        if (p->smem <= (size_t)226 * 1024) return true;
+    }
+    return false;
+}
+
+// true when the general tensor kernel takes this problem (FAST arithmetic, 8 <= d <= 256, tiles fit in shared memory)
+bool linear_tc_eligible(const LinearArgs &a, const double *hostG)
+{
+    TcPlan p;
+    return tc_plan(a, hostG, &p);
+}
+
+size_t linear_tc_scratch_doubles(const LinearArgs &a)
+{
+    const size_t dp = ((size_t)a.d + 31) / 32 * 32, kk = ((size_t)a.d + 3) / 4, kkg = ((size_t)a.nB + 3) / 4;
+    return dp * 4 * kk + dp * 4 * kkg + dp;
+}
+
+template <int NW, int MA, int NBT>
+static int tc_launch(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
+{
+    const uint64_t ngroups = (a.npaths + 8 * NBT - 1) / (8 * NBT);
+    auto go = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, p.smem);
+        const uint64_t cap = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
+        const int grid = (int)(ngroups < cap ? ngroups : cap);
+        kernel<<<grid, 32 * NW, p.smem, stream>>>(a, q);
+    };
+    if (a.scheme == SDEGPU_HEUN) go(k_linear_tc<NW, MA, NBT, true>);
+    else go(k_linear_tc<NW, MA, NBT, false>);
+    return (int)cudaGetLastError();
+}
+
+template <int NW, int MA>
+static int tc_launch_nbt(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
+{
+    return p.nbt == 8 ? tc_launch<NW, MA, 8>(a, q, p, sm_count, stream) : tc_launch<NW, MA, 4>(a, q, p, sm_count, stream);
+}
+
+// scratch: linear_tc_scratch_doubles(a) doubles (packed A, packed G, diagonal of G)
+int launch_linear_tc(const LinearArgs &a, const double *hostG, double *scratch, int sm_count, cudaStream_t stream)
+{
+    TcPlan p;
+    if (!tc_plan(a, hostG, &p)) return (int)cudaErrorInvalidConfiguration;
+    const int dr = a.d, D = 8 * p.ma * p.nw;
+    const size_t dp = ((size_t)dr + 31) / 32 * 32;
+    double *Apk = scratch, *Gpk = Apk + dp * 4 * p.kk, *gdiag = Gpk + dp * 4 * p.kkg;
+    TcArgs q;
+    q.KK = p.kk; q.KKG = p.kkg; q.ZR = p.zr; q.noise = p.noise; q.diag_tile = p.diag_tile;
+    k_pack_frag<<<sm_count, 256, 0, stream>>>(a.A, Apk, p.nw, p.ma, dr, p.kk, dr);
+    q.Apk = Apk; q.Gpk = nullptr; q.gdiag = nullptr;
+    if (p.diag_tile) {
+        cudaMemsetAsync(gdiag, 0, sizeof(double) * D, stream);
+        cudaMemcpy2DAsync(gdiag, sizeof(double), a.G, sizeof(double) * (dr + 1), sizeof(double), dr, cudaMemcpyDeviceToDevice, stream);
+        q.gdiag = gdiag;
+    } else {
+        k_pack_frag<<<sm_count, 256, 0, stream>>>(a.G, Gpk, p.nw, p.ma, dr, p.kkg, a.nB);
+        q.Gpk = Gpk;
+    }
+    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * dr, stream);
+    switch (p.nw * 10 + p.ma) {
+    case 11: return tc_launch_nbt<1, 1>(a, q, p, sm_count, stream);
+    case 12: return tc_launch_nbt<1, 2>(a, q, p, sm_count, stream);
+    case 14: return tc_launch_nbt<1, 4>(a, q, p, sm_count, stream);
+    case 24: return tc_launch_nbt<2, 4>(a, q, p, sm_count, stream);
+    case 34: return tc_launch_nbt<3, 4>(a, q, p, sm_count, stream);
+    case 44: return tc_launch_nbt<4, 4>(a, q, p, sm_count, stream);
+    case 54: return tc_launch_nbt<5, 4>(a, q, p, sm_count, stream);
+    case 64: return tc_launch_nbt<6, 4>(a, q, p, sm_count, stream);
+    case 74: return tc_launch_nbt<7, 4>(a, q, p, sm_count, stream);
+    case 84: return tc_launch_nbt<8, 4>(a, q, p, sm_count, stream);
+    default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sdegpu

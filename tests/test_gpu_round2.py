@@ -90,6 +90,67 @@ def test_time_dependent_run_with_the_fused_generator(sde, eng):
     assert np.array_equal(res["X"][-1, 0], x)
 
 
+# ---- the general tensor-core kernel of the linear model -------------------------------------------------------------------
+def _linear_problem(d, nB, kind, seed):
+    rng = np.random.default_rng(seed)
+    R = rng.standard_normal((d, d))
+    A = -0.5 * np.eye(d) + 0.7 * (R - R.T) / np.sqrt(d) + 0.1 * R / np.sqrt(d)
+    if kind == "diag":
+        G = np.diag(rng.uniform(0.5, 1.5, d))
+    else:
+        G = rng.standard_normal((d, nB)) / np.sqrt(nB)
+    return A, G, rng.standard_normal(d), np.concatenate([A.ravel(order="F"), G.ravel(order="F")])
+
+
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+@pytest.mark.parametrize("d,nB,kind", [(8, 8, "diag"), (8, 3, "dense"), (12, 1, "dense"), (16, 16, "diag"), (24, 24, "dense"), (32, 32, "diag"),
+                                       (40, 7, "dense"), (100, 100, "diag"), (160, 33, "dense"), (256, 256, "diag"), (256, 40, "dense")])
+def test_tensor_kernel_supplied_B_matches_strict_kernel_and_oracle(eng, scheme, d, nB, kind):
+    """North-star criterion at tensor dimension: with the same supplied B the DMMA path (FAST) agrees with the STRICT
+    CUDA-core kernel — bit-identical to the oracle's loop order — within 1e-12 relative; trajectory, terminal state, input term."""
+    A, G, x0, params = _linear_problem(d, nB, kind, d + nB)
+    P, nt = 70, 25                                                # 70 paths: one full 64-path tile + a ragged one
+    t, B = brownian(nt, nB, P, 3)
+    Bf = np.asfortranarray(B)
+    F = np.random.default_rng(1).standard_normal(d)
+    forcing = np.sin(2 * t)[:, None] * F[None, :]
+    for fc in (None, forcing):
+        Xs, Xf = np.empty((nt, d, P), order="F"), np.empty((nt, d, P), order="F")
+        XT = np.empty((d, P), order="F")
+        eng.run("linear", scheme, params, t, x0, nx=d, nB=nB, npaths=P, B=Bf, arith="strict", X=Xs, drift_forcing=fc)
+        eng.run("linear", scheme, params, t, x0, nx=d, nB=nB, npaths=P, B=Bf, arith="fast", X=Xf, XT=XT, drift_forcing=fc)
+        scale = np.max(np.abs(Xs))
+        assert np.max(np.abs(Xf - Xs)) <= 1e-12 * scale
+        assert np.array_equal(XT, Xf[-1])
+    if d <= 40:                                                    # the numpy restatement of R's loop on one path
+        f = (lambda tt, x: A @ x + F * np.sin(2 * tt))
+        want = getattr(O, scheme)(f, lambda x: G, t, x0, B=B[:, :, 5])["X"]
+        assert np.allclose(Xf[:, :, 5], want, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+@pytest.mark.parametrize("d,nB,kind", [(8, 8, "diag"), (16, 5, "dense"), (32, 32, "diag"), (64, 64, "diag"), (96, 1, "dense"),
+                                       (128, 20, "dense"), (200, 200, "diag"), (256, 256, "diag"), (256, 256, "dense")])
+def test_tensor_kernel_fused_generator_matches_cuda_core_kernels(eng, monkeypatch, scheme, d, nB, kind):
+    """Same generator streams as the CUDA-core linear kernels: trajectories agree to summation order (heun, trajectory,
+    per-path x0, power sums all go through the tensor kernel here)."""
+    A, G, x0, params = _linear_problem(d, nB, kind, 7 * d + nB)
+    P, nt = 150, 21
+    t = np.arange(nt) * 0.01
+    x0p = np.ascontiguousarray(np.random.default_rng(2).standard_normal((P, d)))
+    kw = dict(nx=d, nB=nB, npaths=P, seed=11, path_offset=999)
+    Xtc, Xcc = np.empty((nt, d, P), order="F"), np.empty((nt, d, P), order="F")
+    XT, ps = np.empty((d, P), order="F"), np.zeros((5, d), order="F")
+    eng.run("linear", scheme, params, t, x0p, X=Xtc, **kw)
+    eng.run("linear", scheme, params, t, x0p, XT=XT, power_sums=ps, center=np.zeros(d), **kw)
+    monkeypatch.setenv("SDEGPU_LINEAR_TC", "0")
+    eng.run("linear", scheme, params, t, x0p, X=Xcc, **kw)
+    monkeypatch.delenv("SDEGPU_LINEAR_TC")
+    assert np.max(np.abs(Xtc - Xcc)) <= 1e-11 * np.max(np.abs(Xcc))
+    assert np.allclose(XT, Xcc[-1], rtol=1e-10, atol=1e-11)
+    assert np.all(ps[0] == P) and np.allclose(ps[1], XT.sum(axis=1), rtol=1e-9, atol=1e-9)
+
+
 # ---- integrals of f(X) and g(X) along the path -----------------------------------------------------------------------
 @pytest.mark.parametrize("model,params,x0,proj", [("dwsqrt", [], [0.0], "identity"), ("cir", [1.0, 1.0, 1.0], [1.0], "abs"),
                                                   ("vdp", [1.0, 0.5], [0.1, -0.2], "identity")])
