@@ -233,6 +233,15 @@ def run_ours(args):
         dist.all_reduce(e2e_wall, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps * P * nsteps / float(e2e_wall.item())
 
+    e2e_modes = None
+    if rank == 0 and world == 1 and not args.no_modes:
+        # the I/O-heavy configurations end to end (host buffers in, host buffers out) through the same library call:
+        # C1 (supplied B) and C3 (full trajectory, without and with a supplied B) — tools/e2e_modes.py
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("e2e_modes", os.path.join(ROOT, "tools", "e2e_modes.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        e2e_modes = [mod.c1(), mod.c3(args.modes_paths), mod.c3(args.modes_paths, True)]
     if rank == 0:
         value = world * args.steps * P * nsteps / (total_ms * 1e-3)
         k_ms = float(np.mean(kernel_ms))
@@ -263,6 +272,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((16 + 48) * nsteps + 8 * 5),
                     "d2h_bytes_per_step": int(8 * (nb + 3) + 8 * 5), "steps": e2e_steps,
                     "api": "sdetools_b200.heun(f, g, times, x0, p=abs, npaths=..., hist=..., moments=True) with host buffers"},
+            "e2e_modes": e2e_modes,
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak and achieved else None,
@@ -307,6 +317,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=10_000_000, help="paths per GPU (default: config C2)")
     ap.add_argument("--nsteps", type=int, default=10_000, help="time steps per path (default: config C2)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the end-to-end measurements of the I/O-heavy configurations (C1, C3)")
+    ap.add_argument("--modes-paths", type=int, default=1 << 17, help="paths of the C3 end-to-end measurement (2^17: 21 GB of trajectory)")
     ap.add_argument("--cpu-paths", type=int, default=0, help="CPU sample size in paths (default 20000 per core; 10000 per core per step for --impl reference)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything libraries print while we run (NCCL's version banner, torch

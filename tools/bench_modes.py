@@ -282,6 +282,56 @@ def main():
             del XT
         torch.cuda.empty_cache()
 
+    # the general tensor kernel (k_linear_tc): heun at d = 256, supplied B at d = 256, small systems on DMMA tiles
+    if want("linear_tc"):
+        d = 256
+        rng = np.random.default_rng(256)
+        R = rng.standard_normal((d, d))
+        A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
+        params = np.concatenate([A.ravel(order="F"), np.eye(d).ravel(order="F")])
+        x0 = np.zeros(d)
+        x0[0] = 1.0
+        P, n = 2 * eng.info["sm_count"] * 32, 500
+        XT = torch.empty(P * d, dtype=torch.float64, device=dev)
+        ms = best_ms(lambda: eng.run("linear", "heun", params, np.arange(n + 1) * (1.0 / n), x0, nx=d, nB=d, npaths=P, seed=4,
+                                     XT=XT, want_time=True), reps=2)
+        fl = 2 * (2.0 * d * d) + 8 * d
+        emit("c4_linear_d256_heun_tc", paths=P, nsteps=n, ms=ms, path_steps_per_s=P * n / ms * 1e3, tflops=fl * P * n / ms / 1e9,
+             frac=fl * P * n / ms / 1e9 / fp64)
+        Pb, nb = eng.info["sm_count"] * 64, 51
+        tb = np.arange(nb) * 0.02
+        B = torch.empty(Pb * d * nb, dtype=torch.float64, device=dev)
+        eng.rvbm(tb, Pb * d, B, seed=2)
+        for scheme in ("euler", "heun"):
+            ms = best_ms(lambda: eng.run("linear", scheme, params, tb, x0, nx=d, nB=d, npaths=Pb, B=B, arith="fast", XT=XT[: Pb * d],
+                                         want_time=True), reps=2)
+            fls = (2.0 * d * d + 4 * d) * (2 if scheme == "heun" else 1)
+            emit(f"linear_d256_suppliedB_{scheme}_tc", paths=Pb, nsteps=nb - 1, ms=ms, path_steps_per_s=Pb * (nb - 1) / ms * 1e3,
+                 tflops=fls * Pb * (nb - 1) / ms / 1e9, b_gbs=8.0 * d * Pb * (nb - 1) / ms / 1e6)
+            ms = best_ms(lambda: eng.run("linear", scheme, params, tb, x0, nx=d, nB=d, npaths=Pb, B=B, arith="strict", XT=XT[: Pb * d],
+                                         want_time=True), reps=1)
+            emit(f"linear_d256_suppliedB_{scheme}_strict_cuda_cores", paths=Pb, nsteps=nb - 1, ms=ms,
+                 path_steps_per_s=Pb * (nb - 1) / ms * 1e3)
+        del B, XT
+        torch.cuda.empty_cache()
+        for dd, PP, nn in ((8, 1 << 20, 500), (16, 1 << 19, 500), (32, 1 << 18, 500)):
+            Rr = np.random.default_rng(dd).standard_normal((dd, dd))
+            Aa = -0.5 * np.eye(dd) + 0.5 * (Rr - Rr.T) / np.sqrt(dd)
+            pp = np.concatenate([Aa.ravel(order="F"), (0.5 * np.eye(dd)).ravel(order="F")])
+            XTs = torch.empty(PP * dd, dtype=torch.float64, device=dev)
+            for scheme in ("euler", "heun"):
+                row = {}
+                for knob, label in (("1", "tc"), ("0", "cuda_cores")):
+                    os.environ["SDEGPU_LINEAR_TC"] = knob
+                    ms = best_ms(lambda: eng.run("linear", scheme, pp, np.arange(nn + 1) / nn, np.ones(dd), nx=dd, nB=dd, npaths=PP, seed=1,
+                                                 XT=XTs, want_time=True), reps=2)
+                    row[label] = PP * nn / ms * 1e3
+                os.environ.pop("SDEGPU_LINEAR_TC", None)
+                emit(f"linear_d{dd}_diag_{scheme}", paths=PP, nsteps=nn, path_steps_per_s_tc=row["tc"],
+                     path_steps_per_s_cuda_cores=row["cuda_cores"], normals_per_s_tc=row["tc"] * dd)
+            del XTs
+        torch.cuda.empty_cache()
+
     # C4: linear SDE d = 256 (A x as a GEMM over paths); 2d^2+4d flops per path-step
     if want("c4"):
         d = 256
