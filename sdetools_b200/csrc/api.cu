@@ -100,7 +100,7 @@ struct sdegpu_ctx {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k0[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev_pin_in[2] = {nullptr, nullptr}, ev_pin_out[2] = {nullptr, nullptr};      // a pinned piece has left / arrived
     unsigned pin_in_turn = 0, pin_out_turn = 0;
-    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill, coef, tdep, lin_x0, lin_center;
+    DevBuf dtsq, partials, stats, in0, in1, out0, out1, out2, params, scratch, times, kill, coef, tdep, lin_x0, lin_center, lin_partials;
     DevBuf pipe_in[2], pipe_out[2];                              // device side of the chunk pipeline
     PinBuf pin_in[2], pin_out[2];                                // its pinned host side
     const double *icdf = nullptr, *icdf32 = nullptr;
@@ -126,7 +126,7 @@ static void release_device(sdegpu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->dtsq, &c->partials, &c->stats, &c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->params, &c->scratch, &c->times,
-                      &c->kill, &c->coef, &c->tdep, &c->lin_x0, &c->lin_center, &c->pipe_in[0], &c->pipe_in[1], &c->pipe_out[0], &c->pipe_out[1]};
+                      &c->kill, &c->coef, &c->tdep, &c->lin_x0, &c->lin_center, &c->lin_partials, &c->pipe_in[0], &c->pipe_in[1], &c->pipe_out[0], &c->pipe_out[1]};
     for (DevBuf *b : bufs) b->release();
     for (int k = 0; k < 2; ++k) {
         c->pin_in[k].release(); c->pin_out[k].release();
@@ -555,6 +555,11 @@ static int enqueue(sdegpu_ctx *c, const sdegpu_problem *pr, const sdegpu_output 
         la.npaths = io.npaths; la.path_offset = io.path_offset; la.seed = make_philox_key(pr->seed);
         la.nt = nt; la.d = nx; la.nB = pr->nB; la.scheme = pr->scheme; la.strict = pr->B && pr->arith == SDEGPU_ARITH_STRICT;
         la.moments = io.ps; la.accumulate = accum ? 1 : 0;
+        if (io.ps) {                                             // per-block slices of the power sums, reduced in block order
+            la.mom_capacity = 8 * c->prop.multiProcessorCount;
+            CU(c->lin_partials.reserve(sizeof(double) * (size_t)la.mom_capacity * 5 * nx));
+            la.mom_partials = (double *)c->lin_partials.p;
+        }
         la.center = pp.lin_center;
         la.forcing = pp.forcing;
         const int mode = dmma_mode(la, pr->params + (size_t)nx * nx);

@@ -119,18 +119,20 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_generic(const LinearArgs
         }
         for (int e = tid; e < np * d; e += LIN_THREADS) {
             const int q = e / d, j = e - q * d;
-            const double v = xs[e];
-            if (a.XT) a.XT[(p0 + q) * d + j] = v;
-            if (a.moments) {
-                const double dd = v - a.center[j];
-                if (isfinite(dd)) {
-                    const double d2 = dd * dd;
-                    atomicAdd(&a.moments[j * 5 + 0], 1.0);
-                    atomicAdd(&a.moments[j * 5 + 1], dd);
-                    atomicAdd(&a.moments[j * 5 + 2], d2);
-                    atomicAdd(&a.moments[j * 5 + 3], d2 * dd);
-                    atomicAdd(&a.moments[j * 5 + 4], d2 * d2);
+            if (a.XT) a.XT[(p0 + q) * d + j] = xs[e];
+        }
+        if (a.moments) {                                         // thread j owns component j: sums over the tile's paths in path order
+            double *slice = a.mom_partials + (size_t)blockIdx.x * 5 * d;
+            for (int j = tid; j < d; j += LIN_THREADS) {
+                double s[5] = {0, 0, 0, 0, 0};
+                for (int q = 0; q < np; ++q) {
+                    const double dd = xs[q * d + j] - a.center[j];
+                    if (isfinite(dd)) {
+                        const double d2 = dd * dd;
+                        s[0] += 1.0; s[1] += dd; s[2] += d2; s[3] += d2 * dd; s[4] += d2 * d2;
+                    }
                 }
+                for (int m = 0; m < 5; ++m) slice[j * 5 + m] = grp == blockIdx.x ? s[m] : slice[j * 5 + m] + s[m];
             }
         }
         __syncthreads();
@@ -256,7 +258,9 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_small(const LinearArgs a
             }
         }
     }
-    if (a.moments) {                                             // per-thread sums -> warp -> one atomic per warp and moment
+    if (a.moments) {                                             // per-thread sums -> warp (shuffle tree) -> warps in index order: no atomics
+        __shared__ double sh_mom[LIN_THREADS / 32][D * 5];
+        __syncthreads();
 #pragma unroll
         for (int j = 0; j < D; ++j)
 #pragma unroll
@@ -264,8 +268,14 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_small(const LinearArgs a
                 double v = mom[j][m];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&a.moments[j * 5 + m], v);
+                if ((threadIdx.x & 31) == 0) sh_mom[threadIdx.x >> 5][j * 5 + m] = v;
             }
+        __syncthreads();
+        if (threadIdx.x < D * 5) {
+            double v = 0.0;
+            for (int w = 0; w < LIN_THREADS / 32; ++w) v += sh_mom[w][threadIdx.x];
+            a.mom_partials[(size_t)blockIdx.x * 5 * D + threadIdx.x] = v;
+        }
     }
 }
 
@@ -385,10 +395,25 @@ __global__ void __launch_bounds__(LIN_THREADS, DP <= 16 ? 2 : 1) k_linear_warp(c
             }
         }
     }
-    if (a.moments && row) {
+    if (a.moments) {                                             // lanes (q, j) -> component j: paths q in order, then warps in index order
+        __shared__ double sh_mom[LIN_THREADS / 32][DP * 5];
+        __syncthreads();
 #pragma unroll
-        for (int m = 0; m < 5; ++m)
-            if (mom[m] != 0.0) atomicAdd(&a.moments[j * 5 + m], mom[m]);
+        for (int m = 0; m < 5; ++m) {
+            double v = mom[m];
+#pragma unroll
+            for (int qq = 1; qq < PPW; ++qq) {
+                const double o = __shfl_sync(0xffffffffu, mom[m], qq * DP + j);
+                if (q == 0) v += o;
+            }
+            if (q == 0) sh_mom[threadIdx.x >> 5][j * 5 + m] = v;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < d * 5; e += LIN_THREADS) {
+            double v = 0.0;
+            for (int w = 0; w < LIN_THREADS / 32; ++w) v += sh_mom[w][e];
+            a.mom_partials[(size_t)blockIdx.x * 5 * d + e] = v;
+        }
     }
 }
 
@@ -407,8 +432,10 @@ static int launch_warp_dp(const LinearArgs &a, int sm_count, cudaStream_t stream
     uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
     const uint64_t ngroups = (a.npaths + (32 / DP) - 1) / (32 / DP), nblk = (ngroups + LIN_THREADS / 32 - 1) / (LIN_THREADS / 32);
     if (grid > nblk) grid = nblk;
+    if (a.moments && grid > (uint64_t)a.mom_capacity) grid = (uint64_t)a.mom_capacity;
     if (a.strict) ks<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
     else kf<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
+    if (a.moments) reduce_moment_partials(a, (int)grid, stream);
     return (int)cudaGetLastError();
 }
 
@@ -427,8 +454,10 @@ static int launch_small_dn(const LinearArgs &a, int sm_count, cudaStream_t strea
     uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
     const uint64_t nblk = (a.npaths + LIN_THREADS - 1) / LIN_THREADS;
     if (grid > nblk) grid = nblk;
+    if (a.moments && grid > (uint64_t)a.mom_capacity) grid = (uint64_t)a.mom_capacity;
     if (a.strict) ks<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
     else kf<<<(int)grid, LIN_THREADS, smem, stream>>>(a);
+    if (a.moments) reduce_moment_partials(a, (int)grid, stream);
     return (int)cudaGetLastError();
 }
 
@@ -443,9 +472,25 @@ static int launch_small_d(const LinearArgs &a, int sm_count, cudaStream_t stream
     }
 }
 
+// moments[v] <- (accumulate ? moments[v] : 0) + sum_b partials[b][v], b in block order
+__global__ void k_reduce_moment_partials(const double *__restrict__ partials, int nblocks, int nvals, double *__restrict__ out, int accumulate)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvals) return;
+    double s = accumulate ? out[v] : 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * nvals + v];
+    out[v] = s;
+}
+
+int reduce_moment_partials(const LinearArgs &a, int nblocks, cudaStream_t stream)
+{
+    const int nvals = 5 * a.d;
+    k_reduce_moment_partials<<<(nvals + 127) / 128, 128, 0, stream>>>(a.mom_partials, nblocks, nvals, a.moments, a.accumulate);
+    return (int)cudaGetLastError();
+}
+
 int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream)
 {
-    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * a.d, stream);
     if (a.d <= LIN_SMALL_MAX && a.nB <= LIN_SMALL_MAX && a.npaths > 0) {
         switch (a.d) {
         case 1: return launch_small_d<1>(a, sm_count, stream);
@@ -479,8 +524,10 @@ int launch_linear(const LinearArgs &a, int sm_count, cudaStream_t stream)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, a.strict ? ks : kf, LIN_THREADS, smem);
     uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
     if (grid > ngroups) grid = ngroups;
+    if (a.moments && grid > (uint64_t)a.mom_capacity) grid = (uint64_t)a.mom_capacity;
     if (a.strict) ks<<<(int)grid, LIN_THREADS, smem, stream>>>(a, PT);
     else kf<<<(int)grid, LIN_THREADS, smem, stream>>>(a, PT);
+    if (a.moments) reduce_moment_partials(a, (int)grid, stream);
     return (int)cudaGetLastError();
 }
 

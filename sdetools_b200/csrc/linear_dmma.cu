@@ -130,21 +130,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs
             const double v = xs[k * DM_LDX + n];
             if (a.XT && k < dr) a.XT[(p0 + n) * dr + k] = v;
         }
-        if (a.moments) {
-            for (int k = tid; k < dr; k += 32 * NWARPS) {
-                double s[5] = {0, 0, 0, 0, 0};
-                const double cen = a.center[k];
-                for (int n = 0; n < np; ++n) {
-                    const double dd = xs[k * DM_LDX + n] - cen;
-                    if (isfinite(dd)) {
-                        const double d2 = dd * dd;
-                        s[0] += 1.0; s[1] += dd; s[2] += d2; s[3] += d2 * dd; s[4] += d2 * d2;
-                    }
-                }
-#pragma unroll
-                for (int m = 0; m < 5; ++m) atomicAdd(&a.moments[k * 5 + m], s[m]);
-            }
-        }
+        if (a.moments) tile_moments(a, xs, DM_LDX, np, tid, 32 * NWARPS, grp == blockIdx.x);
     }
 }
 
@@ -254,21 +240,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma_dense(const Line
             const int n = e / D, k = e - n * D;
             if (a.XT && k < dr) a.XT[(p0 + n) * dr + k] = xs[k * DM_LDX + n];
         }
-        if (a.moments) {
-            for (int k = tid; k < dr; k += 32 * NWARPS) {
-                double s[5] = {0, 0, 0, 0, 0};
-                const double cen = a.center[k];
-                for (int n = 0; n < np; ++n) {
-                    const double dd = xs[k * DM_LDX + n] - cen;
-                    if (isfinite(dd)) {
-                        const double d2 = dd * dd;
-                        s[0] += 1.0; s[1] += dd; s[2] += d2; s[3] += d2 * dd; s[4] += d2 * d2;
-                    }
-                }
-#pragma unroll
-                for (int m = 0; m < 5; ++m) atomicAdd(&a.moments[k * 5 + m], s[m]);
-            }
-        }
+        if (a.moments) tile_moments(a, xs, DM_LDX, np, tid, 32 * NWARPS, grp == blockIdx.x);
     }
 }
 
@@ -297,7 +269,6 @@ int launch_linear_dmma_dense(const LinearArgs &a, double *scratch, int sm_count,
     double *Apk = scratch, *Gpk = scratch + (size_t)d * d;
     k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d, dr, d / 4, dr);
     k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.G, Gpk, d, dr, kkg, a.nB);
-    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * dr, stream);
     const size_t smem = dense_smem(d, kkg);
     const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
 #define SDEGPU_DMMA_DENSE_CASE(NW)                                                                             \
@@ -307,8 +278,10 @@ int launch_linear_dmma_dense(const LinearArgs &a, double *scratch, int sm_count,
         int per_sm = 1;                                                                                        \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 32 * NW, smem);                              \
         const uint64_t cap = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;                                   \
-        const int grid = (int)(ngroups < cap ? ngroups : cap);                                                 \
+        int grid = (int)(ngroups < cap ? ngroups : cap);                                                       \
+        if (a.moments && grid > a.mom_capacity) grid = a.mom_capacity;                                         \
         k<<<grid, 32 * NW, smem, stream>>>(a, Apk, Gpk, kkg);                                                  \
+        if (a.moments) reduce_moment_partials(a, grid, stream);                                                \
     } break;
     switch (d / 32) {
         SDEGPU_DMMA_DENSE_CASE(2) SDEGPU_DMMA_DENSE_CASE(3) SDEGPU_DMMA_DENSE_CASE(4) SDEGPU_DMMA_DENSE_CASE(5)
@@ -329,7 +302,6 @@ int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaS
     k_pack_A<<<sm_count * 2, 256, 0, stream>>>(a.A, Apk, d, dr, d / 4, dr);
     cudaMemsetAsync(gdiag, 0, sizeof(double) * d, stream);
     cudaMemcpy2DAsync(gdiag, sizeof(double), a.G, sizeof(double) * (dr + 1), sizeof(double), dr, cudaMemcpyDeviceToDevice, stream);
-    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * dr, stream);
     const size_t smem = sizeof(double) * ((size_t)ICDF_TABLE_DOUBLES + (size_t)d * DM_LDX);
     const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
     // small d leaves room for several CTAs per SM (d = 64: two warps per CTA): as many as registers and shared memory allow
@@ -340,8 +312,10 @@ int launch_linear_dmma(const LinearArgs &a, double *scratch, int sm_count, cudaS
         int per_sm = 1;                                                                                        \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 32 * NW, smem);                              \
         const uint64_t cap = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;                                   \
-        const int grid = (int)(ngroups < cap ? ngroups : cap);                                                 \
+        int grid = (int)(ngroups < cap ? ngroups : cap);                                                       \
+        if (a.moments && grid > a.mom_capacity) grid = a.mom_capacity;                                         \
         k<<<grid, 32 * NW, smem, stream>>>(a, Apk, gdiag);                                                     \
+        if (a.moments) reduce_moment_partials(a, grid, stream);                                                \
     } break;
     switch (d / 32) {
         SDEGPU_DMMA_CASE(1) SDEGPU_DMMA_CASE(2) SDEGPU_DMMA_CASE(3) SDEGPU_DMMA_CASE(4)

@@ -264,21 +264,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_linear_tc(const LinearArgs a, co
             const int n = e / D, k = e - n * D;
             if (a.XT && k < dr) a.XT[(p0 + n) * dr + k] = xs[k * LDX + n];
         }
-        if (a.moments) {
-            for (int k = tid; k < dr; k += NT) {
-                double s[5] = {0, 0, 0, 0, 0};
-                const double cen = a.center[k];
-                for (int n = 0; n < np; ++n) {
-                    const double dd = xs[k * LDX + n] - cen;
-                    if (isfinite(dd)) {
-                        const double d2 = dd * dd;
-                        s[0] += 1.0; s[1] += dd; s[2] += d2; s[3] += d2 * dd; s[4] += d2 * d2;
-                    }
-                }
-#pragma unroll
-                for (int m = 0; m < 5; ++m) atomicAdd(&a.moments[k * 5 + m], s[m]);
-            }
-        }
+        if (a.moments) tile_moments(a, xs, LDX, np, tid, NT, grp == blockIdx.x);
     }
 }
 
@@ -339,8 +325,10 @@ static int tc_launch(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int 
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, p.smem);
         const uint64_t cap = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
-        const int grid = (int)(ngroups < cap ? ngroups : cap);
+        int grid = (int)(ngroups < cap ? ngroups : cap);
+        if (a.moments && grid > a.mom_capacity) grid = a.mom_capacity;
         kernel<<<grid, 32 * NW, p.smem, stream>>>(a, q);
+        if (a.moments) reduce_moment_partials(a, grid, stream);
     };
     if (a.scheme == SDEGPU_HEUN) go(k_linear_tc<NW, MA, NBT, true>);
     else go(k_linear_tc<NW, MA, NBT, false>);
@@ -373,7 +361,6 @@ int launch_linear_tc(const LinearArgs &a, const double *hostG, double *scratch, 
         k_pack_frag<<<sm_count, 256, 0, stream>>>(a.G, Gpk, p.nw, p.ma, dr, p.kkg, a.nB);
         q.Gpk = Gpk;
     }
-    if (a.moments && !a.accumulate) cudaMemsetAsync(a.moments, 0, sizeof(double) * 5 * dr, stream);
     switch (p.nw * 10 + p.ma) {
     case 11: return tc_launch_nbt<1, 1>(a, q, p, sm_count, stream);
     case 12: return tc_launch_nbt<1, 2>(a, q, p, sm_count, stream);
