@@ -105,6 +105,35 @@ for (scheme in c("euler", "heun")) {
   }
 }
 
+## time-dependent closures (R/sdetools.R:381-394): f(t,x) = f0(x) + c(t), g(t,x) = s(t) g0(x) on the CIR model, and the
+## reference's own example f(t,x) = A %*% x + F*sin(2*t) (:211,:363) on the linear inputs
+cfun <- function(t) 0.3 * sin(2 * t); sfun <- function(t) 1 + 0.5 * cos(3 * t)
+Fin <- x0 * 0 + c(0.5, -1, 0.25)[seq_along(x0)]
+for (scheme in c("euler", "heun")) {
+  fn <- get(scheme)
+  X <- array(NA_real_, c(nt, 1, P))
+  for (p in 1:P) X[, 1, p] <- fn(function(t, x) 1.0 * (1.0 - x) + cfun(t), function(t, x) sfun(t) * (1.0 * sqrt(abs(x))), times, 1.0,
+                                 B = B[, 1, p], p = abs)$X
+  write.hex(sprintf("td_X_%s", scheme), X)
+  XL <- array(NA_real_, c(nt, length(x0), P))
+  for (p in 1:P) XL[, , p] <- fn(function(t, x) A %*% x + Fin * sin(2 * t), function(x) G, times, x0, B = B2[, , p])$X
+  write.hex(sprintf("td_lin_X_%s", scheme), XL)
+}
+
+## the linear laws on the same system: lyap (:593-600) and dLinSDE (:508-572) with no input, a constant input
+## (zero-order hold) and an input affine in time (first-order hold)
+if (requireNamespace("Matrix", quietly = TRUE)) {
+  GG <- G %*% t(G)
+  write.hex("law_lyap", lyap(A, GG))
+  S0 <- diag(seq_along(x0) / 10)
+  u1 <- Fin; u2 <- cbind(Fin, 2 * Fin)
+  l0 <- dLinSDE(A, G, 0.7); write.hex("law_eAt", as.matrix(l0$eAt)); write.hex("law_St", as.matrix(l0$St))
+  write.hex("law_St_S0", as.matrix(dLinSDE(A, G, 0.7, S0 = S0)$St))
+  write.hex("law_EX", as.numeric(dLinSDE(A, G, 0.7, x0 = x0)$EX))
+  write.hex("law_EX_zoh", as.numeric(dLinSDE(A, G, 0.7, x0 = x0, u = u1)$EX))
+  write.hex("law_EX_foh", as.numeric(dLinSDE(A, G, 0.7, x0 = x0, u = u2)$EX))
+}
+
 ## integrals: columns of int_f / int_g (nc x n in the file, one vector per row)
 fcol <- read.hex("int_f"); gcol <- read.hex("int_g")
 nc <- dim(fcol)[1]; n <- dim(fcol)[2]

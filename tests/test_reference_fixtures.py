@@ -24,7 +24,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 from make_golden import read_hex  # noqa: E402
 
 IN = os.path.join(ROOT, "tests", "golden", "reference_R_inputs")
-OUT = os.path.join(ROOT, "tests", "golden", "reference_R")
+# SDEGPU_REFERENCE_R_DIR: another directory of outputs in the same format (tools/selfcheck_reference_fixtures.py uses it to
+# exercise this file's plumbing with the oracle's outputs standing in for R's — a check of the tests, not of parity)
+OUT = os.environ.get("SDEGPU_REFERENCE_R_DIR") or os.path.join(ROOT, "tests", "golden", "reference_R")
 HAVE = os.path.isdir(OUT) and any(f.endswith(".txt") for f in os.listdir(OUT))
 needs_R = pytest.mark.skipif(not HAVE, reason="no outputs of R under tests/golden/reference_R/ (R is not installed here): "
                                              "run `Rscript tests/golden/make_reference_fixtures.R <reference checkout>` on a box with R")
@@ -130,6 +132,47 @@ def test_oracle_matches_R_integrals_and_rbm():
     assert same(np.stack([O.rBM(tb, sigma=0.7, B0=0.25, u=-0.1, z=z[:, p]) for p in range(z.shape[1])], axis=1), ref("rbm_B"))
 
 
+def _td():
+    cfun = lambda t: 0.3 * np.sin(2 * t)
+    sfun = lambda t: 1 + 0.5 * np.cos(3 * t)
+    Fin = np.array([0.5, -1.0, 0.25])[: inp("lin_x0").size]
+    return cfun, sfun, Fin
+
+
+@needs_R
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+def test_oracle_matches_R_time_dependent_closures(scheme):
+    from oracle import sde_oracle as O
+    if not os.path.exists(os.path.join(OUT, f"td_X_{scheme}.txt")):
+        pytest.skip("fixtures predate the time-dependent cases: re-run make_reference_fixtures.R")
+    cfun, sfun, Fin = _td()
+    t, B, B2 = inp("times"), inp("B"), inp("lin_B")
+    fn = getattr(O, scheme)
+    X = np.stack([fn(lambda tt, x: 1.0 * (1.0 - x) + cfun(tt), lambda tt, x: sfun(tt) * (1.0 * np.sqrt(np.abs(x))), t, [1.0],
+                     B=B[:, :, p], p=abs)["X"].reshape(t.size, 1) for p in range(B.shape[2])], axis=2)
+    assert same(X, ref(f"td_X_{scheme}"), 1e-15)                  # sin/cos: C library vs numpy, last ulp
+    A, G, x0 = inp("lin_A"), inp("lin_G"), inp("lin_x0")
+    XL = np.stack([fn(lambda tt, x: A @ x + Fin * np.sin(2 * tt), lambda x: G, t, x0, B=B2[:, :, p])["X"] for p in range(B2.shape[2])], axis=2)
+    assert same(XL, ref(f"td_lin_X_{scheme}"), 1e-14)
+
+
+@needs_R
+def test_oracle_matches_R_linear_laws():
+    from oracle import laws
+    if not os.path.exists(os.path.join(OUT, "law_lyap.txt")):
+        pytest.skip("no law fixtures (the Matrix package was not available to make_reference_fixtures.R)")
+    A, G, x0 = inp("lin_A"), inp("lin_G"), inp("lin_x0")
+    _, _, Fin = _td()
+    S0 = np.diag(np.arange(1, x0.size + 1) / 10)
+    assert same(laws.lyap(A, G @ G.T), ref("law_lyap"), 1e-12)
+    l0 = laws.dLinSDE(A, G, 0.7)
+    assert same(l0["eAt"], ref("law_eAt"), 1e-12) and same(l0["St"], ref("law_St"), 1e-12)
+    assert same(laws.dLinSDE(A, G, 0.7, S0=S0)["St"], ref("law_St_S0"), 1e-12)
+    assert same(np.ravel(laws.dLinSDE(A, G, 0.7, x0=x0)["EX"]), ref("law_EX"), 1e-12)
+    assert same(np.ravel(laws.dLinSDE(A, G, 0.7, x0=x0, u=Fin)["EX"]), ref("law_EX_zoh"), 1e-12)
+    assert same(np.ravel(laws.dLinSDE(A, G, 0.7, x0=x0, u=np.stack([Fin, 2 * Fin], axis=1))["EX"]), ref("law_EX_foh"), 1e-12)
+
+
 # ---- the CUDA path against R (through the C ABI) -----------------------------------------------------------
 @needs_R
 @pytest.mark.gpu
@@ -180,3 +223,34 @@ def test_cuda_matches_R_integrals():
     assert same(sde.itointegral(f, g).T, ref("int_ito"))
     assert same(sde.QuadraticVariation(g).T, ref("int_qv"))
     assert same(sde.CrossVariation(f, g).T, ref("int_cv"))
+
+
+@needs_R
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+def test_cuda_matches_R_time_dependent_closures(scheme):
+    import sdetools_b200 as sde
+    if not os.path.exists(os.path.join(OUT, f"td_X_{scheme}.txt")):
+        pytest.skip("fixtures predate the time-dependent cases: re-run make_reference_fixtures.R")
+    cfun, sfun, Fin = _td()
+    f0, g0 = sde.catalogue.cir(1.0, 1.0, 1.0)
+    X = getattr(sde, scheme)(sde.catalogue.forced(f0, cfun), sde.catalogue.scaled(g0, sfun), inp("times"), 1.0, inp("B"), p=abs)["X"]
+    assert same(X, ref(f"td_X_{scheme}"), 1e-15)
+    fl, gl = sde.catalogue.linear(inp("lin_A"), inp("lin_G"))
+    XL = getattr(sde, scheme)(sde.catalogue.forced(fl, lambda tt: Fin * np.sin(2 * tt)), gl, inp("times"), inp("lin_x0"), inp("lin_B"))["X"]
+    assert same(XL, ref(f"td_lin_X_{scheme}"), 1e-14)
+
+
+@needs_R
+@pytest.mark.gpu
+def test_cuda_library_matches_R_linear_laws():
+    import sdetools_b200 as sde
+    if not os.path.exists(os.path.join(OUT, "law_lyap.txt")):
+        pytest.skip("no law fixtures (the Matrix package was not available to make_reference_fixtures.R)")
+    A, G, x0 = inp("lin_A"), inp("lin_G"), inp("lin_x0")
+    _, _, Fin = _td()
+    assert same(sde.lyap(A, G @ G.T), ref("law_lyap"), 1e-12)
+    l0 = sde.dLinSDE(A, G, 0.7)
+    assert same(l0["eAt"], ref("law_eAt"), 1e-12) and same(l0["St"], ref("law_St"), 1e-12)
+    assert same(sde.dLinSDE(A, G, 0.7, x0=x0, u=Fin)["EX"], ref("law_EX_zoh"), 1e-12)
+    assert same(sde.dLinSDE(A, G, 0.7, x0=x0, u=np.stack([Fin, 2 * Fin], axis=1))["EX"], ref("law_EX_foh"), 1e-12)

@@ -20,7 +20,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--paths", type=float, default=1e10)
     ap.add_argument("--nsteps", type=int, default=1000)
+    ap.add_argument("--seed", type=lambda v: int(v, 0), default=0x5DE70005)
+    ap.add_argument("--abi-devices", type=int, default=0,
+                    help="run in ONE process through the C ABI's multi-GPU context (sdegpu_create_multi) on this many devices "
+                         "instead of one torch.distributed rank per GPU")
     args = ap.parse_args()
+    if args.abi_devices:
+        return main_abi(args)
     import torch
     import torch.distributed as dist
     import sdetools_b200 as sde
@@ -47,7 +53,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ev0.record()
-    packed, mine, _ = sdist.run_sharded(eng, "ou", "euler", [lam, xi, sig], t, [x0], nx=1, npaths_total=N, seed=0x5DE70005,
+    packed, mine, _ = sdist.run_sharded(eng, "ou", "euler", [lam, xi, sig], t, [x0], nx=1, npaths_total=N, seed=args.seed,
                                         center=[mean], hist=hist, rank=rank, world=world)
     ev1.record()
     torch.cuda.synchronize()
@@ -66,7 +72,7 @@ def main():
         obs, exp = hc[1:nb + 1][keep].astype(float), p[keep] * cnt
         chi2 = float(((obs - exp) ** 2 / exp).sum())
         exact_mean, exact_sd = xi + (x0 - xi) * np.exp(-lam), sig * np.sqrt((1 - np.exp(-2 * lam)) / 2 / lam)
-        out = {"config": "C5 OU euler", "paths": N, "nsteps": n, "n_gpus": world, "ms": float(ms[0]),
+        out = {"config": "C5 OU euler", "paths": N, "nsteps": n, "n_gpus": world, "seed": args.seed, "ms": float(ms[0]),
                "path_steps_per_s": N * n / float(ms[0]) * 1e3, "counted": int(cnt), "hist_total": int(hc.sum()),
                "mean_err_in_se": float((m_hat - mean) / (sd / np.sqrt(cnt))),
                "var_err_in_se": float((v_hat - var) / (var * np.sqrt(2.0 / cnt))),
@@ -76,6 +82,43 @@ def main():
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def main_abi(args):
+    """The same run through sdegpu_run on a multi-device context: host pointers, path ranges per device, one all-reduce."""
+    import time
+    from scipy import stats
+    from sdetools_b200.engine import Engine
+    eng = Engine(list(range(args.abi_devices)))
+    lam, xi, sig, x0, n = 1.3, 0.7, 0.9, 2.0, args.nsteps
+    h = 1.0 / n
+    t = np.arange(n + 1) * h
+    N = int(args.paths)
+    a = 1 - lam * h
+    mean = xi + (x0 - xi) * a ** n
+    var = sig * sig * h * (1 - a ** (2 * n)) / (1 - a * a)
+    sd = np.sqrt(var)
+    nb = 512
+    hist = (mean - 6 * sd, mean + 6 * sd, nb)
+    ps, hc = np.zeros(5), np.zeros(nb + 3, dtype=np.uint64)
+    eng.run("ou", "euler", [lam, xi, sig], t, [x0], nx=1, npaths=1 << 20, seed=args.seed, power_sums=ps, center=[mean], hist_counts=hc, hist=hist)
+    t0 = time.perf_counter()
+    ms = eng.run("ou", "euler", [lam, xi, sig], t, [x0], nx=1, npaths=N, seed=args.seed, power_sums=ps, center=[mean], hist_counts=hc,
+                 hist=hist, want_time=True)
+    wall = time.perf_counter() - t0
+    cnt, s1, s2 = ps[0], ps[1], ps[2]
+    m_hat, v_hat = mean + s1 / cnt, (s2 - s1 * s1 / cnt) / (cnt - 1)
+    edges = np.linspace(hist[0], hist[1], nb + 1)
+    p = np.diff(stats.norm.cdf(edges, mean, sd))
+    keep = p * cnt > 50
+    obs, exp = hc[1:nb + 1][keep].astype(float), p[keep] * cnt
+    chi2 = float(((obs - exp) ** 2 / exp).sum())
+    print(json.dumps({"config": "C5 OU euler through sdegpu_create_multi (one process, C ABI)", "paths": N, "nsteps": n, "n_gpus": args.abi_devices,
+                      "seed": args.seed, "reduction": eng.last_reduction, "wall_s": wall, "slowest_device_kernel_ms": ms,
+                      "path_steps_per_s_wall": N * n / wall, "counted": int(cnt), "hist_total": int(hc.sum()),
+                      "mean_err_in_se": float((m_hat - mean) / (sd / np.sqrt(cnt))),
+                      "var_err_in_se": float((v_hat - var) / (var * np.sqrt(2.0 / cnt))),
+                      "chi2": chi2, "chi2_dof": int(keep.sum()) - 1, "chi2_p": float(stats.chi2.sf(chi2, int(keep.sum()) - 1))}))
 
 
 if __name__ == "__main__":
