@@ -66,8 +66,11 @@ typedef enum { SDEGPU_EULER = 0, SDEGPU_HEUN = 1 } sdegpu_scheme;            /* 
 typedef enum { SDEGPU_PROJ_IDENTITY = 0, SDEGPU_PROJ_ABS = 1, SDEGPU_PROJ_RELU = 2 } sdegpu_projection; /* `p` argument */
 
 /* STRICT: one correctly rounded IEEE op per R operator, reference order, no FMA
- *         -> bit-identical to the reference arithmetic for nB = 1.
- * FAST:   FMA contraction and algebraically equivalent regrouping allowed. */
+ *         -> bit-identical to the reference arithmetic for nB = 1 and closures made of + - * / sqrt abs.
+ *         Closures that call exp() (SDEGPU_MODEL_LOGLOGISTIC, SDEGPU_KILL_EXP, the survival update exp(-r dt)) agree to
+ *         exp()'s last ulp only: CUDA's exp and the C library's are each within 1 ulp but not identical.
+ * FAST:   FMA contraction and algebraically equivalent regrouping allowed (1e-12 relative); the linear model then
+ *         runs on the FP64 tensor cores where its shape allows (8 <= nx <= 256). */
 typedef enum { SDEGPU_ARITH_STRICT = 0, SDEGPU_ARITH_FAST = 1 } sdegpu_arith;
 
 /* Killing rate r(x) and stopping function h(t,x) of euler()/heun() (R/sdetools.R:397-416,455-457;
@@ -210,7 +213,9 @@ SDEGPU_API int sdegpu_reset_stream(sdegpu_ctx *ctx);
 SDEGPU_API int sdegpu_synchronize(sdegpu_ctx *ctx);
 
 /* Replaces sapply/replicate around euler() (R/sdetools.R:375-470) or heun() (:240-338).
- * Blocking unless SDEGPU_DEVICE_PTRS is set, in which case work is only enqueued on the stream. */
+ * Host pointers: blocking; large runs move through the chunk pipeline (pinned staging, copy streams) and poll the
+ * interrupt callback between chunks.  SDEGPU_DEVICE_PTRS: the per-run tables (times, parameters) are uploaded with one
+ * stream synchronisation, then the kernels are only enqueued on the stream (unless elapsed_ms is requested). */
 SDEGPU_API int sdegpu_run(sdegpu_ctx *ctx, const sdegpu_problem *prob, sdegpu_output *out);
 
 /* Stochastic integrals on stored paths, batched over ncols columns of length n
