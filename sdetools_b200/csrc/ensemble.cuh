@@ -339,8 +339,22 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 #ifndef SDEGPU_TRAJ_MAX_THREADS
 #define SDEGPU_TRAJ_MAX_THREADS 256
 #endif
-constexpr int TRAJ_REPL = SDEGPU_TRAJ_REPL, TRAJ_CH = SDEGPU_TRAJ_CH, TRAJ_MAX_THREADS = SDEGPU_TRAJ_MAX_THREADS;
-constexpr int TRAJ_NSLOT = 2 * TRAJ_CH;                          // chunk slots in a component's ring
+constexpr int TRAJ_REPL = SDEGPU_TRAJ_REPL;
+// Per state dimension: a scalar model owns one row per path, so 12 warps (384 rows in flight) with single-chunk stores
+// (128 B per row) still sit on the memory system's good side and give the generator and the step — which co-limit these
+// models — three warps per scheduler (tuned, profiles/r2_tune_traj_scalar.txt: OU 4.8e11 -> 5.3e11, CIR/heun 2.7e11 ->
+// 3.4e11 path-steps/s); two-component models keep 4 warps x 2 rows x 2-chunk stores (256 rows).
+#ifndef SDEGPU_TRAJ_CH_NX1
+#define SDEGPU_TRAJ_CH_NX1 1
+#endif
+#ifndef SDEGPU_TRAJ_MAX_THREADS_NX1
+#define SDEGPU_TRAJ_MAX_THREADS_NX1 384
+#endif
+template <int NX> struct TrajCfg {
+    static constexpr int CH = NX == 1 ? SDEGPU_TRAJ_CH_NX1 : SDEGPU_TRAJ_CH;          // chunks per bulk store
+    static constexpr int NSLOT = 2 * CH;                                              // chunk slots in a component's ring
+    static constexpr int MAX_THREADS = NX == 1 ? SDEGPU_TRAJ_MAX_THREADS_NX1 : SDEGPU_TRAJ_MAX_THREADS;
+};
 constexpr int TRAJ_MAX_CLASSES = 4;                              // lcm(4, nx) for nx <= 2
 
 struct __align__(64) TrajMaps {
@@ -392,10 +406,10 @@ __device__ __forceinline__ void traj_put(const double (&v)[16], uint32_t cur, ui
 }
 
 template <class M, int SCHEME, int PROJ, bool UNIFORM>
-__global__ void __launch_bounds__(TRAJ_MAX_THREADS, 1)
+__global__ void __launch_bounds__(TrajCfg<M::NX>::MAX_THREADS, 1)
 k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps, const __grid_constant__ TrajGeom geo)
 {
-    constexpr int NX = M::NX, CH = TRAJ_CH, NSLOT = TRAJ_NSLOT;
+    constexpr int NX = M::NX, CH = TrajCfg<NX>::CH, NSLOT = TrajCfg<NX>::NSLOT;
     constexpr uint32_t CHUNK = 4096u, RING = NSLOT * CHUNK;
     using FS = FastStep<M, SCHEME, PROJ>;
     using TL = Icdf32Layout<TRAJ_REPL>;

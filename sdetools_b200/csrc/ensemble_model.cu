@@ -43,7 +43,7 @@ static int launch_terminal(const RunArgs &a, const LaunchCfg &c, int *grid_used)
 // Warps per CTA of k_traj (one CTA per SM).  Rows in flight per SM = 32 * warps * nx; the memory system prefers ~256
 // (profiles/r1_tma_store_microbench.txt), the generator wants warps.  The environment variable is a tuning knob.
 #ifndef SDEGPU_TRAJ_WARPS_NX1
-#define SDEGPU_TRAJ_WARPS_NX1 8
+#define SDEGPU_TRAJ_WARPS_NX1 12
 #endif
 #ifndef SDEGPU_TRAJ_WARPS_NX2
 #define SDEGPU_TRAJ_WARPS_NX2 4
@@ -95,7 +95,7 @@ static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
             const uint64_t nq = nrows > (uint64_t)cls ? (nrows - cls + S - 1) / S : 1;
             cuuint64_t dims[3] = {16, (cuuint64_t)nq, (cuuint64_t)geo.nchunks};
             cuuint64_t strides[2] = {(cuuint64_t)S * (cuuint64_t)a.nt * 8u, 128u};
-            cuuint32_t box[3] = {16, 32, (cuuint32_t)TRAJ_CH}, es[3] = {1, 1, 1};
+            cuuint32_t box[3] = {16, 32, (cuuint32_t)TrajCfg<NX>::CH}, es[3] = {1, 1, 1};
             const CUresult r = enc(reinterpret_cast<CUtensorMap *>(maps.m[cls]), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
                                    a.X + (uint64_t)cls * a.nt + geo.head[cls], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -103,7 +103,7 @@ static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
         }
     }
     const size_t fixed = Icdf32Layout<TRAJ_REPL>::BYTES + (a.hist ? (size_t)((a.hist_nbins + 3 + 3) & ~3) * 4 : 0);
-    const size_t per_warp = (size_t)NX * TRAJ_NSLOT * 4096 + sizeof(double) * 5 * NX;
+    const size_t per_warp = (size_t)NX * TrajCfg<NX>::NSLOT * 4096 + sizeof(double) * 5 * NX;
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -111,7 +111,7 @@ static int launch_traj(const RunArgs &a, const LaunchCfg &c, int *grid_used)
     if (const char *e = getenv("SDEGPU_TRAJ_WARPS")) warps = atoi(e) > 0 ? atoi(e) : warps;
     const int fit = (int)(((size_t)max_smem - 1024 - fixed) / per_warp);
     if (warps > fit) warps = fit;
-    if (warps > TRAJ_MAX_THREADS / 32) warps = TRAJ_MAX_THREADS / 32;
+    if (warps > TrajCfg<NX>::MAX_THREADS / 32) warps = TrajCfg<NX>::MAX_THREADS / 32;
     if (warps < 1) return (int)cudaErrorInvalidConfiguration;
     const size_t smem = fixed + per_warp * warps;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
