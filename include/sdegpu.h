@@ -70,7 +70,7 @@ typedef enum { SDEGPU_PROJ_IDENTITY = 0, SDEGPU_PROJ_ABS = 1, SDEGPU_PROJ_RELU =
  *         Closures that call exp() (SDEGPU_MODEL_LOGLOGISTIC, SDEGPU_KILL_EXP, the survival update exp(-r dt)) agree to
  *         exp()'s last ulp only: CUDA's exp and the C library's are each within 1 ulp but not identical.
  * FAST:   FMA contraction and algebraically equivalent regrouping allowed (1e-12 relative); the linear model then
- *         runs on the FP64 tensor cores where its shape allows (8 <= nx <= 256). */
+ *         runs on the FP64 tensor cores where its shape allows (5 <= nx <= 512). */
 typedef enum { SDEGPU_ARITH_STRICT = 0, SDEGPU_ARITH_FAST = 1 } sdegpu_arith;
 
 /* Killing rate r(x) and stopping function h(t,x) of euler()/heun() (R/sdetools.R:397-416,455-457;

@@ -104,10 +104,11 @@ def _linear_problem(d, nB, kind, seed):
 
 @pytest.mark.parametrize("scheme", ["euler", "heun"])
 @pytest.mark.parametrize("d,nB,kind", [(8, 8, "diag"), (8, 3, "dense"), (12, 1, "dense"), (16, 16, "diag"), (24, 24, "dense"), (32, 32, "diag"),
-                                       (40, 7, "dense"), (100, 100, "diag"), (160, 33, "dense"), (256, 256, "diag"), (256, 40, "dense")])
+                                       (40, 7, "dense"), (100, 100, "diag"), (160, 33, "dense"), (256, 256, "diag"), (256, 40, "dense"),
+                                       (5, 5, "diag"), (7, 7, "diag"), (300, 300, "diag"), (384, 10, "dense"), (512, 512, "diag")])
 def test_tensor_kernel_supplied_B_matches_strict_kernel_and_oracle(eng, scheme, d, nB, kind):
-    """North-star criterion at tensor dimension: with the same supplied B the DMMA path (FAST) agrees with the STRICT
-    CUDA-core kernel — bit-identical to the oracle's loop order — within 1e-12 relative; trajectory, terminal state, input term."""
+    """North-star criterion at tensor dimension (5 <= d <= 512: one to four tiles, eight warps, two row blocks per warp): with the
+    same supplied B the DMMA path (FAST) agrees with the STRICT CUDA-core kernel — bit-identical to the oracle's loop order — within 1e-12 relative; trajectory, terminal state, input term."""
     A, G, x0, params = _linear_problem(d, nB, kind, d + nB)
     P, nt = 70, 25                                                # 70 paths: one full 64-path tile + a ragged one
     t, B = brownian(nt, nB, P, 3)
@@ -130,7 +131,8 @@ def test_tensor_kernel_supplied_B_matches_strict_kernel_and_oracle(eng, scheme, 
 
 @pytest.mark.parametrize("scheme", ["euler", "heun"])
 @pytest.mark.parametrize("d,nB,kind", [(8, 8, "diag"), (16, 5, "dense"), (32, 32, "diag"), (64, 64, "diag"), (96, 1, "dense"),
-                                       (128, 20, "dense"), (200, 200, "diag"), (256, 256, "diag"), (256, 256, "dense")])
+                                       (128, 20, "dense"), (200, 200, "diag"), (256, 256, "diag"), (256, 256, "dense"),
+                                       (6, 6, "diag"), (257, 257, "diag"), (400, 400, "diag"), (512, 512, "diag"), (512, 64, "dense")])
 def test_tensor_kernel_fused_generator_matches_cuda_core_kernels(eng, monkeypatch, scheme, d, nB, kind):
     """Same generator streams as the CUDA-core linear kernels: trajectories agree to summation order (heun, trajectory,
     per-path x0, power sums all go through the tensor kernel here)."""

@@ -314,6 +314,29 @@ def main():
                  path_steps_per_s=Pb * (nb - 1) / ms * 1e3)
         del B, XT
         torch.cuda.empty_cache()
+        # 256 < d <= 512: two row blocks per warp
+        d5 = 512
+        R5 = np.random.default_rng(512).standard_normal((d5, d5))
+        A5 = -0.5 * np.eye(d5) + (R5 - R5.T) / np.sqrt(d5)
+        p5 = np.concatenate([A5.ravel(order="F"), np.eye(d5).ravel(order="F")])
+        x5 = np.zeros(d5)
+        x5[0] = 1.0
+        P5, n5 = 2 * eng.info["sm_count"] * 32, 200
+        XT5 = torch.empty(P5 * d5, dtype=torch.float64, device=dev)
+        for scheme in ("euler", "heun"):
+            row = {}
+            for knob, label in (("1", "tc"), ("0", "cuda_cores")):
+                os.environ["SDEGPU_LINEAR_TC"] = knob
+                PPk = P5 if knob == "1" else P5 // 8
+                ms = best_ms(lambda: eng.run("linear", scheme, p5, np.arange(n5 + 1) * (1.0 / n5), x5, nx=d5, nB=d5, npaths=PPk, seed=4,
+                                             XT=XT5[: PPk * d5], want_time=True), reps=1)
+                row[label] = PPk * n5 / ms * 1e3
+            os.environ.pop("SDEGPU_LINEAR_TC", None)
+            fl5 = (2.0 * d5 * d5 + 4 * d5) * (2 if scheme == "heun" else 1)
+            emit(f"linear_d512_{scheme}", paths=P5, nsteps=n5, path_steps_per_s_tc=row["tc"], path_steps_per_s_cuda_cores=row["cuda_cores"],
+                 tflops_tc=fl5 * row["tc"] / 1e12, frac=fl5 * row["tc"] / 1e12 / fp64)
+        del XT5
+        torch.cuda.empty_cache()
         for dd, PP, nn in ((8, 1 << 20, 500), (16, 1 << 19, 500), (32, 1 << 18, 500)):
             Rr = np.random.default_rng(dd).standard_normal((dd, dd))
             Aa = -0.5 * np.eye(dd) + 0.5 * (Rr - Rr.T) / np.sqrt(dd)
