@@ -11,6 +11,9 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -120,6 +123,9 @@ struct sdegpu_ctx {
 
 static const int MODEL_NX[9] = {1, 1, 2, 1, 1, 1, 0, 1, 1};      // [6] linear: nx is free
 static const int MODEL_NP[9] = {3, 3, 2, 2, 2, 1, 0, 0, 1};
+
+static void copy_pool_acquire();
+static void copy_pool_release();
 
 static void release_device(sdegpu_ctx *c)
 {
@@ -242,6 +248,7 @@ int sdegpu_create_multi(const int *devices, int ndev, sdegpu_ctx **out)
         lead->peers.push_back(peer);
     }
     cudaSetDevice(ids[0]);
+    copy_pool_acquire();
     *out = lead;
     return SDEGPU_OK;
 }
@@ -260,6 +267,7 @@ int sdegpu_destroy(sdegpu_ctx *c)
     if (c->nccl_comm && n.ok) n.CommDestroy((ncclComm_t)c->nccl_comm);
     release_device(c);
     delete c;
+    copy_pool_release();
     return SDEGPU_OK;
 }
 
@@ -618,24 +626,93 @@ static int run_device_ptrs(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_outpu
 static const size_t PIECE_BYTES = (size_t)64 << 20;
 static const size_t STAGE_MIN_BYTES = (size_t)32 << 20;          // smaller slices take the driver's pageable path (C1: 8 MB each way)
 
+// Persistent host threads for those copies (creating 15 threads per 64 MB piece cost about a third of the copy itself).
+// The pool lives while at least one context exists: sdegpu_create takes a reference, sdegpu_destroy drops it and the last
+// one joins the threads, so nothing of this library runs after its last context is gone (R may dlclose it then).
+class CopyPool {
+public:
+    struct Task { void *dst; const void *src; size_t n; std::atomic<int> *left; };
+    static void acquire()
+    {
+        std::lock_guard<std::mutex> g(life());
+        if (refs()++ == 0) instance() = new CopyPool();
+    }
+    static void release()
+    {
+        std::lock_guard<std::mutex> g(life());
+        if (--refs() == 0) { delete instance(); instance() = nullptr; }
+    }
+    static CopyPool *get() { return instance(); }
+    unsigned size() const { return (unsigned)th_.size(); }
+    void submit(const Task &t)
+    {
+        { std::lock_guard<std::mutex> g(m_); q_.push_back(t); }
+        cv_.notify_one();
+    }
+private:
+    CopyPool()
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned n = hw > 16 ? 15 : (hw > 1 ? hw - 1 : 0);       // the submitting thread copies a slice itself
+        if (const char *e = getenv("SDEGPU_COPY_THREADS")) if (atoi(e) > 0) n = (unsigned)atoi(e) - 1;
+        for (unsigned k = 0; k < n; ++k) th_.emplace_back([this] { work(); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void work()
+    {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.front();
+                q_.pop_front();
+            }
+            memcpy(t.dst, t.src, t.n);
+            t.left->fetch_sub(1, std::memory_order_release);
+        }
+    }
+    static CopyPool *&instance() { static CopyPool *p = nullptr; return p; }
+    static int &refs() { static int r = 0; return r; }
+    static std::mutex &life() { static std::mutex m; return m; }
+    std::vector<std::thread> th_;
+    std::deque<Task> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+static void copy_pool_acquire() { CopyPool::acquire(); }
+static void copy_pool_release() { CopyPool::release(); }
+
 static void parallel_copy(void *dst, const void *src, size_t bytes)
 {
-    static const unsigned hw = std::thread::hardware_concurrency();
-    unsigned nth = hw > 16 ? 16 : (hw < 1 ? 1 : hw);
-    if (const char *e = getenv("SDEGPU_COPY_THREADS")) if (atoi(e) > 0) nth = (unsigned)atoi(e);
+    CopyPool *pool = CopyPool::get();
+    unsigned nth = pool ? pool->size() + 1 : 1;
     const unsigned by_size = (unsigned)(bytes >> 22);            // a thread per 4 MB
     if (nth > by_size) nth = by_size;
     if (nth <= 1) { memcpy(dst, src, bytes); return; }
     const size_t slice = ((bytes + nth - 1) / nth + 4095) & ~(size_t)4095;
-    std::vector<std::thread> th;
+    std::atomic<int> left{0};
+    int handed = 0;
     for (unsigned k = 1; k < nth; ++k) {
         const size_t off = slice * k;
         if (off >= bytes) break;
-        const size_t n = bytes - off < slice ? bytes - off : slice;
-        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, n); });
+        ++handed;
+    }
+    left.store(handed);
+    for (int k = 1; k <= handed; ++k) {
+        const size_t off = slice * (size_t)k, n = bytes - off < slice ? bytes - off : slice;
+        pool->submit({(char *)dst + off, (const char *)src + off, n, &left});
     }
     memcpy(dst, src, slice < bytes ? slice : bytes);
-    for (auto &t : th) t.join();
+    while (left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
 }
 
 // host -> device on the H2D stream.  Large slices go piece by piece through the pinned pair; small ones directly.
@@ -893,10 +970,13 @@ static int run_multi(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out
 
     c->abort_flag.store(0);
     std::atomic<int> running{ndev};
+    std::mutex done_m;
+    std::condition_variable done_cv;
+    auto finished = [&] { { std::lock_guard<std::mutex> g(done_m); running.fetch_sub(1); } done_cv.notify_one(); };
     std::vector<std::thread> th;
     for (int k = 0; k < ndev; ++k)
         th.emplace_back([&, k] {
-            if (prs[k].npaths == 0 && !use_nccl) { running.fetch_sub(1); return; }
+            if (prs[k].npaths == 0 && !use_nccl) { finished(); return; }
             if (prs[k].npaths == 0) {                            // an empty range still takes part in the all-reduce: zeros
                 sdegpu_ctx *d = devs[k];
                 cudaSetDevice(d->device);
@@ -907,11 +987,21 @@ static int run_multi(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out
                 rcs[k] = run_host(devs[k], &prs[k], &outs[k], use_nccl, &c->abort_flag);
                 if (rcs[k]) errs[k] = g_err;
             }
-            running.fetch_sub(1);
+            finished();
         });
-    while (running.load() > 0) {                                 // the interrupt callback runs on the calling thread only
-        if (c->intr && !c->abort_flag.load() && c->intr(c->intr_user)) c->abort_flag.store(1);
-        std::this_thread::sleep_for(std::chrono::milliseconds(c->intr ? 20 : 2));
+    {                                                            // the interrupt callback runs on the calling thread only: poll it
+        std::unique_lock<std::mutex> g(done_m);                  // every 20 ms while waiting for the device threads
+        while (running.load() > 0) {
+            if (c->intr) {
+                done_cv.wait_for(g, std::chrono::milliseconds(20));
+                if (running.load() > 0 && !c->abort_flag.load()) {
+                    g.unlock();
+                    if (c->intr(c->intr_user)) c->abort_flag.store(1);
+                    g.lock();
+                }
+            } else
+                done_cv.wait(g, [&] { return running.load() == 0; });
+        }
     }
     for (auto &t : th) t.join();
     for (int k = 0; k < ndev; ++k)
