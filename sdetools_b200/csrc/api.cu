@@ -923,7 +923,6 @@ static int run_multi(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out
     const int ndev = 1 + (int)c->peers.size(), nx = pr->nx, nt = pr->nt;
     const uint64_t np = pr->npaths, per = (np + ndev - 1) / ndev;
     const int nps = 5 * nx, nh = out->hist_counts ? out->hist_nbins + 3 : 0;
-    const bool accum = (pr->flags & SDEGPU_ACCUMULATE) != 0;
     std::vector<sdegpu_ctx *> devs{c};
     devs.insert(devs.end(), c->peers.begin(), c->peers.end());
     std::vector<sdegpu_problem> prs((size_t)ndev, *pr);
@@ -1039,7 +1038,6 @@ static int run_multi(sdegpu_ctx *c, const sdegpu_problem *pr, sdegpu_output *out
         }
     } else
         c->last_reduction = "none";
-    (void)accum;
     CU(cudaSetDevice(c->device));
     return SDEGPU_OK;
 }
