@@ -485,16 +485,20 @@ static const R_CallMethodDef call_methods[] = {
     {"C_sdegpu_info", (DL_FUNC)&C_sdegpu_info, 0},
     {NULL, NULL, 0}};
 
-void R_init_SDEtools(DllInfo *dll)
+/* R calls R_init_<package>: `sdegpu` as the stand-alone package under r/ (DESCRIPTION, NAMESPACE, src/Makevars), `SDEtools`
+ * when the two files are merged into the reference package. */
+void R_init_sdegpu(DllInfo *dll)
 {
     R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
     R_useDynamicSymbols(dll, FALSE);
 }
+void R_init_SDEtools(DllInfo *dll) { R_init_sdegpu(dll); }
 
-void R_unload_SDEtools(DllInfo *dll)
+void R_unload_sdegpu(DllInfo *dll)
 {
     (void)dll;
     if (g_ctx) sdegpu_destroy(g_ctx);
     g_ctx = NULL;
     g_ndev = 0;
 }
+void R_unload_SDEtools(DllInfo *dll) { R_unload_sdegpu(dll); }
