@@ -198,6 +198,27 @@ def test_model_integrals_equal_itointegral_on_the_stored_path(sde, model, params
         assert res["integrals"]["QV"][0, k] == O.QuadraticVariation(X[:, 0])[-1]
 
 
+def test_model_integrals_with_time_dependent_closures(sde):
+    """Integrands are f(t_i, X_i) = f0(X_i) + c(t_i) and g(t_i, X_i) = s(t_i) g0(X_i): bit-identical to itointegral on the stored
+    path with the restated closures, and drift + noise integral = X_T - X_0 for euler()."""
+    t, B = brownian(120, 1, 5, 31)
+    f0, g0 = sde.catalogue.dwsqrt()
+    fo, go, _, _ = O.catalogue("dwsqrt", [])
+    c = lambda tt: 0.4 * np.cos(tt)
+    s = lambda tt: 1.0 + 0.25 * np.sin(5 * tt)
+    f, g = sde.catalogue.forced(f0, c), sde.catalogue.scaled(g0, s)
+    path = sde.euler(f, g, t, 0.1, B)["X"]
+    res = sde.euler(f, g, t, 0.1, B, model_integrals=True)
+    for k in range(5):
+        X = path[:, 0, k]
+        fX = np.array([fo(X[i]) + c(t[i]) for i in range(t.size)]).ravel()
+        gX = np.array([s(t[i]) * go(X[i]) for i in range(t.size)]).ravel()
+        assert res["model_integrals"]["drift"][0, k] == O.itointegral(fX, t)[-1]
+        assert res["model_integrals"]["noise"][0, k] == O.itointegral(gX, B[:, 0, k])[-1]
+        assert abs(res["model_integrals"]["drift"][0, k] + res["model_integrals"]["noise"][0, k] - (X[-1] - X[0])) < 1e-13
+        assert res["XT"][0, k] == X[-1]
+
+
 # ---- the chunk pipeline ------------------------------------------------------------------------------------------------
 def test_chunked_host_runs_equal_single_launch(sde, eng):
     """Host-pointer runs cut into path ranges (pinned staging, copy streams) give the same bytes as one launch: supplied-B
