@@ -342,3 +342,64 @@ def test_multi_device_host_reduction_fallback(sde, monkeypatch):
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stderr
     assert r.stdout.split() == ["host", "50001", "50001"]
+
+
+# ---- guard bands: compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with canaries -------------------
+SENTINEL = -7.2340172838076673e+125          # 0xDA...: every byte of it is distinctive
+
+
+def _guarded(torch, n, guard=4096):
+    buf = torch.full((n + 2 * guard,), SENTINEL, dtype=torch.float64, device="cuda")
+    return buf, buf[guard:guard + n]
+
+
+def _intact(torch, buf, n, guard=4096):
+    ref = torch.full((guard,), SENTINEL, dtype=torch.float64, device="cuda").view(torch.int64)
+    return bool(torch.equal(buf[:guard].view(torch.int64), ref) and torch.equal(buf[guard + n:].view(torch.int64), ref))
+
+
+@pytest.mark.parametrize("nt", [2, 5, 17, 18, 19, 20, 33, 100, 131])
+@pytest.mark.parametrize("P", [1, 31, 33, 250, 777])
+def test_trajectory_kernels_write_nothing_outside_their_arrays(eng, nt, P):
+    """The TMA-staged writers (van der Pol: 4 warps x 2 rows, 2-chunk stores; scalar models: 12 warps, 1-chunk stores) and the
+    sector writer of the supplied-B kernel for every row phase (nt mod 4), rows shorter than one chunk, ragged path counts."""
+    import torch
+    t = np.arange(nt) * 0.01
+    for model, scheme, params, x0, nx, proj in (("vdp", "euler", [1.0, 0.5], [0.1, -0.2], 2, "identity"), ("cir", "heun", [1.0, 1.0, 1.0], [1.0], 1, "abs")):
+        n = P * nx * nt
+        buf, X = _guarded(torch, n)
+        tb, XT = _guarded(torch, P * nx)
+        eng.run(model, scheme, params, t, x0, nx=nx, npaths=P, projection=proj, seed=5, X=X, XT=XT)
+        torch.cuda.synchronize()
+        assert _intact(torch, buf, n) and _intact(torch, tb, P * nx), (model, "generator")
+        assert bool(torch.isfinite(X).all()) and bool(torch.equal(X.view(P, nx, nt)[:, :, -1].reshape(-1), XT))
+        Bb, B = _guarded(torch, P * nt)
+        eng.rvbm(t, P, B, seed=2)
+        buf2, X2 = _guarded(torch, n)
+        eng.run(model, scheme, params, t, x0, nx=nx, npaths=P, projection=proj, B=B, X=X2)
+        torch.cuda.synchronize()
+        assert _intact(torch, buf2, n) and _intact(torch, Bb, P * nt), (model, "supplied B")
+        assert bool(torch.isfinite(X2).all())
+
+
+@pytest.mark.parametrize("d,nB,P", [(5, 5, 3), (8, 8, 65), (13, 4, 70), (32, 32, 1), (100, 100, 97), (256, 9, 33), (300, 300, 40), (512, 512, 17)])
+@pytest.mark.parametrize("scheme", ["euler", "heun"])
+def test_tensor_kernels_write_nothing_outside_their_arrays(eng, d, nB, P, scheme):
+    import torch
+    A, G, x0, params = _linear_problem(d, nB, "diag" if nB == d else "dense", d)
+    nt = 7
+    t = np.arange(nt) * 0.01
+    buf, X = _guarded(torch, P * d * nt)
+    tb, XT = _guarded(torch, P * d)
+    pb, ps = _guarded(torch, 5 * d)
+    eng.run("linear", scheme, params, t, x0, nx=d, nB=nB, npaths=P, seed=1, X=X, XT=XT, power_sums=ps, center=np.zeros(d))
+    torch.cuda.synchronize()
+    assert _intact(torch, buf, P * d * nt) and _intact(torch, tb, P * d) and _intact(torch, pb, 5 * d)
+    assert bool(torch.isfinite(X).all()) and bool(torch.equal(X.view(P, d, nt)[:, :, -1].reshape(-1), XT))
+    assert bool((ps.view(d, 5)[:, 0] == P).all())
+    Bb, B = _guarded(torch, P * nB * nt)
+    eng.rvbm(t, P * nB, B, seed=2)
+    buf2, X2 = _guarded(torch, P * d * nt)
+    eng.run("linear", scheme, params, t, x0, nx=d, nB=nB, npaths=P, B=B, arith="fast", X=X2)
+    torch.cuda.synchronize()
+    assert _intact(torch, buf2, P * d * nt) and _intact(torch, Bb, P * nB * nt) and bool(torch.isfinite(X2).all())
