@@ -202,7 +202,7 @@ def euler(f, g, times, x0, B=None, p=lambda x: x, h=None, r=None, S0=1.0, Stau=N
         X[i + 1, :] = p((X[i, :] + fX * dt[i]) + _matvec(gX, dB[i, :]))      # :453
         if h(times[i + 1], X[i + 1, :]) <= 0:                                # :455
             break
-        S[i + 1] = S[i] * np.exp(-rr(times[i], X[i, :]) * dt[i])             # :456 (App. B quirk 2: `t` there is base::t)
+        S[i + 1] = np.ravel(S[i] * np.exp(-rr(times[i], X[i, :]) * dt[i]))[0]             # :456 (App. B quirk 2: `t` there is base::t)
         if S[i + 1] < Stau:                                                  # :457
             break
     return _epilogue(times, X, S, i, no_mort)
@@ -228,7 +228,7 @@ def heun(f, g, times, x0, B=None, p=lambda x: x, h=None, r=None, S0=1.0, Stau=No
         X[i + 1, :] = p((X[i, :] + (0.5 * (fX + fY)) * dt[i]) + 0.5 * _matvec(gX + gY, dB[i, :]))
         if h(times[i + 1], X[i + 1, :]) <= 0:                                # :325
             break
-        S[i + 1] = S[i] * np.exp(-rr(times[i], X[i, :]) * dt[i])             # :326
+        S[i + 1] = np.ravel(S[i] * np.exp(-rr(times[i], X[i, :]) * dt[i]))[0]             # :326
         if S[i + 1] < Stau:                                                  # :327
             break
     return _epilogue(times, X, S, i, no_mort)

@@ -24,7 +24,7 @@ here <- if (length(args) >= 2) args[2] else {
   if (length(f)) dirname(normalizePath(f)) else "tests/golden"
 }
 indir <- file.path(here, "reference_R_inputs")
-outdir <- file.path(here, "reference_R")
+outdir <- file.path(here, if (length(args) >= 3) args[3] else "reference_R")
 dir.create(outdir, showWarnings = FALSE)
 
 ## recorded normals for rBM: the reference calls rnorm(n, mean, sd) (R/sdetools.R:19); sourced into the global

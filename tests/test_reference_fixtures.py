@@ -1,11 +1,16 @@
-"""Parity against outputs of the reference ITSELF (R/sdetools.R run by R), when they exist.
+"""Parity against outputs of the reference ITSELF, from two independent executions of its source.
 
-R is not installed in the build image, so tests/golden/reference_R/ is empty in the repository and these tests
-skip with that reason.  On any box with R:
+`tests/golden/reference_minir/` (committed): the unmodified `/root/reference/R/sdetools.R`, parsed and evaluated by `oracle/minir`
+— a minimal evaluator for the R subset the reference is written in (GNU R is not installed in the build image).  The functions that
+ran are the reference's own bodies; only the base-R primitives underneath them are restated (oracle/minir/interp.py).  Made by
+`python tests/golden/make_minir_fixtures.py`, which runs the recipe below under that evaluator.
+
+`tests/golden/reference_R/` (absent in the repository): the same recipe run by GNU R on any box that has it:
 
     Rscript tests/golden/make_reference_fixtures.R /path/to/SDEtools     # writes tests/golden/reference_R/*.txt
     python -m pytest tests/test_reference_fixtures.py                    # CPU: oracle == R;  -m gpu: CUDA == R
 
+Every test below runs once per source that is present ([minir] always, [R] skipped with that reason when absent).
 The inputs (tests/golden/reference_R_inputs/, C99 hex doubles written by make_golden.py) are committed; outputs
 use the same exact format, so every comparison below is bit for bit unless a tolerance is written next to it.
 Reference lines: euler R/sdetools.R:375-470, heun :240-338, stochint :105-113, QuadraticVariation :134-137,
@@ -26,10 +31,27 @@ from make_golden import read_hex  # noqa: E402
 IN = os.path.join(ROOT, "tests", "golden", "reference_R_inputs")
 # SDEGPU_REFERENCE_R_DIR: another directory of outputs in the same format (tools/selfcheck_reference_fixtures.py uses it to
 # exercise this file's plumbing with the oracle's outputs standing in for R's — a check of the tests, not of parity)
-OUT = os.environ.get("SDEGPU_REFERENCE_R_DIR") or os.path.join(ROOT, "tests", "golden", "reference_R")
-HAVE = os.path.isdir(OUT) and any(f.endswith(".txt") for f in os.listdir(OUT))
-needs_R = pytest.mark.skipif(not HAVE, reason="no outputs of R under tests/golden/reference_R/ (R is not installed here): "
-                                             "run `Rscript tests/golden/make_reference_fixtures.R <reference checkout>` on a box with R")
+SOURCES = {"R": os.environ.get("SDEGPU_REFERENCE_R_DIR") or os.path.join(ROOT, "tests", "golden", "reference_R"),
+           "minir": os.path.join(ROOT, "tests", "golden", "reference_minir")}
+OUT = SOURCES["minir"]
+
+
+@pytest.fixture(autouse=True, params=["minir", "R"])
+def reference_source(request):
+    """Each test runs against every set of reference outputs that exists."""
+    global OUT
+    d = SOURCES[request.param]
+    if not (os.path.isdir(d) and any(f.endswith(".txt") for f in os.listdir(d))):
+        pytest.skip("no outputs of GNU R under tests/golden/reference_R/ (R is not installed here): run `Rscript "
+                    "tests/golden/make_reference_fixtures.R <reference checkout>` on a box with R" if request.param == "R" else
+                    "tests/golden/reference_minir/ is missing: run `python tests/golden/make_minir_fixtures.py`")
+    OUT = d
+    yield request.param
+
+
+def needs_R(fn):                           # kept as a marker of which tests read reference outputs; skipping is the fixture's job
+    return fn
+
 
 # (model, params, x0, projection) — the closures make_reference_fixtures.R writes out, in its order
 CASES = [("ou", [1.3, 0.7, 0.9], [2.0], "identity"), ("cir", [1.0, 1.0, 1.0], [1.0], "abs"),
