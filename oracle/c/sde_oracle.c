@@ -2,10 +2,11 @@
  * TEST INFRASTRUCTURE ONLY: the product (sdetools_b200/, libsdegpu.so) never
  * links or calls this; tests, __graft_entry__.smoke() and bench.py's CPU legs do.
  *
- * PARITY UNPINNED: the reference (/root/reference/R/sdetools.R) has no numeric
- * golden vector for euler/heun and R is not installed; this file is pinned
- * against the numpy restatement (oracle/sde_oracle.py) and through it against
- * the vignette identities (tests/test_oracle.py).
+ * PARITY: the reference (/root/reference/R/sdetools.R) has no numeric golden
+ * vector for euler/heun and GNU R is not installed; this file is pinned bit for
+ * bit against the numpy restatement (oracle/sde_oracle.py), and both against the
+ * reference's own source text executed by oracle/minir — config C1 at full size
+ * (1,000 paths x 1,000 steps) by SHA-256 (tests/test_minir.py).
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).
  * -ffp-contract=off + SSE2 doubles = one correctly rounded IEEE op per R operator

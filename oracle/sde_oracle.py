@@ -8,8 +8,10 @@ R semantics reproduced on purpose:
     sum to double (R `src/main/cum.c`); numpy `longdouble` is that type here;
   * matrices are column-major; `X` is `nt x nx` (time fastest).
 
-PARITY UNPINNED (see oracle/__init__.py): no numeric golden vector exists in
-the reference for these functions; the identities in tests/test_oracle.py pin it.
+PARITY (see oracle/__init__.py): no numeric golden vector exists in the reference
+for these functions; this restatement is pinned bit for bit to the reference's own
+source executed by oracle/minir (tests/golden/reference_minir/, tests/test_minir.py,
+tests/test_reference_fixtures.py) and by the identities in tests/test_oracle.py.
 """
 from __future__ import annotations
 
