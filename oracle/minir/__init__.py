@@ -30,6 +30,8 @@ def to_numpy(x):
     if isinstance(x, RList):
         names = x.names()
         return {n or i: to_numpy(v) for i, (n, v) in enumerate(zip(names, x.v))}
+    if not isinstance(x, RVec):
+        return x                                   # functions, language objects: handed back as they are
     d = x.dim()
     v = np.array(x.v, dtype=np.float64) if x.kind != "character" else np.array(list(x.v), dtype=object)
     return v if d is None else v.reshape(d, order="F")

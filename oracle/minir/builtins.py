@@ -1,6 +1,5 @@
 """TEST INFRASTRUCTURE ONLY — the slice of base R (plus `Matrix::expm` and the `testthat` expectations) that the reference's
 sample-path code, its tests and the fixture recipe call.  See interp.py for what is restated exactly and what is a stand-in."""
-import glob
 import math
 import os
 import re
@@ -8,7 +7,7 @@ import sys
 
 import numpy as np
 
-from .interp import (NA_REAL, NULL, Builtin, Closure, Env, RError, RList, RNull, RVec, ReturnEx, arith, as_bool, c_hexfloat, chr_,
+from .interp import (NA_REAL, NULL, Builtin, Closure, Env, RError, RLang, RList, RNull, RVec, ReturnEx, arith, as_bool, c_hexfloat, chr_,
                      compare, cumsum_ld, dbl, dimnames_of, fmt_num, from_mat, higher_kind, index_vec, int_, is_fn, lgl,
                      make_dimnames, mat, matprod, recycle, scalar, sint, sstr, strip, sum_ld, KINDS)
 
@@ -124,7 +123,15 @@ def install(I):
 
     def data_frame(interp, a, k):
         k = {q: v for q, v in k.items() if q not in ("stringsAsFactors", "check.names")}
-        r = RList(list(a) + list(k.values()), [f"V{i + 1}" for i in range(len(a))] + list(k.keys()))
+        cols, names = [], []
+        for i, x in enumerate(a):
+            if isinstance(x, RList):                             # data.frame(<list>): one column per element
+                cols.extend(x.v)
+                names.extend(n or f"V{j + 1}" for j, n in enumerate(x.names()))
+            else:
+                cols.append(x)
+                names.append(f"V{i + 1}")
+        r = RList(cols + list(k.values()), names + list(k.keys()))
         r.attrs["class"] = chr_("data.frame")
         return r
     reg("data.frame", data_frame)
@@ -373,11 +380,54 @@ def install(I):
     reg("attr", attr_get)
     reg("attr<-", lambda interp, a, k: set_attr_any(a[0], sstr(a[1]), k.get("value", a[2] if len(a) > 2 else NULL)))
 
+    def copy_fn(x):
+        y = Closure(x.params, x.body, x.env, x.src) if isinstance(x, Closure) else Builtin(x.name, x.fn)
+        y.attrs = dict(x.attrs)
+        return y
+
     def set_attr_any(x, key, value):
-        if is_fn(x):
-            x.attrs[key] = value
-            return x
+        if is_fn(x):                                             # attributes on a function: copy, like every R value
+            y = copy_fn(x)
+            if isinstance(value, RNull):
+                y.attrs.pop(key, None)
+            else:
+                y.attrs[key] = value
+            return y
         return set_attr(x, key, value)
+
+    def attributes(interp, a, k):
+        at = a[0].attrs
+        return RList(list(at.values()), list(at.keys())) if at else NULL
+    reg("attributes", attributes)
+
+    def set_attributes(interp, a, k):
+        x, value = a[0], k.get("value", a[1] if len(a) > 1 else NULL)
+        new = {} if isinstance(value, RNull) else dict(zip(value.names(), value.v))
+        if is_fn(x):
+            y = copy_fn(x)
+            y.attrs = new
+            return y
+        y = RVec(x.kind, x.v) if isinstance(x, RVec) else RList(x.v)
+        y.attrs = new
+        return y
+    reg("attributes<-", set_attributes)
+
+    def set_storage_mode(interp, a, k):
+        x, value = a[0], sstr(k.get("value", a[1] if len(a) > 1 else NULL))
+        return RVec({"numeric": "double"}.get(value, value), x.v, x.attrs)
+    reg("storage.mode<-", set_storage_mode)
+    reg("body", lambda interp, a, k: RLang(a[0].body) if isinstance(a[0], Closure) else NULL)
+
+    def rmatch(interp, a, k):
+        table = list(a[1].v)
+        return int_([table.index(e) + 1 if e in table else NA_REAL for e in a[0].v])
+    reg("match", rmatch)
+
+    def dotcall(interp, a, k):
+        if interp.dotcall is None:
+            raise RError(".Call: no native library is attached to this evaluator")
+        return interp.dotcall(sstr(a[0]), list(a[1:]))
+    reg(".Call", dotcall)
 
     reg("class", lambda interp, a, k: a[0].attrs.get("class", chr_("function" if is_fn(a[0]) else ("list" if isinstance(a[0], RList)
                 else ("NULL" if isinstance(a[0], RNull) else ("matrix" if a[0].dim() and len(a[0].dim()) == 2 else
@@ -985,8 +1035,30 @@ def install(I):
             raise RError("expect_true: FALSE")
         return NULL
     reg("expect_true", expect_true)
-    reg("all.equal", lambda interp, a, k: lgl([1.0]) if all_equal_num(a[0], a[1], scalar(k["tolerance"]) if "tolerance" in k else 1.5e-8) is None
-        else chr_(all_equal_num(a[0], a[1])))
+    def same_obj(x, y):
+        if isinstance(x, RNull) or isinstance(y, RNull):
+            return isinstance(x, RNull) and isinstance(y, RNull)
+        if is_fn(x) or is_fn(y):
+            if isinstance(x, Builtin) and isinstance(y, Builtin):
+                return x.fn is y.fn and same_attrs(x, y)
+            return x is y
+        if isinstance(x, RLang) or isinstance(y, RLang):
+            return isinstance(x, RLang) and isinstance(y, RLang) and x.node == y.node
+        if isinstance(x, RList) or isinstance(y, RList):
+            return (isinstance(x, RList) and isinstance(y, RList) and len(x) == len(y) and all(same_obj(p, q) for p, q in zip(x.v, y.v))
+                    and same_attrs(x, y))
+        return (x.kind == y.kind and len(x) == len(y) and all((p == q) or (p != p and q != q) for p, q in zip(x.v, y.v))
+                and same_attrs(x, y))
+
+    def same_attrs(x, y):
+        return set(x.attrs) == set(y.attrs) and all(same_obj(x.attrs[q], y.attrs[q]) for q in x.attrs)
+
+    def all_equal(interp, a, k):
+        x, y = a[0], a[1]
+        if isinstance(x, RVec) and isinstance(y, RVec) and x.kind != "character" and y.kind != "character":
+            msg = all_equal_num(x, y, scalar(k["tolerance"]) if "tolerance" in k else 1.5e-8)
+            return lgl([1.0]) if msg is None else chr_(msg)
+        return lgl([1.0]) if same_obj(x, y) else chr_("objects differ")
+    reg("all.equal", all_equal)
+    reg("identical", lambda interp, a, k: lgl([1.0 if same_obj(a[0], a[1]) else 0.0]))
     reg("isTRUE", lambda interp, a, k: lgl([1.0 if isinstance(a[0], RVec) and a[0].kind == "logical" and len(a[0]) == 1 and a[0].v[0] == 1 else 0.0]))
-    reg("identical", lambda interp, a, k: lgl([1.0 if (isinstance(a[0], RVec) and isinstance(a[1], RVec) and a[0].kind == a[1].kind and
-                                                        len(a[0]) == len(a[1]) and all((p == q) or (p != p and q != q) for p, q in zip(a[0].v, a[1].v))) else 0.0]))

@@ -120,6 +120,14 @@ class Builtin:
         self.attrs = {}
 
 
+class RLang:
+    """An unevaluated expression (quote(x), body(f))."""
+    attrs = {}
+
+    def __init__(self, node):
+        self.node = node
+
+
 class Promise:
     __slots__ = ("expr", "env", "value", "forced", "is_default")
 
@@ -524,7 +532,7 @@ def index_list(x, args, double, drop=True):
         return RList(colv, [names[p] for p in pos], {"class": chr_("data.frame")})
     if len(args) != 1:
         raise RError("incorrect number of subscripts on a list")
-    pos = resolve_sub(args[0], len(x), names, allow_extend=double)
+    pos = resolve_sub(args[0], len(x), names, allow_extend=True)
     if double:
         if len(pos) != 1:
             raise RError("subscript out of bounds")
@@ -534,7 +542,7 @@ def index_list(x, args, double, drop=True):
             raise RError("subscript out of bounds")
         return x.v[pos[0]]
     keep_attrs = {k: v for k, v in x.attrs.items() if k == "class"}
-    return RList([x.v[p] for p in pos], [names[p] for p in pos], keep_attrs)
+    return RList([x.v[p] if 0 <= p < len(x) else NULL for p in pos], [names[p] if 0 <= p < len(x) else "NA" for p in pos], keep_attrs)
 
 
 def assign_index(x, args, named, value, double):
@@ -640,6 +648,8 @@ class Interp:
         self.rng = np.random.default_rng(seed)
         self.script_args = list(args)
         self.script_file = None
+        self.namespaces = {}                      # package name -> Env (load_namespace); `pkg::name` looks there first
+        self.dotcall = None                       # hook for .Call(symbol, ...): callable(symbol_name, [values]) -> value
         self.out = sys.stdout
         from . import builtins as B
         B.install(self)
@@ -655,6 +665,13 @@ class Interp:
     def source(self, path, env=None):
         with open(path) as fh:
             return self.run(fh.read(), env)
+
+    def load_namespace(self, name, *paths):
+        """Source files into an environment of their own, reachable as `name::fn` (what library(name) provides)."""
+        env = self.namespaces.setdefault(name, Env(self.base))
+        for p in paths:
+            self.source(p, env)
+        return env
 
     def call(self, fn, *args, **kwargs):
         """Call an R function value from Python with already evaluated arguments."""
@@ -765,6 +782,8 @@ class Interp:
             raise NextEx()
         if k == "ns":
             name = f"{node[1]}::{node[2]}"
+            if node[1] in self.namespaces and node[2] in self.namespaces[node[1]].vars:
+                return self.force(self.namespaces[node[1]].vars[node[2]])
             if self.base.has(name):
                 return self.base.lookup(name)
             return self.force(env.lookup(node[2]))
@@ -888,7 +907,9 @@ class Interp:
             return lgl([1.0 if (isinstance(v, Missing) or (isinstance(v, Promise) and v.is_default)) else 0.0])
         if name in ("suppressWarnings", "suppressMessages"):
             return self.ev(argnodes[0][1], env)
-        if name in ("quote", "substitute", "on.exit", "library", "require"):
+        if name == "quote":
+            return RLang(argnodes[0][1])
+        if name in ("substitute", "on.exit", "library", "require"):
             return NULL
         if name == "tryCatch":
             handlers, body = {}, None
