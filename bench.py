@@ -241,7 +241,7 @@ def run_ours(args):
         spec = importlib.util.spec_from_file_location("e2e_modes", os.path.join(ROOT, "tools", "e2e_modes.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        e2e_modes = [mod.c1(), mod.c3(args.modes_paths), mod.c3(args.modes_paths, True)]
+        e2e_modes = [mod.pcie_peak(), mod.c1(), mod.c3(args.modes_paths), mod.c3(args.modes_paths, True)]
     if rank == 0:
         value = world * args.steps * P * nsteps / (total_ms * 1e-3)
         k_ms = float(np.mean(kernel_ms))

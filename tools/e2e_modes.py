@@ -57,8 +57,42 @@ def c3(P, supplied_b=False):
             "d2h_bytes": X.nbytes, "gb_per_s": (X.nbytes + (0 if B is None else B.nbytes)) / s / 1e9}
 
 
+def pcie_peak(nbytes=1 << 30, reps=5):
+    """The denominators: one pinned buffer of 1 GiB moved by the driver, each direction alone and both at once."""
+    import torch
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    host2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dev2 = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    out = {}
+
+    def bw(fn, moved):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return moved * reps / (time.perf_counter() - t0) / 1e9
+
+    out["d2h_pinned_gb_per_s"] = bw(lambda: host.copy_(dev, non_blocking=True), nbytes)
+    out["h2d_pinned_gb_per_s"] = bw(lambda: dev.copy_(host, non_blocking=True), nbytes)
+
+    def both():
+        with torch.cuda.stream(s1):
+            host.copy_(dev, non_blocking=True)
+        with torch.cuda.stream(s2):
+            dev2.copy_(host2, non_blocking=True)
+    out["bidirectional_pinned_gb_per_s"] = bw(both, 2 * nbytes)
+    out["host_threads"] = os.cpu_count()
+    return {"config": "PCIe peak, pinned 1 GiB copies by the driver", **out}
+
+
 if __name__ == "__main__":
     P = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 15
+    if os.environ.get("E2E_PCIE_PEAK", "1") != "0":
+        print(json.dumps(pcie_peak()))
     print(json.dumps(c1()))
     print(json.dumps(c3(P)))
     print(json.dumps(c3(P, True)))
