@@ -565,7 +565,7 @@ static int enqueue(sdegpu_ctx *c, const sdegpu_problem *pr, const sdegpu_output 
         la.nt = nt; la.d = nx; la.nB = pr->nB; la.scheme = pr->scheme; la.strict = pr->B && pr->arith == SDEGPU_ARITH_STRICT;
         la.moments = io.ps; la.accumulate = accum ? 1 : 0;
         if (io.ps) {                                             // per-block slices of the power sums, reduced in block order
-            la.mom_capacity = 8 * c->prop.multiProcessorCount;
+            la.mom_capacity = (nx <= 32 ? 32 : 8) * c->prop.multiProcessorCount;      // small systems: up to 16 path tiles per CTA, each with its slice
             CU(c->lin_partials.reserve(sizeof(double) * (size_t)la.mom_capacity * 5 * nx));
             la.mom_partials = (double *)c->lin_partials.p;
         }

@@ -34,9 +34,10 @@ int reduce_moment_partials(const LinearArgs &a, int nblocks, cudaStream_t stream
 // Per-component power sums of one tile of terminal states held in shared memory as tile[k*ld + n] (component k, path n):
 // thread tid owns components tid, tid+nthreads, ... and adds their sums over the tile's np paths, in path order, to its
 // block's slice.  No atomics: a component's sums have one writer, so they do not depend on scheduling.
-__device__ __forceinline__ void tile_moments(const LinearArgs &a, const double *tile, int ld, int np, int tid, int nthreads, bool first)
+__device__ __forceinline__ void tile_moments(const LinearArgs &a, const double *tile, int ld, int np, int tid, int nthreads, bool first,
+                                             int slice_index = -1)
 {
-    double *slice = a.mom_partials + (size_t)blockIdx.x * 5 * a.d;
+    double *slice = a.mom_partials + (size_t)(slice_index < 0 ? (int)blockIdx.x : slice_index) * 5 * a.d;
     for (int k = tid; k < a.d; k += nthreads) {
         double s[5] = {0, 0, 0, 0, 0};
         const double cen = a.center[k];

@@ -52,19 +52,30 @@ struct TcArgs {
     int diag_tile;                         // noise == 1 with a diagonal G: elementwise product with the tile instead of a GEMM
 };
 
-template <int NW, int MA, int NBT, int RB, bool HEUN>
-__global__ void __launch_bounds__(32 * NW, 1) k_linear_tc(const LinearArgs a, const TcArgs q)
+template <int NW, int MA, int NBT, int RB, bool HEUN, int NG, bool HOT>
+__global__ void __launch_bounds__(32 * NW * NG, 1) k_linear_tc(const LinearArgs a, const TcArgs q)
 {
     // a warp owns RB row blocks of 8*MA rows: rows 8*MA*(RB*w + rb) + 8*mi + lane/4.  RB = 2 carries 256 < d <= 512: the
     // accumulators of both blocks stay in registers until every warp has read X_i, so X is still updated in place.
+    // NG > 1 (small systems, d <= 32, where one warp carries the whole state): a CTA holds NG independent path tiles, one per
+    // warp, behind ONE copy of the quantile table — with one warp per CTA the 53 KB table capped an SM at three warps and the
+    // kernel was latency-bound; warp-private tiles also turn every barrier into __syncwarp.
+    // HOT: the quantile table in its bank-replicated layout (151 KB instead of 53): with 8-16 warps drawing normals the plain
+    // table's bank conflicts (5.4 wavefronts per 16-byte read, philox.cuh) make the load/store unit the limiter.
+    static_assert(NG == 1 || NW == 1, "several path tiles per CTA only when a single warp owns a tile");
+    constexpr int TABLE = HOT ? ICDF_HOT_TABLE_DOUBLES : ICDF_TABLE_DOUBLES;
     constexpr int D = 8 * MA * NW * RB, PT = 8 * NBT, LDX = PT + 4, NT = 32 * NW;
     extern __shared__ __align__(16) double sm[];
     double *sh_tab = sm;                                         // quantile table (fused generator only)
-    double *xs = sm + (a.B ? 0 : ICDF_TABLE_DOUBLES);            // X tile  xs[k*LDX + n]
+    const int gi = NG == 1 ? 0 : (int)(threadIdx.x >> 5);        // this warp's path tile
+    const int tile_doubles = (D * (HEUN ? 2 : 1) + q.ZR) * LDX;
+    double *xs = sm + (a.B ? 0 : TABLE) + gi * tile_doubles;      // X tile  xs[k*LDX + n]
     double *ys = xs + D * LDX;                                   // Y tile (Heun)
     double *zs = ys + (HEUN ? D * LDX : 0);                      // increment tile zs[k*LDX + n], k < ZR (noise == 1)
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
-    if (!a.B) icdf_stage(sh_tab, a.icdf, tid, NT);
+    const int tid = NG == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31), lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    auto tile_sync = [] { if (NG == 1) __syncthreads(); else __syncwarp(); };
+    if (!a.B) { if (HOT) icdf_stage_hot(sh_tab, a.icdf, (int)threadIdx.x, NT * NG); else icdf_stage(sh_tab, a.icdf, (int)threadIdx.x, NT * NG); }
+    if (NG > 1) __syncthreads();                                 // the table is in place; from here on warps run on their own
     const int nsteps = a.nt - 1, dr = a.d, nB = a.nB, KK = q.KK, KKG = q.KKG;
     const uint64_t ngroups = (a.npaths + PT - 1) / PT;
     const double *Aw = q.Apk + (size_t)(RB * w) * KK * MA * 32 + lane;                      // block rb: + rb*KK*MA*32
@@ -76,10 +87,12 @@ __global__ void __launch_bounds__(32 * NW, 1) k_linear_tc(const LinearArgs a, co
 #pragma unroll
         for (int mi = 0; mi < MA; ++mi) grow[rb][mi] = q.gdiag ? q.gdiag[row(rb, mi)] : 0.0;
 
-    for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    if (NG > 1 && a.moments && (uint64_t)blockIdx.x * NG + gi >= ngroups)      // a warp without a tile still owns a slice of partial sums
+        for (int e = tid; e < 5 * a.d; e += NT) a.mom_partials[(size_t)(blockIdx.x * NG + gi) * 5 * a.d + e] = 0.0;
+    for (uint64_t grp = (uint64_t)blockIdx.x * NG + gi; grp < ngroups; grp += (uint64_t)gridDim.x * NG) {
         const uint64_t p0 = grp * PT;
         const int np = (int)((a.npaths - p0 < (uint64_t)PT) ? (a.npaths - p0) : PT);
-        __syncthreads();
+        tile_sync();
         for (int e = tid; e < D * PT; e += NT) {
             const int n = e / D, k = e - n * D;                  // consecutive threads walk one path's state vector
             const double v = (n < np && k < dr) ? (a.x0 ? a.x0[(p0 + n) * dr + k] : a.x0_shared[k]) : 0.0;
@@ -107,25 +120,25 @@ __global__ void __launch_bounds__(32 * NW, 1) k_linear_tc(const LinearArgs a, co
                         if (nB == 1) {                           // a single channel draws from the scalar models' stream
                             if (kp == 0 && n < np) {
                                 double zq[4];
-                                normal_quad(a.seed, a.path_offset + p0 + n, (uint32_t)(i >> 2), 0u, sh_tab, zq);
+                                normal_quad<HOT>(a.seed, a.path_offset + p0 + n, (uint32_t)(i >> 2), 0u, sh_tab, zq);
                                 const int s4 = i & 3;
                                 z0 = s4 == 0 ? zq[0] : (s4 == 1 ? zq[1] : (s4 == 2 ? zq[2] : zq[3]));
                             }
                         } else if (2 * kp < nB && n < np)
-                            normal_pair(a.seed, a.path_offset + p0 + n, (uint32_t)i, 0x80000000u + (uint32_t)kp, sh_tab, z0, z1);
+                            normal_pair<HOT>(a.seed, a.path_offset + p0 + n, (uint32_t)i, 0x80000000u + (uint32_t)kp, sh_tab, z0, z1);
                         zs[(2 * kp) * LDX + n] = ds.y * z0;
                         zs[(2 * kp + 1) * LDX + n] = (2 * kp + 1 < nB) ? ds.y * z1 : 0.0;
                     }
                 }
             }
-            __syncthreads();                                     // X_i (and the increment tile) are in place
+            tile_sync();                                          // X_i (and the increment tile) are in place
             // noise == 0: this lane's normals.  Heun keeps them in registers between predictor and corrector (the plan
             // gives it the smaller path tile then); Euler draws them where they are consumed.
             auto draw = [&](int rb, int mi, int ni, double &z0, double &z1) {
                 const int r = row(rb, mi), c = 8 * ni + 2 * tig;
                 // channel pair (r & ~1, r | 1): even-row lane draws for path c, odd-row lane for path c+1
                 double za, zb;
-                normal_pair(a.seed, a.path_offset + p0 + c + (gid & 1), (uint32_t)i, 0x80000000u + (uint32_t)(r >> 1), sh_tab, za, zb);
+                normal_pair<HOT>(a.seed, a.path_offset + p0 + c + (gid & 1), (uint32_t)i, 0x80000000u + (uint32_t)(r >> 1), sh_tab, za, zb);
                 const double send = (gid & 1) ? za : zb;
                 const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
                 z0 = (gid & 1) ? recv : za;                      // this lane's row, path c
@@ -255,10 +268,10 @@ __global__ void __launch_bounds__(32 * NW, 1) k_linear_tc(const LinearArgs a, co
             };
             double acc[RB][MA][NBT][2];
             half_step(xs, i, acc);
-            __syncthreads();                                     // every warp is done reading X_i
+            tile_sync();                                          // every warp is done reading X_i
             update(acc, HEUN ? 0.5 : 1.0, HEUN);
             if (HEUN) {
-                __syncthreads();                                 // the predictor tile is complete
+                tile_sync();                                      // the predictor tile is complete
                 half_step(ys, i + 1, acc);                       // ff(times[i+1], Y)  (:321)
                 update(acc, 0.5, false);                         // rows of X are private to their warp: no barrier needed before this
             }
@@ -277,22 +290,22 @@ __global__ void __launch_bounds__(32 * NW, 1) k_linear_tc(const LinearArgs a, co
                         }
                     }
             }
-            __syncthreads();                                     // X_{i+1} complete; the increment tile may be refilled
+            tile_sync();                                          // X_{i+1} complete; the increment tile may be refilled
         }
         for (int e = tid; e < D * np; e += NT) {
             const int n = e / D, k = e - n * D;
             if (a.XT && k < dr) a.XT[(p0 + n) * dr + k] = xs[k * LDX + n];
         }
-        if (a.moments) tile_moments(a, xs, LDX, np, tid, NT, grp == blockIdx.x);
+        if (a.moments) tile_moments(a, xs, LDX, np, tid, NT, grp == (uint64_t)blockIdx.x * NG + gi, blockIdx.x * NG + gi);
     }
 }
 
-static size_t tc_smem(bool has_b, int D, int PT, bool heun, int zrows)
+static size_t tc_smem(bool has_b, int D, int PT, bool heun, int zrows, int ng = 1, bool hot = false)
 {
-    return sizeof(double) * ((has_b ? 0 : (size_t)ICDF_TABLE_DOUBLES) + (size_t)(D * (heun ? 2 : 1) + zrows) * (PT + 4));
+    return sizeof(double) * ((has_b ? 0 : (size_t)(hot ? ICDF_HOT_TABLE_DOUBLES : ICDF_TABLE_DOUBLES)) + (size_t)ng * (size_t)(D * (heun ? 2 : 1) + zrows) * (PT + 4));
 }
 
-struct TcPlan { int nw, ma, nbt, rb, noise, diag_tile, kk, kkg, zr; size_t smem; };
+struct TcPlan { int nw, ma, nbt, rb, noise, diag_tile, kk, kkg, zr, ng, hot; size_t smem; };
 
 static bool tc_plan(const LinearArgs &a, const double *hostG, TcPlan *p)
 {
@@ -317,11 +330,36 @@ static bool tc_plan(const LinearArgs &a, const double *hostG, TcPlan *p)
     // path tiles: 64 / 32 paths for one row block, 32 / 16 for two (the accumulators of both blocks share the register file);
     // Heun with its normals in registers takes the smaller one
     const int big = p->rb == 1 ? 8 : 4, small = big / 2;
+    // one warp per tile, normals in registers: the smaller path tile lets twice as many warps share an SM (d = 16: 1.22e10 -> 1.59e10,
+    // d = 32: 4.55e9 -> 5.19e9 path-steps/s)
+    bool small_first = p->noise == 0;
+    if (const char *e = getenv("SDEGPU_TC_SMALL_TILE")) small_first = atoi(e) != 0;
     for (int nbt : {big, small}) {
         if (nbt == big && heun && p->noise == 0) continue;
+        if (nbt == big && small_first && p->nw == 1 && p->rb == 1) continue;
         p->nbt = nbt;
+        p->ng = 1;
+        p->hot = 0;
         p->smem = tc_smem(a.B != nullptr, D, 8 * nbt, heun, zrows);
-        if (p->smem <= (size_t)226 * 1024) return true;
+        if (p->smem > (size_t)226 * 1024) continue;
+        if (p->nw == 1 && p->rb == 1) {                          // one warp per tile: as many tiles per CTA as fit, 16 at most
+            int ng_max = p->ma * nbt <= 8 ? 16 : 8;      // 512 threads leave 128 registers each: enough for 16 accumulator doubles, not for 32
+            if (const char *e = getenv("SDEGPU_TC_NG")) if (atoi(e) > 0) ng_max = atoi(e);
+            int want_hot = a.B ? 0 : 1;
+            if (const char *e = getenv("SDEGPU_TC_HOT")) want_hot = a.B ? 0 : atoi(e);
+            auto fit = [&](bool hot) {
+                for (int ng : {16, 8, 4}) {
+                    if (ng > ng_max) continue;
+                    if (tc_smem(a.B != nullptr, D, 8 * nbt, heun, zrows, ng, hot) <= (size_t)226 * 1024) return ng;
+                }
+                return 1;
+            };
+            const int ng_hot = want_hot ? fit(true) : 1, ng_plain = fit(false);
+            if (ng_hot >= 8 || (ng_hot >= 4 && ng_hot == ng_plain)) { p->ng = ng_hot; p->hot = 1; }
+            else p->ng = ng_plain;
+            p->smem = tc_smem(a.B != nullptr, D, 8 * nbt, heun, zrows, p->ng, p->hot != 0);
+        }
+        return true;
     }
     return false;
 }
@@ -339,28 +377,49 @@ size_t linear_tc_scratch_doubles(const LinearArgs &a)
     return dp * 4 * kk + dp * 4 * kkg + dp;
 }
 
-template <int NW, int MA, int NBT, int RB>
+template <int NW, int MA, int NBT, int RB, int NG = 1, bool HOT = false>
 static int tc_launch(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
 {
-    const uint64_t ngroups = (a.npaths + 8 * NBT - 1) / (8 * NBT);
+    const uint64_t ngroups = (a.npaths + 8 * NBT - 1) / (8 * NBT), nblocks = (ngroups + NG - 1) / NG;
     auto go = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, p.smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW * NG, p.smem);
         const uint64_t cap = (uint64_t)(per_sm < 1 ? 1 : per_sm) * sm_count;
-        int grid = (int)(ngroups < cap ? ngroups : cap);
-        if (a.moments && grid > a.mom_capacity) grid = a.mom_capacity;
-        kernel<<<grid, 32 * NW, p.smem, stream>>>(a, q);
-        if (a.moments) reduce_moment_partials(a, grid, stream);
+        int grid = (int)(nblocks < cap ? nblocks : cap);
+        if (a.moments && grid * NG > a.mom_capacity) grid = a.mom_capacity / NG;      // one slice of partial sums per path tile in flight
+        if (grid < 1) grid = 1;
+        kernel<<<grid, 32 * NW * NG, p.smem, stream>>>(a, q);
+        if (a.moments) reduce_moment_partials(a, grid * NG, stream);
     };
-    if (a.scheme == SDEGPU_HEUN) go(k_linear_tc<NW, MA, NBT, RB, true>);
-    else go(k_linear_tc<NW, MA, NBT, RB, false>);
+    if (a.scheme == SDEGPU_HEUN) go(k_linear_tc<NW, MA, NBT, RB, true, NG, HOT>);
+    else go(k_linear_tc<NW, MA, NBT, RB, false, NG, HOT>);
     return (int)cudaGetLastError();
+}
+
+// one warp per tile (d <= 32): NG tiles per CTA
+template <int MA, int NBT>
+static int tc_launch_ng(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
+{
+    if (p.hot) {
+        switch (p.ng) {
+        case 16: return tc_launch<1, MA, NBT, 1, 16, true>(a, q, p, sm_count, stream);
+        case 8: return tc_launch<1, MA, NBT, 1, 8, true>(a, q, p, sm_count, stream);
+        default: return tc_launch<1, MA, NBT, 1, 4, true>(a, q, p, sm_count, stream);
+        }
+    }
+    switch (p.ng) {
+    case 16: return tc_launch<1, MA, NBT, 1, 16>(a, q, p, sm_count, stream);
+    case 8: return tc_launch<1, MA, NBT, 1, 8>(a, q, p, sm_count, stream);
+    case 4: return tc_launch<1, MA, NBT, 1, 4>(a, q, p, sm_count, stream);
+    default: return tc_launch<1, MA, NBT, 1, 1>(a, q, p, sm_count, stream);
+    }
 }
 
 template <int NW, int MA>
 static int tc_launch_nbt(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
 {
+    if (NW == 1) return p.nbt == 8 ? tc_launch_ng<MA, 8>(a, q, p, sm_count, stream) : tc_launch_ng<MA, 4>(a, q, p, sm_count, stream);
     return p.nbt == 8 ? tc_launch<NW, MA, 8, 1>(a, q, p, sm_count, stream) : tc_launch<NW, MA, 4, 1>(a, q, p, sm_count, stream);
 }
 
