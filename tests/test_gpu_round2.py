@@ -2,6 +2,8 @@
 model's own drift and diffusion (vignettes/ItoIntegrals.Rmd:82-93), the chunk pipeline of host-pointer runs, the
 interrupt callback and the multi-GPU context.  Bar as in test_gpu_parity.py: bit-exact against the oracle with a
 supplied B (1e-12 relative where `%*%` is involved), chunking/sharding invariance bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -403,3 +405,23 @@ def test_tensor_kernels_write_nothing_outside_their_arrays(eng, d, nB, P, scheme
     eng.run("linear", scheme, params, t, x0, nx=d, nB=nB, npaths=P, B=B, arith="fast", X=X2)
     torch.cuda.synchronize()
     assert _intact(torch, buf2, P * d * nt) and _intact(torch, Bb, P * nB * nt) and bool(torch.isfinite(X2).all())
+
+
+# ---- the generator alone: every word of the Philox block through the inversion, against N(0,1) -------------
+def test_generator_alone_matches_the_normal_law(eng):
+    """tools/generator_check.py at 4e8 draws (the 1e10-draw run is profiles/r2_generator_check.json): OU with lambda = 0 on grids with
+    one dominant interval isolates word k of the block; mean, variance, fourth moment within 4.5 SE, chi-square over 512 bins, tails."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("generator_check", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                                  "tools", "generator_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.check(eng, 4e8, 0x5DE7000B)
+    for v in [out["all_words"]] + out["per_word"]:
+        assert v["draws"] in (100000000, 400000000) and v["nan"] == 0
+        assert abs(v["mean_err_in_se"]) < 4.5 and abs(v["var_err_in_se"]) < 4.5 and abs(v["m4_err_in_se"]) < 4.5, v
+        assert v["chi2_p"] > 1e-4, v
+        assert v["tail_poisson_p"] > 1e-4, v
+    # the four words are different draws: their means are not copies of each other
+    means = [w["mean_err_in_se"] for w in out["per_word"]]
+    assert len(set(round(m, 6) for m in means)) == 4
