@@ -274,11 +274,7 @@ def run_ours(args):
                     "api": "sdetools_b200.heun(f, g, times, x0, p=abs, npaths=..., hist=..., moments=True) with host buffers"},
             "e2e_modes": e2e_modes,
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak and achieved else None,
-                         "definition": "FP64-pipe utilisation: FP64 instructions in the kernel's SASS step loop (DFMA/DADD/DMUL/DSETP, "
-                                       "tools/sass_count.py -> profiles/r2_sass_k_terminal.json) x live path-steps/s x 2, over the DFMA-stream "
-                                       "peak measured in this run; not the survey's 85-flop convention (VERDICT r1 weak #2)",
+            "roofline": roofline_head(achieved, fp64_peak, issue_achieved, issue_peak, n64, nins, rate_k) | {
                          "executed": {"fp64_instructions_per_path_step": n64, "instructions_per_path_step": nins,
                                       "fp64_flops_per_path_step": sass.get("fp64_flops_per_path_step"),
                                       "fp64_tflops_true": sass.get("fp64_flops_per_path_step", 0) * rate_k / 1e12 if sass else None,
@@ -307,6 +303,30 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def roofline_head(fp64_achieved, fp64_peak, issue_achieved, issue_peak, n64, nins, rate_k):
+    """The kernel is CUDA-core FP64 work with no HBM traffic, so its roofline has two ceilings, both from the executed SASS
+    (tools/sass_count.py): the FP64 pipe (FP64 instructions per path-step against the DFMA-stream rate measured in this run) and the
+    issue slots (all instructions per path-step against 4 schedulers x 1 instruction per cycle per SM).  `frac` is the fraction of the
+    LOWER ceiling — the one that binds; the fraction of each ceiling is carried beside it, as is the survey's flop convention."""
+    frac_fp64 = fp64_achieved / fp64_peak if fp64_peak and fp64_achieved else None
+    frac_issue = issue_achieved / issue_peak if issue_achieved else None
+    ceil_fp64 = fp64_peak * 1e12 / 2.0 / n64 if n64 and fp64_peak else None              # path-steps/s the FP64 pipe allows
+    ceil_issue = issue_peak * 32.0 / nins if nins else None                                # path-steps/s the issue slots allow
+    issue_binds = ceil_issue is not None and (ceil_fp64 is None or ceil_issue <= ceil_fp64)
+    head = {"bound": "issue" if issue_binds else "fp64",
+            "achieved": issue_achieved if issue_binds else fp64_achieved, "peak": issue_peak if issue_binds else fp64_peak,
+            "unit": "warp-instructions/s" if issue_binds else "TFLOP/s", "frac": frac_issue if issue_binds else frac_fp64,
+            "frac_issue": frac_issue, "frac_fp64_pipe": frac_fp64,
+            "frac_convention": FLOPS_PER_PATH_STEP * rate_k / 1e12 / fp64_peak if fp64_peak else None,
+            "ceilings_path_steps_per_s": {"issue_slots": ceil_issue, "fp64_pipe": ceil_fp64},
+            "definition": "two ceilings from the executed SASS of the step loop (tools/sass_count.py -> profiles/r2_sass_k_terminal.json): "
+                          "issue slots = instructions per path-step x live path-steps/s / 32 over 4 schedulers x SMs x clock; FP64 pipe = FP64 "
+                          "instructions (DFMA/DADD/DMUL/DSETP) x rate x 2 over the DFMA-stream peak measured in this run. frac = fraction of the "
+                          "lower (binding) ceiling; frac_issue, frac_fp64_pipe = fraction of each; frac_convention = the survey's 85-flop "
+                          "Box-Muller-priced count over the same peak (reads > 1: the convention overprices the generator; VERDICT r1 weak #2)"}
+    return head
 
 
 def main():

@@ -174,14 +174,39 @@ __device__ __forceinline__ void sde_step(const KParams &P, double (&x)[M::NX], d
 constexpr int FAST_NCOEF = 6;
 
 // sqrt(k |x|) for finite x, k = 1 or 4, without the special cases of the IEEE routine: a = k|x| + 2^-1000 keeps the
-// MUFU.RSQ64H seed y finite at x = 0 (one FP64 instruction, no integer clamp), then one second-order step
-// sqrt(a) = t + t e / 2, t = a y, e = 1 - t y  (seed error e ~ 2^-22: relative error 3 e^2 / 8 ~ 2e-14), or the
-// third-order step of Fast::sqrt_ when ORDER = 3.
+// MUFU.RSQ64H seed y finite at x = 0 (one FP64 instruction, no integer clamp), then one second-order step.
+//   ORDER 21 (default)  Heron's step on the residual: t = a y, r = a - t^2, sqrt(a) = t + r (y/2) with y/2 an exponent decrement
+//                       of the seed's high word: 4 FP64 + 1 integer instruction per root, relative error ~ e^2/2 ~ 1e-14 (seed
+//                       error e ~ 2^-22).  Measured on config C2: 4.53e11 -> 4.60e11 path-steps/s against ORDER 2.
+//   ORDER 22            also forms a with integer operations on the high word: two FP64 instructions fewer, six integer ones more
+//                       — slower (4.35e11); kept as the record of the experiment (profiles/r2_tune_terminal_sqrt.txt).
+//   ORDER 2             sqrt(a) = t + t e / 2, e = 1 - t y: 5 FP64.      ORDER 3: the third-order step of Fast::sqrt_.
 #ifndef SDEGPU_FASTSQRT_ORDER
-#define SDEGPU_FASTSQRT_ORDER 2
+#define SDEGPU_FASTSQRT_ORDER 21
 #endif
 template <int K> __device__ __forceinline__ double fast_sqrt_abs(double x)
 {
+#if SDEGPU_FASTSQRT_ORDER == 21 || SDEGPU_FASTSQRT_ORDER == 22
+    // Heron's step on the residual: t = a y, r = a - t^2 (one FMA, exact product), sqrt(a) = t + r (y/2).  y/2 is an exponent
+    // decrement of the seed's high word (its low word is zero), so the step is DMUL + 2 DFMA and one integer add: one FP64
+    // instruction fewer than t + (t e)/2 with e = 1 - t y, same second-order error (~ e^2/2, e ~ 2^-22).
+    // ORDER 22 also forms a = K|x| (kept away from zero) with integer operations on the high word instead of an FP64 add.
+    double a;
+    if (SDEGPU_FASTSQRT_ORDER == 22) {
+        const int hi = __double2hiint(x) & 0x7FFFFFFF;
+        // K = 4: two exponent steps up (x = 0 becomes 2^-1021); K = 1: at least the smallest normal exponent
+        a = __hiloint2double(K == 4 ? hi + 0x00200000 : max(hi, 0x00100000), __double2loint(x));
+    } else {
+        const double tiny = 9.3326361850321888e-302;             // 2^-1000
+        a = K == 1 ? fabs(x) + tiny : fma((double)K, fabs(x), tiny);
+    }
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double t = a * y;
+    const double r = fma(-t, t, a);
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, 0);
+    return fma(r, h, t);
+#else
     const double tiny = 9.3326361850321888e-302;                 // 2^-1000
     const double a = K == 1 ? fabs(x) + tiny : fma((double)K, fabs(x), tiny);
     double y;
@@ -191,6 +216,7 @@ template <int K> __device__ __forceinline__ double fast_sqrt_abs(double x)
     if (SDEGPU_FASTSQRT_ORDER == 2) return fma(t * e, 0.5, t);
     const double p = fma(0.375, e, 0.5);
     return fma(t, p * e, t);
+#endif
 }
 
 template <class M, int SCHEME, int PROJ> struct FastStep {
