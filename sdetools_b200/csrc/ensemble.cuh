@@ -240,8 +240,10 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
             load_x0<NX>(a, pl, x[q]);
             philox_block(a.seed, a.path_offset + pl, 0u, 0u, r[q][0], r[q][1], r[q][2], r[q][3]);
         }
-        int i = 0;
-        for (; i + 3 < nsteps; i += 4) {
+        // one loop counter: the block index (the Philox counter of the block generated ahead is blk + 1, rows start at 4 blk)
+        const uint32_t nfull = (uint32_t)nsteps >> 2;
+        for (uint32_t blk = 0; blk < nfull; ++blk) {
+            const int i = (int)(blk << 2);
             CoefRow row[4];
             if (!UNIFORM) {
 #pragma unroll
@@ -255,14 +257,14 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) n[k] = r[q][k] * 1664525u + 1013904223u + (uint32_t)gp;
 #else
-                philox_block(a.seed, gp, (uint32_t)(i >> 2) + 1u, 0u, n[0], n[1], n[2], n[3]);
+                philox_block(a.seed, gp, blk + 1u, 0u, n[0], n[1], n[2], n[3]);
 #endif
                 double z[4];
 #ifdef SDEGPU_EXP_NOICDF                                         // decomposition experiment: a uniform instead of a normal
 #pragma unroll
                 for (int k = 0; k < 4; ++k) z[k] = (__hiloint2double(0x43300000, (int)r[q][k]) - 4503601774854144.0) * 4.6566128730773926e-10;
 #else
-                gen.quad(a.seed, gp, (uint32_t)(i >> 2), 0u, r[q], z);
+                gen.quad(a.seed, gp, blk, 0u, r[q], z);
 #endif
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
                 }
             }
         }
+        const int i = (int)(nfull << 2);
         if (i < nsteps) {                                        // up to three trailing steps of the last block
 #pragma unroll
             for (int q = 0; q < NP; ++q) {

@@ -308,9 +308,51 @@ template <int REPL> struct NormalGen {
     }
 
     // scale * z for steps 4*block .. 4*block+3 of (path, channel) from the words of its Philox block
+    // bulk() with s and its segment bits already at hand
+    __device__ __forceinline__ double bulk_at(double s, uint32_t seg) const
+    {
+        const uint32_t addr = base + (seg >> (11 - L::LOG));
+        const double2 c01 = lds_f64x2(addr), c23 = lds_f64x2(addr + L::PLANE_BYTES);
+        const double v = fabs(s);
+        double a = fma(c23.y, v, c23.x);
+        a = fma(a, v, c01.y);
+#ifndef SDEGPU_GEN_PLAIN_SIGN
+        // sign(s) (c0 + b |s|) = sign(s) c0 + b s: the sign goes onto the loaded constant term (in place, off the critical path)
+        // and the last Horner step multiplies by s itself, so the result needs no sign fix-up and no copy of its low word
+        const double c0s = __hiloint2double(__double2hiint(c01.x) ^ (__double2hiint(s) & (int)0x80000000u), __double2loint(c01.x));
+        return fma(a, s, c0s);
+#else
+        a = fma(a, v, c01.x);
+        return __hiloint2double(__double2hiint(a) ^ (__double2hiint(s) & (int)0x80000000u), __double2loint(a));
+#endif
+    }
+
     __device__ __forceinline__ void quad(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
                                          const uint32_t (&r)[4], double (&z)[4]) const
     {
+#ifndef SDEGPU_GEN_PLAIN_QUAD
+        // the masked high words feed both the tail test and the table addresses: pinned in registers so that the compiler does
+        // not derive the address from the high word a second time (one LOP3 per normal less)
+        double s[4];
+        uint32_t sg[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s[k] = word_to_s(r[k]);
+            sg[k] = seg_bits(s[k]);
+            asm volatile("" : "+r"(sg[k]));
+        }
+        if (min(min(sg[0], sg[1]), min(sg[2], sg[3])) < 0x41200000u) {
+            double zt[4];
+            icdf32_tail_quad(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, r[0], r[1], r[2], r[3],
+                             g52, scale, zt);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z[k] = zt[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z[k] = bulk_at(s[k], sg[k]);
+        }
+        return;
+#endif
         if (has_tail(r)) {
             double zt[4];                                        // its address is taken: kept apart from z, which stays in registers
             icdf32_tail_quad(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, r[0], r[1], r[2], r[3],
