@@ -371,6 +371,35 @@ template <int REPL> struct NormalGen {
     __device__ __forceinline__ void multi(const PhiloxKey &key, uint64_t path, uint32_t block0, uint32_t channel,
                                           const uint32_t (&r)[NB][4], double (&z)[4 * NB]) const
     {
+#ifndef SDEGPU_GEN_PLAIN_QUAD
+        // as in quad(): s and its masked high word once per normal, used by the tail test and by the evaluation
+        double s[NB][4];
+        uint32_t sg[NB][4], lowest = 0xFFFFFFFFu;
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s[b][k] = word_to_s(r[b][k]);
+                sg[b][k] = seg_bits(s[b][k]);
+                asm volatile("" : "+r"(sg[b][k]));
+                lowest = min(lowest, sg[b][k]);
+            }
+        if (lowest >= 0x41200000u) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[4 * b + k] = bulk_at(s[b][k], sg[b][k]);
+            return;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            double zq[4];
+            quad(key, path, block0 + (uint32_t)b, channel, r[b], zq);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z[4 * b + k] = zq[k];
+        }
+        return;
+#endif
         bool tail = false;
 #pragma unroll
         for (int b = 0; b < NB; ++b) tail |= has_tail(r[b]);

@@ -106,8 +106,20 @@ def main():
         ms = best_ms(lambda: eng.run("ou", "euler", [1.3, 0.7, 0.9], t, [2.0], nx=1, npaths=P, seed=0x5DE70005, power_sums=ps,
                                      center=[1.05], hist_counts=hc, hist=(-2.2, 4.3, 512), want_time=True))
         steps = P * n
-        emit("c5_ou_euler_terminal", paths=P, nsteps=n, ms=ms, path_steps_per_s=steps / ms * 1e3,
-             tflops_conv=71.0 * steps / ms / 1e9, fp64_peak=fp64, frac=71.0 * steps / ms / 1e9 / fp64)
+        rate = steps / ms * 1e3
+        # executed-instruction fractions from the SASS count of this kernel's step loop (tools/sass_count.py --loop, see
+        # profiles/r2_sass_k_terminal_ou_euler.json); the survey's 71-flop convention reads > 1 and is kept only under that name
+        try:
+            sass = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                                               "r2_sass_k_terminal_ou_euler.json")))
+        except Exception:
+            sass = {}
+        nins, n64 = sass.get("instructions_per_path_step"), sass.get("fp64_per_path_step")
+        issue_peak = eng.info["sm_count"] * 4 * eng.info["clock_khz"] * 1e3
+        emit("c5_ou_euler_terminal", paths=P, nsteps=n, ms=ms, path_steps_per_s=rate, fp64_peak=fp64,
+             instructions_per_path_step=nins, fp64_instructions_per_path_step=n64,
+             frac_issue=nins * rate / 32.0 / issue_peak if nins else None, frac_fp64_pipe=2.0 * n64 * rate / 1e12 / fp64 if n64 else None,
+             frac_convention=71.0 * rate / 1e12 / fp64)
 
     # integrals: stochint l/r/c on stored paths (16 B read, 24 B written per element)
     if want("integrals"):

@@ -92,6 +92,7 @@ def main():
     ap.add_argument("--steps-per-iter", type=int, default=4)
     ap.add_argument("--json", default=None)
     ap.add_argument("--listing", action="store_true", help="print the loop body")
+    ap.add_argument("--loop", default="", help="START:END addresses (hex) of the loop when the heuristic picks another one, e.g. 0xc00:0x1330")
     args = ap.parse_args()
     kernels = disassemble(args.obj)
     names = [k for k in kernels if re.search(args.kernel, k)]
@@ -100,6 +101,10 @@ def main():
     name = names[0]
     ins = kernels[name]
     j, i = hot_loop(ins)
+    if args.loop:
+        lo, hi = (int(v, 16) for v in args.loop.split(":"))
+        j = next(k for k, x in enumerate(ins) if x[0] == lo)
+        i = next(k for k, x in enumerate(ins) if x[0] == hi)
     body = ins[j:i + 1]
     cats = {}
     for a, op, ar, _ in body:
