@@ -565,13 +565,19 @@ static int enqueue(sdegpu_ctx *c, const sdegpu_problem *pr, const sdegpu_output 
         la.nt = nt; la.d = nx; la.nB = pr->nB; la.scheme = pr->scheme; la.strict = pr->B && pr->arith == SDEGPU_ARITH_STRICT;
         la.moments = io.ps; la.accumulate = accum ? 1 : 0;
         if (io.ps) {                                             // per-block slices of the power sums, reduced in block order
-            la.mom_capacity = (nx <= 32 ? 32 : 8) * c->prop.multiProcessorCount;      // small systems: up to 16 path tiles per CTA, each with its slice
+            la.mom_capacity = (nx <= 128 ? 32 : 8) * c->prop.multiProcessorCount;     // d <= 128: up to 16 path tiles per CTA, each with its slice
             CU(c->lin_partials.reserve(sizeof(double) * (size_t)la.mom_capacity * 5 * nx));
             la.mom_partials = (double *)c->lin_partials.p;
         }
         la.center = pp.lin_center;
         la.forcing = pp.forcing;
-        const int mode = dmma_mode(la, pr->params + (size_t)nx * nx);
+        int mode = dmma_mode(la, pr->params + (size_t)nx * nx);
+        // 32 < d <= 128: the general tensor kernel with two or four path tiles per CTA behind one quantile table keeps 8 warps per SM
+        // where the tuned C4 kernels keep 4 (measured, euler, fused generator: d = 64 0.45 -> 0.50 of FP64 peak, d = 100 0.36 -> 0.46,
+        // d = 128 0.59 -> 0.64; dense noise d = 64 0.26 -> 0.45, d = 100 level, d = 128 0.62 stays with k_linear_dmma_dense)
+        if (((mode == 1 && nx <= 128) || (mode == 2 && nx <= 96)) && !getenv("SDEGPU_LINEAR_DMMA") &&
+            linear_tc_eligible(la, pr->params + (size_t)nx * nx))
+            mode = 0;
         const size_t dp = ((size_t)nx + 31) / 32 * 32;              // the tensor kernels pad to a multiple of 32 rows
         if (mode == 1) {
             CU(c->scratch.reserve(sizeof(double) * (dp * dp + dp)));

@@ -13,6 +13,7 @@
 //    Z comes from the fused Philox generator, one block per (path, step, channel pair), the two
 //    rows of a pair live in lanes L and L^4 and swap one normal each by shuffle.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "../../include/sdegpu.h"
@@ -253,6 +254,7 @@ static size_t dense_smem(int dp, int kkg)
 int dmma_mode(const LinearArgs &a, const double *hostG)
 {
     if (a.B || a.forcing || a.scheme != SDEGPU_EULER || a.X || a.d <= 32 || a.d > 256 || a.nB < 1) return 0;
+    if (const char *e = getenv("SDEGPU_LINEAR_DMMA")) if (atoi(e) == 0) return 0;          // 0: leave every size to k_linear_tc; 1: every eligible size here
     bool diag = a.nB == a.d;
     for (int c = 0; c < a.nB && diag; ++c)
         for (int r = 0; r < a.d; ++r)

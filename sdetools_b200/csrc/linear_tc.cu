@@ -62,18 +62,23 @@ __global__ void __launch_bounds__(32 * NW * NG, 1) k_linear_tc(const LinearArgs 
     // kernel was latency-bound; warp-private tiles also turn every barrier into __syncwarp.
     // HOT: the quantile table in its bank-replicated layout (151 KB instead of 53): with 8-16 warps drawing normals the plain
     // table's bank conflicts (5.4 wavefronts per 16-byte read, philox.cuh) make the load/store unit the limiter.
-    static_assert(NG == 1 || NW == 1, "several path tiles per CTA only when a single warp owns a tile");
+    // NG > 1 with NW > 1 (32 < d <= 128): the NW warps of a tile meet at a named barrier of their own (bar.sync id, 32*NW).
+    static_assert(NW == 1 || NG <= 15, "named barriers 1..15");
     constexpr int TABLE = HOT ? ICDF_HOT_TABLE_DOUBLES : ICDF_TABLE_DOUBLES;
     constexpr int D = 8 * MA * NW * RB, PT = 8 * NBT, LDX = PT + 4, NT = 32 * NW;
     extern __shared__ __align__(16) double sm[];
     double *sh_tab = sm;                                         // quantile table (fused generator only)
-    const int gi = NG == 1 ? 0 : (int)(threadIdx.x >> 5);        // this warp's path tile
+    const int gi = NG == 1 ? 0 : (int)(threadIdx.x / NT);        // this warp group's path tile
     const int tile_doubles = (D * (HEUN ? 2 : 1) + q.ZR) * LDX;
     double *xs = sm + (a.B ? 0 : TABLE) + gi * tile_doubles;      // X tile  xs[k*LDX + n]
     double *ys = xs + D * LDX;                                   // Y tile (Heun)
     double *zs = ys + (HEUN ? D * LDX : 0);                      // increment tile zs[k*LDX + n], k < ZR (noise == 1)
-    const int tid = NG == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31), lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
-    auto tile_sync = [] { if (NG == 1) __syncthreads(); else __syncwarp(); };
+    const int tid = NG == 1 ? (int)threadIdx.x : (int)(threadIdx.x % NT), lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    auto tile_sync = [gi] {
+        if (NG == 1) __syncthreads();
+        else if (NW == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(gi + 1), "n"(NT) : "memory");
+    };
     if (!a.B) { if (HOT) icdf_stage_hot(sh_tab, a.icdf, (int)threadIdx.x, NT * NG); else icdf_stage(sh_tab, a.icdf, (int)threadIdx.x, NT * NG); }
     if (NG > 1) __syncthreads();                                 // the table is in place; from here on warps run on their own
     const int nsteps = a.nt - 1, dr = a.d, nB = a.nB, KK = q.KK, KKG = q.KKG;
@@ -342,6 +347,15 @@ static bool tc_plan(const LinearArgs &a, const double *hostG, TcPlan *p)
         p->hot = 0;
         p->smem = tc_smem(a.B != nullptr, D, 8 * nbt, heun, zrows);
         if (p->smem > (size_t)226 * 1024) continue;
+        if (p->nw >= 2 && p->nw <= 4 && p->rb == 1) {            // 32 < d <= 128: two or four tiles per CTA behind one table
+            int ng_max = 4;
+            if (const char *e = getenv("SDEGPU_TC_NG")) if (atoi(e) > 0) ng_max = atoi(e);
+            for (int ng : {4, 2}) {
+                if (ng > ng_max || 32 * p->nw * ng > 256) continue;     // 256 threads keep 255 registers each: the accumulators need them
+                const size_t sm = tc_smem(a.B != nullptr, D, 8 * nbt, heun, zrows, ng, false);
+                if (sm <= (size_t)226 * 1024) { p->ng = ng; p->smem = sm; break; }
+            }
+        }
         if (p->nw == 1 && p->rb == 1) {                          // one warp per tile: as many tiles per CTA as fit, 16 at most
             int ng_max = p->ma * nbt <= 8 ? 16 : 8;      // 512 threads leave 128 registers each: enough for 16 accumulator doubles, not for 32
             if (const char *e = getenv("SDEGPU_TC_NG")) if (atoi(e) > 0) ng_max = atoi(e);
@@ -416,10 +430,21 @@ static int tc_launch_ng(const LinearArgs &a, const TcArgs &q, const TcPlan &p, i
     }
 }
 
+template <int NW, int MA, int NBT>
+static int tc_launch_groups(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
+{
+    if (NW >= 2 && NW <= 4) {
+        if (p.ng == 4 && 32 * NW * 4 <= 256) return tc_launch<NW, MA, NBT, 1, (32 * NW * 4 <= 256 ? 4 : 1)>(a, q, p, sm_count, stream);
+        if (p.ng == 2) return tc_launch<NW, MA, NBT, 1, 2>(a, q, p, sm_count, stream);
+    }
+    return tc_launch<NW, MA, NBT, 1>(a, q, p, sm_count, stream);
+}
+
 template <int NW, int MA>
 static int tc_launch_nbt(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
 {
     if (NW == 1) return p.nbt == 8 ? tc_launch_ng<MA, 8>(a, q, p, sm_count, stream) : tc_launch_ng<MA, 4>(a, q, p, sm_count, stream);
+    if (NW <= 4) return p.nbt == 8 ? tc_launch_groups<NW, MA, 8>(a, q, p, sm_count, stream) : tc_launch_groups<NW, MA, 4>(a, q, p, sm_count, stream);
     return p.nbt == 8 ? tc_launch<NW, MA, 8, 1>(a, q, p, sm_count, stream) : tc_launch<NW, MA, 4, 1>(a, q, p, sm_count, stream);
 }
 

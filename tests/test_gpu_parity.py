@@ -423,12 +423,17 @@ def test_argument_errors(sde, eng):
 
 
 # ---- high-dimensional linear SDE on the FP64 tensor path (DMMA) ------------------------------------------
+@pytest.mark.parametrize("force_dmma", [False, True])
 @pytest.mark.parametrize("d", [32, 40, 96, 100, 250, 256])
-def test_linear_dmma_matches_generic_kernel_and_oracle(eng, d):
-    """Config C4 at test size: dX = AX dt + diag(g) dB, euler, fused generator.  The DMMA kernel (terminal
+def test_linear_dmma_matches_generic_kernel_and_oracle(eng, d, force_dmma, monkeypatch):
+    """(force_dmma: 32 < d <= 128 is routed to k_linear_tc with several path tiles per CTA by default; SDEGPU_LINEAR_DMMA=1 keeps
+    the tuned C4 kernel k_linear_dmma on those sizes so that both stay covered.)
+    Config C4 at test size: dX = AX dt + diag(g) dB, euler, fused generator.  The DMMA kernel (terminal
     output; any 32 < d <= 256, zero-padded to a multiple of 32 rows) must agree with the generic kernel (taken
     when the trajectory is requested) to summation order, and with the CPU oracle's own fused generator to the
     quantile table's accuracy.  (d = 32 runs the warp-shuffle kernel.)"""
+    if force_dmma:
+        monkeypatch.setenv("SDEGPU_LINEAR_DMMA", "1")
     rng = np.random.default_rng(d)
     R = rng.standard_normal((d, d))
     A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
@@ -806,11 +811,15 @@ def test_c_abi_from_plain_c(gpu, tmp_path):
     assert r.returncode == 0 and "abi smoke ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("force_dmma", [False, True])
 @pytest.mark.parametrize("d,nB", [(64, 64), (100, 7), (128, 128), (160, 160), (256, 5), (40, 1)])
-def test_linear_dmma_dense_noise_matrix(eng, d, nB):
-    """Correlated noise (dense G, any nB) on the tensor path: the increment term is a second GEMM on a tile of
+def test_linear_dmma_dense_noise_matrix(eng, d, nB, force_dmma, monkeypatch):
+    """(force_dmma as above: d <= 96 runs on k_linear_tc by default, k_linear_dmma_dense when forced.)
+    Correlated noise (dense G, any nB) on the tensor path: the increment term is a second GEMM on a tile of
     normals.  Must agree with the generic kernel (taken when the trajectory is requested) to summation order and
     with the CPU oracle's fused generator to the quantile table's accuracy; moments = those of the terminal states."""
+    if force_dmma:
+        monkeypatch.setenv("SDEGPU_LINEAR_DMMA", "1")
     rng = np.random.default_rng(1000 * d + nB)
     R = rng.standard_normal((d, d))
     A = -0.5 * np.eye(d) + (R - R.T) / np.sqrt(d)
