@@ -29,8 +29,8 @@ dir.create(outdir, showWarnings = FALSE)
 
 ## recorded normals for rBM: the reference calls rnorm(n, mean, sd) (R/sdetools.R:19); sourced into the global
 ## environment, rBM finds this definition before stats::rnorm
-.z <- NULL
-rnorm <- function(n, mean = 0, sd = 1) mean + sd * .z[seq_len(n)]
+.z <- NULL; .zpos <- 0                  # successive rnorm() calls (rvBM: one per channel) walk through .z
+rnorm <- function(n, mean = 0, sd = 1) { i <- .zpos + seq_len(n); .zpos <<- .zpos + n; mean + sd * .z[i] }
 
 source(file.path(ref, "R", "sdetools.R"))
 
@@ -154,7 +154,13 @@ write.hex("int_ito", res$ito); write.hex("int_qv", res$qv); write.hex("int_cv", 
 zz <- read.hex("rbm_z")                  # nt x P
 tb <- read.hex("rbm_times")
 BM <- array(0, dim(zz))
-for (p in 1:dim(zz)[2]) { .z <- zz[, p]; BM[, p] <- rBM(tb, sigma = 0.7, B0 = 0.25, u = -0.1) }
+for (p in 1:dim(zz)[2]) { .z <- zz[, p]; .zpos <- 0; BM[, p] <- rBM(tb, sigma = 0.7, B0 = 0.25, u = -0.1) }
 write.hex("rbm_B", BM)
+
+## rvBM (R/sdetools.R:40-46: one rBM per channel through sapply, vector sigma / B0 / u) and rBrownianBridge (:62-73)
+.z <- as.numeric(zz); .zpos <- 0         # the columns of rbm_z, consumed channel by channel
+write.hex("rvbm_B", rvBM(tb, n = dim(zz)[2], sigma = c(0.7, 1.3, 0.2), B0 = c(0.25, -1, 0), u = c(-0.1, 0, 0.4)))
+.z <- zz[, 2]; .zpos <- 0
+write.hex("bridge_B", rBrownianBridge(tb, B0T = c(1, -2), sigma = 0.8))
 
 cat("wrote", length(list.files(outdir)), "files to", outdir, "\n")

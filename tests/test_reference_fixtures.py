@@ -152,6 +152,9 @@ def test_oracle_matches_R_integrals_and_rbm():
     assert same(np.stack([O.CrossVariation(f[c], g[c]) for c in range(nc)]), ref("int_cv"))
     z, tb = inp("rbm_z"), inp("rbm_times")
     assert same(np.stack([O.rBM(tb, sigma=0.7, B0=0.25, u=-0.1, z=z[:, p]) for p in range(z.shape[1])], axis=1), ref("rbm_B"))
+    if os.path.exists(os.path.join(OUT, "rvbm_B.txt")):          # fixtures made since rvBM / rBrownianBridge joined the recipe
+        assert same(O.rvBM(tb, z.shape[1], sigma=[0.7, 1.3, 0.2], B0=[0.25, -1, 0], u=[-0.1, 0, 0.4], z=z), ref("rvbm_B"))
+        assert same(O.rBrownianBridge(tb, B0T=(1.0, -2.0), sigma=0.8, z=z[:, 1]), ref("bridge_B"))
 
 
 def _td():
