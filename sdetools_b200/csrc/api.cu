@@ -660,10 +660,11 @@ public:
 private:
     CopyPool()
     {
-        // One copy thread per physical core (half the logical CPUs), 16 at most; the submitting thread is one of them.  Measured on
-        // the B200 box (16 logical CPUs, streaming stores): 8 threads 55 GB/s, 16 threads 52, 32 threads 49 (profiles/r2_e2e_modes.txt).
+        // Copy threads: three quarters of the logical CPUs, 16 at most; the submitting thread is one of them.  Measured on two B200
+        // boxes of the pool (16 logical CPUs, streaming stores; profiles/r2_e2e_staging_experiment.txt): box A 8 threads 55 GB/s,
+        // 16 threads 52, 32 threads 49; box B 6 threads 38.5, 8 threads 41.9, 12 threads 44.0, 16 threads 42.8.
         unsigned hw = std::thread::hardware_concurrency();
-        unsigned n = hw >= 4 ? hw / 2 - 1 : (hw > 1 ? hw - 1 : 0);
+        unsigned n = hw >= 4 ? hw * 3 / 4 - 1 : (hw > 1 ? hw - 1 : 0);
         if (n > 15) n = 15;
         if (const char *e = getenv("SDEGPU_COPY_THREADS")) if (atoi(e) > 0) n = (unsigned)atoi(e) - 1;
         for (unsigned k = 0; k < n; ++k) th_.emplace_back([this] { work(); });
