@@ -26,6 +26,9 @@ namespace sdegpu {
 #ifndef SDEGPU_INT_MAX_BLOCKS_PER_SM
 #define SDEGPU_INT_MAX_BLOCKS_PER_SM 0         // 0: as many as fit
 #endif
+#ifndef SDEGPU_INT_DEPTH
+#define SDEGPU_INT_DEPTH 1                     // sectors per input stream in flight ahead of the one being summed
+#endif
 constexpr int INT_THREADS = SDEGPU_INT_THREADS;
 
 
@@ -79,18 +82,36 @@ __global__ void __launch_bounds__(INT_THREADS, MODE == 1 ? 3 : SDEGPU_INT_MIN_BL
             if (MODE == 0 && q.c) q.c[base + s + 1] = oc;
         }
         double na[4], nb[4];                                     // next sectors, in flight while this group is summed
+#if SDEGPU_INT_DEPTH == 2
+        double na2[4], nb2[4];                                   // and the ones after: two sectors per stream in flight
+#endif
         if (ngroups > 0) {
             ld_sector(pa + s + 1, na);
             if (pb != pa) ld_sector(pb + s + 1, nb);
+#if SDEGPU_INT_DEPTH == 2
+            if (ngroups > 1) {
+                ld_sector(pa + s + 5, na2);
+                if (pb != pa) ld_sector(pb + s + 5, nb2);
+            }
+#endif
         }
         for (uint64_t m = 0; m < ngroups; ++m, s += 4) {
             double va[4], vb[4], vl[4], vr[4], vc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { va[k] = na[k]; vb[k] = pb != pa ? nb[k] : na[k]; }
+#if SDEGPU_INT_DEPTH == 2
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { na[k] = na2[k]; nb[k] = nb2[k]; }
+            if (m + 2 < ngroups) {
+                ld_sector(pa + s + 9, na2);
+                if (pb != pa) ld_sector(pb + s + 9, nb2);
+            }
+#else
             if (m + 1 < ngroups) {
                 ld_sector(pa + s + 5, na);
                 if (pb != pa) ld_sector(pb + s + 5, nb);
             }
+#endif
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 element(va[k], vb[k]);
