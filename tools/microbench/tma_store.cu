@@ -71,8 +71,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_fill(double* X, size_t n4) {
 }
 
 // 3-D box: [16 doubles][32 rows][NCH chunks] -> NCH*128 bytes per row in one TMA store
-template <int NCH, int NW = 8>
+template <int NCH, int NW = 8, int HINT = 0>       // HINT: L2 cache policy of the store, 0 none, 1 evict_first, 2 evict_last, 3 evict_unchanged
 __global__ void __launch_bounds__(NW * 32, 1) k_tma3(const __grid_constant__ Maps maps, int Q, int nq, int nt) {
+    uint64_t policy = 0;
+    if (HINT == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (HINT == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    if (HINT == 3) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(policy));
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int TILE = NCH * 32 * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,8 +101,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_tma3(const __grid_constant__ Map
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                             ::"l"(&maps.m[cls]), "r"(0), "r"(q0), "r"(g * NCH), "r"(smem_u32(tile)) : "memory");
+                if (HINT == 0)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                 ::"l"(&maps.m[cls]), "r"(0), "r"(q0), "r"(g * NCH), "r"(smem_u32(tile)) : "memory");
+                else
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+                                 ::"l"(&maps.m[cls]), "r"(0), "r"(q0), "r"(g * NCH), "r"(smem_u32(tile)), "l"(policy) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
@@ -235,6 +243,11 @@ int main(int argc, char** argv) {
     run3(k_tma3<2, 4>, 2, "tma 3-D box 256 B/row, 4 warps", 4);
     run3(k_tma3<4, 4>, 4, "tma 3-D box 512 B/row, 4 warps", 4);
     run3(k_tma3<12, 4>, 12, "tma 3-D box 1536 B/row, 4 warps", 4);
+    run3(k_tma3<2, 8, 1>, 2, "tma 3-D box 256 B/row, 8 warps, evict_first");
+    run3(k_tma3<2, 8, 2>, 2, "tma 3-D box 256 B/row, 8 warps, evict_last");
+    run3(k_tma3<2, 8, 3>, 2, "tma 3-D box 256 B/row, 8 warps, evict_unchanged");
+    run3(k_tma3<2, 16, 1>, 2, "tma 3-D box 256 B/row, 16 warps, evict_first", 16);
+    run3(k_tma3<2, 4, 1>, 2, "tma 3-D box 256 B/row, 4 warps, evict_first", 4);
     run3(k_tma3<2, 2>, 2, "tma 3-D box 256 B/row, 2 warps", 2);
     run3(k_tma3<8, 2>, 8, "tma 3-D box 1024 B/row, 2 warps", 2);
     CK(cudaDeviceSynchronize());
