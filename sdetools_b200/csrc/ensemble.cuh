@@ -342,6 +342,9 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 #ifndef SDEGPU_TRAJ_MAX_THREADS
 #define SDEGPU_TRAJ_MAX_THREADS 256
 #endif
+#ifndef SDEGPU_TRAJ_PIPE
+#define SDEGPU_TRAJ_PIPE 1                     // generator software-pipelined one Philox block ahead of the step chain
+#endif
 constexpr int TRAJ_REPL = SDEGPU_TRAJ_REPL;
 // Per state dimension: a scalar model owns one row per path, so 12 warps (384 rows in flight) with single-chunk stores
 // (128 B per row) still sit on the memory system's good side and give the generator and the step — which co-limit these
@@ -393,6 +396,16 @@ __device__ __forceinline__ void traj_put(const double (&v)[16], uint32_t cur, ui
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
         const int vs = u + D;                                    // slot in chunk m; negative: slot 16 + vs of chunk m-1
+        if ((D & 1) != 0) {
+            // odd shift: a 128-bit store would pair (v[1], v[2]), ... — registers that are not an aligned quad, which costs two
+            // moves per value (36 per component and body); sixteen 64-bit stores move the same bytes in the same wavefronts
+            if (vs < 0) {
+                if (first) {
+                    if (valid) grow[1 + u] = v[u];
+                } else sts_f64(prev + traj_slot(lane_row, l7, 16 + vs), v[u]);
+            } else sts_f64(cur + traj_slot(lane_row, l7, vs), v[u]);
+            continue;
+        }
         const bool even = (vs & 1) == 0, pair = even && u + 1 < 16;
         if (!even && u != 0) continue;                           // second half of the pair stored at u - 1
         if (vs < 0) {
@@ -455,6 +468,50 @@ k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps,
             hd[j] = geo.head[w * NX + j];
             if (valid) grow[j][0] = x[j];                        // X[1,] <- x0 (:441)
         }
+#if SDEGPU_TRAJ_PIPE
+        // Software pipeline over Philox blocks (four steps each).  While block g integrates — a dependent FP64 chain —
+        // the normals of block g+1 are evaluated from words generated during block g-1 and the words of block g+2 are
+        // generated: three independent instruction streams in ONE basic block, which is what a kernel that runs one
+        // warp per scheduler needs (before, the 16 inversions, the 16 steps and the stores ran one after the other and
+        // a warp-step took ~130 cycles for ~45 instructions).  A tail word (1 block in ~1000) is evaluated on the
+        // clamped segment first and replaced behind the block, so the common path has no branch in front of it.
+        double zc[4];                                            // scale * normals of block g
+        uint32_t wn[4];                                          // words of block g+1
+        {
+            uint32_t w0[4];
+            philox_block(a.seed, gp, 0u, 0u, w0[0], w0[1], w0[2], w0[3]);
+            gen.quad(a.seed, gp, 0u, 0u, w0, zc);
+            philox_block(a.seed, gp, 1u, 0u, wn[0], wn[1], wn[2], wn[3]);
+        }
+        int issued = 0;
+        uint32_t cur = 0u, prev = (NSLOT - 1) * CHUNK;           // ring offsets of chunks m and m-1
+        for (int m = 0; m < nbody; ++m) {
+            double v[NX][16];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t g = (uint32_t)(4 * m + b);
+                double zn[4];
+                uint32_t wk[4];
+                const bool tail = gen.bulk_quad_clamped(wn, zn);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) wk[k] = wn[k];
+                philox_block(a.seed, gp, g + 2u, 0u, wn[0], wn[1], wn[2], wn[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (UNIFORM) FS::apply(a.P, x, cu, zc[k]);
+                    else {
+                        CoefRow row;
+                        row.load(a.coef + (size_t)(16 * m + 4 * b + k) * FAST_NCOEF);
+                        FS::apply(a.P, x, row, row[0] * zc[k]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) v[j][4 * b + k] = x[j];
+                }
+                if (tail) gen.fix_tail(a.seed, gp, g + 1u, 0u, wk, zn);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) zc[k] = zn[k];
+            }
+#else
         uint32_t r[4][4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) philox_block(a.seed, gp, (uint32_t)b, 0u, r[b][0], r[b][1], r[b][2], r[b][3]);
@@ -478,6 +535,7 @@ k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps,
                     for (int j = 0; j < NX; ++j) v[j][4 * b + k] = x[j];
                 }
             }
+#endif
             if (m % CH == 0) {                                   // entering the ring half the store before last read from
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
@@ -512,8 +570,19 @@ k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps,
         // rest of the row is written element by element
         for (int i = 16 * nbody; i < nsteps; i += 4) {
             double z[4];
+#if SDEGPU_TRAJ_PIPE
+            if (i == 16 * nbody) {                               // the pipeline's current block
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[k] = zc[k];
+            } else {
+                uint32_t w[4];
+                philox_block(a.seed, gp, (uint32_t)(i >> 2), 0u, w[0], w[1], w[2], w[3]);
+                gen.quad(a.seed, gp, (uint32_t)(i >> 2), 0u, w, z);
+            }
+#else
             if (i != 16 * nbody) philox_block(a.seed, gp, (uint32_t)(i >> 2), 0u, r[0][0], r[0][1], r[0][2], r[0][3]);
             gen.quad(a.seed, gp, (uint32_t)(i >> 2), 0u, r[0], z);
+#endif
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (i + k < nsteps) {

@@ -161,8 +161,8 @@ __device__ __forceinline__ void philox_block(const PhiloxKey &key, uint64_t path
 
 // Extension block of the tail draws, out of line on purpose: it runs for ~1 block in 1000 and, inlined, its
 // twenty round keys would be copied into vector registers at the top of every iteration of the hot loop.
-static __device__ __noinline__ uint4 philox_extension(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
-                                               uint32_t block, uint32_t channel)
+__device__ __forceinline__ uint4 philox_extension_inl(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+                                                      uint32_t block, uint32_t channel)
 {
     uint32_t c0 = path_lo, c1 = path_hi, c2 = block, c3 = channel | 0x40000000u, k0 = seed_lo, k1 = seed_hi;
 #pragma unroll 1
@@ -174,6 +174,11 @@ static __device__ __noinline__ uint4 philox_extension(uint32_t seed_lo, uint32_t
         k0 += PHILOX_W0; k1 += PHILOX_W1;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+static __device__ __noinline__ uint4 philox_extension(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+                                               uint32_t block, uint32_t channel)
+{
+    return philox_extension_inl(seed_lo, seed_hi, path_lo, path_hi, block, channel);
 }
 
 // is any of the four words a tail draw?  v < 2^19  <=>  (w|1) - (2^31 - 2^19) < 2^20 as unsigned
@@ -255,17 +260,17 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
     return v;
 }
 
-// The tail of the fast path, out of line on purpose (one block in ~1000): all four normals of the block through
-// the generic tables in global memory, scaled like the staged table.  zout is a scratch array of the caller.
-static __device__ __noinline__ void icdf32_tail_quad(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
-                                                     uint32_t block, uint32_t channel, uint32_t w0, uint32_t w1, uint32_t w2,
-                                                     uint32_t w3, const double *g52, double scale, double *zout)
+// The tail of the fast path, out of line on purpose.  A lane holds a tail draw in one block of ~1000, but the branch is
+// taken by the warp: with 32 lanes, one block in 32 pays for it, so it is kept short — ONE word per call (the extension
+// block, then the generic tables in global memory, scaled like the staged table) and the result in registers; the other
+// words of the block stay on the bulk path, so a normal is a function of its own word (and its extension word) alone.
+static __device__ __noinline__ double icdf32_tail_one(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+                                                      uint32_t block, uint32_t channel, uint32_t k, uint32_t w, const double *g52,
+                                                      double scale)
 {
-    const uint4 e = philox_extension(seed_lo, seed_hi, path_lo, path_hi, block, channel);
-    zout[0] = scale * icdf_normal32<false>(w0, e.x, g52);
-    zout[1] = scale * icdf_normal32<false>(w1, e.y, g52);
-    zout[2] = scale * icdf_normal32<false>(w2, e.z, g52);
-    zout[3] = scale * icdf_normal32<false>(w3, e.w, g52);
+    const uint4 e = philox_extension_inl(seed_lo, seed_hi, path_lo, path_hi, block, channel);
+    const uint32_t ew = k == 0u ? e.x : (k == 1u ? e.y : (k == 2u ? e.z : e.w));
+    return scale * icdf_normal32<false>(w, ew, g52);
 }
 
 template <int REPL> struct NormalGen {
@@ -327,6 +332,34 @@ template <int REPL> struct NormalGen {
 #endif
     }
 
+    // the tail words of a block (|s| < 2^19, segment bits below the first bulk octave) replaced through the generic tables
+    __device__ __forceinline__ void fix_tail(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
+                                             const uint32_t (&r)[4], double (&z)[4]) const
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (seg_bits(word_to_s(r[k])) < 0x41200000u)
+                z[k] = icdf32_tail_one(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, (uint32_t)k, r[k],
+                                       g52, scale);
+    }
+
+    // The four normals of a block on the bulk path WITHOUT a branch: a tail word (|s| < 2^19) is evaluated on the lowest
+    // bulk segment (a finite placeholder) and the return value tells the caller to replace the block through quad().  For
+    // kernels that schedule the evaluation into the shadow of another dependent chain.
+    __device__ __forceinline__ bool bulk_quad_clamped(const uint32_t (&r)[4], double (&z)[4]) const
+    {
+        uint32_t lowest = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double s = word_to_s(r[k]);
+            uint32_t sg = seg_bits(s);
+            asm volatile("" : "+r"(sg));
+            lowest = min(lowest, sg);
+            z[k] = bulk_at(s, max(sg, 0x41200000u));
+        }
+        return lowest < 0x41200000u;
+    }
+
     __device__ __forceinline__ void quad(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
                                          const uint32_t (&r)[4], double (&z)[4]) const
     {
@@ -342,11 +375,11 @@ template <int REPL> struct NormalGen {
             asm volatile("" : "+r"(sg[k]));
         }
         if (min(min(sg[0], sg[1]), min(sg[2], sg[3])) < 0x41200000u) {
-            double zt[4];
-            icdf32_tail_quad(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, r[0], r[1], r[2], r[3],
-                             g52, scale, zt);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) z[k] = zt[k];
+            for (int k = 0; k < 4; ++k)
+                z[k] = sg[k] < 0x41200000u ? icdf32_tail_one(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel,
+                                                             (uint32_t)k, r[k], g52, scale)
+                                           : bulk_at(s[k], sg[k]);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) z[k] = bulk_at(s[k], sg[k]);
@@ -354,11 +387,11 @@ template <int REPL> struct NormalGen {
         return;
 #endif
         if (has_tail(r)) {
-            double zt[4];                                        // its address is taken: kept apart from z, which stays in registers
-            icdf32_tail_quad(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, r[0], r[1], r[2], r[3],
-                             g52, scale, zt);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) z[k] = zt[k];
+            for (int k = 0; k < 4; ++k)
+                z[k] = seg_bits(word_to_s(r[k])) < 0x41200000u
+                           ? icdf32_tail_one(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, (uint32_t)k, r[k], g52, scale)
+                           : bulk(r[k]);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) z[k] = bulk(r[k]);
