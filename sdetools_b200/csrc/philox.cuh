@@ -260,10 +260,18 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
     return v;
 }
 
-// The tail of the fast path, out of line on purpose.  A lane holds a tail draw in one block of ~1000, but the branch is
-// taken by the warp: with 32 lanes, one block in 32 pays for it, so it is kept short — ONE word per call (the extension
-// block, then the generic tables in global memory, scaled like the staged table) and the result in registers; the other
-// words of the block stay on the bulk path, so a normal is a function of its own word (and its extension word) alone.
+// The rare path of the fast evaluation, out of line on purpose (defined behind NormalGen).  A lane holds a tail draw in one
+// block of ~1000, but the branch is taken by the warp: with 32 lanes, one block in 32 pays for it.  Per word: a tail word
+// (|s| < 2^19) goes through the extension block and the generic tables in global memory, every other word through the same
+// bulk table as on the common path — so a normal is a function of its own word (and its extension word) alone, whichever
+// kernel draws it.  zout is a scratch array of the caller.
+template <int REPL>
+static __device__ __noinline__ void icdf32_rare_quad(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+                                                     uint32_t block, uint32_t channel, uint32_t w0, uint32_t w1, uint32_t w2,
+                                                     uint32_t w3, const double *g52, double scale, uint32_t base, double *zout);
+
+// One tail word alone (extension block, generic tables), result in registers: for the kernels that run one warp per
+// scheduler and feel the length of the rare path (k_traj; measured against icdf32_rare_quad there: 0.760 vs 0.749 on C3).
 static __device__ __noinline__ double icdf32_tail_one(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
                                                       uint32_t block, uint32_t channel, uint32_t k, uint32_t w, const double *g52,
                                                       double scale)
@@ -316,6 +324,8 @@ template <int REPL> struct NormalGen {
     // bulk() with s and its segment bits already at hand
     __device__ __forceinline__ double bulk_at(double s, uint32_t seg) const
     {
+        // (the same address by one IMAD.HI on the FMA pipe instead of this LEA.HI on the ALU pipe was measured: 5 % slower,
+        // profiles/r2_tune_terminal_imad.txt — its 64-bit addend costs two moves per normal)
         const uint32_t addr = base + (seg >> (11 - L::LOG));
         const double2 c01 = lds_f64x2(addr), c23 = lds_f64x2(addr + L::PLANE_BYTES);
         const double v = fabs(s);
@@ -332,7 +342,18 @@ template <int REPL> struct NormalGen {
 #endif
     }
 
-    // the tail words of a block (|s| < 2^19, segment bits below the first bulk octave) replaced through the generic tables
+    // a block that holds a tail draw, out of line (see icdf32_rare_quad)
+    __device__ __forceinline__ void rare(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
+                                         const uint32_t (&r)[4], double (&z)[4]) const
+    {
+        double zt[4];                                            // its address is taken: kept apart from z, which stays in registers
+        icdf32_rare_quad<REPL>(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, r[0], r[1], r[2], r[3],
+                               g52, scale, base, zt);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = zt[k];
+    }
+
+    // the tail words of a block whose other words are evaluated already (bulk_quad_clamped): same values as rare()
     __device__ __forceinline__ void fix_tail(const PhiloxKey &key, uint64_t path, uint32_t block, uint32_t channel,
                                              const uint32_t (&r)[4], double (&z)[4]) const
     {
@@ -344,7 +365,7 @@ template <int REPL> struct NormalGen {
     }
 
     // The four normals of a block on the bulk path WITHOUT a branch: a tail word (|s| < 2^19) is evaluated on the lowest
-    // bulk segment (a finite placeholder) and the return value tells the caller to replace the block through quad().  For
+    // bulk segment (a finite placeholder) and the return value tells the caller to replace them through fix_tail().  For
     // kernels that schedule the evaluation into the shadow of another dependent chain.
     __device__ __forceinline__ bool bulk_quad_clamped(const uint32_t (&r)[4], double (&z)[4]) const
     {
@@ -374,25 +395,15 @@ template <int REPL> struct NormalGen {
             sg[k] = seg_bits(s[k]);
             asm volatile("" : "+r"(sg[k]));
         }
-        if (min(min(sg[0], sg[1]), min(sg[2], sg[3])) < 0x41200000u) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                z[k] = sg[k] < 0x41200000u ? icdf32_tail_one(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel,
-                                                             (uint32_t)k, r[k], g52, scale)
-                                           : bulk_at(s[k], sg[k]);
-        } else {
+        if (min(min(sg[0], sg[1]), min(sg[2], sg[3])) < 0x41200000u) rare(key, path, block, channel, r, z);
+        else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) z[k] = bulk_at(s[k], sg[k]);
         }
         return;
 #endif
-        if (has_tail(r)) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                z[k] = seg_bits(word_to_s(r[k])) < 0x41200000u
-                           ? icdf32_tail_one(key.k[0], key.k[1], (uint32_t)path, (uint32_t)(path >> 32), block, channel, (uint32_t)k, r[k], g52, scale)
-                           : bulk(r[k]);
-        } else {
+        if (has_tail(r)) rare(key, path, block, channel, r, z);
+        else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) z[k] = bulk(r[k]);
         }
@@ -452,5 +463,22 @@ template <int REPL> struct NormalGen {
         }
     }
 };
+
+template <int REPL>
+static __device__ __noinline__ void icdf32_rare_quad(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
+                                                     uint32_t block, uint32_t channel, uint32_t w0, uint32_t w1, uint32_t w2,
+                                                     uint32_t w3, const double *g52, double scale, uint32_t base, double *zout)
+{
+    NormalGen<REPL> gen;
+    gen.base = base; gen.g52 = g52; gen.scale = scale;
+    const uint4 e = philox_extension_inl(seed_lo, seed_hi, path_lo, path_hi, block, channel);
+    const uint32_t w[4] = {w0, w1, w2, w3}, ew[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double s = NormalGen<REPL>::word_to_s(w[k]);
+        const uint32_t sg = NormalGen<REPL>::seg_bits(s);
+        zout[k] = sg < 0x41200000u ? scale * icdf_normal32<false>(w[k], ew[k], g52) : gen.bulk_at(s, sg);
+    }
+}
 
 }  // namespace sdegpu
