@@ -129,11 +129,15 @@ int main()
     const int n = 1001;
     const long ncols = 524288;
     Arrs q;
-    for (int i = 0; i < 2; ++i) { double* p; CK(cudaMalloc(&p, sizeof(double) * n * ncols)); CK(cudaMemset(p, 0, sizeof(double) * n * ncols)); q.in[i] = p; }
-    for (int i = 0; i < 3; ++i) { CK(cudaMalloc(&q.out[i], sizeof(double) * n * ncols)); }
+    const size_t elems = (size_t)10001 * 75776;                   // the larger of the two shapes
+    for (int i = 0; i < 2; ++i) { double* p; CK(cudaMalloc(&p, sizeof(double) * elems)); CK(cudaMemset(p, 0, sizeof(double) * elems)); q.in[i] = p; }
+    for (int i = 0; i < 3; ++i) { CK(cudaMalloc(&q.out[i], sizeof(double) * elems)); }
     run<2, 3>("stochint l/r/c (2 in 3 out)", q, n, ncols, sm);
     run<2, 1>("itointegral (2 in 1 out)", q, n, ncols, sm);
     run<1, 1>("quadratic var (1 in 1 out)", q, n, ncols, sm);
     run<1, 0>("read only (1 in)", q, n, ncols, sm);
+    // config C3 with a supplied B: 75,776 paths x 10,001 points, one row of B in, two rows of X out per path
+    run<1, 2>("C3 supplied B (1 in 2 out)", q, 10001, 75776, sm);
+    run<0 + 1, 2>("C3 supplied B, 2 waves", q, 10001, 75776, 2 * sm);
     return 0;
 }
