@@ -430,7 +430,9 @@ k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps,
     using FS = FastStep<M, SCHEME, PROJ>;
     using TL = Icdf32Layout<TRAJ_REPL>;
     extern __shared__ __align__(1024) unsigned char sh_raw[];    // [rings: warps x NX x NSLOT chunks][quantile table][histogram][scratch]
-    const int nthreads = blockDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+    // the warp index through a shuffle from lane 0: the compiler then knows it is warp-uniform, so the task bookkeeping (task and
+    // ring offsets, TMA coordinates) lives in uniform registers and the bulk stores need no register-to-uniform conversion loops
+    const int nthreads = blockDim.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, nwarps = nthreads >> 5;
     double *sh_tab = reinterpret_cast<double *>(sh_raw + (size_t)nwarps * NX * RING);
     unsigned int *sh_hist = reinterpret_cast<unsigned int *>(sh_tab + TL::DOUBLES);
     const int nhist = a.hist ? ((a.hist_nbins + 3 + 3) & ~3) : 0;
@@ -543,11 +545,14 @@ k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps,
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
                 const uint32_t rj = ring0 + (uint32_t)j * RING;
-                switch (hd[j]) {                                 // warp-uniform
-                case 1: traj_put<0>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
-                case 2: traj_put<-1>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
-                case 3: traj_put<-2>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
-                default: traj_put<-3>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]); break;
+                // warp-uniform; two compare-and-branch levels instead of a switch: ptxas turns the switch into a jump table
+                // (LDC + SHF + BRX), which costs a kernel that runs one warp per scheduler ~3 % of its time per component
+                if (hd[j] <= 2) {
+                    if (hd[j] == 1) traj_put<0>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]);
+                    else traj_put<-1>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]);
+                } else {
+                    if (hd[j] == 3) traj_put<-2>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]);
+                    else traj_put<-3>(v[j], rj + cur, rj + prev, lane_row, l7, m == 0, valid, grow[j]);
                 }
             }
             if (m > 0 && m % CH == 0) {                          // chunks m-CH .. m-1 are complete for every component

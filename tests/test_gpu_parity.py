@@ -119,6 +119,30 @@ def test_device_normals_match_reference_stream(eng):
     assert not np.array_equal(eng.normals(seed, off, 4, 6, channel=1), z[:6, :4])
 
 
+@pytest.mark.parametrize("model,params,x0,nx", [("ou", [1.3, 0.7, 0.9], [2.0], 1), ("vdp", [1.0, 0.5], [0.1, -0.2], 2)])
+def test_tail_draws_agree_across_the_fast_kernels(eng, model, params, x0, nx):
+    """A draw beyond 2^-12 in the tail leaves the fast table: the register-resident kernel replaces the block out of line, the
+    trajectory kernel evaluates it on a clamped segment first and replaces the word behind the block (philox.cuh, NormalGen).
+    Both must give every path that holds such a draw the value the generic evaluation (sdegpu_normals) gives it — a normal is a
+    function of its own word, whichever kernel draws it."""
+    P, nt, seed, off = 4096, 1030, 20261020, (1 << 35) + 17                    # 4.2e6 draws: ~1000 of them in the tail
+    t = np.arange(nt) * 1e-3
+    X = np.empty((nt, nx, P), order="F")
+    XT = np.empty((nx, P), order="F")
+    eng.run(model, "euler", params, t, x0, nx=nx, npaths=P, seed=seed, path_offset=off, X=X)
+    eng.run(model, "euler", params, t, x0, nx=nx, npaths=P, seed=seed, path_offset=off, XT=XT)
+    z = eng.normals(seed, off, P, nt - 1)
+    from scipy.stats import norm
+    zt = -norm.ppf(2.0 ** -13)                                                # |z| beyond it: u < 2^-12
+    tail_paths = np.unique(np.nonzero(np.abs(z) > zt)[1])
+    assert 600 < tail_paths.size < 1400, tail_paths.size
+    dB = (np.sqrt(O.r_diff(t))[:, None] * z)[:, None, :]
+    want = O.ensemble("euler", model, params, t, x0, dB=dB)
+    assert np.allclose(X[..., tail_paths], want[..., tail_paths], rtol=1e-12, atol=1e-13)
+    assert np.allclose(X, want, rtol=1e-12, atol=1e-13)
+    assert np.array_equal(XT, X[-1])                                          # both kernels take the folded FAST step
+
+
 @pytest.mark.parametrize("scheme,model,params,x0,proj", [("heun", "cir", [1.0, 1.0, 1.0], [1.0], "abs"),
                                                          ("euler", "vdp", [1.0, 0.5], [0.0, 0.0], "identity"),
                                                          ("euler", "ou", [1.3, 0.7, 0.9], [2.0], "identity")])
