@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma(const LinearArgs
     extern __shared__ __align__(16) double sm[];
     double *sh_tab = sm;                                         // quantile table
     double *xs = sm + ICDF_TABLE_DOUBLES;                        // X tile, xs[k*DM_LDX + n]
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0), gid = lane >> 2, tig = lane & 3;   // w through a shuffle: known to be warp-uniform
     icdf_stage(sh_tab, a.icdf, tid, 32 * NWARPS);
     const int nsteps = a.nt - 1, dr = a.d;                       // dr: the system's dimension; rows dr..D-1 are zero padding
     const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) k_linear_dmma_dense(const Line
     double *sh_tab = sm;
     double *xs = sm + ICDF_TABLE_DOUBLES;                        // X tile, xs[k*DM_LDX + n]
     double *zs = xs + D * DM_LDX;                                // Z tile, zs[k*DM_LDX + n], k < 4*KKG
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0), gid = lane >> 2, tig = lane & 3;   // w through a shuffle: known to be warp-uniform
     icdf_stage(sh_tab, a.icdf, tid, 32 * NWARPS);
     const int nsteps = a.nt - 1, dr = a.d, nB = a.nB, npairs = 2 * KKG;            // channel pairs incl. zero padding
     const uint64_t ngroups = (a.npaths + DM_PT - 1) / DM_PT;

@@ -68,12 +68,16 @@ __global__ void __launch_bounds__(32 * NW * NG, 1) k_linear_tc(const LinearArgs 
     constexpr int D = 8 * MA * NW * RB, PT = 8 * NBT, LDX = PT + 4, NT = 32 * NW;
     extern __shared__ __align__(16) double sm[];
     double *sh_tab = sm;                                         // quantile table (fused generator only)
-    const int gi = NG == 1 ? 0 : (int)(threadIdx.x / NT);        // this warp group's path tile
+    // One warp per tile (NW == 1): the warp index through a shuffle from lane 0 — same value, but known to be warp-uniform, so the
+    // tile bookkeeping lives in uniform registers (d = 8 / 16 / 32: +5..10 %; with several warps per tile it measured 1-3 % slower,
+    // profiles/r2_tune_tc_uni.txt, so those keep the plain index)
+    const int wcta = NW == 1 ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
+    const int gi = NG == 1 ? 0 : wcta / NW;                      // this warp group's path tile
     const int tile_doubles = (D * (HEUN ? 2 : 1) + q.ZR) * LDX;
     double *xs = sm + (a.B ? 0 : TABLE) + gi * tile_doubles;      // X tile  xs[k*LDX + n]
     double *ys = xs + D * LDX;                                   // Y tile (Heun)
     double *zs = ys + (HEUN ? D * LDX : 0);                      // increment tile zs[k*LDX + n], k < ZR (noise == 1)
-    const int tid = NG == 1 ? (int)threadIdx.x : (int)(threadIdx.x % NT), lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int lane = (int)(threadIdx.x & 31u), w = NG == 1 ? wcta : wcta % NW, tid = 32 * w + lane, gid = lane >> 2, tig = lane & 3;
     auto tile_sync = [gi] {
         if (NG == 1) __syncthreads();
         else if (NW == 1) __syncwarp();
