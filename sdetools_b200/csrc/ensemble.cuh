@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) n[k] = r[q][k] * 1664525u + 1013904223u + (uint32_t)gp;
 #else
+                // (PhiloxPath — the path's share of the rounds computed once, 17 instead of 20 wide multiplies per block — was measured
+                // here: 0.4 % slower, profiles/r2_tune_philox_path.txt; the wide multiplies are not what this kernel waits for)
                 philox_block(a.seed, gp, blk + 1u, 0u, n[0], n[1], n[2], n[3]);
 #endif
                 double z[4];
@@ -479,11 +481,13 @@ k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps,
         // clamped segment first and replaced behind the block, so the common path has no branch in front of it.
         double zc[4];                                            // scale * normals of block g
         uint32_t wn[4];                                          // words of block g+1
+        PhiloxPath pp;                                           // the path's share of the Philox rounds, computed once
+        pp.init(a.seed, gp, 0u);
         {
             uint32_t w0[4];
-            philox_block(a.seed, gp, 0u, 0u, w0[0], w0[1], w0[2], w0[3]);
+            pp.block(a.seed, 0u, w0[0], w0[1], w0[2], w0[3]);
             gen.quad(a.seed, gp, 0u, 0u, w0, zc);
-            philox_block(a.seed, gp, 1u, 0u, wn[0], wn[1], wn[2], wn[3]);
+            pp.block(a.seed, 1u, wn[0], wn[1], wn[2], wn[3]);
         }
         int issued = 0;
         uint32_t cur = 0u, prev = (NSLOT - 1) * CHUNK;           // ring offsets of chunks m and m-1
@@ -497,7 +501,7 @@ k_traj(const __grid_constant__ RunArgs a, const __grid_constant__ TrajMaps maps,
                 const bool tail = gen.bulk_quad_clamped(wn, zn);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) wk[k] = wn[k];
-                philox_block(a.seed, gp, g + 2u, 0u, wn[0], wn[1], wn[2], wn[3]);
+                pp.block(a.seed, g + 2u, wn[0], wn[1], wn[2], wn[3]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (UNIFORM) FS::apply(a.P, x, cu, zc[k]);

@@ -159,6 +159,47 @@ __device__ __forceinline__ void philox_block(const PhiloxKey &key, uint64_t path
     philox4x32_10(r0, r1, r2, r3, key);
 }
 
+// The same 128 bits for many blocks of ONE path and channel, with what depends on the path alone computed once.  Round 1
+// multiplies M0 by the path's low word (fixed) and M1 by the block index (the same in every lane: a loop counter the compiler
+// keeps in the uniform datapath); behind it c2 and c3 depend on the path only, so round 2's M1 * c2 is fixed as well: 17
+// instead of 20 wide multiplies per block (they are the generator's expensive instruction, 5 cycles each), the same bits.
+struct PhiloxPath {
+    uint32_t a;              // path hi ^ k[0]:         c0 after round 1 is hi(M1 * block) ^ a
+    uint32_t c3;             // lo(M0 * path lo):       c3 after round 1
+    uint32_t h1, l1;         // hi, lo of M1 * c2 with c2 = hi(M0 * path lo) ^ channel ^ k[1], the c2 after round 1
+
+    __device__ __forceinline__ void init(const PhiloxKey &key, uint64_t path, uint32_t channel)
+    {
+        const uint32_t plo = (uint32_t)path, phi = (uint32_t)(path >> 32);
+        a = phi ^ key.k[0];
+        c3 = PHILOX_M0 * plo;
+        const uint32_t c2 = __umulhi(PHILOX_M0, plo) ^ channel ^ key.k[1];
+        h1 = __umulhi(PHILOX_M1, c2);
+        l1 = PHILOX_M1 * c2;
+    }
+
+    __device__ __forceinline__ void block(const PhiloxKey &key, uint32_t blk, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) const
+    {
+        // round 1: only M1 * block is left of it
+        uint32_t c0 = __umulhi(PHILOX_M1, blk) ^ a, c1 = PHILOX_M1 * blk;
+        // round 2: M1 * c2 is (h1, l1)
+        {
+            const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+            const uint32_t n0 = h1 ^ c1 ^ key.k[2], n2 = hi0 ^ c3 ^ key.k[3];
+            c0 = n0; c1 = l1; r2 = n2; r3 = lo0;
+        }
+        uint32_t c2 = r2, c3r = r3;
+#pragma unroll
+        for (int r = 2; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+            const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ key.k[2 * r], n2 = hi0 ^ c3r ^ key.k[2 * r + 1];
+            c0 = n0; c1 = lo1; c2 = n2; c3r = lo0;
+        }
+        r0 = c0; r1 = c1; r2 = c2; r3 = c3r;
+    }
+};
+
 // Extension block of the tail draws, out of line on purpose: it runs for ~1 block in 1000 and, inlined, its
 // twenty round keys would be copied into vector registers at the top of every iteration of the hot loop.
 __device__ __forceinline__ uint4 philox_extension_inl(uint32_t seed_lo, uint32_t seed_hi, uint32_t path_lo, uint32_t path_hi,
