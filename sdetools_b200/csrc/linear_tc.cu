@@ -343,7 +343,12 @@ static bool tc_plan(const LinearArgs &a, const double *hostG, TcPlan *p)
     // d = 32: 4.55e9 -> 5.19e9 path-steps/s)
     bool small_first = p->noise == 0;
     if (const char *e = getenv("SDEGPU_TC_SMALL_TILE")) small_first = atoi(e) != 0;
-    for (int nbt : {big, small}) {
+    // 16 < d <= 32, one warp per tile: 16-path tiles halve the accumulator registers once more, so 16 warps share an SM
+    int tiny = 0;
+    if (p->nw == 1 && p->rb == 1 && p->ma == 4) tiny = 1;
+    if (const char *e = getenv("SDEGPU_TC_NBT2")) tiny = (atoi(e) != 0 && p->nw == 1 && p->rb == 1 && p->ma == 4) ? 1 : 0;
+    for (int nbt : {tiny ? 2 : big, big, small}) {
+        if (nbt == big && tiny) continue;
         if (nbt == big && heun && p->noise == 0) continue;
         if (nbt == big && small_first && p->nw == 1 && p->rb == 1) continue;
         p->nbt = nbt;
@@ -447,7 +452,10 @@ static int tc_launch_groups(const LinearArgs &a, const TcArgs &q, const TcPlan &
 template <int NW, int MA>
 static int tc_launch_nbt(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
 {
-    if (NW == 1) return p.nbt == 8 ? tc_launch_ng<MA, 8>(a, q, p, sm_count, stream) : tc_launch_ng<MA, 4>(a, q, p, sm_count, stream);
+    if (NW == 1) {
+        if constexpr (MA == 4) { if (p.nbt == 2) return tc_launch_ng<MA, 2>(a, q, p, sm_count, stream); }
+        return p.nbt == 8 ? tc_launch_ng<MA, 8>(a, q, p, sm_count, stream) : tc_launch_ng<MA, 4>(a, q, p, sm_count, stream);
+    }
     if (NW <= 4) return p.nbt == 8 ? tc_launch_groups<NW, MA, 8>(a, q, p, sm_count, stream) : tc_launch_groups<NW, MA, 4>(a, q, p, sm_count, stream);
     return p.nbt == 8 ? tc_launch<NW, MA, 8, 1>(a, q, p, sm_count, stream) : tc_launch<NW, MA, 4, 1>(a, q, p, sm_count, stream);
 }
