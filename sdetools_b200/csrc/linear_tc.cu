@@ -347,6 +347,14 @@ static bool tc_plan(const LinearArgs &a, const double *hostG, TcPlan *p)
     int tiny = 0;
     if (p->nw == 1 && p->rb == 1 && p->ma == 4) tiny = 1;
     if (const char *e = getenv("SDEGPU_TC_NBT2")) tiny = (atoi(e) != 0 && p->nw == 1 && p->rb == 1 && p->ma == 4) ? 1 : 0;
+    // 32 < d <= 64 (tiles of two warps): the same 16-path tiles, eight of them per CTA (512 threads x 128 registers) — d = 64: 0.50 -> 0.53
+    // of FP64 peak, dense noise 0.45 -> 0.66 (profiles/r2_tune_tc_nbt2.txt).  Tiles of 3-4 warps (64 < d <= 128) measured the same
+    // either way and keep the larger tiles; SDEGPU_TC_NBT2_MID=1 / 0 forces / forbids it for all of 32 < d <= 128.
+    if (p->nw == 2 && p->rb == 1) tiny = 2;
+    if (const char *e = getenv("SDEGPU_TC_NBT2_MID")) {
+        if (atoi(e) != 0 && p->nw >= 2 && p->nw <= 4 && p->rb == 1) tiny = 2;
+        if (atoi(e) == 0 && p->nw >= 2) tiny = 0;
+    }
     for (int nbt : {tiny ? 2 : big, big, small}) {
         if (nbt == big && tiny) continue;
         if (nbt == big && heun && p->noise == 0) continue;
@@ -359,8 +367,9 @@ static bool tc_plan(const LinearArgs &a, const double *hostG, TcPlan *p)
         if (p->nw >= 2 && p->nw <= 4 && p->rb == 1) {            // 32 < d <= 128: two or four tiles per CTA behind one table
             int ng_max = 4;
             if (const char *e = getenv("SDEGPU_TC_NG")) if (atoi(e) > 0) ng_max = atoi(e);
-            for (int ng : {4, 2}) {
-                if (ng > ng_max || 32 * p->nw * ng > 256) continue;     // 256 threads keep 255 registers each: the accumulators need them
+            if (nbt == 2) ng_max = 8;
+            for (int ng : {8, 4, 2}) {
+                if (ng > ng_max || 32 * p->nw * ng > (nbt == 2 ? 512 : 256)) continue;     // 256 threads keep 255 registers each: the accumulators need them (16-path tiles: 512 x 128)
                 const size_t sm = tc_smem(a.B != nullptr, D, 8 * nbt, heun, zrows, ng, false);
                 if (sm <= (size_t)226 * 1024) { p->ng = ng; p->smem = sm; break; }
             }
@@ -443,6 +452,10 @@ template <int NW, int MA, int NBT>
 static int tc_launch_groups(const LinearArgs &a, const TcArgs &q, const TcPlan &p, int sm_count, cudaStream_t stream)
 {
     if (NW >= 2 && NW <= 4) {
+        if constexpr (NBT == 2) {
+            if (p.ng == 8 && 32 * NW * 8 <= 512) return tc_launch<NW, MA, NBT, 1, (32 * NW * 8 <= 512 ? 8 : 1)>(a, q, p, sm_count, stream);
+            if (p.ng == 4 && 32 * NW * 4 <= 512) return tc_launch<NW, MA, NBT, 1, (32 * NW * 4 <= 512 ? 4 : 1)>(a, q, p, sm_count, stream);
+        }
         if (p.ng == 4 && 32 * NW * 4 <= 256) return tc_launch<NW, MA, NBT, 1, (32 * NW * 4 <= 256 ? 4 : 1)>(a, q, p, sm_count, stream);
         if (p.ng == 2) return tc_launch<NW, MA, NBT, 1, 2>(a, q, p, sm_count, stream);
     }
@@ -456,7 +469,10 @@ static int tc_launch_nbt(const LinearArgs &a, const TcArgs &q, const TcPlan &p, 
         if constexpr (MA == 4) { if (p.nbt == 2) return tc_launch_ng<MA, 2>(a, q, p, sm_count, stream); }
         return p.nbt == 8 ? tc_launch_ng<MA, 8>(a, q, p, sm_count, stream) : tc_launch_ng<MA, 4>(a, q, p, sm_count, stream);
     }
-    if (NW <= 4) return p.nbt == 8 ? tc_launch_groups<NW, MA, 8>(a, q, p, sm_count, stream) : tc_launch_groups<NW, MA, 4>(a, q, p, sm_count, stream);
+    if (NW <= 4) {
+        if (p.nbt == 2) return tc_launch_groups<NW, MA, 2>(a, q, p, sm_count, stream);
+        return p.nbt == 8 ? tc_launch_groups<NW, MA, 8>(a, q, p, sm_count, stream) : tc_launch_groups<NW, MA, 4>(a, q, p, sm_count, stream);
+    }
     return p.nbt == 8 ? tc_launch<NW, MA, 8, 1>(a, q, p, sm_count, stream) : tc_launch<NW, MA, 4, 1>(a, q, p, sm_count, stream);
 }
 
