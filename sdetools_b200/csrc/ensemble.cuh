@@ -322,8 +322,10 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
 //   tile      per warp and component, a ring of 2*CH chunks; a chunk is 32 rows (one per lane) x 16 time points
 //             (128 bytes per row, 4 KB), laid out as the 3-D TMA box {16 doubles, 32 rows, CH chunks} with the
 //             128-byte hardware swizzle, so a lane's 16-byte store lands in bank quad (k ^ lane%8).
-//   body      16 steps (four Philox blocks) advance in registers, then every component's 16 values go to its tile
-//             as 128-bit shared stores; after CH bodies ONE elected lane issues one `cp.async.bulk.tensor.3d` per
+//   body      16 steps (four Philox blocks) advance in registers — the generator software-pipelined one block ahead, so that
+//             the step's FP64 chain, the next block's inversion and the Philox rounds of the block after share one basic
+//             block (SDEGPU_TRAJ_PIPE) — then every component's 16 values go to its tile as 128-bit shared stores (64-bit
+//             ones for odd row phases); after CH bodies ONE elected lane issues one `cp.async.bulk.tensor.3d` per
 //             component (SASS UTMASTG): CH*128 bytes per row, 32 rows.  The other half of the ring is being read
 //             by the previous store meanwhile (cp.async.bulk.wait_group.read 0 before it is overwritten).
 //   alignment rows start at arbitrary element offsets (nt is usually odd) but TMA wants 16-byte and the memory system
