@@ -242,6 +242,13 @@ __global__ void __launch_bounds__(TERMINAL_THREADS, SDEGPU_TERMINAL_MIN_BLOCKS) 
         }
         // one loop counter: the block index (the Philox counter of the block generated ahead is blk + 1, rows start at 4 blk)
         const uint32_t nfull = (uint32_t)nsteps >> 2;
+#if defined(SDEGPU_TERMINAL_UNROLL4)
+#pragma unroll 4
+#elif defined(SDEGPU_TERMINAL_UNROLL3)
+#pragma unroll 3
+#elif !defined(SDEGPU_TERMINAL_UNROLL1)
+#pragma unroll 2
+#endif
         for (uint32_t blk = 0; blk < nfull; ++blk) {
             const int i = (int)(blk << 2);
             CoefRow row[4];
